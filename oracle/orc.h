@@ -1,0 +1,123 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_field.h header).
+ * Public surface of the CPU restatement.  Each function cites the reference
+ * file:line it follows.  Built into oracle/liborc.so by oracle/Makefile.
+ *
+ * Parity status: PINNED by (i) the Poseidon2 KAT (reference
+ * primitives/poseidon31/src/implementation.rs:157-173), (ii) the known answers
+ * embedded in the reference's 15 Poseidon31 proof fixtures (PoW low bits,
+ * Merkle roots, logup sum, OODS equality, FRI last-layer equality) and
+ * (iii) the survey-probe golden values in SURVEY.md App. F.  The Rust
+ * reference itself cannot be built here (no cargo/rustc; stwo git dependency
+ * absent), so there is no oracle/_ref.
+ */
+#ifndef ORC_H
+#define ORC_H
+#include <stddef.h>
+#include <stdint.h>
+#include "orc_field.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Poseidon2 / Merkle / channel --------------------------------------- */
+void orc_poseidon2_permute(uint32_t state[16]);
+void orc_poseidon2_permute_batch(uint32_t *states, size_t n);
+/* stwo Poseidon31MerkleHasher::hash_node; children may be NULL (leaf) */
+void orc_hash_node(const uint32_t *left, const uint32_t *right,
+                   const uint32_t *cols, size_t n_cols, uint32_t out[8]);
+void orc_hash_column_get_capacity(const uint32_t *cols, size_t n_cols, uint32_t out[8]);
+/* full Merkle tree over 2^log_n leaves of n_cols M31 each (row-major leaves);
+ * layers[0] = leaf hashes ... ; out_nodes holds (2^(log_n+1)-1)*8 words, layer
+ * of size 2^k starting at word offset (2^k - 1)*8. Returns perms executed. */
+uint64_t orc_merkle_build(const uint32_t *leaves, uint32_t log_n, uint32_t n_cols,
+                          uint32_t *out_nodes);
+/* verify one leaf->root path (single-tree, columns only at the leaf layer) */
+int orc_merkle_path_verify(const uint32_t *leaf, uint32_t n_cols, uint32_t index,
+                           const uint32_t *siblings, uint32_t depth,
+                           const uint32_t root[8], uint32_t out_root[8]);
+
+typedef struct { uint32_t digest[8]; uint32_t n_sent; uint64_t n_perms; } orc_channel;
+void orc_channel_init(orc_channel *c);
+void orc_channel_mix_root(orc_channel *c, const uint32_t root[8]);
+void orc_channel_mix_felts2(orc_channel *c, const uint32_t a[4], const uint32_t b[4]);
+void orc_channel_draw(orc_channel *c, uint32_t out[8]);
+
+/* ---- proof wire format ----------------------------------- */
+#define ORC_MAX_INNER 32
+#define ORC_MAX_COLS 64
+typedef struct {
+    const uint32_t *hash_witness; uint64_t n_hash_witness;   /* x8 words */
+    uint64_t n_column_witness;
+} orc_decommitment;
+typedef struct {
+    const uint32_t *fri_witness; uint64_t n_fri_witness;     /* x4 words */
+    orc_decommitment decommitment;
+    const uint32_t *commitment;                               /* 8 words */
+} orc_fri_layer;
+typedef struct {
+    uint32_t log_size_plonk, log_size_poseidon;
+    qm31 plonk_total_sum, poseidon_total_sum;
+    uint32_t pow_bits, log_blowup, log_last, n_queries;
+    const uint32_t *commitments[4];
+    uint32_t n_cols[4];
+    uint32_t n_masks[4][ORC_MAX_COLS];
+    const uint32_t *sampled[4][ORC_MAX_COLS];                 /* n_masks x4 words */
+    uint32_t n_sampled_total;
+    orc_decommitment decommitments[4];
+    const uint32_t *queried_values[4]; uint64_t n_queried_values[4];
+    uint64_t pow_nonce;
+    orc_fri_layer first_layer;
+    uint32_t n_inner;
+    orc_fri_layer inner[ORC_MAX_INNER];
+    const uint32_t *last_coeffs; uint64_t n_last_coeffs; uint32_t last_log_size;
+} orc_proof;
+/* returns 0 on success, negative on malformed input */
+int orc_proof_parse(const uint8_t *blob, size_t len, orc_proof *out);
+
+/* ---- full native verifier ------------------------------------------------- */
+#define ORC_MAX_QUERIES 128
+#define ORC_MAX_LOGS 4
+enum {
+    ORC_OK = 0,
+    ORC_STAGE_PARSE = 1, ORC_STAGE_POW = 2, ORC_STAGE_LOGUP = 3, ORC_STAGE_OODS = 4,
+    ORC_STAGE_MERKLE = 5, ORC_STAGE_FRI_FIRST = 6, ORC_STAGE_FRI_INNER = 7,
+    ORC_STAGE_FRI_LAST = 8, ORC_STAGE_UNSUPPORTED = 9
+};
+typedef struct {
+    /* Fiat-Shamir (reference components/recursive/fiat_shamir/src/lib.rs:31-131) */
+    qm31 z, alpha, random_coeff, oods_t, oods_x, oods_y, after_coeff;
+    qm31 fri_alphas[ORC_MAX_INNER + 1];
+    uint32_t digest_after_nonce[8];
+    uint32_t raw_queries[ORC_MAX_QUERIES];
+    uint32_t n_transcript_perms;
+    /* shape */
+    uint32_t max_first_log, n_inner, n_queries, n_logs;
+    uint32_t log_sizes[ORC_MAX_LOGS];                 /* descending */
+    uint32_t query_pos[ORC_MAX_LOGS][ORC_MAX_QUERIES];
+    /* OODS */
+    qm31 oods_computed, oods_expected;
+    /* answers / folds, [log idx][query] */
+    cpoint domain_points[ORC_MAX_LOGS][ORC_MAX_QUERIES];
+    qm31 fri_answers[ORC_MAX_LOGS][ORC_MAX_QUERIES];
+    qm31 circle_folds[ORC_MAX_LOGS][ORC_MAX_QUERIES];
+    qm31 line_folds[ORC_MAX_INNER][ORC_MAX_QUERIES];  /* value after inner layer i */
+    qm31 last_layer_evals[ORC_MAX_QUERIES];
+    /* Merkle: recomputed roots per (tree, query); trees 0-3, 4 = FRI first, 5.. inner */
+    uint32_t path_roots[5 + ORC_MAX_INNER][ORC_MAX_QUERIES][8];
+    uint64_t n_perms_hints;     /* partial-tree rebuild */
+    uint64_t n_perms_paths;     /* per-query path verification (incl. transcript) */
+    int32_t verdict;            /* 0 accept, 1 reject, 2 unsupported */
+    int32_t stage;              /* first failing ORC_STAGE_* */
+} orc_verify_out;
+
+/* inputs: (idx, value) public-input pairs for the logup sum
+ * (reference components/recursive/fiat_shamir/src/lib.rs:133-141) */
+int orc_verify_proof(const uint8_t *blob, size_t len,
+                     const uint32_t *input_idx, const uint32_t *input_vals /* n x4 */,
+                     uint32_t n_inputs, orc_verify_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
