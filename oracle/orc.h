@@ -37,6 +37,16 @@ int orc_merkle_path_verify(const uint32_t *leaf, uint32_t n_cols, uint32_t index
                            const uint32_t *siblings, uint32_t depth,
                            const uint32_t root[8], uint32_t out_root[8]);
 
+void orc_merkle_path_root_mixed(uint32_t depth, const uint32_t *n_cols, uint32_t index,
+                                const uint32_t *cols, const uint32_t *siblings, uint32_t out[8]);
+
+/* pthread drivers for the CPU baseline */
+void orc_poseidon2_permute_batch_mt(uint32_t *states, size_t n, unsigned n_threads);
+uint64_t orc_merkle_build_mt(const uint32_t *leaves, uint32_t log_n, uint32_t n_cols, uint32_t *nodes, unsigned n_threads);
+void orc_merkle_paths_verify_mt(uint32_t depth, const uint32_t *n_cols, size_t n_paths, const uint32_t *index,
+                                const uint32_t *cols, const uint32_t *sib, const uint32_t *root, uint8_t *verdict,
+                                unsigned n_threads);
+
 typedef struct { uint32_t digest[8]; uint32_t n_sent; uint64_t n_perms; } orc_channel;
 void orc_channel_init(orc_channel *c);
 void orc_channel_mix_root(orc_channel *c, const uint32_t root[8]);

@@ -146,3 +146,88 @@ void orc_channel_draw(orc_channel *c, uint32_t out[8]) {
     orc_poseidon2_permute(st);
     memcpy(out, st, 32); c->n_perms++;
 }
+
+/* Mixed-degree authentication path: columns injected at inner layers
+ * (reference components/recursive/data_structures/src/lib.rs:315-354;
+ * components/hints/src/decommit.rs:22-42).  n_cols[h] = columns at the layer of
+ * log size h (h = depth is the leaf layer); cols = leaf layer values first,
+ * then each injected layer in descending h; siblings leaf level first. */
+void orc_merkle_path_root_mixed(uint32_t depth, const uint32_t *n_cols, uint32_t index,
+                                const uint32_t *cols, const uint32_t *siblings, uint32_t out[8]) {
+    uint32_t cur[8];
+    orc_hash_node(NULL, NULL, cols, n_cols[depth], cur);
+    cols += n_cols[depth];
+    for (uint32_t i = 0; i < depth; i++) {
+        uint32_t h = depth - 1 - i;
+        const uint32_t *sib = siblings + 8 * i;
+        if ((index >> i) & 1) orc_hash_node(sib, cur, cols, n_cols[h], cur);
+        else orc_hash_node(cur, sib, cols, n_cols[h], cur);
+        cols += n_cols[h];
+    }
+    memcpy(out, cur, 32);
+}
+
+/* ---- multi-threaded drivers for the CPU baseline (pthreads; the reference itself is
+ * single-threaded -- constraint_system/src/lib.rs:33 -- so threads only ever split
+ * independent states / nodes / trees) ------------------------------------------------ */
+#include <pthread.h>
+typedef struct { void (*fn)(size_t, size_t, void *); size_t lo, hi; void *ctx; } orc_job;
+static void *orc_job_run(void *p) { orc_job *j = (orc_job *)p; j->fn(j->lo, j->hi, j->ctx); return NULL; }
+static void orc_parallel_for(size_t n, unsigned n_threads, void (*fn)(size_t, size_t, void *), void *ctx) {
+    if (n_threads <= 1 || n < 2 * (size_t)n_threads) { fn(0, n, ctx); return; }
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256]; orc_job jobs[256];
+    for (unsigned t = 0; t < n_threads; t++) {
+        jobs[t].fn = fn; jobs[t].ctx = ctx;
+        jobs[t].lo = n * t / n_threads; jobs[t].hi = n * (t + 1) / n_threads;
+        pthread_create(&th[t], NULL, orc_job_run, &jobs[t]);
+    }
+    for (unsigned t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+}
+static void permute_range(size_t lo, size_t hi, void *ctx) {
+    uint32_t *s = (uint32_t *)ctx;
+    for (size_t i = lo; i < hi; i++) orc_poseidon2_permute(s + 16 * i);
+}
+void orc_poseidon2_permute_batch_mt(uint32_t *states, size_t n, unsigned n_threads) {
+    orc_parallel_for(n, n_threads, permute_range, states);
+}
+typedef struct { const uint32_t *leaves; uint32_t n_cols; uint32_t *layer; const uint32_t *child; } build_ctx;
+static void leaf_range(size_t lo, size_t hi, void *p) {
+    build_ctx *c = (build_ctx *)p;
+    for (size_t i = lo; i < hi; i++) orc_hash_node(NULL, NULL, c->leaves + i * c->n_cols, c->n_cols, c->layer + 8 * i);
+}
+static void node_range(size_t lo, size_t hi, void *p) {
+    build_ctx *c = (build_ctx *)p;
+    for (size_t i = lo; i < hi; i++) orc_hash_node(c->child + 16 * i, c->child + 16 * i + 8, NULL, 0, c->layer + 8 * i);
+}
+uint64_t orc_merkle_build_mt(const uint32_t *leaves, uint32_t log_n, uint32_t n_cols, uint32_t *nodes, unsigned n_threads) {
+    size_t n = (size_t)1 << log_n;
+    build_ctx c = { leaves, n_cols, nodes + (n - 1) * 8, NULL };
+    orc_parallel_for(n, n_threads, leaf_range, &c);
+    uint64_t perms = n * ((n_cols + 7) / 8 + 1);
+    for (uint32_t k = log_n; k-- > 0;) {
+        size_t m = (size_t)1 << k;
+        c.child = nodes + (2 * m - 1) * 8; c.layer = nodes + (m - 1) * 8;
+        orc_parallel_for(m, n_threads, node_range, &c);
+        perms += m;
+    }
+    return perms;
+}
+typedef struct { uint32_t depth; const uint32_t *n_cols; const uint32_t *index, *cols, *sib, *roots; uint32_t cpp; uint8_t *verdict; } path_ctx;
+static void path_range(size_t lo, size_t hi, void *p) {
+    path_ctx *c = (path_ctx *)p;
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t r[8];
+        orc_merkle_path_root_mixed(c->depth, c->n_cols, c->index[i], c->cols + i * c->cpp, c->sib + i * c->depth * 8, r);
+        c->verdict[i] = memcmp(r, c->roots, 32) == 0;
+    }
+}
+/* all paths against roots[0..8] */
+void orc_merkle_paths_verify_mt(uint32_t depth, const uint32_t *n_cols, size_t n_paths, const uint32_t *index,
+                                const uint32_t *cols, const uint32_t *sib, const uint32_t *root, uint8_t *verdict,
+                                unsigned n_threads) {
+    uint32_t cpp = 0;
+    for (uint32_t h = 0; h <= depth; h++) cpp += n_cols[h];
+    path_ctx c = { depth, n_cols, index, cols, sib, root, cpp, verdict };
+    orc_parallel_for(n_paths, n_threads, path_range, &c);
+}

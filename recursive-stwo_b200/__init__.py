@@ -1,0 +1,16 @@
+"""stwo_b200 — B200-native (sm_100a) verifier hot path of recursive-stwo.
+
+Host-side mirror of the reference's primitives for the accelerated path.  Everything here calls
+the C ABI in libstwo_b200.so (include/stwo_b200.h); torch is used only to own device memory and
+streams.  The directory name has a hyphen: import it with
+`importlib.import_module("recursive-stwo_b200")` (see __graft_entry__.py).
+"""
+from . import _lib
+from ._lib import PathShape, StwoB200Error
+from .hashing import (init, poseidon2_permute, poseidon2_permute_host, hash_node_batch, merkle_commit,
+                      merkle_commit_host, merkle_decommit, merkle_path_verify, merkle_path_verify_host,
+                      launch_count, path_perms)
+
+__all__ = ["init", "poseidon2_permute", "poseidon2_permute_host", "hash_node_batch", "merkle_commit",
+           "merkle_commit_host", "merkle_decommit", "merkle_path_verify", "merkle_path_verify_host", "launch_count",
+           "path_perms", "PathShape", "StwoB200Error"]

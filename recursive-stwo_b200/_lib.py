@@ -1,0 +1,100 @@
+"""ctypes binding of libstwo_b200.so (the C ABI in include/stwo_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is present,
+every product entry point raises.  The library is built in-tree by
+`make -C recursive-stwo_b200/csrc` (see __graft_entry__.build).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstwo_b200.so")
+MAX_DEPTH = 32
+
+OK = 0
+E_NO_DEVICE = -1000
+E_BAD_ARG = -1001
+E_SHAPE = -1002
+
+
+class PathShape(ctypes.Structure):
+    """stwo_b200_path_shape"""
+    _fields_ = [("depth", ctypes.c_uint32), ("n_cols", ctypes.c_uint32 * (MAX_DEPTH + 1))]
+
+    @classmethod
+    def make(cls, depth, cols_by_log_size):
+        """cols_by_log_size: {log_size: n_columns}; the leaf layer (log_size == depth) must be present."""
+        s = cls()
+        s.depth = depth
+        for h, n in cols_by_log_size.items():
+            if not 0 <= h <= depth:
+                raise ValueError("column log size outside the tree")
+            s.n_cols[h] = n
+        if s.n_cols[depth] == 0:
+            raise ValueError("leaf layer has no columns")
+        return s
+
+    def cols_per_path(self):
+        return sum(self.n_cols[h] for h in range(self.depth + 1))
+
+
+class StwoB200Error(RuntimeError):
+    def __init__(self, fn, status):
+        self.status = status
+        if status <= -1000:
+            what = {E_NO_DEVICE: "no sm_100 CUDA device / library not initialised", E_BAD_ARG: "bad argument",
+                    E_SHAPE: "unsupported shape"}.get(status, "error")
+        else:
+            what = "cudaError %d" % (-status)
+        super().__init__("%s failed: %s (status %d)" % (fn, what, status))
+
+
+_vp, _u32, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_size_t, ctypes.c_uint64
+_SHAPE_P = ctypes.POINTER(PathShape)
+
+# name -> (restype, argtypes); the test-suite checks this list against include/stwo_b200.h
+SIGNATURES = {
+    "stwo_b200_init": (_i32, [_i32]),
+    "stwo_b200_shutdown": (_i32, []),
+    "stwo_b200_version": (_u32, []),
+    "stwo_b200_launch_count": (_u64, []),
+    "stwo_b200_poseidon2_permute": (_i32, [_vp, _sz]),
+    "stwo_b200_poseidon2_permute_dev": (_i32, [_vp, _sz, _vp]),
+    "stwo_b200_poseidon2_permute_dev_variant": (_i32, [_vp, _sz, _i32, _vp]),
+    "stwo_b200_hash_node_batch_dev": (_i32, [_vp, _vp, _u32, _sz, _sz, _vp, _vp]),
+    "stwo_b200_hash_node_batch": (_i32, [_vp, _vp, _u32, _sz, _sz, _vp]),
+    "stwo_b200_merkle_commit_dev": (_i32, [_vp, _u32, _u32, _u32, _vp, _vp]),
+    "stwo_b200_merkle_commit": (_i32, [_vp, _u32, _u32, _u32, _vp]),
+    "stwo_b200_merkle_decommit_dev": (_i32, [_vp, _u32, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "stwo_b200_merkle_path_verify_dev": (_i32, [_SHAPE_P, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_merkle_path_verify": (_i32, [_SHAPE_P, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "stwo_b200_path_perms": (_u32, [_SHAPE_P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no device needed) and set the prototypes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libstwo_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C recursive-stwo_b200/csrc`; there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(fn, status):
+    if status != OK:
+        raise StwoB200Error(fn, status)
+
+
+def call(name, *args):
+    status = getattr(load(), name)(*args)
+    check(name, status)
