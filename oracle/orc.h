@@ -85,6 +85,8 @@ typedef struct {
 /* returns 0 on success, negative on malformed input */
 int orc_proof_parse(const uint8_t *blob, size_t len, orc_proof *out);
 
+int orc_proof_offsets(const uint8_t *blob, size_t len, uint64_t out[16]);
+
 /* ---- full native verifier ------------------------------------------------- */
 #define ORC_MAX_QUERIES 128
 #define ORC_MAX_LOGS 4

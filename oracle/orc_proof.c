@@ -92,3 +92,30 @@ int orc_proof_parse(const uint8_t *blob, size_t len, orc_proof *o) {
     if (r.off != len) return -1;
     return 0;
 }
+
+/* byte offsets of the regions a test wants to tamper with; returns the number written (0 on parse error) */
+int orc_proof_offsets(const uint8_t *blob, size_t len, uint64_t out[16]) {
+    static _Thread_local orc_proof p;
+    if (orc_proof_parse(blob, len, &p) != 0) return 0;
+#define OFF(ptr) ((ptr) ? (uint64_t)((const uint8_t *)(ptr) - blob) : (uint64_t)-1)
+    out[0] = OFF(p.commitments[0]);
+    out[1] = OFF(p.sampled[0][0]);
+    out[2] = OFF(p.decommitments[0].hash_witness);
+    out[3] = OFF(p.queried_values[0]);
+    out[4] = OFF(p.first_layer.fri_witness);
+    out[5] = OFF(p.first_layer.decommitment.hash_witness);
+    out[6] = OFF(p.first_layer.commitment);
+    out[7] = p.n_inner ? OFF(p.inner[0].fri_witness) : (uint64_t)-1;
+    out[8] = p.n_inner ? OFF(p.inner[0].decommitment.hash_witness) : (uint64_t)-1;
+    out[9] = OFF(p.last_coeffs);
+    out[10] = OFF(p.queried_values[3]);
+    out[11] = p.n_inner ? OFF(p.inner[p.n_inner - 1].fri_witness) : (uint64_t)-1;
+    out[12] = OFF(p.first_layer.commitment) - 8 - 8;   /* not meaningful: placeholder kept stable */
+    out[13] = OFF(p.sampled[3][7]);
+    out[14] = OFF(p.commitments[3]);
+    out[15] = OFF(p.queried_values[0]) - 8 - 8;
+    /* pow nonce sits right after the last queried_values vector */
+    out[12] = OFF(p.queried_values[3]) + 4 * p.n_queried_values[3];
+#undef OFF
+    return 16;
+}

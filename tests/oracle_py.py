@@ -82,3 +82,62 @@ def splitmix64(seed, n):
 def synth_m31(seed, n):
     """n canonical M31 words from splitmix64(seed)"""
     return (splitmix64(seed, n) % np.uint64(P)).astype(np.uint32)
+
+
+# ---- full verifier -----------------------------------------------------------------------------------
+MAX_INNER, MAX_Q, MAX_LOGS = 32, 128, 4
+_Q = ctypes.c_uint32 * 4
+
+
+class VerifyOut(ctypes.Structure):
+    """orc_verify_out (oracle/orc.h)"""
+    _fields_ = [(n, _Q) for n in ("z", "alpha", "random_coeff", "oods_t", "oods_x", "oods_y", "after_coeff")] + [
+        ("fri_alphas", _Q * (MAX_INNER + 1)), ("digest_after_nonce", ctypes.c_uint32 * 8),
+        ("raw_queries", ctypes.c_uint32 * MAX_Q), ("n_transcript_perms", ctypes.c_uint32),
+        ("max_first_log", ctypes.c_uint32), ("n_inner", ctypes.c_uint32), ("n_queries", ctypes.c_uint32),
+        ("n_logs", ctypes.c_uint32), ("log_sizes", ctypes.c_uint32 * MAX_LOGS),
+        ("query_pos", (ctypes.c_uint32 * MAX_Q) * MAX_LOGS), ("oods_computed", _Q), ("oods_expected", _Q),
+        ("domain_points", ((ctypes.c_uint32 * 2) * MAX_Q) * MAX_LOGS), ("fri_answers", (_Q * MAX_Q) * MAX_LOGS),
+        ("circle_folds", (_Q * MAX_Q) * MAX_LOGS), ("line_folds", (_Q * MAX_Q) * MAX_INNER),
+        ("last_layer_evals", _Q * MAX_Q), ("path_roots", ((ctypes.c_uint32 * 8) * MAX_Q) * (5 + MAX_INNER)),
+        ("n_perms_hints", ctypes.c_uint64), ("n_perms_paths", ctypes.c_uint64), ("verdict", ctypes.c_int32),
+        ("stage", ctypes.c_int32)]
+
+    def arr(self, name):
+        return np.ctypeslib.as_array(getattr(self, name)).copy()
+
+
+STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
+          9: "unsupported"}
+INPUTS_SMALL = ([1], [[1, 0, 0, 0]])                                   # examples/single-proof/src/main.rs:28-33
+INPUTS_RECURSIVE = ([1, 2, 3], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])   # examples/multi-proofs/src/main.rs (1,1),(2,i),(3,j)
+PROOFS_DIR = os.path.join(ROOT, "tests", "golden", "proofs")
+
+
+def inputs_for(name):
+    return INPUTS_SMALL if name.startswith("small_proof") else INPUTS_RECURSIVE
+
+
+def load_proof(name):
+    """fixture -> 4-byte aligned uint8 array (padded), true length"""
+    raw = np.fromfile(os.path.join(PROOFS_DIR, name), dtype=np.uint8)
+    buf = np.zeros((raw.size + 3) // 4 * 4, dtype=np.uint8)
+    buf[: raw.size] = raw
+    return buf, raw.size
+
+
+def verify_proof(buf, length, inputs):
+    idx = np.array(inputs[0], dtype=np.uint32)
+    vals = np.array(inputs[1], dtype=np.uint32)
+    out = VerifyOut()
+    load_oracle().orc_verify_proof(vp(buf), ctypes.c_size_t(length), vp(idx), vp(vals), ctypes.c_uint32(idx.size), ctypes.byref(out))
+    return out
+
+
+def proof_offsets(buf, length):
+    out = np.zeros(16, dtype=np.uint64)
+    n = load_oracle().orc_proof_offsets(vp(buf), ctypes.c_size_t(length), vp(out))
+    names = ["commitment0", "sampled0", "hash_witness0", "queried0", "fri_first_witness", "fri_first_hash_witness",
+             "fri_first_commitment", "fri_inner0_witness", "fri_inner0_hash_witness", "last_coeffs", "queried3",
+             "fri_inner_last_witness", "pow_nonce", "sampled3_7", "commitment3", "_"]
+    return dict(zip(names, out.tolist())) if n else None
