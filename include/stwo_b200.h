@@ -108,6 +108,91 @@ int32_t stwo_b200_merkle_path_verify(const stwo_b200_path_shape *shape, size_t n
 /* number of Poseidon2 permutations one path of this shape costs */
 uint32_t stwo_b200_path_perms(const stwo_b200_path_shape *shape);
 
+/* ---- K3-K5 + driver: batched native verification of PlonkWithPoseidon proofs ----------------------------------------
+ * Replaces, for Poseidon31-hash proofs, the value side of the whole verifier run of
+ * examples/single-proof/src/main.rs:33-83 and examples/multi-proofs/src/main.rs:49-139:
+ *   FiatShamirHints::new / FiatShamirResults::compute   components/hints/src/fiat_shamir.rs:69-307,
+ *                                                       components/recursive/fiat_shamir/src/lib.rs:31-176
+ *   CompositionCheck::compute                           components/recursive/composition/src/lib.rs:33-121
+ *   DecommitHints::compute                              components/hints/src/decommit.rs:194-241
+ *   AnswerHints / AnswerResults::compute                components/recursive/answer/src/lib.rs:34-382
+ *   FirstLayerHints / InnerLayersHints::compute         components/hints/src/folding.rs:296-601
+ *   FoldingResults::compute                             components/recursive/folding/src/lib.rs:12-205
+ * A blob is the bincode serialisation of PlonkWithPoseidonProof<Poseidon31MerkleHasher> (little endian, 4-byte aligned).
+ * verdict: 0 accept, 1 reject, 2 unsupported (the reference panics: duplicated queries at the largest domain,
+ * components/recursive/answer/src/lib.rs:190-195).  stage: first failing STWO_B200_STAGE_*. */
+typedef struct {
+    uint32_t log_size_plonk, log_size_poseidon;     /* stmt0 */
+    uint32_t pow_bits, log_blowup, log_last;        /* PcsConfig / FriConfig */
+    uint32_t n_queries, n_inner;                    /* FriConfig.n_queries, number of inner FRI layers */
+} stwo_b200_proof_shape;
+
+#define STWO_B200_VERDICT_ACCEPT 0
+#define STWO_B200_VERDICT_REJECT 1
+#define STWO_B200_VERDICT_UNSUPPORTED 2
+#define STWO_B200_STAGE_OK 0
+#define STWO_B200_STAGE_PARSE 1
+#define STWO_B200_STAGE_POW 2
+#define STWO_B200_STAGE_LOGUP 3
+#define STWO_B200_STAGE_OODS 4
+#define STWO_B200_STAGE_MERKLE 5
+#define STWO_B200_STAGE_FRI_FIRST 6
+#define STWO_B200_STAGE_FRI_INNER 7
+#define STWO_B200_STAGE_FRI_LAST 8
+#define STWO_B200_STAGE_UNSUPPORTED 9
+
+/* flags */
+#define STWO_B200_VERIFY_FULL 1u   /* also recompute every per-query authentication path (what the verifier circuit does) */
+
+/* host-side header read (no device needed): shape of one blob; STWO_B200_E_SHAPE when it does not parse */
+int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stwo_b200_proof_shape *out);
+/* bytes of device workspace a batch of n_proofs of this shape needs (0: unsupported shape) */
+size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint32_t n_proofs);
+/* Poseidon2 permutations of the per-query paths of one proof of this shape (transcript excluded) */
+uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape);
+
+/* Device entry: blobs = all proofs back to back as u32 words, blob_off = n_proofs+1 WORD offsets, every proof of the
+ * same shape.  input_idx / input_vals: the (index, QM31 value) public inputs of the logup sum
+ * (components/recursive/fiat_shamir/src/lib.rs:133-141).  verdict/stage: n_proofs bytes each (stage may be NULL). */
+int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                          const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
+                                          const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags,
+                                          void *workspace, size_t workspace_bytes, uint8_t *verdict, uint8_t *stage,
+                                          void *stream);
+/* Host entry: host blobs of any mix of shapes (grouped internally), verdicts back in the caller's arrays. */
+int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs,
+                                      const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
+                                      uint32_t flags, uint8_t *verdict, uint8_t *stage);
+
+/* Per-proof intermediate values kept in the workspace after a batch (what a prover of the NEXT recursion level, or a
+ * parity test, reads back): every Fiat-Shamir draw, the OODS values, the counters. */
+typedef struct {
+    struct {
+        uint32_t z[4], alpha[4], random_coeff[4], oods_t[4], oods_x[4], oods_y[4], after_coeff[4];
+        uint32_t fri_alphas[33][4];
+        uint32_t digest_after_nonce[8];
+        uint32_t raw_queries[128];
+        uint32_t n_transcript_perms, pow_ok;
+    } fs;
+    uint32_t oods_computed[4], oods_expected[4];
+    uint32_t n_logs, log_sizes[3];          /* committed column log sizes, descending */
+    uint32_t fail_mask, verdict, stage;
+    uint32_t n_perms_hints, n_perms_paths;
+} stwo_b200_verify_detail;
+
+#define STWO_B200_FETCH_DETAIL 0          /* stwo_b200_verify_detail */
+#define STWO_B200_FETCH_DOMAIN_POINTS 1   /* [3][n_queries][2]   circle-domain point of each query per log size */
+#define STWO_B200_FETCH_ANSWERS 2         /* [3][n_queries][4]   DEEP quotient answers */
+#define STWO_B200_FETCH_CIRCLE_FOLDS 3    /* [3][n_queries][4] */
+#define STWO_B200_FETCH_LINE_FOLDS 4      /* [32][n_queries][4]  value after each inner layer */
+#define STWO_B200_FETCH_LAST_EVALS 5      /* [n_queries][4] */
+#define STWO_B200_FETCH_PATH_ROOTS 6      /* [4 + 1 + n_inner][n_queries][8]  (STWO_B200_VERIFY_FULL) */
+#define STWO_B200_FETCH_PATH_COLS 7       /* [4][n_queries][64]  per-query column values of the commitment trees */
+#define STWO_B200_FETCH_PATH_SIBLINGS 8   /* [4][n_queries][30][8] */
+#define STWO_B200_FETCH_PAIR_HINTS 9      /* [1 + n_inner][n_queries * 256] packed FRI pair hints */
+int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
+                               uint32_t what, void *out, size_t out_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -535,7 +535,7 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
     const uint32_t nq = p->n_queries, blow = p->log_blowup;
     if (p->n_last_coeffs != (1ull << p->log_last) || p->n_inner + 1 > ORC_MAX_INNER) FAIL(ORC_STAGE_PARSE, 1);
     const uint32_t max_first = p->log_last + blow + 1 + p->n_inner;
-    if (max_first > 30 || p->log_size_plonk + blow > max_first || p->log_size_poseidon + blow > max_first) FAIL(ORC_STAGE_PARSE, 1);
+    if (max_first > 29 || p->log_size_plonk + blow > max_first || p->log_size_poseidon + blow > max_first) FAIL(ORC_STAGE_PARSE, 1);
     o->max_first_log = max_first; o->n_inner = p->n_inner; o->n_queries = nq;
 
     /* 1. transcript + PoW */

@@ -49,8 +49,44 @@ class StwoB200Error(RuntimeError):
         super().__init__("%s failed: %s (status %d)" % (fn, what, status))
 
 
+class ProofShape(ctypes.Structure):
+    """stwo_b200_proof_shape"""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last",
+                                               "n_queries", "n_inner")]
+
+    def key(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+    @property
+    def max_first(self):
+        return self.log_last + self.log_blowup + 1 + self.n_inner
+
+
+_Q = ctypes.c_uint32 * 4
+
+
+class _FsOut(ctypes.Structure):
+    _fields_ = [(n, _Q) for n in ("z", "alpha", "random_coeff", "oods_t", "oods_x", "oods_y", "after_coeff")] + [
+        ("fri_alphas", _Q * 33), ("digest_after_nonce", ctypes.c_uint32 * 8), ("raw_queries", ctypes.c_uint32 * 128),
+        ("n_transcript_perms", ctypes.c_uint32), ("pow_ok", ctypes.c_uint32)]
+
+
+class VerifyDetail(ctypes.Structure):
+    """stwo_b200_verify_detail"""
+    _fields_ = [("fs", _FsOut), ("oods_computed", _Q), ("oods_expected", _Q), ("n_logs", ctypes.c_uint32),
+                ("log_sizes", ctypes.c_uint32 * 3), ("fail_mask", ctypes.c_uint32), ("verdict", ctypes.c_uint32),
+                ("stage", ctypes.c_uint32), ("n_perms_hints", ctypes.c_uint32), ("n_perms_paths", ctypes.c_uint32)]
+
+
+VERIFY_FULL = 1
+FETCH = {"detail": 0, "domain_points": 1, "answers": 2, "circle_folds": 3, "line_folds": 4, "last_evals": 5, "path_roots": 6,
+         "path_cols": 7, "path_siblings": 8, "pair_hints": 9}
+STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
+          9: "unsupported"}
+
 _vp, _u32, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_size_t, ctypes.c_uint64
 _SHAPE_P = ctypes.POINTER(PathShape)
+_PSHAPE_P = ctypes.POINTER(ProofShape)
 
 # name -> (restype, argtypes); the test-suite checks this list against include/stwo_b200.h
 SIGNATURES = {
@@ -69,6 +105,12 @@ SIGNATURES = {
     "stwo_b200_merkle_path_verify_dev": (_i32, [_SHAPE_P, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_merkle_path_verify": (_i32, [_SHAPE_P, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_path_perms": (_u32, [_SHAPE_P]),
+    "stwo_b200_proof_shape_of": (_i32, [_vp, _sz, _PSHAPE_P]),
+    "stwo_b200_verify_workspace_bytes": (_sz, [_PSHAPE_P, _u32]),
+    "stwo_b200_proof_perms": (_u64, [_PSHAPE_P]),
+    "stwo_b200_verify_proofs_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
+    "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
 }
 
 _lib = None

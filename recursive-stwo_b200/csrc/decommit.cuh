@@ -1,0 +1,263 @@
+// Hint pre-pass on device: stwo's batched Merkle decommitments are replayed layer by layer
+// (recomputing every node the batch touches, consuming `hash_witness` and the queried values in
+// stream order) and re-shaped into independent per-query authentication paths, which is what the
+// verifier circuit consumes.  One thread owns one tree of one proof; node tables are small sorted
+// arrays in a caller-provided scratch area.
+//
+// Follows
+//   components/hints/src/decommit.rs:44-183   SinglePathMerkleProof::from_stwo_proof (commitment trees)
+//   components/hints/src/folding.rs:93-287    SinglePairMerkleProof::from_stwo_proof (FRI layer trees)
+//   components/hints/src/folding.rs:33-91     SinglePairMerkleProof::verify
+#pragma once
+#include "fiat_shamir.cuh"
+
+namespace decommit {
+
+using fs::permute_mem;
+
+// hash_node with separate child pointers (L == nullptr: leaf).  primitives/merkle/src/lib.rs:9-181
+HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr) {
+    u32 st[16];
+    u32 tree[8];
+    if (L) {
+        for (int i = 0; i < 8; i++) { st[i] = L[i]; st[8 + i] = R[i]; }
+        permute_mem(st);
+        if (tree_out) for (int i = 0; i < 8; i++) tree_out[i] = st[i];
+        if (nc == 0) { for (int i = 0; i < 8; i++) out[i] = st[i]; return; }
+        for (int i = 0; i < 8; i++) tree[i] = st[i];
+    }
+    for (int i = 8; i < 16; i++) st[i] = 0;
+    u32 n_chunks = nc ? (nc + 7) / 8 : 1;
+    for (u32 c = 0; c < n_chunks; c++) {
+        for (u32 i = 0; i < 8; i++) st[i] = 8 * c + i < nc ? cols[8 * c + i] : 0u;
+        permute_mem(st);
+    }
+    for (int i = 0; i < 8; i++) st[i] = L ? tree[i] : 0u;
+    permute_mem(st);
+    for (int i = 0; i < 8; i++) out[i] = st[i];
+}
+HD u32 node_perms(bool leaf, u32 nc) { return leaf ? (nc ? (nc + 7) / 8 : 1) + 1 : 1 + (nc ? (nc + 7) / 8 + 1 : 0); }
+
+HD bool eq8(const u32 *a, const u32 *b) {
+    u32 d = 0;
+    for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+    return d == 0;
+}
+HD void cp8(u32 *dst, const u32 *src) { for (int i = 0; i < 8; i++) dst[i] = src[i]; }
+
+// in-place insertion sort + dedup of n <= 256 values; returns the unique count
+HD u32 sort_unique(u32 *v, u32 n) {
+    for (u32 i = 1; i < n; i++) {
+        u32 x = v[i], j = i;
+        while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
+        v[j] = x;
+    }
+    u32 m = 0;
+    for (u32 i = 0; i < n; i++) if (m == 0 || v[m - 1] != v[i]) v[m++] = v[i];
+    return m;
+}
+HD int find(const u32 *v, u32 n, u32 x) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) { u32 mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+    return (lo < n && v[lo] == x) ? (int)lo : -1;
+}
+
+// ---- commitment trees ---------------------------------------------------------------------------------
+constexpr u32 SINGLE_SCRATCH_WORDS_PER_QUERY = 22;
+
+// Columns live at two layers at most: nA columns at log size hA and nB at hB (the Plonk and the Poseidon
+// component; composition tree: nB = 0).  depth = max(hA, hB) = log size of the leaf layer.
+struct SingleShape {
+    u32 depth, hA, nA, hB, nB;
+    HDM u32 ncols(u32 h) const { return (h == hA ? nA : 0u) + (h == hB ? nB : 0u); }
+};
+
+// q[nq]: query positions at the leaf layer.  Writes, for query i, its column values (leaf layer first, then the
+// injected layer) to path_cols + i*cpp and its sibling hashes (leaf level first) to path_sib + i*sib_stride.
+// Returns true iff both streams are consumed exactly and the recomputed root equals `root`.
+HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *values, u32 n_values, const u32 *hw, u32 n_hw,
+                    const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, u32 *scratch, u32 *perms) {
+    u32 *cpos = scratch, *chash = cpos + nq, *ppos = chash + 8 * nq, *phash = ppos + nq;
+    u32 *sibsrc = phash + 8 * nq, *par = sibsrc + nq, *colsrc = par + nq, *qnode = colsrc + nq;
+    const u32 depth = sh.depth;
+    for (u32 i = 0; i < nq; i++) cpos[i] = q[i];
+    u32 m = sort_unique(cpos, nq);
+    for (u32 i = 0; i < nq; i++) qnode[i] = (u32)find(cpos, m, q[i]);
+    u32 vi = 0, wi = 0, np = 0;
+    u32 nc = sh.ncols(depth);
+    for (u32 k = 0; k < m; k++) {
+        if (vi + nc > n_values) return false;
+        hash_node2(nullptr, nullptr, values + vi, nc, chash + 8 * k);
+        np += node_perms(true, nc);
+        colsrc[k] = vi;
+        vi += nc;
+    }
+    for (u32 i = 0; i < nq; i++)
+        for (u32 c = 0; c < nc; c++) path_cols[i * cpp + c] = values[colsrc[qnode[i]] + c];
+    u32 colpos = nc;
+    for (u32 h = depth; h-- > 0;) {
+        nc = sh.ncols(h);
+        u32 j = 0, k = 0;
+        while (k < m) {
+            const u32 ps = cpos[k];
+            const bool pair = k + 1 < m && cpos[k + 1] == (ps ^ 1u);
+            const u32 *L, *R;
+            if (pair) {
+                L = chash + 8 * k; R = chash + 8 * (k + 1);
+                sibsrc[k] = k + 1; sibsrc[k + 1] = k; par[k] = par[k + 1] = j;
+            } else {
+                if (wi >= n_hw) return false;
+                const u32 *W = hw + 8 * wi;
+                sibsrc[k] = 0x80000000u | wi;
+                par[k] = j;
+                wi++;
+                if (ps & 1u) { L = W; R = chash + 8 * k; } else { L = chash + 8 * k; R = W; }
+            }
+            if (vi + nc > n_values) return false;
+            hash_node2(L, R, values + vi, nc, phash + 8 * j);
+            np += node_perms(false, nc);
+            ppos[j] = ps >> 1;
+            colsrc[j] = vi;
+            vi += nc;
+            j++;
+            k += pair ? 2 : 1;
+        }
+        for (u32 i = 0; i < nq; i++) {
+            const u32 kq = qnode[i];
+            const u32 s = sibsrc[kq];
+            cp8(path_sib + (size_t)i * sib_stride + (depth - 1 - h) * 8, (s & 0x80000000u) ? hw + 8 * (s & 0x7fffffffu) : chash + 8 * s);
+            const u32 pj = par[kq];
+            qnode[i] = pj;
+            for (u32 c = 0; c < nc; c++) path_cols[i * cpp + colpos + c] = values[colsrc[pj] + c];
+        }
+        colpos += nc;
+        u32 *t;
+        t = cpos; cpos = ppos; ppos = t;
+        t = chash; chash = phash; phash = t;
+        m = j;
+    }
+    if (perms) *perms += np;
+    return vi == n_values && wi == n_hw && m == 1 && eq8(chash, root);
+}
+
+// ---- FRI layer trees (query and sibling both opened; QM31 leaf = 4 words) -------------------------------------
+constexpr u32 PAIR_SCRATCH_WORDS_PER_QUERY = 2 * 44;
+constexpr u32 MAX_DATA_LAYERS = 3;
+
+// data_mask bit h set <=> evaluations are committed at the layer of log size h (bit `depth` always set).
+// vals: the decommitted evaluations in stream order (layer by layer descending, positions ascending, 4 words each).
+// Per query i:  self_vals/sib_vals [(i*MAX_DATA_LAYERS + d)*4] for the d-th data layer (descending),
+//               sib_hashes [(i*(depth-1) + j)*8], j = depth-1-h for layers h = depth-1 .. 1:
+//               the sibling's hash (plain layers) or the sibling's hash *without* its own evaluation (data layers).
+HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *vals, u32 n_vals, const u32 *hw, u32 n_hw,
+                  const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, u32 *scratch, u32 *perms) {
+    const u32 cap = 2 * nq;
+    u32 *qs = scratch, *cpos = qs + cap, *chash = cpos + cap, *npos = chash + 8 * cap, *nhash = npos + cap;
+    u32 *ntree = nhash + 8 * cap, *nL = ntree + 8 * cap, *nR = nL + 8 * cap, *nval = nR + 8 * cap;
+    for (u32 i = 0; i < nq; i++) qs[i] = q[i];
+    u32 n = sort_unique(qs, nq);
+    u32 cm = 0;                    // child table size
+    u32 vi = 0, wi = 0, np = 0, d_idx = 0;
+    for (u32 h = depth + 1; h-- > 0;) {
+        if (h < depth) {
+            for (u32 k = 0; k < n; k++) qs[k] >>= 1;
+            n = sort_unique(qs, n);
+        }
+        const bool data = (data_mask >> h) & 1u;
+        u32 m = 0;
+        if (data) {
+            for (u32 k = 0; k < n; k++) { npos[m++] = qs[k]; npos[m++] = qs[k] ^ 1u; }
+            m = sort_unique(npos, m);
+        } else {
+            if (h == depth) return false;
+            for (u32 k = 0; k < n; k++) npos[m++] = qs[k];
+        }
+        for (u32 a = 0; a < m; a++) {
+            const u32 *val = nullptr;
+            if (data) {
+                if (vi + 4 > n_vals) return false;
+                val = vals + vi; nval[a] = vi; vi += 4;
+            }
+            if (h == depth) {
+                hash_node2(nullptr, nullptr, val, 4, nhash + 8 * a);
+                np += 2;
+            } else {
+                const u32 p = npos[a];
+                int li = find(cpos, cm, p << 1), ri = find(cpos, cm, (p << 1) + 1);
+                const u32 *L, *R;
+                if (li >= 0) L = chash + 8 * li; else { if (wi >= n_hw) return false; L = hw + 8 * wi++; }
+                if (ri >= 0) R = chash + 8 * ri; else { if (wi >= n_hw) return false; R = hw + 8 * wi++; }
+                cp8(nL + 8 * a, L); cp8(nR + 8 * a, R);
+                hash_node2(L, R, val, data ? 4 : 0, nhash + 8 * a, ntree + 8 * a);
+                np += data ? 3 : 1;
+            }
+        }
+        // per-query extraction
+        for (u32 i = 0; i < nq; i++) {
+            const u32 qh = q[i] >> (depth - h);
+            if (data) {
+                int a_self = find(npos, m, qh), a_sib = find(npos, m, qh ^ 1u);
+                if (a_self < 0 || (a_sib < 0 && h > 0)) return false;
+                for (int c = 0; c < 4; c++) self_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[nval[a_self] + c];
+                if (a_sib >= 0) for (int c = 0; c < 4; c++) sib_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[nval[a_sib] + c];
+                if (h != depth && h >= 1) cp8(sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - h)) * 8, ntree + 8 * a_sib);
+            }
+            // the child layer h+1, when it carries no data, takes its sibling from this parent's two children
+            const u32 hc = h + 1;
+            if (h < depth && hc < depth && !((data_mask >> hc) & 1u)) {
+                int pa = find(npos, m, qh);
+                if (pa < 0) return false;
+                const u32 qc = q[i] >> (depth - hc);
+                cp8(sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - hc)) * 8, (qc & 1u) ? nL + 8 * pa : nR + 8 * pa);
+            }
+        }
+        if (data) d_idx++;
+        // this layer becomes the child table
+        for (u32 a = 0; a < m; a++) { cpos[a] = npos[a]; cp8(chash + 8 * a, nhash + 8 * a); }
+        cm = m;
+    }
+    if (perms) *perms += np;
+    return vi == n_vals && wi == n_hw && cm == 1 && eq8(chash, root);
+}
+
+// SinglePairMerkleProof::verify for one query (components/hints/src/folding.rs:33-91): recompute the root from the
+// per-query hints.  Returns the root in out[8].
+HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals, const u32 *sib_vals, const u32 *sib_hashes,
+                       u32 *out, u32 *perms) {
+    u32 self_h[8], sib_h[8];
+    u32 d_idx = 0, np = 4;
+    hash_node2(nullptr, nullptr, self_vals, 4, self_h);
+    hash_node2(nullptr, nullptr, sib_vals, 4, sib_h);
+    d_idx = 1;
+    for (u32 i = 0; i < depth; i++) {
+        const u32 h = depth - i - 1;
+        const bool data = (data_mask >> h) & 1u;
+        const u32 *L = ((qpos >> i) & 1u) ? sib_h : self_h, *R = ((qpos >> i) & 1u) ? self_h : sib_h;
+        u32 nxt[8];
+        if (!data) {
+            hash_node2(L, R, nullptr, 0, nxt);
+            np += 1;
+            if (i != depth - 1) cp8(sib_h, sib_hashes + 8 * i);
+        } else {
+            hash_node2(L, R, self_vals + 4 * d_idx, 4, nxt);
+            np += 3;
+            if (h >= 1) {
+                // sibling = rate(perm(sibling tree hash || capacity(sibling evaluation)))
+                u32 st[16];
+                for (int k = 0; k < 4; k++) st[k] = sib_vals[4 * d_idx + k];
+                for (int k = 4; k < 16; k++) st[k] = 0;
+                permute_mem(st);
+                for (int k = 0; k < 8; k++) st[k] = sib_hashes[8 * i + k];
+                permute_mem(st);
+                cp8(sib_h, st);
+                np += 2;
+            }
+            d_idx++;
+        }
+        cp8(self_h, nxt);
+    }
+    cp8(out, self_h);
+    if (perms) *perms += np;
+}
+
+}  // namespace decommit

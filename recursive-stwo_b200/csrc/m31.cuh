@@ -19,8 +19,10 @@
 
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__
+#define HDM __host__ __device__ __forceinline__      // member functions
 #else
 #define HD static inline
+#define HDM inline
 #endif
 
 #define M31_P 0x7fffffffu

@@ -1,0 +1,417 @@
+// Batched native verification of PlonkWithPoseidon stwo proofs: workspace layout and the per-thread
+// stage functions the kernels in verify_kernels.cu dispatch.  Proofs of one batch share a shape
+// (PcsConfig + component log sizes), so every per-proof array has a fixed stride.
+//
+// Stage order and failure codes follow the reference driver examples/single-proof/src/main.rs:33-83:
+//   FiatShamirHints/Results -> CompositionCheck -> DecommitHints + AnswerResults -> FirstLayerHints,
+//   InnerLayersHints + FoldingResults.
+#pragma once
+#include "fri.cuh"
+#include "merkle.cuh"
+
+namespace verify {
+
+using proof::Desc;
+
+struct Shape {            // mirror of stwo_b200_proof_shape (include/stwo_b200.h)
+    u32 log_size_plonk, log_size_poseidon, pow_bits, log_blowup, log_last, n_queries, n_inner;
+    HDM u32 max_first() const { return log_last + log_blowup + 1 + n_inner; }
+    HDM u32 log_plonk() const { return log_size_plonk + log_blowup; }
+    HDM u32 log_pos() const { return log_size_poseidon + log_blowup; }
+    HDM u32 tree_depth(u32 t) const { return t == 3 ? max_first() : (log_plonk() > log_pos() ? log_plonk() : log_pos()); }
+    HDM u32 tree_cols(u32 t) const { return proof::n_cols(t); }
+    HDM u32 n_fri_trees() const { return 1 + n_inner; }
+    HDM u32 fri_depth(u32 f) const { return f == 0 ? max_first() : max_first() - f; }
+    HDM u32 fri_data_mask(u32 f) const {
+        if (f) return 1u << fri_depth(f);
+        return (1u << max_first()) | (1u << log_plonk()) | (1u << log_pos());
+    }
+    HDM u32 n_trees() const { return 4 + n_fri_trees(); }
+    HDM bool matches(const Desc &d) const {
+        return d.log_size_plonk == log_size_plonk && d.log_size_poseidon == log_size_poseidon && d.pow_bits == pow_bits &&
+               d.log_blowup == log_blowup && d.log_last == log_last && d.n_queries == n_queries && d.n_inner == n_inner;
+    }
+};
+
+constexpr u32 MAX_DEPTH = 30;
+constexpr u32 PATH_COLS_STRIDE = 64;                           // >= widest tree (60 columns)
+constexpr u32 PAIR_HINT_WORDS = 2 * decommit::MAX_DATA_LAYERS * 4 + (MAX_DEPTH - 1) * 8;   // self, sib, sibling hashes
+
+// Per-proof results kept for the caller (every Fiat-Shamir draw, the OODS values, the counters).
+struct Detail {
+    fs::Out fs;
+    qm31_t oods_computed, oods_expected;
+    u32 n_logs, log_sizes[fri::MAX_LOGS];
+    u32 fail_mask;                       // bit s set <=> stage s failed
+    u32 verdict, stage;
+    u32 n_perms_hints, n_perms_paths;
+};
+
+struct Workspace {
+    Shape shape;
+    u32 n_proofs;
+    const u32 *blobs;                    // all proofs, word-addressed
+    const u64 *blob_off;                 // n_proofs + 1 word offsets
+    const u32 *input_idx; const u32 *input_vals; u32 n_inputs;
+    Desc *desc;
+    Detail *detail;
+    // commitment trees: [p][t][i]
+    u32 *path_cols;                      // PATH_COLS_STRIDE words
+    u32 *path_sib;                       // MAX_DEPTH * 8 words
+    u32 *path_roots;                     // [p][tree 0..n_trees)[i][8]   recomputed per-query roots (full mode)
+    u32 *single_scratch;                 // [p][t][22 * nq]
+    // answers / folds
+    fri::Group *groups;                  // [p][g]
+    u32 *domain_points;                  // [p][g][i][2]
+    u32 *answers;                        // [p][g][i][4]
+    u32 *circle_folds;                   // [p][g][i][4]
+    u32 *line_folds;                     // [p][li][i][4]
+    u32 *last_evals;                     // [p][i][4]
+    u32 *fri_vals;                       // [p][f][2 * nq * MAX_LOGS... see fri_vals_stride][4]
+    u32 *n_fri_vals;                     // [p][f]
+    u32 *pair_hints;                     // [p][f][i][PAIR_HINT_WORDS]
+    u32 *pair_scratch;                   // [p][f][88 * nq]
+
+    HDM const u32 *blob(u32 p) const { return blobs + blob_off[p]; }
+    HDM size_t blob_words(u32 p) const { return (size_t)(blob_off[p + 1] - blob_off[p]); }
+    HDM u32 nq() const { return shape.n_queries; }
+    HDM u32 *cols_of(u32 p, u32 t, u32 i) const { return path_cols + (((size_t)p * 4 + t) * nq() + i) * PATH_COLS_STRIDE; }
+    HDM u32 *sib_of(u32 p, u32 t, u32 i) const { return path_sib + (((size_t)p * 4 + t) * nq() + i) * (MAX_DEPTH * 8); }
+    HDM u32 *root_of(u32 p, u32 tree, u32 i) const { return path_roots + (((size_t)p * shape.n_trees() + tree) * nq() + i) * 8; }
+    HDM u32 fri_vals_stride() const { return 2 * nq() * fri::MAX_LOGS * 4; }
+    HDM u32 *vals_of(u32 p, u32 f) const { return fri_vals + ((size_t)p * shape.n_fri_trees() + f) * fri_vals_stride(); }
+    HDM u32 *nvals_of(u32 p, u32 f) const { return n_fri_vals + (size_t)p * shape.n_fri_trees() + f; }
+    HDM u32 *hint_of(u32 p, u32 f, u32 i) const { return pair_hints + (((size_t)p * shape.n_fri_trees() + f) * nq() + i) * PAIR_HINT_WORDS; }
+    HDM u32 *q4(u32 *base, u32 p, u32 a, u32 na, u32 i) const { return base + (((size_t)p * na + a) * nq() + i) * 4; }
+};
+
+HD void fail(Detail &dt, u32 stage) { dt.fail_mask |= 1u << stage; }
+#if defined(__CUDA_ARCH__)
+#define VERIFY_ATOMIC_OR(ptr, v) atomicOr((ptr), (v))
+#define VERIFY_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
+#else
+#define VERIFY_ATOMIC_OR(ptr, v) (*(ptr) |= (v))
+#define VERIFY_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
+#endif
+HD void fail_shared(Detail *dt, u32 stage) { VERIFY_ATOMIC_OR(&dt->fail_mask, 1u << stage); }
+
+// ---- stage 1: parse + transcript + logup + OODS (one thread per proof) ---------------------------------------------
+HD void stage_fiat_shamir(const Workspace &ws, u32 p) {
+    Desc &d = ws.desc[p];
+    Detail &dt = ws.detail[p];
+    dt.fail_mask = 0; dt.verdict = proof::REJECT; dt.stage = 0; dt.n_perms_hints = 0; dt.n_perms_paths = 0; dt.n_logs = 0;
+    const u32 *w = ws.blob(p);
+    if (!proof::parse(w, ws.blob_words(p), d) || !ws.shape.matches(d)) { d.ok = 0; fail(dt, proof::ST_PARSE); return; }
+    fs::transcript(w, d, dt.fs);
+    dt.n_perms_paths = dt.fs.n_transcript_perms;
+    if (!dt.fs.pow_ok) fail(dt, proof::ST_POW);
+    if (!fs::logup_sum_ok(w, d, dt.fs, ws.input_idx, ws.input_vals, ws.n_inputs)) fail(dt, proof::ST_LOGUP);
+    if (!fs::oods_ok(w, d, dt.fs, &dt.oods_computed, &dt.oods_expected)) fail(dt, proof::ST_OODS);
+    dt.n_logs = fri::log_sizes(d, dt.log_sizes);
+    // duplicated queries at the largest size are not supported by the reference (answer/src/lib.rs:190-195)
+    for (u32 i = 0; i < d.n_queries; i++)
+        for (u32 j = 0; j < i; j++)
+            if (fri::position(d, dt.fs.raw_queries[i], d.max_first) == fri::position(d, dt.fs.raw_queries[j], d.max_first)) {
+                fail(dt, proof::ST_UNSUPPORTED);
+                i = d.n_queries; break;
+            }
+}
+
+// ---- stage 2: commitment-tree decommitment -> per-query paths (one thread per (proof, tree)) -----------------------
+HD void stage_single_tree(const Workspace &ws, u32 p, u32 t) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries;
+    decommit::SingleShape sh;
+    if (t < 3) {
+        sh.hA = d.log_plonk; sh.nA = proof::plonk_cols(t); sh.hB = d.log_pos; sh.nB = proof::n_cols(t) - proof::plonk_cols(t);
+        sh.depth = sh.hA > sh.hB ? sh.hA : sh.hB;
+    } else { sh.hA = d.max_first; sh.nA = 8; sh.hB = 0; sh.nB = 0; sh.depth = d.max_first; }
+    u32 q[proof::MAX_QUERIES];
+    for (u32 i = 0; i < nq; i++) q[i] = fri::position(d, dt.fs.raw_queries[i], sh.depth);
+    u32 perms = 0;
+    bool ok = decommit::single_tree(sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
+                                    w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
+                                    ws.single_scratch + ((size_t)p * 4 + t) * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq, &perms);
+    VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
+    if (!ok) fail_shared(&dt, proof::ST_MERKLE);
+}
+
+// full mode: SinglePathMerkleProofVar::verify for one (proof, tree, query)
+HD void stage_single_path(const Workspace &ws, u32 p, u32 t, u32 i) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    stwo_b200_path_shape shp;
+    const u32 depth = ws.shape.tree_depth(t);
+    shp.depth = depth;
+    for (u32 h = 0; h <= depth; h++) shp.n_cols[h] = 0;
+    if (t < 3) { shp.n_cols[d.log_plonk] += proof::plonk_cols(t); shp.n_cols[d.log_pos] += proof::n_cols(t) - proof::plonk_cols(t); }
+    else shp.n_cols[d.max_first] = 8;
+    u32 root[8];
+    merkle::path_root(shp, fri::position(d, dt.fs.raw_queries[i], depth), ws.cols_of(p, t, i), ws.sib_of(p, t, i), root);
+    decommit::cp8(ws.root_of(p, t, i), root);
+    VERIFY_ATOMIC_ADD(&dt.n_perms_paths, merkle::path_perms(shp));
+    if (!decommit::eq8(root, ws.blob(p) + d.commitments[t])) fail_shared(&dt, proof::ST_MERKLE);
+}
+
+// ---- stage 3: answers (thread per (proof, group) then per (proof, group, query)) -------------------------------------
+HD void stage_group(const Workspace &ws, u32 p, u32 g) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    if (g >= dt.n_logs) return;
+    if (!fri::build_group(ws.blob(p), d, dt.fs, dt.log_sizes[g], ws.groups[(size_t)p * fri::MAX_LOGS + g])) fail_shared(&dt, proof::ST_PARSE);
+}
+HD void stage_answer(const Workspace &ws, u32 p, u32 g, u32 i) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    if (g >= dt.n_logs) return;
+    const u32 L = dt.log_sizes[g];
+    const u32 q = fri::position(d, dt.fs.raw_queries[i], L);
+    const cpoint_t dp = fri::domain_point(L, q);
+    u32 *dpo = ws.domain_points + (((size_t)p * fri::MAX_LOGS + g) * ws.nq() + i) * 2;
+    dpo[0] = dp.x; dpo[1] = dp.y;
+    u32 row[fri::MAX_GROUP_SAMPLES];
+    const u32 *paths[4] = {ws.cols_of(p, 0, i), ws.cols_of(p, 1, i), ws.cols_of(p, 2, i), ws.cols_of(p, 3, i)};
+    fri::gather_row(d, L, paths, row);
+    qm31_t ans = qm31::zero();
+    if (!fri::row_quotient(ws.groups[(size_t)p * fri::MAX_LOGS + g], row, dp, ans)) fail_shared(&dt, proof::ST_FRI_FIRST);
+    fs::qstore(ws.q4(ws.answers, p, g, fri::MAX_LOGS, i), ans);
+}
+
+// ---- stage 4: folds (one thread per proof): first-layer evaluations, circle folds, line folds, last layer ---------------
+HD void stage_folds(const Workspace &ws, u32 p) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries, max_first = d.max_first;
+    u32 pos[proof::MAX_QUERIES], sp[proof::MAX_QUERIES];
+    // first layer: per log size descending, per sorted pair subset, both evaluations (queried: answer, else fri_witness)
+    {
+        u32 *vals = ws.vals_of(p, 0), nv = 0, wi = 0;
+        bool ok = true;
+        for (u32 g = 0; g < dt.n_logs && ok; g++) {
+            const u32 L = dt.log_sizes[g];
+            for (u32 i = 0; i < nq; i++) sp[i] = pos[i] = fri::position(d, dt.fs.raw_queries[i], L);
+            const u32 ns = decommit::sort_unique(sp, nq);
+            for (u32 k = 0; k < ns && ok;) {
+                const u32 start = sp[k] & ~1u;
+                for (u32 e = start; e < start + 2; e++) {
+                    const u32 *src;
+                    if (k < ns && sp[k] == e) {
+                        u32 i = 0;
+                        while (pos[i] != e) i++;
+                        src = ws.q4(ws.answers, p, g, fri::MAX_LOGS, i);
+                        k++;
+                    } else {
+                        if (wi >= d.fl_n_fri_witness) { ok = false; break; }
+                        src = w + d.fl_fri_witness + 4 * wi++;
+                    }
+                    for (int c = 0; c < 4; c++) vals[nv++] = src[c];
+                }
+            }
+        }
+        if (wi != d.fl_n_fri_witness) ok = false;
+        *ws.nvals_of(p, 0) = nv;
+        if (!ok) fail_shared(&dt, proof::ST_FRI_FIRST);
+    }
+    // circle folds: sibling evaluation of query i at log L = the other member of its pair in the first-layer values
+    for (u32 g = 0; g < dt.n_logs; g++) {
+        const u32 L = dt.log_sizes[g];
+        for (u32 i = 0; i < nq; i++) pos[i] = fri::position(d, dt.fs.raw_queries[i], L);
+        // locate each pair inside vals: pairs are stored in sorted order per group; recompute the offsets
+        u32 base = 0;
+        for (u32 g2 = 0; g2 < g; g2++) {
+            for (u32 i = 0; i < nq; i++) sp[i] = fri::position(d, dt.fs.raw_queries[i], dt.log_sizes[g2]) >> 1;
+            base += decommit::sort_unique(sp, nq) * 8;
+        }
+        for (u32 i = 0; i < nq; i++) sp[i] = pos[i] >> 1;
+        const u32 npairs = decommit::sort_unique(sp, nq);
+        const u32 *vals = ws.vals_of(p, 0);
+        for (u32 i = 0; i < nq; i++) {
+            const int pi = decommit::find(sp, npairs, pos[i] >> 1);
+            const u32 *pr = vals + base + 8 * (u32)pi;
+            const qm31_t l = fs::qload(pr), r = fs::qload(pr + 4);
+            const qm31_t self = (pos[i] & 1u) ? r : l, sib = (pos[i] & 1u) ? l : r;
+            const cpoint_t pt = circle::dbl(fri::absolute_point(L, pos[i]));
+            const qm31_t f = fri::fold_pair(self, sib, pos[i], fs::minv(pt.y), dt.fs.fri_alphas[max_first - L]);
+            fs::qstore(ws.q4(ws.circle_folds, p, g, fri::MAX_LOGS, i), f);
+        }
+    }
+    // inner layers
+    qm31_t folded[proof::MAX_QUERIES];
+    for (u32 i = 0; i < nq; i++) folded[i] = qm31::zero();
+    u32 log_size = max_first;
+    bool inner_ok = true;
+    for (u32 li = 0; li < d.n_inner; li++) {
+        for (u32 g = 0; g < dt.n_logs; g++)
+            if (dt.log_sizes[g] == log_size) {
+                const qm31_t a2 = fs::qmul(dt.fs.fri_alphas[li], dt.fs.fri_alphas[li]);
+                for (u32 i = 0; i < nq; i++) folded[i] = fs::qadd(fs::qmul(a2, folded[i]), fs::qload(ws.q4(ws.circle_folds, p, g, fri::MAX_LOGS, i)));
+            }
+        log_size -= 1;
+        for (u32 i = 0; i < nq; i++) sp[i] = pos[i] = fri::position(d, dt.fs.raw_queries[i], log_size);
+        const u32 ns = decommit::sort_unique(sp, nq);
+        u32 *vals = ws.vals_of(p, 1 + li), nv = 0, wi = 0;
+        // decommitted evaluations: one (left, right) pair per sorted pair index; a missing sibling comes from fri_witness
+        qm31_t sib_of_unique[proof::MAX_QUERIES];
+        for (u32 k = 0; k < ns; k++) {
+            const u32 e = sp[k];
+            u32 i = 0;
+            while (pos[i] != e) i++;
+            qm31_t sv;
+            const int sk = decommit::find(sp, ns, e ^ 1u);
+            if (sk >= 0) { u32 j = 0; while (pos[j] != (e ^ 1u)) j++; sv = folded[j]; }
+            else if (wi < d.in_n_fri_witness[li]) sv = fs::qload(w + d.in_fri_witness[li] + 4 * wi++);
+            else { inner_ok = false; sv = qm31::zero(); }
+            sib_of_unique[k] = sv;
+            if (k == 0 || (sp[k - 1] >> 1) != (e >> 1)) {
+                const qm31_t l = (e & 1u) ? sv : folded[i], r = (e & 1u) ? folded[i] : sv;
+                fs::qstore(vals + nv, l); fs::qstore(vals + nv + 4, r); nv += 8;
+            }
+        }
+        if (wi != d.in_n_fri_witness[li]) inner_ok = false;
+        *ws.nvals_of(p, 1 + li) = nv;
+        for (u32 i = 0; i < nq; i++) {
+            const int k = decommit::find(sp, ns, pos[i]);
+            const u32 x_inv = fs::minv(fri::absolute_point(log_size, pos[i]).x);
+            folded[i] = fri::fold_pair(folded[i], sib_of_unique[k], pos[i], x_inv, dt.fs.fri_alphas[li + 1]);
+        }
+        for (u32 i = 0; i < nq; i++) fs::qstore(ws.q4(ws.line_folds, p, li, proof::MAX_INNER, i), folded[i]);
+    }
+    if (!inner_ok) fail_shared(&dt, proof::ST_FRI_INNER);
+    // last layer
+    bool last_ok = true;
+    qm31_t *buf = (qm31_t *)(ws.pair_scratch + (size_t)p * ws.shape.n_fri_trees() * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq);
+    for (u32 i = 0; i < nq; i++) {
+        const cpoint_t ab = fri::absolute_point(log_size, fri::position(d, dt.fs.raw_queries[i], log_size));
+        const u32 x = m31::subc(m31::mulc(ab.x, ab.x), m31::mulc(ab.y, ab.y));
+        // the scratch of the FRI trees is free until stage 5 runs; it holds the 2^log_last fold buffer (<= 4096 QM31)
+        qm31_t ev;
+        if (d.log_last == 0) ev = fs::qload(w + d.last_coeffs);
+        else {
+            u32 dbl[16];
+            dbl[0] = x;
+            for (u32 k = 1; k < d.log_last; k++) { u32 sq = m31::mulc(dbl[k - 1], dbl[k - 1]); dbl[k] = m31::subc(m31::addc(sq, sq), 1); }
+            // fold without a buffer larger than the scratch allows: recursive halves evaluated iteratively per level
+            u32 n = 1u << d.log_last;
+            const u32 cap = (u32)((size_t)ws.shape.n_fri_trees() * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq / 4);
+            if (n / 2 > cap) { last_ok = false; ev = qm31::zero(); }
+            else {
+                n >>= 1;
+                for (u32 k = 0; k < n; k++)
+                    buf[k] = fs::qadd(fs::qload(w + d.last_coeffs + 8 * k), qm31::mul_m31(fs::qload(w + d.last_coeffs + 8 * k + 4), dbl[d.log_last - 1]));
+                for (u32 lev = d.log_last - 1; lev-- > 0;) {
+                    n >>= 1;
+                    for (u32 k = 0; k < n; k++) buf[k] = fs::qadd(buf[2 * k], qm31::mul_m31(buf[2 * k + 1], dbl[lev]));
+                }
+                ev = buf[0];
+            }
+        }
+        fs::qstore(ws.last_evals + ((size_t)p * nq + i) * 4, ev);
+        if (!qm31::eq(ev, folded[i])) last_ok = false;
+    }
+    if (!last_ok) fail_shared(&dt, proof::ST_FRI_LAST);
+}
+
+// ---- stage 5: FRI layer trees (one thread per (proof, layer)) ---------------------------------------------------------
+HD void stage_pair_tree(const Workspace &ws, u32 p, u32 f) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries, depth = ws.shape.fri_depth(f);
+    u32 q[proof::MAX_QUERIES];
+    for (u32 i = 0; i < nq; i++) q[i] = fri::position(d, dt.fs.raw_queries[i], depth);
+    const u32 *hw = w + (f ? d.in_hash_witness[f - 1] : d.fl_hash_witness);
+    const u32 n_hw = f ? d.in_n_hash_witness[f - 1] : d.fl_n_hash_witness;
+    const u32 *root = w + (f ? d.in_commitment[f - 1] : d.fl_commitment);
+    u32 *hint = ws.hint_of(p, f, 0);
+    // pair_tree writes packed per-query arrays; give it strided views by running it on a packed scratch tail and spreading
+    u32 *scratch = ws.pair_scratch + ((size_t)p * ws.shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq;
+    u32 perms = 0;
+    // packed outputs live at the start of the hint block of this tree (nq * PAIR_HINT_WORDS words available)
+    u32 *self_vals = hint, *sib_vals = hint + nq * decommit::MAX_DATA_LAYERS * 4, *sib_hashes = sib_vals + nq * decommit::MAX_DATA_LAYERS * 4;
+    bool ok = decommit::pair_tree(depth, ws.shape.fri_data_mask(f), q, nq, ws.vals_of(p, f), *ws.nvals_of(p, f), hw, n_hw, root,
+                                  self_vals, sib_vals, sib_hashes, scratch, &perms);
+    VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
+    if (!ok) fail_shared(&dt, f ? proof::ST_FRI_INNER : proof::ST_FRI_FIRST);
+}
+// packed hint accessors (see stage_pair_tree)
+HD const u32 *hint_self(const Workspace &ws, u32 p, u32 f, u32 i) { return ws.hint_of(p, f, 0) + i * decommit::MAX_DATA_LAYERS * 4; }
+HD const u32 *hint_sib(const Workspace &ws, u32 p, u32 f, u32 i) {
+    return ws.hint_of(p, f, 0) + ws.nq() * decommit::MAX_DATA_LAYERS * 4 + i * decommit::MAX_DATA_LAYERS * 4;
+}
+HD const u32 *hint_hashes(const Workspace &ws, u32 p, u32 f, u32 i) {
+    return ws.hint_of(p, f, 0) + 2 * ws.nq() * decommit::MAX_DATA_LAYERS * 4 + (size_t)i * (ws.shape.fri_depth(f) - 1) * 8;
+}
+
+// full mode: SinglePairMerkleProofVar::verify for one (proof, layer, query) + consistency of the opened values with the folds
+HD void stage_pair_path(const Workspace &ws, u32 p, u32 f, u32 i) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 depth = ws.shape.fri_depth(f);
+    const u32 q = fri::position(d, dt.fs.raw_queries[i], depth);
+    u32 root[8], perms = 0;
+    decommit::pair_path_root(depth, ws.shape.fri_data_mask(f), q, hint_self(ws, p, f, i), hint_sib(ws, p, f, i), hint_hashes(ws, p, f, i), root, &perms);
+    decommit::cp8(ws.root_of(p, 4 + f, i), root);
+    VERIFY_ATOMIC_ADD(&dt.n_perms_paths, perms);
+    const u32 *want = ws.blob(p) + (f ? d.in_commitment[f - 1] : d.fl_commitment);
+    if (!decommit::eq8(root, want)) fail_shared(&dt, f ? proof::ST_FRI_INNER : proof::ST_FRI_FIRST);
+}
+
+// ---- stage 6: verdict (one thread per proof) ------------------------------------------------------------------------
+HD void stage_verdict(const Workspace &ws, u32 p) {
+    Detail &dt = ws.detail[p];
+    const u32 order[9] = {proof::ST_PARSE, proof::ST_POW, proof::ST_LOGUP, proof::ST_OODS, proof::ST_UNSUPPORTED, proof::ST_MERKLE,
+                          proof::ST_FRI_FIRST, proof::ST_FRI_INNER, proof::ST_FRI_LAST};
+    dt.verdict = proof::ACCEPT; dt.stage = proof::ST_OK;
+    for (int k = 0; k < 9; k++)
+        if (dt.fail_mask & (1u << order[k])) {
+            dt.stage = order[k];
+            dt.verdict = order[k] == proof::ST_UNSUPPORTED ? proof::UNSUPPORTED : proof::REJECT;
+            break;
+        }
+}
+
+
+// ---- workspace sizing (host) ------------------------------------------------------------------------------------------
+struct Carver {
+    uint8_t *base; size_t at;
+    template <class T> T *take(size_t n) {
+        at = (at + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + at) : nullptr;
+        at += n * sizeof(T);
+        return p;
+    }
+};
+// lays the per-proof arrays out behind `base` (nullptr: only measures); returns the bytes needed
+inline size_t carve(Workspace &ws, uint8_t *base) {
+    Carver c{base, 0};
+    const size_t n = ws.n_proofs, nq = ws.shape.n_queries, nf = ws.shape.n_fri_trees(), nt = ws.shape.n_trees();
+    ws.desc = c.take<Desc>(n);
+    ws.detail = c.take<Detail>(n);
+    ws.path_cols = c.take<u32>(n * 4 * nq * PATH_COLS_STRIDE);
+    ws.path_sib = c.take<u32>(n * 4 * nq * MAX_DEPTH * 8);
+    ws.path_roots = c.take<u32>(n * nt * nq * 8);
+    ws.single_scratch = c.take<u32>(n * 4 * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq);
+    ws.groups = c.take<fri::Group>(n * fri::MAX_LOGS);
+    ws.domain_points = c.take<u32>(n * fri::MAX_LOGS * nq * 2);
+    ws.answers = c.take<u32>(n * fri::MAX_LOGS * nq * 4);
+    ws.circle_folds = c.take<u32>(n * fri::MAX_LOGS * nq * 4);
+    ws.line_folds = c.take<u32>(n * proof::MAX_INNER * nq * 4);
+    ws.last_evals = c.take<u32>(n * nq * 4);
+    ws.fri_vals = c.take<u32>(n * nf * ws.fri_vals_stride());
+    ws.n_fri_vals = c.take<u32>(n * nf);
+    ws.pair_hints = c.take<u32>(n * nf * nq * PAIR_HINT_WORDS);
+    ws.pair_scratch = c.take<u32>(n * nf * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq);
+    return (c.at + 255) & ~(size_t)255;
+}
+
+}  // namespace verify

@@ -1,0 +1,244 @@
+// K3-K5 and the batch driver: kernels that dispatch the per-thread verifier stages of verify.cuh, and the C ABI of
+// stwo_b200_verify_proofs_batch*.  Grid layouts keep the lanes of a warp on the same tree / log-size group of
+// different proofs, so same-shape batches execute almost divergence-free.
+#include "common.cuh"
+#include "verify.cuh"
+#include <vector>
+#include <map>
+#include <array>
+#include <string.h>
+
+using namespace stwo_b200;
+using verify::Workspace;
+
+namespace {
+constexpr int kT = 64;
+
+__global__ void __launch_bounds__(kT) k_fiat_shamir(const Workspace ws) {
+    u32 p = blockIdx.x * kT + threadIdx.x;
+    if (p < ws.n_proofs) verify::stage_fiat_shamir(ws, p);
+}
+__global__ void __launch_bounds__(kT) k_single_tree(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < ws.n_proofs * 4) verify::stage_single_tree(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+}
+__global__ void __launch_bounds__(kT) k_group(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < ws.n_proofs * fri::MAX_LOGS) verify::stage_group(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+}
+__global__ void __launch_bounds__(kT) k_answer(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    const u32 per_g = ws.n_proofs * ws.shape.n_queries;
+    if (idx < per_g * fri::MAX_LOGS) {
+        u32 g = idx / per_g, r = idx % per_g;
+        verify::stage_answer(ws, r / ws.shape.n_queries, g, r % ws.shape.n_queries);
+    }
+}
+__global__ void __launch_bounds__(kT) k_folds(const Workspace ws) {
+    u32 p = blockIdx.x * kT + threadIdx.x;
+    if (p < ws.n_proofs) verify::stage_folds(ws, p);
+}
+__global__ void __launch_bounds__(kT) k_pair_tree(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < ws.n_proofs * ws.shape.n_fri_trees()) verify::stage_pair_tree(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+}
+__global__ void __launch_bounds__(kT) k_single_path(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    const u32 per_t = ws.n_proofs * ws.shape.n_queries;
+    if (idx < per_t * 4) {
+        u32 t = idx / per_t, r = idx % per_t;
+        verify::stage_single_path(ws, r / ws.shape.n_queries, t, r % ws.shape.n_queries);
+    }
+}
+__global__ void __launch_bounds__(kT) k_pair_path(const Workspace ws) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    const u32 per_f = ws.n_proofs * ws.shape.n_queries;
+    if (idx < per_f * ws.shape.n_fri_trees()) {
+        u32 f = idx / per_f, r = idx % per_f;
+        verify::stage_pair_path(ws, r / ws.shape.n_queries, f, r % ws.shape.n_queries);
+    }
+}
+__global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, uint8_t *verdict, uint8_t *stage) {
+    u32 p = blockIdx.x * kT + threadIdx.x;
+    if (p >= ws.n_proofs) return;
+    verify::stage_verdict(ws, p);
+    if (verdict) verdict[p] = (uint8_t)ws.detail[p].verdict;
+    if (stage) stage[p] = (uint8_t)ws.detail[p].stage;
+}
+
+inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
+
+bool shape_ok(const stwo_b200_proof_shape *s) {
+    if (!s || s->n_queries == 0 || s->n_queries > proof::MAX_QUERIES || s->n_inner >= proof::MAX_INNER || s->log_last > 12 || s->pow_bits >= 32)
+        return false;
+    verify::Shape v;
+    memcpy(&v, s, sizeof v);
+    return v.max_first() <= 29 && v.log_plonk() <= v.max_first() && v.log_pos() <= v.max_first() && s->log_size_plonk && s->log_size_poseidon;
+}
+}  // namespace
+
+static_assert(sizeof(stwo_b200_proof_shape) == sizeof(verify::Shape), "shape mirrors");
+static_assert(sizeof(stwo_b200_verify_detail) == sizeof(verify::Detail), "detail mirrors");
+
+extern "C" int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stwo_b200_proof_shape *out) {
+    if (!blob || !out || (len & 3) || ((uintptr_t)blob & 3)) return STWO_B200_E_BAD_ARG;
+    static thread_local proof::Desc d;
+    if (!proof::parse(reinterpret_cast<const u32 *>(blob), len / 4, d)) return STWO_B200_E_SHAPE;
+    out->log_size_plonk = d.log_size_plonk; out->log_size_poseidon = d.log_size_poseidon; out->pow_bits = d.pow_bits;
+    out->log_blowup = d.log_blowup; out->log_last = d.log_last; out->n_queries = d.n_queries; out->n_inner = d.n_inner;
+    return STWO_B200_OK;
+}
+
+extern "C" size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint32_t n_proofs) {
+    if (!shape_ok(shape)) return 0;
+    Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs;
+    return verify::carve(ws, nullptr);
+}
+
+extern "C" uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape) {
+    // permutations of the per-query (circuit) path of one proof, excluding the transcript: trees 0-3 + FRI layers
+    if (!shape_ok(shape)) return 0;
+    verify::Shape v;
+    memcpy(&v, shape, sizeof v);
+    uint64_t n = 0;
+    for (u32 t = 0; t < 4; t++) {
+        stwo_b200_path_shape ps;
+        ps.depth = v.tree_depth(t);
+        for (u32 h = 0; h <= ps.depth; h++) ps.n_cols[h] = 0;
+        if (t < 3) { ps.n_cols[v.log_plonk()] += proof::plonk_cols(t); ps.n_cols[v.log_pos()] += proof::n_cols(t) - proof::plonk_cols(t); }
+        else ps.n_cols[v.max_first()] = 8;
+        n += (uint64_t)merkle::path_perms(ps) * v.n_queries;
+    }
+    for (u32 f = 0; f < v.n_fri_trees(); f++) {
+        u32 depth = v.fri_depth(f), mask = v.fri_data_mask(f), per = 4;
+        for (u32 h = 0; h < depth; h++) per += ((mask >> h) & 1u) ? (h >= 1 ? 5 : 3) : 1;
+        n += (uint64_t)per * v.n_queries;
+    }
+    return n;
+}
+
+extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                                     const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
+                                                     const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags,
+                                                     void *workspace, size_t workspace_bytes, uint8_t *verdict, uint8_t *stage,
+                                                     void *stream) {
+    STWO_CHECK_DEVICE();
+    if (n_proofs == 0) return STWO_B200_OK;
+    if (!shape_ok(shape)) return STWO_B200_E_SHAPE;
+    if (!blobs || !blob_off || !workspace || (n_inputs && (!input_idx || !input_vals))) return STWO_B200_E_BAD_ARG;
+    Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs; ws.blobs = blobs; ws.blob_off = blob_off;
+    ws.input_idx = input_idx; ws.input_vals = input_vals; ws.n_inputs = n_inputs;
+    if (verify::carve(ws, (uint8_t *)workspace) > workspace_bytes) return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = n_proofs, nq = shape->n_queries, nf = ws.shape.n_fri_trees();
+    k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws);
+    k_single_tree<<<nblk(n * 4), kT, 0, st>>>(ws);
+    k_group<<<nblk(n * fri::MAX_LOGS), kT, 0, st>>>(ws);
+    k_answer<<<nblk(n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws);
+    k_folds<<<nblk(n), kT, 0, st>>>(ws);
+    k_pair_tree<<<nblk(n * nf), kT, 0, st>>>(ws);
+    note_launch(6);
+    if (flags & STWO_B200_VERIFY_FULL) {
+        k_single_path<<<nblk(n * 4 * nq), kT, 0, st>>>(ws);
+        k_pair_path<<<nblk(n * nf * nq), kT, 0, st>>>(ws);
+        note_launch(2);
+    }
+    k_verdict<<<nblk(n), kT, 0, st>>>(ws, verdict, stage);
+    note_launch(1);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
+                                          uint32_t what, void *out, size_t out_bytes, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!shape_ok(shape) || p >= n_proofs || !workspace || !out) return STWO_B200_E_BAD_ARG;
+    Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs;
+    verify::carve(ws, (uint8_t *)const_cast<void *>(workspace));
+    const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees(), nt = ws.shape.n_trees();
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case STWO_B200_FETCH_DETAIL: src = ws.detail + p; bytes = sizeof(verify::Detail); break;
+        case STWO_B200_FETCH_DOMAIN_POINTS: src = ws.domain_points + (size_t)p * fri::MAX_LOGS * nq * 2; bytes = fri::MAX_LOGS * nq * 8; break;
+        case STWO_B200_FETCH_ANSWERS: src = ws.answers + (size_t)p * fri::MAX_LOGS * nq * 4; bytes = fri::MAX_LOGS * nq * 16; break;
+        case STWO_B200_FETCH_CIRCLE_FOLDS: src = ws.circle_folds + (size_t)p * fri::MAX_LOGS * nq * 4; bytes = fri::MAX_LOGS * nq * 16; break;
+        case STWO_B200_FETCH_LINE_FOLDS: src = ws.line_folds + (size_t)p * proof::MAX_INNER * nq * 4; bytes = proof::MAX_INNER * nq * 16; break;
+        case STWO_B200_FETCH_LAST_EVALS: src = ws.last_evals + (size_t)p * nq * 4; bytes = nq * 16; break;
+        case STWO_B200_FETCH_PATH_ROOTS: src = ws.path_roots + (size_t)p * nt * nq * 8; bytes = nt * nq * 32; break;
+        case STWO_B200_FETCH_PATH_COLS: src = ws.path_cols + (size_t)p * 4 * nq * verify::PATH_COLS_STRIDE; bytes = 4 * nq * verify::PATH_COLS_STRIDE * 4; break;
+        case STWO_B200_FETCH_PATH_SIBLINGS: src = ws.path_sib + (size_t)p * 4 * nq * verify::MAX_DEPTH * 8; bytes = 4 * nq * verify::MAX_DEPTH * 32; break;
+        case STWO_B200_FETCH_PAIR_HINTS: src = ws.pair_hints + (size_t)p * nf * nq * verify::PAIR_HINT_WORDS; bytes = nf * nq * verify::PAIR_HINT_WORDS * 4; break;
+        default: return STWO_B200_E_BAD_ARG;
+    }
+    if (out_bytes < bytes) return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    STWO_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st));
+    return cuda_status(cudaStreamSynchronize(st));
+}
+
+// Host-pointer batch entry: blobs may have different shapes; they are grouped by shape and verified one group at a time.
+extern "C" int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs,
+                                                 const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
+                                                 uint32_t flags, uint8_t *verdict, uint8_t *stage) {
+    STWO_CHECK_DEVICE();
+    if (n_proofs == 0) return STWO_B200_OK;
+    if (!blobs || !lens || !verdict) return STWO_B200_E_BAD_ARG;
+    std::map<std::array<uint32_t, 7>, std::vector<uint32_t>> groups;
+    for (uint32_t i = 0; i < n_proofs; i++) {
+        stwo_b200_proof_shape s;
+        // header-only shape read; malformed blobs are rejected here exactly as the device parse would
+        if (!blobs[i] || stwo_b200_proof_shape_of(blobs[i], lens[i], &s) != STWO_B200_OK) {
+            verdict[i] = proof::REJECT;
+            if (stage) stage[i] = proof::ST_PARSE;
+            continue;
+        }
+        std::array<uint32_t, 7> k;
+        memcpy(k.data(), &s, sizeof s);
+        groups[k].push_back(i);
+    }
+    cudaStream_t st = stage_stream();
+    for (auto &kv : groups) {
+        stwo_b200_proof_shape s;
+        memcpy(&s, kv.first.data(), sizeof s);
+        const std::vector<uint32_t> &ids = kv.second;
+        const uint32_t n = (uint32_t)ids.size();
+        std::vector<uint64_t> off(n + 1, 0);
+        for (uint32_t k = 0; k < n; k++) off[k + 1] = off[k] + lens[ids[k]] / 4;
+        const size_t b_blobs = align_up(off[n] * 4, 256), b_off = align_up((n + 1) * 8, 256), b_in = align_up((size_t)n_inputs * 20 + 4, 256);
+        const size_t b_ws = stwo_b200_verify_workspace_bytes(&s, n), b_out = align_up(2 * (size_t)n, 256);
+        int32_t rc = stage_reserve(b_blobs + b_off + b_in + b_ws + b_out);
+        if (rc) return rc;
+        uint8_t *d = stage_dev();
+        u32 *d_blobs = (u32 *)d; d += b_blobs;
+        u64 *d_off = (u64 *)d; d += b_off;
+        u32 *d_idx = (u32 *)d, *d_vals = d_idx + n_inputs; d += b_in;
+        uint8_t *d_ws = d; d += b_ws;
+        uint8_t *d_verdict = d, *d_stage = d + n;
+        for (uint32_t k = 0; k < n; k++)
+            STWO_CUDA(cudaMemcpyAsync(d_blobs + off[k], blobs[ids[k]], lens[ids[k]], cudaMemcpyHostToDevice, st));
+        STWO_CUDA(cudaMemcpyAsync(d_off, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n_inputs) {
+            STWO_CUDA(cudaMemcpyAsync(d_idx, input_idx, n_inputs * 4, cudaMemcpyHostToDevice, st));
+            STWO_CUDA(cudaMemcpyAsync(d_vals, input_vals, n_inputs * 16, cudaMemcpyHostToDevice, st));
+        }
+        rc = stwo_b200_verify_proofs_batch_dev(d_blobs, d_off, n, &s, d_idx, d_vals, n_inputs, flags, d_ws, b_ws, d_verdict, d_stage, st);
+        if (rc) return rc;
+        std::vector<uint8_t> out(2 * (size_t)n);
+        STWO_CUDA(cudaMemcpyAsync(out.data(), d_verdict, 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        STWO_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t k = 0; k < n; k++) {
+            verdict[ids[k]] = out[k];
+            if (stage) stage[ids[k]] = out[n + k];
+        }
+    }
+    return STWO_B200_OK;
+}

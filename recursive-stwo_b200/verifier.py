@@ -1,0 +1,113 @@
+"""Batched native verification of PlonkWithPoseidon proofs over the C ABI.
+
+Host-side mirror of the reference's verifier driver for the accelerated path:
+  examples/single-proof/src/main.rs:33-83   (hints -> fiat_shamir -> composition -> answer -> folding),
+  examples/multi-proofs/src/main.rs:49-139  (the same verifier applied to several proofs).
+`verify_proofs` is the call a user of the reference switches to (host blobs in, verdicts out, any mix of shapes);
+`VerifyBatch` keeps a same-shape batch resident on the device (the bench's device-resident leg and the parity
+tests, which read every intermediate value back).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import ProofShape, VerifyDetail, VERIFY_FULL, FETCH, STAGES
+from .hashing import _need_init, _stream, _dptr
+
+INPUTS_SINGLE = ([1], [[1, 0, 0, 0]])                                            # examples/single-proof/src/main.rs:28-33
+INPUTS_RECURSIVE = ([1, 2, 3], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])      # (1,1), (2,i), (3,j)
+
+
+def _as_aligned(blob):
+    """bytes / uint8 array -> (uint8 array whose buffer is 4-byte aligned, length)"""
+    a = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
+    n = a.size
+    buf = np.zeros((n + 3) // 4, dtype=np.uint32).view(np.uint8)
+    buf[:n] = a
+    return buf, n
+
+
+def proof_shape(blob):
+    """Shape of one proof blob (host-side header walk, no device needed); raises ValueError if it does not parse."""
+    buf, n = _as_aligned(blob)
+    s = ProofShape()
+    rc = _lib.load().stwo_b200_proof_shape_of(buf.ctypes.data_as(ctypes.c_void_p), n, ctypes.byref(s))
+    if rc != _lib.OK:
+        raise ValueError("not a PlonkWithPoseidon/Poseidon31 proof blob (status %d)" % rc)
+    return s
+
+
+def proof_perms(shape):
+    return int(_lib.load().stwo_b200_proof_perms(ctypes.byref(shape)))
+
+
+def verify_proofs(blobs, inputs=INPUTS_RECURSIVE, full=True):
+    """Verify host blobs (any mix of shapes) -> (verdict uint8[n], stage uint8[n]).  Copies are inside the call."""
+    _need_init()
+    n = len(blobs)
+    keep = [_as_aligned(b) for b in blobs]
+    ptrs = (ctypes.c_void_p * n)(*[k[0].ctypes.data for k in keep])
+    lens = (ctypes.c_size_t * n)(*[k[1] for k in keep])
+    idx = np.ascontiguousarray(inputs[0], dtype=np.uint32)
+    vals = np.ascontiguousarray(inputs[1], dtype=np.uint32)
+    verdict = np.full(n, 255, dtype=np.uint8)
+    stage = np.full(n, 255, dtype=np.uint8)
+    _lib.call("stwo_b200_verify_proofs_batch", ptrs, lens, n, idx.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p),
+              idx.size, VERIFY_FULL if full else 0, verdict.ctypes.data_as(ctypes.c_void_p), stage.ctypes.data_as(ctypes.c_void_p))
+    return verdict, stage
+
+
+class VerifyBatch:
+    """A same-shape batch resident in HBM: blobs, offsets, workspace, verdicts."""
+
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, shape=None, device=None):
+        import torch
+        _need_init()
+        self.n = len(blobs)
+        keep = [_as_aligned(b) for b in blobs]
+        self.shape = shape if shape is not None else proof_shape(blobs[0])
+        words = [np.frombuffer(k[0][: (k[1] + 3) // 4 * 4].tobytes(), dtype=np.uint32) for k in keep]
+        off = np.zeros(self.n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([w.size for w in words])
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.h_words = torch.from_numpy(np.concatenate(words).view(np.int32)).pin_memory()
+        self.h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
+        self.d_words = self.h_words.to(dev)
+        self.d_off = self.h_off.to(dev)
+        self.d_idx = torch.from_numpy(np.ascontiguousarray(inputs[0], dtype=np.uint32).view(np.int32)).to(dev)
+        self.d_vals = torch.from_numpy(np.ascontiguousarray(inputs[1], dtype=np.uint32).view(np.int32)).to(dev)
+        self.n_inputs = len(inputs[0])
+        self.ws_bytes = int(_lib.load().stwo_b200_verify_workspace_bytes(ctypes.byref(self.shape), self.n))
+        if self.ws_bytes == 0:
+            raise ValueError("unsupported proof shape")
+        self.d_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.d_verdict = torch.empty(self.n, dtype=torch.uint8, device=dev)
+        self.d_stage = torch.empty(self.n, dtype=torch.uint8, device=dev)
+
+    def upload(self):
+        """host (pinned) -> device copy of the blobs, on the current stream"""
+        self.d_words.copy_(self.h_words, non_blocking=True)
+        self.d_off.copy_(self.h_off, non_blocking=True)
+
+    def run(self, full=True):
+        _lib.call("stwo_b200_verify_proofs_batch_dev", _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape),
+                  _dptr(self.d_idx), _dptr(self.d_vals), self.n_inputs, VERIFY_FULL if full else 0, _dptr(self.d_ws), self.ws_bytes,
+                  _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
+        return self.d_verdict, self.d_stage
+
+    def fetch(self, p, what):
+        """Read one proof's intermediate values back (see STWO_B200_FETCH_* in include/stwo_b200.h)."""
+        nq, nf = self.shape.n_queries, 1 + self.shape.n_inner
+        if what == "detail":
+            out = VerifyDetail()
+            _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what], ctypes.byref(out),
+                      ctypes.sizeof(out), _stream())
+            return out
+        shapes = {"domain_points": (3, nq, 2), "answers": (3, nq, 4), "circle_folds": (3, nq, 4), "line_folds": (32, nq, 4),
+                  "last_evals": (nq, 4), "path_roots": (4 + nf, nq, 8), "path_cols": (4, nq, 64), "path_siblings": (4, nq, 30, 8),
+                  "pair_hints": (nf, nq * 256)}
+        out = np.zeros(shapes[what], dtype=np.uint32)
+        _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what],
+                  out.ctypes.data_as(ctypes.c_void_p), out.nbytes, _stream())
+        return out

@@ -30,3 +30,38 @@ void hs_path_root(const stwo_b200_path_shape *shape, u32 index, const u32 *cols,
     merkle::path_root(*shape, index, cols, sib, out);
 }
 }
+
+// ---- full verifier on the host: same stage functions the CUDA kernels dispatch, grids emulated by loops -----------------
+#include "../../recursive-stwo_b200/csrc/verify.cuh"
+#include <stdlib.h>
+#include <string.h>
+extern "C" {
+size_t hs_detail_size() { return sizeof(verify::Detail); }
+// returns the workspace (caller frees with hs_free); detail_out: n * sizeof(Detail)
+void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *shape7, const u32 *input_idx, const u32 *input_vals,
+                      u32 n_inputs, int full, verify::Detail *detail_out, verify::Workspace *ws_out) {
+    verify::Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape7, 7 * 4);
+    ws.n_proofs = n; ws.blobs = blobs; ws.blob_off = blob_off; ws.input_idx = input_idx; ws.input_vals = input_vals; ws.n_inputs = n_inputs;
+    size_t bytes = verify::carve(ws, nullptr);
+    uint8_t *base = (uint8_t *)calloc(bytes, 1);
+    verify::carve(ws, base);
+    const u32 nq = ws.shape.n_queries, nf = ws.shape.n_fri_trees();
+    for (u32 p = 0; p < n; p++) verify::stage_fiat_shamir(ws, p);
+    for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) verify::stage_single_tree(ws, p, t);
+    for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) verify::stage_group(ws, p, g);
+    for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) for (u32 i = 0; i < nq; i++) verify::stage_answer(ws, p, g, i);
+    for (u32 p = 0; p < n; p++) verify::stage_folds(ws, p);
+    for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) verify::stage_pair_tree(ws, p, f);
+    if (full) {
+        for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) for (u32 i = 0; i < nq; i++) verify::stage_single_path(ws, p, t, i);
+        for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) for (u32 i = 0; i < nq; i++) verify::stage_pair_path(ws, p, f, i);
+    }
+    for (u32 p = 0; p < n; p++) verify::stage_verdict(ws, p);
+    memcpy(detail_out, ws.detail, n * sizeof(verify::Detail));
+    if (ws_out) *ws_out = ws;
+    return base;
+}
+void hs_free(void *p) { free(p); }
+}

@@ -8,6 +8,8 @@ tail -5 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 ./build/intpipe gpurun_out/intpipe.json > gpurun_out/intpipe.log 2>&1; tail -20 gpurun_out/intpipe.log
 python tools/k1_variants.py > gpurun_out/k1_variants.json 2> gpurun_out/k1_variants.err; cat gpurun_out/k1_variants.json
+python tools/verify_bench.py small_proof.bin 4096 > gpurun_out/verify_small.json 2> gpurun_out/verify_small.err; cat gpurun_out/verify_small.json; tail -3 gpurun_out/verify_small.err
+python tools/verify_bench.py recursive_proof_16_15.bin 2048 > gpurun_out/verify_rec.json 2> gpurun_out/verify_rec.err; cat gpurun_out/verify_rec.json; tail -3 gpurun_out/verify_rec.err
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
 if [ "$1" = "ncu" ]; then
