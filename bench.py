@@ -4,12 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
     python bench.py --impl reference ...                      (the CPU oracle port on the host cores)
 
-Workload (BASELINE.json configs[2]): synthetic Poseidon31 Merkle decommitment sweep — per GPU,
-T trees of 2^20 leaves x C M31 columns (splitmix64(seed = tree id)), committed with Poseidon2-M31,
-Q queries per tree decommitted and every authentication path recomputed and compared with the
-root.  One "step" = commit + decommit + verify of all T trees.  Metric: Poseidon2 permutations/s
-(whole job, all GPUs).  `value` has inputs resident in HBM; `e2e` goes through the host-pointer
-C ABI (pinned host columns / paths -> device -> roots / verdicts back) every step.
+Workload (BASELINE.json configs[4], the single-GPU share of it): a batch of
+--proofs replicas per GPU of the reference's own fixture components/test_data/small_proof.bin (shape S:
+pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers), verified natively: transcript + PoW, logup sum,
+OODS, batched Merkle decommitment re-shaped into per-query paths, DEEP answers, circle/line folds, last
+layer, and every per-query authentication path recomputed (what the verifier circuit does).
+One "step" = one batch.  Metric: verified proofs/s over all GPUs; `poseidon31_perms_per_sec` rides along
+(the permutations that batch executed, and the K1 / Merkle-sweep rates of BASELINE configs[2]).
+`value`: blobs already in HBM.  `e2e`: pinned host blobs -> device -> verdicts back on the host, every step.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -28,12 +30,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "poseidon31_perms_per_sec"
-UNIT = "perms/s"
-# executed integer lane-instructions per permutation of the rolled kernel shape (SASS dynamic count:
-# 5 ext-MDS + 4*... see DESIGN.md §roofline) and the measured issue peak (profiles/intpipe_r01.json)
-LANE_OPS_PER_PERM = 4264
-INT_PEAK_TLOPS_FALLBACK = 30.9
+METRIC = "verified_proofs_per_sec"
+UNIT = "proofs/s"
+FIXTURE = "small_proof.bin"
+# warp instructions one permutation executes in the path kernels (ncu smsp__inst_executed / permutations,
+# profiles/r01*_ncu.txt) — the unit of the integer-issue roofline
+LANE_OPS_PER_PERM = 4719
 
 
 def peaks():
@@ -48,7 +50,7 @@ def peaks():
         p["int_tlops"] = float(ip["peak_tera_lane_ops_per_s"])
         p["int_src"] = "measured (profiles/intpipe_r01.json)"
     except Exception:
-        p["int_tlops"] = INT_PEAK_TLOPS_FALLBACK
+        p["int_tlops"] = 30.9
         p["int_src"] = "fallback"
     return p
 
@@ -64,8 +66,9 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
@@ -76,7 +79,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
@@ -86,78 +89,105 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def perms_per_tree(log_n, n_cols, n_q):
-    n = 1 << log_n
-    leaf = (n_cols + 7) // 8 + 1
-    return n * leaf + (n - 1) + n_q * (leaf + log_n)
+def load_fixture():
+    return open(os.path.join(ROOT, "tests", "golden", "proofs", FIXTURE), "rb").read()
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """The reference's CPU implementation of the path = the oracle port (the Rust workspace cannot be built here:
-    no cargo, stwo git dependency absent).  Bounded sample of the same workload on all host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_verify_rate(n_proofs, seconds, cores):
+    """oracle port (oracle/orc_verify.c) on `cores` pthreads over replicas of the fixture"""
     import oracle_py as O
     lib = O.load_oracle()
-    lib.orc_merkle_build_mt.restype = ctypes.c_uint64
+    lib.orc_verify_batch_mt.restype = ctypes.c_uint64
+    buf, n = O.load_proof(FIXTURE)
+    blobs = np.tile(buf[:n], n_proofs)
+    off = np.arange(n_proofs + 1, dtype=np.uint64) * n
+    idx = np.array(O.INPUTS_SMALL[0], dtype=np.uint32)
+    vals = np.array(O.INPUTS_SMALL[1], dtype=np.uint32)
+    v = np.zeros(n_proofs, np.uint8)
+    s = np.zeros(n_proofs, np.uint8)
+
+    def run():
+        return lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n_proofs, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
+
+    run()
+    reps, perms, t0 = 0, 0, time.perf_counter()
+    while True:
+        perms += run()
+        reps += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    assert not v.any()
+    return reps * n_proofs / dt, perms / dt, reps, dt
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path.  The Rust workspace cannot be built here (no cargo/rustc; its
+    stwo git dependency is absent), so this is the C restatement in oracle/ — kind "port" — on all host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     cores = os.cpu_count() or 1
-    log_n, C, Q = args.ref_log_n, args.cols, args.queries
-    n = 1 << log_n
-    leaves = O.synth_m31(0, n * C).reshape(n, C)
-    nodes = np.zeros((2 * n - 1, 8), dtype=np.uint32)
-    idx = (O.splitmix64(0xABCDEF, Q) & np.uint64(n - 1)).astype(np.uint32)
-    ncols = np.zeros(log_n + 1, dtype=np.uint32)
-    ncols[log_n] = C
-    verdict = np.zeros(Q, dtype=np.uint8)
-
-    def step():
-        lib.orc_merkle_build_mt(O.vp(leaves), log_n, C, O.vp(nodes), cores)
-        pc = np.ascontiguousarray(leaves[idx])
-        sib = np.stack([np.stack([nodes[(1 << (log_n - l)) - 1 + ((int(i) >> l) ^ 1)] for l in range(log_n)]) for i in idx])
-        lib.orc_merkle_paths_verify_mt(log_n, O.vp(ncols), ctypes.c_size_t(Q), O.vp(idx), O.vp(pc), O.vp(np.ascontiguousarray(sib)),
-                                       O.vp(nodes[0].copy()), O.vp(verdict), cores)
-        assert verdict.all()
-
+    n = max(cores * 4, 64)
+    import oracle_py as O
+    lib = O.load_oracle()
+    lib.orc_verify_batch_mt.restype = ctypes.c_uint64
+    buf, ln = O.load_proof(FIXTURE)
+    blobs = np.tile(buf[:ln], n)
+    off = np.arange(n + 1, dtype=np.uint64) * ln
+    idx = np.array(O.INPUTS_SMALL[0], dtype=np.uint32)
+    vals = np.array(O.INPUTS_SMALL[1], dtype=np.uint32)
+    v, s = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    perms = 0
     for _ in range(args.warmup):
-        step()
+        lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        perms += lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
     dt = time.perf_counter() - t0
-    perms = perms_per_tree(log_n, C, Q) * args.steps
-    v = perms / dt
-    sample = "1 tree of 2^%d leaves x %d cols, %d queries per step (the GPU arm's step is %d trees of 2^%d leaves per GPU)" % (
-        log_n, C, Q, args.trees, args.log_n)
+    assert not v.any()
+    val = n * args.steps / dt
+    sample = "%d replicas of %s per step on %d pthreads (the GPU arm's step is %d per GPU)" % (n, FIXTURE, cores, args.proofs)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
-        "config": {"workload": "merkle-decommit-sweep", "log_leaves": args.log_n, "cols": C, "queries": Q, "trees_per_gpu": args.trees},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full"},
+        "poseidon31_perms_per_sec": perms / dt,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_baseline(args):
+def merkle_sweep(pkg, dev, log_n=20, C=8, Q=128, T=2, reps=3):
+    """BASELINE configs[2]: commit T trees of 2^log_n leaves, decommit Q queries, verify every path -> perms/s"""
+    import torch
     import oracle_py as O
-    lib = O.load_oracle()
-    lib.orc_merkle_build_mt.restype = ctypes.c_uint64
-    cores = os.cpu_count() or 1
-    log_n, C = args.ref_log_n, args.cols
     n = 1 << log_n
-    leaves = O.synth_m31(0, n * C).reshape(n, C)
-    nodes = np.zeros((2 * n - 1, 8), dtype=np.uint32)
-    lib.orc_merkle_build_mt(O.vp(leaves), 12, C, O.vp(nodes), cores)     # warm-up
-    reps, perms, t0 = 0, 0, time.perf_counter()
-    while time.perf_counter() - t0 < args.cpu_seconds:
-        perms += lib.orc_merkle_build_mt(O.vp(leaves), log_n, C, O.vp(nodes), cores)
-        reps += 1
-    dt = time.perf_counter() - t0
-    return {"value": perms / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d x commit of one 2^%d-leaf x %d-col tree with the oracle port on %d pthreads (%.1f s)" % (reps, log_n, C, cores, dt)}
+    cols = torch.from_numpy(np.stack([O.synth_m31(t, C * n).reshape(C, n) for t in range(T)]).view(np.int32)).to(dev)
+    idx = torch.from_numpy(np.stack([(O.splitmix64(t ^ 0xABCDEF, Q) & np.uint64(n - 1)).astype(np.uint32) for t in range(T)]).view(np.int32)).to(dev)
+    nodes = torch.empty((T, 2 * n - 1, 8), dtype=torch.int32, device=dev)
+    rid = torch.arange(T, dtype=torch.int32, device=dev).repeat_interleave(Q).contiguous()
+    shape = pkg.PathShape.make(log_n, {log_n: C})
+
+    def step():
+        pkg.merkle_commit(cols, nodes)
+        pc, sib = pkg.merkle_decommit(cols, nodes, idx)
+        return pkg.merkle_path_verify(shape, idx.reshape(-1), pc, sib, nodes[:, 0, :].contiguous(), rid)
+
+    for _ in range(3):
+        v = step()
+    assert bool(v.all().item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    leaf = (C + 7) // 8 + 1
+    perms = T * (n * leaf + n - 1 + Q * (leaf + log_n))
+    return perms * reps / (e0.elapsed_time(e1) * 1e-3)
 
 
 def main():
@@ -166,13 +196,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log-n", type=int, default=20)
-    ap.add_argument("--cols", type=int, default=8)
-    ap.add_argument("--queries", type=int, default=128)
-    ap.add_argument("--trees", type=int, default=4, help="trees per GPU per step")
-    ap.add_argument("--ref-log-n", type=int, default=18)
+    ap.add_argument("--proofs", type=int, default=4096, help="proofs per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the K1 / Merkle-sweep side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,7 +207,7 @@ def main():
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("recursive-stwo_b200")
-    import oracle_py as O     # only for the synthetic-input generator and the cpu_baseline leg
+    sharding = importlib.import_module("recursive-stwo_b200.sharding")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,39 +218,32 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pkg.init(local)
+    warmup = max(args.warmup, 3)
 
-    log_n, C, Q, T = args.log_n, args.cols, args.queries, args.trees
-    n = 1 << log_n
-    # synthetic inputs: tree id = rank*T + t (weak scaling: T trees per GPU)
-    h_cols_t = torch.empty((T, C, n), dtype=torch.int32).pin_memory()
-    h_cols = h_cols_t.numpy().view(np.uint32)
-    h_idx = np.empty((T, Q), dtype=np.uint32)
-    for t in range(T):
-        tid = rank * T + t
-        h_cols[t] = O.synth_m31(tid, C * n).reshape(C, n)
-        h_idx[t] = (O.splitmix64(tid ^ 0xABCDEF, Q) & np.uint64(n - 1)).astype(np.uint32)
-    d_cols = h_cols_t.to(dev)
-    d_idx = torch.from_numpy(h_idx.view(np.int32)).to(dev)
-    nodes = torch.empty((T, 2 * n - 1, 8), dtype=torch.int32, device=dev)
-    root_id = torch.arange(T, dtype=torch.int32, device=dev).repeat_interleave(Q).contiguous()
-    shape = pkg.PathShape.make(log_n, {log_n: C})
-    perms_step = perms_per_tree(log_n, C, Q) * T
-    l2_note = "inputs larger than L2: %d MB of columns + %d MB of tree nodes per step" % (h_cols.nbytes >> 20, nodes.numel() * 4 >> 20)
-
-    def step():
-        pkg.merkle_commit(d_cols, nodes)
-        pcols, sib = pkg.merkle_decommit(d_cols, nodes, d_idx)
-        roots = nodes[:, 0, :].contiguous()
-        return pkg.merkle_path_verify(shape, d_idx.reshape(-1), pcols, sib, roots, root_id)
+    blob = load_fixture()
+    n_total = args.proofs * world                       # weak scaling: --proofs per GPU
+    lo, hi = sharding.shard_range(n_total, rank, world)
+    vb = pkg.VerifyBatch([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
+    ws_mb = vb.ws_bytes >> 20
+    blob_mb = vb.h_words.numel() * 4 >> 20
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        v = step()
-    assert bool(v.all().item()), "honest paths must verify"
+    def step():
+        v, s = vb.run(full=True)
+        return sharding.gather_verdicts(v, s, n_total)
+
+    for _ in range(warmup):
+        v, s = step()
+    torch.cuda.synchronize()
+    assert int(v.sum().item()) == 0 and v.numel() == n_total, "every replica of the fixture must be accepted"
+    dt0 = vb.fetch(0, "detail")
+    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths
+    assert dt0.n_perms_paths == 3481, "permutation count of the per-query paths differs from the reference's (SURVEY App. C)"
+
     # ---- timed region: device-resident ----------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -233,7 +253,7 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        v = step()
+        v, s = step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -243,82 +263,124 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    value = perms_step * world * args.steps / (ms * 1e-3)
+    value = n_total * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host buffers through the host-pointer C ABI -------------------------------------------------
-    pcols, sib = pkg.merkle_decommit(d_cols, nodes, d_idx)
-    h_pcols = pcols.cpu().numpy().view(np.uint32).copy()
-    h_sib = sib.cpu().numpy().view(np.uint32).copy()
-    h_rid = root_id.cpu().numpy().view(np.uint32).copy()
-    h_flat_idx = h_idx.reshape(-1).copy()
-
+    # ---- e2e: pinned host blobs -> device -> verdicts on the host, every step ---------------------------
     def e2e_step():
-        roots = pkg.merkle_commit_host(h_cols)                                   # H2D columns, D2H roots
-        return pkg.merkle_path_verify_host(shape, h_flat_idx, h_pcols, h_sib, roots, h_rid)   # H2D paths, D2H verdicts
+        vb.upload()
+        v, s = vb.run(full=True)
+        v, s = sharding.gather_verdicts(v, s, n_total)
+        return v.cpu(), s.cpu()
 
     for _ in range(2):
-        hv = e2e_step()
-    assert hv.all()
+        hv, hs = e2e_step()
+    assert int(hv.sum()) == 0
+    e2e_steps = max(2, args.steps // 2)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, args.steps // 2)
     for _ in range(e2e_steps):
-        hv = e2e_step()
+        hv, hs = e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_perms = (perms_per_tree(log_n, C, Q) - (0)) * T      # the e2e step verifies the same paths; decommit gather is host-side input
-    e2e_value = e2e_perms * world * e2e_steps / float(t_e.item())
-    h2d = h_cols.nbytes + h_flat_idx.nbytes + h_pcols.nbytes + h_sib.nbytes + h_rid.nbytes + T * 32
-    d2h = T * 32 + T * Q
+    e2e_value = n_total * e2e_steps / float(t_e.item())
+    h2d = vb.h_words.numel() * 4 + vb.h_off.numel() * 8
+    d2h = 2 * n_total
 
-    # ---- roofline of the dominant kernel (leaf layer of the commit = 2/3 of all permutations) ----------------
+    # ---- stage breakdown + roofline of the dominant kernel (CUDA events between the stage kernels) -------
     pk = peaks()
-    leaf_out = torch.empty((T * n, 8), dtype=torch.int32, device=dev)
-    flat_cols = d_cols            # [T, C, n]; hash the leaf layer of tree 0..T-1 with the same kernel code path
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    reps = 5
-    pkg.hash_node_batch(None, flat_cols[0], n)
-    torch.cuda.synchronize()
-    ev[0].record()
-    for r in range(reps):
-        for t in range(T):
-            pkg.hash_node_batch(None, flat_cols[t], n)
-    ev[1].record()
-    torch.cuda.synchronize()
-    leaf_ms = ev[0].elapsed_time(ev[1]) / (reps * T)
-    leaf_perms = n * ((C + 7) // 8 + 1)
-    leaf_rate = leaf_perms / (leaf_ms * 1e-3)
-    achieved_tlops = leaf_rate * LANE_OPS_PER_PERM / 1e12
-    alg_bytes = n * (C * 4 + 32)
+    acc = {}
+    reps = 3
+    for _ in range(reps):
+        vb.run(full=True, timed=True)
+        for k, t in vb.stage_ms().items():
+            acc[k] = acc.get(k, 0.0) + t / reps
+    total_ms = sum(acc.values())
+    dom = max(acc, key=acc.get)
+    n_local = hi - lo
+    sh = vb.shape
+    # permutations each stage kernel executes per proof (counted by the kernels themselves)
+    single_paths = sum(pkg.path_perms(pkg.PathShape.make(d, lay)) for d, lay in _tree_shapes(sh)) * sh.n_queries
+    pair_paths = pkg.proof_perms(sh) - single_paths
+    perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths}
+    hints_total = dt0.n_perms_hints
+    if dom not in perms_of:
+        # the two hint kernels split n_perms_hints; attribute by the per-query path permutations of their trees
+        share = single_paths / float(single_paths + pair_paths)
+        perms_of["single_tree"], perms_of["pair_tree"] = hints_total * share, hints_total * (1 - share)
+    dom_perms = perms_of.get(dom, 0) * n_local
+    dom_rate = dom_perms / (acc[dom] * 1e-3) if acc[dom] > 0 else 0.0
+    achieved = dom_rate * LANE_OPS_PER_PERM / 1e12
+    path_bytes = n_local * sh.n_queries * (4 * (64 * 4 + 30 * 32))      # what the path kernels stream per proof (cols + siblings)
     roofline = {
-        "bound": "int32-issue", "kernel": "k_hash_node_layer (leaf sponge)", "achieved": achieved_tlops, "peak": pk["int_tlops"],
-        "unit": "T lane-ops/s", "frac": achieved_tlops / pk["int_tlops"], "peak_src": pk["int_src"],
-        "lane_ops_per_perm": LANE_OPS_PER_PERM, "perms_per_s": leaf_rate, "launch_ms": leaf_ms, "traffic": None,
-        "hbm": {"bound": "hbm", "achieved": alg_bytes / (leaf_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / (leaf_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_src": pk["src"]},
+        "bound": "int32-issue", "kernel": "k_" + dom, "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
+        "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
+        "perms_per_launch": dom_perms, "launch_ms": acc[dom], "share_of_step": acc[dom] / total_ms, "traffic": None,
+        "stage_ms": acc,
+        "hbm": {"bound": "hbm", "achieved": path_bytes / (acc[dom] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": path_bytes / (acc[dom] * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": path_bytes,
+                "peak_src": pk["src"], "note": "hashing is integer-bound; HBM figure shown for completeness"},
     }
+
+    secondary = {}
+    if not args.no_secondary and rank == 0:
+        n_states = 1 << 22
+        st = torch.randint(0, 2**31 - 1, (n_states, 16), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            pkg.poseidon2_permute(st)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(5):
+            pkg.poseidon2_permute(st)
+        k1.record()
+        torch.cuda.synchronize()
+        k1_rate = n_states * 5 / (k0.elapsed_time(k1) * 1e-3)
+        del st
+        secondary = {"k1_permute_perms_per_sec": k1_rate, "k1_frac_of_int_peak": k1_rate * 4264 / 1e12 / pk["int_tlops"],
+                     "merkle_sweep_perms_per_sec": merkle_sweep(pkg, dev),
+                     "merkle_sweep_config": "2 trees x 2^20 leaves x 8 cols, 128 queries (BASELINE configs[2])"}
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (M31)", "data": "synthetic",
-            "config": {"workload": "merkle-decommit-sweep", "log_leaves": log_n, "cols": C, "queries": Q, "trees_per_gpu": T,
-                       "perms_per_step_per_gpu": perms_step, "l2": l2_note, "parallelism": "trees sharded by rank, no data-path collective"},
+            "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full",
+                       "shape": dict(zip(("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last", "n_queries", "n_inner"), sh.key())),
+                       "perms_per_proof": perms_per_proof,
+                       "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace per step" % (blob_mb, ws_mb),
+                       "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only"},
+            "poseidon31_perms_per_sec": value * perms_per_proof,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t_e.item()) / e2e_steps * 1e3},
             "roofline": roofline,
+            "secondary": secondary,
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(args)
+            cores = os.cpu_count() or 1
+            rate, prate, reps_c, dtc = cpu_verify_rate(max(cores * 4, 64), args.cpu_seconds, cores)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "poseidon31_perms_per_sec": prate,
+                                   "sample": "%d x %d replicas of %s with the oracle port on %d pthreads (%.1f s)" % (
+                                       reps_c, max(cores * 4, 64), FIXTURE, cores, dtc)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _tree_shapes(sh):
+    """(depth, {log_size: n_cols}) of the four commitment trees of a proof shape"""
+    lp, ls, mf = sh.log_size_plonk + sh.log_blowup, sh.log_size_poseidon + sh.log_blowup, sh.max_first
+    out = []
+    for a, b in ((10, 40), (12, 48), (8, 8)):
+        lay = {}
+        lay[lp] = lay.get(lp, 0) + a
+        lay[ls] = lay.get(ls, 0) + b
+        out.append((max(lp, ls), lay))
+    out.append((mf, {mf: 8}))
+    return out
 
 
 if __name__ == "__main__":

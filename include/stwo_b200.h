@@ -143,6 +143,11 @@ typedef struct {
 
 /* flags */
 #define STWO_B200_VERIFY_FULL 1u   /* also recompute every per-query authentication path (what the verifier circuit does) */
+#define STWO_B200_VERIFY_TIMED 2u  /* record CUDA events between the stage kernels (read with stwo_b200_verify_stage_ms) */
+/* stage kernels in launch order: fiat_shamir, single_tree, group, answer, folds, pair_tree, single_path, pair_path, verdict */
+#define STWO_B200_N_STAGE_KERNELS 9
+/* device time of each stage kernel of the last STWO_B200_VERIFY_TIMED batch on this thread (synchronises) */
+int32_t stwo_b200_verify_stage_ms(float *ms /* [STWO_B200_N_STAGE_KERNELS] */);
 
 /* host-side header read (no device needed): shape of one blob; STWO_B200_E_SHAPE when it does not parse */
 int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stwo_b200_proof_shape *out);

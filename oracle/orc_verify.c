@@ -842,3 +842,37 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
     return 0;
 #undef FAIL
 }
+
+/* ---- pthread batch driver for the CPU baseline: proofs are independent ----------------------------------- */
+#include <pthread.h>
+typedef struct {
+    const uint8_t *blobs; const uint64_t *off; uint32_t lo, hi;
+    const uint32_t *idx, *vals; uint32_t n_inputs; uint8_t *verdict, *stage; uint64_t perms;
+} vjob;
+static void *vjob_run(void *p) {
+    vjob *j = (vjob *)p;
+    orc_verify_out *o = malloc(sizeof *o);
+    for (uint32_t i = j->lo; i < j->hi; i++) {
+        orc_verify_proof(j->blobs + j->off[i], (size_t)(j->off[i + 1] - j->off[i]), j->idx, j->vals, j->n_inputs, o);
+        j->verdict[i] = (uint8_t)o->verdict; j->stage[i] = (uint8_t)o->stage;
+        j->perms += o->n_perms_hints + o->n_perms_paths;
+    }
+    free(o);
+    return NULL;
+}
+/* blobs: back to back, off: n+1 BYTE offsets (each 4-byte aligned); returns the permutations executed */
+uint64_t orc_verify_batch_mt(const uint8_t *blobs, const uint64_t *off, uint32_t n, const uint32_t *idx, const uint32_t *vals,
+                             uint32_t n_inputs, uint8_t *verdict, uint8_t *stage, unsigned n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads > n) n_threads = n ? n : 1;
+    pthread_t th[256]; vjob jobs[256];
+    for (unsigned t = 0; t < n_threads; t++) {
+        vjob j = { blobs, off, (uint32_t)((uint64_t)n * t / n_threads), (uint32_t)((uint64_t)n * (t + 1) / n_threads), idx, vals, n_inputs, verdict, stage, 0 };
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, vjob_run, &jobs[t]);
+    }
+    uint64_t perms = 0;
+    for (unsigned t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); perms += jobs[t].perms; }
+    return perms;
+}

@@ -79,6 +79,8 @@ class VerifyDetail(ctypes.Structure):
 
 
 VERIFY_FULL = 1
+VERIFY_TIMED = 2
+STAGE_KERNELS = ("fiat_shamir", "single_tree", "group", "answer", "folds", "pair_tree", "single_path", "pair_path", "verdict")
 FETCH = {"detail": 0, "domain_points": 1, "answers": 2, "circle_folds": 3, "line_folds": 4, "last_evals": 5, "path_roots": 6,
          "path_cols": 7, "path_siblings": 8, "pair_hints": 9}
 STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
@@ -110,6 +112,7 @@ SIGNATURES = {
     "stwo_b200_proof_perms": (_u64, [_PSHAPE_P]),
     "stwo_b200_verify_proofs_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
 }
 

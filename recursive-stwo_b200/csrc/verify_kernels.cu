@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, uint8_t *ver
     if (stage) stage[p] = (uint8_t)ws.detail[p].stage;
 }
 
+cudaEvent_t g_ev[STWO_B200_N_STAGE_KERNELS + 1] = {nullptr};
+bool g_timed_valid = false;
 inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
 
 bool shape_ok(const stwo_b200_proof_shape *s) {
@@ -137,21 +139,38 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
     if (verify::carve(ws, (uint8_t *)workspace) > workspace_bytes) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = n_proofs, nq = shape->n_queries, nf = ws.shape.n_fri_trees();
-    k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws);
-    k_single_tree<<<nblk(n * 4), kT, 0, st>>>(ws);
-    k_group<<<nblk(n * fri::MAX_LOGS), kT, 0, st>>>(ws);
-    k_answer<<<nblk(n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws);
-    k_folds<<<nblk(n), kT, 0, st>>>(ws);
-    k_pair_tree<<<nblk(n * nf), kT, 0, st>>>(ws);
+    const bool timed = flags & STWO_B200_VERIFY_TIMED;
+    if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
+    int e = 0;
+#define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
+    MARK(); k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws);
+    MARK(); k_single_tree<<<nblk(n * 4), kT, 0, st>>>(ws);
+    MARK(); k_group<<<nblk(n * fri::MAX_LOGS), kT, 0, st>>>(ws);
+    MARK(); k_answer<<<nblk(n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws);
+    MARK(); k_folds<<<nblk(n), kT, 0, st>>>(ws);
+    MARK(); k_pair_tree<<<nblk(n * nf), kT, 0, st>>>(ws);
     note_launch(6);
+    MARK();
     if (flags & STWO_B200_VERIFY_FULL) {
         k_single_path<<<nblk(n * 4 * nq), kT, 0, st>>>(ws);
+        MARK();
         k_pair_path<<<nblk(n * nf * nq), kT, 0, st>>>(ws);
         note_launch(2);
-    }
-    k_verdict<<<nblk(n), kT, 0, st>>>(ws, verdict, stage);
+    } else MARK();
+    MARK(); k_verdict<<<nblk(n), kT, 0, st>>>(ws, verdict, stage);
+    MARK();
+#undef MARK
+    g_timed_valid = timed;
     note_launch(1);
     return cuda_status(cudaGetLastError());
+}
+
+extern "C" int32_t stwo_b200_verify_stage_ms(float *ms) {
+    STWO_CHECK_DEVICE();
+    if (!ms || !g_timed_valid) return STWO_B200_E_BAD_ARG;
+    STWO_CUDA(cudaEventSynchronize(g_ev[STWO_B200_N_STAGE_KERNELS]));
+    for (int i = 0; i < STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
+    return STWO_B200_OK;
 }
 
 extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,

@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import ProofShape, VerifyDetail, VERIFY_FULL, FETCH, STAGES
+from ._lib import ProofShape, VerifyDetail, VERIFY_FULL, VERIFY_TIMED, STAGE_KERNELS, FETCH, STAGES
 from .hashing import _need_init, _stream, _dptr
 
 INPUTS_SINGLE = ([1], [[1, 0, 0, 0]])                                            # examples/single-proof/src/main.rs:28-33
@@ -90,11 +90,21 @@ class VerifyBatch:
         self.d_words.copy_(self.h_words, non_blocking=True)
         self.d_off.copy_(self.h_off, non_blocking=True)
 
-    def run(self, full=True):
+    def run(self, full=True, timed=False):
+        flags = (VERIFY_FULL if full else 0) | (VERIFY_TIMED if timed else 0)
         _lib.call("stwo_b200_verify_proofs_batch_dev", _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape),
-                  _dptr(self.d_idx), _dptr(self.d_vals), self.n_inputs, VERIFY_FULL if full else 0, _dptr(self.d_ws), self.ws_bytes,
+                  _dptr(self.d_idx), _dptr(self.d_vals), self.n_inputs, flags, _dptr(self.d_ws), self.ws_bytes,
                   _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
         return self.d_verdict, self.d_stage
+
+    def stage_ms(self):
+        """device time of each stage kernel of the last run(timed=True) -> {kernel: ms}"""
+        ms = (ctypes.c_float * len(STAGE_KERNELS))()
+        _lib.call("stwo_b200_verify_stage_ms", ms)
+        return dict(zip(STAGE_KERNELS, [float(x) for x in ms]))
+
+    def verdicts_to_host(self):
+        return self.d_verdict.cpu().numpy(), self.d_stage.cpu().numpy()
 
     def fetch(self, p, what):
         """Read one proof's intermediate values back (see STWO_B200_FETCH_* in include/stwo_b200.h)."""
