@@ -143,6 +143,7 @@ typedef struct {
 
 /* flags */
 #define STWO_B200_VERIFY_FULL 1u   /* also recompute every per-query authentication path (what the verifier circuit does) */
+#define STWO_B200_VERIFY_ONE_STREAM 4u /* do not slice the batch over the library's stream pool */
 #define STWO_B200_VERIFY_TIMED 2u  /* record CUDA events between the stage kernels (read with stwo_b200_verify_stage_ms) */
 /* stage kernels in launch order: fiat_shamir, single_tree, group, answer, folds, pair_tree, single_path, pair_path, verdict */
 #define STWO_B200_N_STAGE_KERNELS 9

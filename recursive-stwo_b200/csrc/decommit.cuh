@@ -15,7 +15,18 @@ namespace decommit {
 
 using fs::permute_mem;
 
-// hash_node with separate child pointers (L == nullptr: leaf).  primitives/merkle/src/lib.rs:9-181
+// Scratch arrays are addressed through a stride so that, on the device, word i of every thread of a warp is adjacent
+// (coalesced) instead of each thread owning a contiguous block; on the host the stride is 1.
+struct Strided {
+    u32 *p; u32 stride;
+    HDM u32 &operator[](u32 i) const { return p[(size_t)i * stride]; }
+    HDM Strided at(u32 off) const { Strided r; r.p = p + (size_t)off * stride; r.stride = stride; return r; }
+};
+HD void ld8(const Strided &s, u32 k, u32 out[8]) { for (u32 i = 0; i < 8; i++) out[i] = s[8 * k + i]; }
+HD void st8(const Strided &s, u32 k, const u32 in[8]) { for (u32 i = 0; i < 8; i++) s[8 * k + i] = in[i]; }
+
+// hash_node on register-resident children (L == nullptr: leaf); cols is contiguous memory (the proof blob).
+// primitives/merkle/src/lib.rs:9-181
 HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr) {
     u32 st[16];
     u32 tree[8];
@@ -46,7 +57,8 @@ HD bool eq8(const u32 *a, const u32 *b) {
 HD void cp8(u32 *dst, const u32 *src) { for (int i = 0; i < 8; i++) dst[i] = src[i]; }
 
 // in-place insertion sort + dedup of n <= 256 values; returns the unique count
-HD u32 sort_unique(u32 *v, u32 n) {
+template <class A>
+HD u32 sort_unique(A v, u32 n) {
     for (u32 i = 1; i < n; i++) {
         u32 x = v[i], j = i;
         while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
@@ -56,7 +68,8 @@ HD u32 sort_unique(u32 *v, u32 n) {
     for (u32 i = 0; i < n; i++) if (m == 0 || v[m - 1] != v[i]) v[m++] = v[i];
     return m;
 }
-HD int find(const u32 *v, u32 n, u32 x) {
+template <class A>
+HD int find(A v, u32 n, u32 x) {
     u32 lo = 0, hi = n;
     while (lo < hi) { u32 mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
     return (lo < n && v[lo] == x) ? (int)lo : -1;
@@ -76,24 +89,28 @@ struct SingleShape {
 // injected layer) to path_cols + i*cpp and its sibling hashes (leaf level first) to path_sib + i*sib_stride.
 // Returns true iff both streams are consumed exactly and the recomputed root equals `root`.
 HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *values, u32 n_values, const u32 *hw, u32 n_hw,
-                    const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, u32 *scratch, u32 *perms) {
-    u32 *cpos = scratch, *chash = cpos + nq, *ppos = chash + 8 * nq, *phash = ppos + nq;
-    u32 *sibsrc = phash + 8 * nq, *par = sibsrc + nq, *colsrc = par + nq, *qnode = colsrc + nq;
+                    const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, Strided scratch, u32 *perms) {
+    Strided cpos = scratch, chash = cpos.at(nq), ppos = chash.at(8 * nq), phash = ppos.at(nq);
+    Strided sibsrc = phash.at(8 * nq), par = sibsrc.at(nq), colsrc = par.at(nq), qnode = colsrc.at(nq);
     const u32 depth = sh.depth;
     for (u32 i = 0; i < nq; i++) cpos[i] = q[i];
     u32 m = sort_unique(cpos, nq);
     for (u32 i = 0; i < nq; i++) qnode[i] = (u32)find(cpos, m, q[i]);
     u32 vi = 0, wi = 0, np = 0;
     u32 nc = sh.ncols(depth);
+    u32 h8[8], l8[8], r8[8];
     for (u32 k = 0; k < m; k++) {
         if (vi + nc > n_values) return false;
-        hash_node2(nullptr, nullptr, values + vi, nc, chash + 8 * k);
+        hash_node2(nullptr, nullptr, values + vi, nc, h8);
+        st8(chash, k, h8);
         np += node_perms(true, nc);
         colsrc[k] = vi;
         vi += nc;
     }
-    for (u32 i = 0; i < nq; i++)
-        for (u32 c = 0; c < nc; c++) path_cols[i * cpp + c] = values[colsrc[qnode[i]] + c];
+    for (u32 i = 0; i < nq; i++) {
+        const u32 src = colsrc[qnode[i]];
+        for (u32 c = 0; c < nc; c++) path_cols[i * cpp + c] = values[src + c];
+    }
     u32 colpos = nc;
     for (u32 h = depth; h-- > 0;) {
         nc = sh.ncols(h);
@@ -101,20 +118,20 @@ HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *valu
         while (k < m) {
             const u32 ps = cpos[k];
             const bool pair = k + 1 < m && cpos[k + 1] == (ps ^ 1u);
-            const u32 *L, *R;
             if (pair) {
-                L = chash + 8 * k; R = chash + 8 * (k + 1);
-                sibsrc[k] = k + 1; sibsrc[k + 1] = k; par[k] = par[k + 1] = j;
+                ld8(chash, k, l8); ld8(chash, k + 1, r8);
+                sibsrc[k] = k + 1; sibsrc[k + 1] = k; par[k] = j; par[k + 1] = j;
             } else {
                 if (wi >= n_hw) return false;
                 const u32 *W = hw + 8 * wi;
                 sibsrc[k] = 0x80000000u | wi;
                 par[k] = j;
                 wi++;
-                if (ps & 1u) { L = W; R = chash + 8 * k; } else { L = chash + 8 * k; R = W; }
+                if (ps & 1u) { cp8(l8, W); ld8(chash, k, r8); } else { ld8(chash, k, l8); cp8(r8, W); }
             }
             if (vi + nc > n_values) return false;
-            hash_node2(L, R, values + vi, nc, phash + 8 * j);
+            hash_node2(l8, r8, values + vi, nc, h8);
+            st8(phash, j, h8);
             np += node_perms(false, nc);
             ppos[j] = ps >> 1;
             colsrc[j] = vi;
@@ -125,19 +142,22 @@ HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *valu
         for (u32 i = 0; i < nq; i++) {
             const u32 kq = qnode[i];
             const u32 s = sibsrc[kq];
-            cp8(path_sib + (size_t)i * sib_stride + (depth - 1 - h) * 8, (s & 0x80000000u) ? hw + 8 * (s & 0x7fffffffu) : chash + 8 * s);
+            u32 *dst = path_sib + (size_t)i * sib_stride + (depth - 1 - h) * 8;
+            if (s & 0x80000000u) cp8(dst, hw + 8 * (s & 0x7fffffffu)); else ld8(chash, s, dst);
             const u32 pj = par[kq];
             qnode[i] = pj;
-            for (u32 c = 0; c < nc; c++) path_cols[i * cpp + colpos + c] = values[colsrc[pj] + c];
+            const u32 src = colsrc[pj];
+            for (u32 c = 0; c < nc; c++) path_cols[i * cpp + colpos + c] = values[src + c];
         }
         colpos += nc;
-        u32 *t;
+        Strided t;
         t = cpos; cpos = ppos; ppos = t;
         t = chash; chash = phash; phash = t;
         m = j;
     }
     if (perms) *perms += np;
-    return vi == n_values && wi == n_hw && m == 1 && eq8(chash, root);
+    ld8(chash, 0, h8);
+    return vi == n_values && wi == n_hw && m == 1 && eq8(h8, root);
 }
 
 // ---- FRI layer trees (query and sibling both opened; QM31 leaf = 4 words) -------------------------------------
@@ -150,14 +170,15 @@ constexpr u32 MAX_DATA_LAYERS = 3;
 //               sib_hashes [(i*(depth-1) + j)*8], j = depth-1-h for layers h = depth-1 .. 1:
 //               the sibling's hash (plain layers) or the sibling's hash *without* its own evaluation (data layers).
 HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *vals, u32 n_vals, const u32 *hw, u32 n_hw,
-                  const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, u32 *scratch, u32 *perms) {
+                  const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, Strided scratch, u32 *perms) {
     const u32 cap = 2 * nq;
-    u32 *qs = scratch, *cpos = qs + cap, *chash = cpos + cap, *npos = chash + 8 * cap, *nhash = npos + cap;
-    u32 *ntree = nhash + 8 * cap, *nL = ntree + 8 * cap, *nR = nL + 8 * cap, *nval = nR + 8 * cap;
+    Strided qs = scratch, cpos = qs.at(cap), chash = cpos.at(cap), npos = chash.at(8 * cap), nhash = npos.at(cap);
+    Strided ntree = nhash.at(8 * cap), nL = ntree.at(8 * cap), nR = nL.at(8 * cap), nval = nR.at(8 * cap);
     for (u32 i = 0; i < nq; i++) qs[i] = q[i];
     u32 n = sort_unique(qs, nq);
     u32 cm = 0;                    // child table size
     u32 vi = 0, wi = 0, np = 0, d_idx = 0;
+    u32 h8[8], t8[8], l8[8], r8[8];
     for (u32 h = depth + 1; h-- > 0;) {
         if (h < depth) {
             for (u32 k = 0; k < n; k++) qs[k] >>= 1;
@@ -179,16 +200,17 @@ HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *val
                 val = vals + vi; nval[a] = vi; vi += 4;
             }
             if (h == depth) {
-                hash_node2(nullptr, nullptr, val, 4, nhash + 8 * a);
+                hash_node2(nullptr, nullptr, val, 4, h8);
+                st8(nhash, a, h8);
                 np += 2;
             } else {
                 const u32 p = npos[a];
                 int li = find(cpos, cm, p << 1), ri = find(cpos, cm, (p << 1) + 1);
-                const u32 *L, *R;
-                if (li >= 0) L = chash + 8 * li; else { if (wi >= n_hw) return false; L = hw + 8 * wi++; }
-                if (ri >= 0) R = chash + 8 * ri; else { if (wi >= n_hw) return false; R = hw + 8 * wi++; }
-                cp8(nL + 8 * a, L); cp8(nR + 8 * a, R);
-                hash_node2(L, R, val, data ? 4 : 0, nhash + 8 * a, ntree + 8 * a);
+                if (li >= 0) ld8(chash, (u32)li, l8); else { if (wi >= n_hw) return false; cp8(l8, hw + 8 * wi++); }
+                if (ri >= 0) ld8(chash, (u32)ri, r8); else { if (wi >= n_hw) return false; cp8(r8, hw + 8 * wi++); }
+                st8(nL, a, l8); st8(nR, a, r8);
+                hash_node2(l8, r8, val, data ? 4 : 0, h8, t8);
+                st8(nhash, a, h8); st8(ntree, a, t8);
                 np += data ? 3 : 1;
             }
         }
@@ -198,9 +220,13 @@ HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *val
             if (data) {
                 int a_self = find(npos, m, qh), a_sib = find(npos, m, qh ^ 1u);
                 if (a_self < 0 || (a_sib < 0 && h > 0)) return false;
-                for (int c = 0; c < 4; c++) self_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[nval[a_self] + c];
-                if (a_sib >= 0) for (int c = 0; c < 4; c++) sib_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[nval[a_sib] + c];
-                if (h != depth && h >= 1) cp8(sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - h)) * 8, ntree + 8 * a_sib);
+                const u32 vs = nval[a_self];
+                for (int c = 0; c < 4; c++) self_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[vs + c];
+                if (a_sib >= 0) {
+                    const u32 vb = nval[a_sib];
+                    for (int c = 0; c < 4; c++) sib_vals[(i * MAX_DATA_LAYERS + d_idx) * 4 + c] = vals[vb + c];
+                }
+                if (h != depth && h >= 1) ld8(ntree, (u32)a_sib, sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - h)) * 8);
             }
             // the child layer h+1, when it carries no data, takes its sibling from this parent's two children
             const u32 hc = h + 1;
@@ -208,16 +234,18 @@ HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *val
                 int pa = find(npos, m, qh);
                 if (pa < 0) return false;
                 const u32 qc = q[i] >> (depth - hc);
-                cp8(sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - hc)) * 8, (qc & 1u) ? nL + 8 * pa : nR + 8 * pa);
+                ld8((qc & 1u) ? nL : nR, (u32)pa, sib_hashes + ((size_t)i * (depth - 1) + (depth - 1 - hc)) * 8);
             }
         }
         if (data) d_idx++;
         // this layer becomes the child table
-        for (u32 a = 0; a < m; a++) { cpos[a] = npos[a]; cp8(chash + 8 * a, nhash + 8 * a); }
+        for (u32 a = 0; a < m; a++) cpos[a] = npos[a];
+        for (u32 a = 0; a < 8 * m; a++) chash[a] = nhash[a];
         cm = m;
     }
     if (perms) *perms += np;
-    return vi == n_vals && wi == n_hw && cm == 1 && eq8(chash, root);
+    ld8(chash, 0, h8);
+    return vi == n_vals && wi == n_hw && cm == 1 && eq8(h8, root);
 }
 
 // SinglePairMerkleProof::verify for one query (components/hints/src/folding.rs:33-91): recompute the root from the

@@ -71,6 +71,7 @@ struct Workspace {
     u32 *n_fri_vals;                     // [p][f]
     u32 *pair_hints;                     // [p][f][i][PAIR_HINT_WORDS]
     u32 *pair_scratch;                   // [p][f][88 * nq]
+    u32 *fold_buf;                       // [p][max(1, 2^(log_last-1))][4]  last-layer polynomial fold buffer
 
     HDM const u32 *blob(u32 p) const { return blobs + blob_off[p]; }
     HDM size_t blob_words(u32 p) const { return (size_t)(blob_off[p + 1] - blob_off[p]); }
@@ -82,6 +83,15 @@ struct Workspace {
     HDM u32 *vals_of(u32 p, u32 f) const { return fri_vals + ((size_t)p * shape.n_fri_trees() + f) * fri_vals_stride(); }
     HDM u32 *nvals_of(u32 p, u32 f) const { return n_fri_vals + (size_t)p * shape.n_fri_trees() + f; }
     HDM u32 *hint_of(u32 p, u32 f, u32 i) const { return pair_hints + (((size_t)p * shape.n_fri_trees() + f) * nq() + i) * PAIR_HINT_WORDS; }
+    // tree-walk scratch: thread (p, tree) owns word i at base[i * n_threads + thread] on the device (coalesced across
+    // the lanes of a warp, which hold the same tree of different proofs); contiguous per thread on the host
+#if defined(__CUDA_ARCH__)
+    HDM decommit::Strided scratch_single(u32 p, u32 t) const { decommit::Strided s; s.p = single_scratch + ((size_t)t * n_proofs + p); s.stride = 4 * n_proofs; return s; }
+    HDM decommit::Strided scratch_pair(u32 p, u32 f) const { decommit::Strided s; s.p = pair_scratch + ((size_t)f * n_proofs + p); s.stride = shape.n_fri_trees() * n_proofs; return s; }
+#else
+    HDM decommit::Strided scratch_single(u32 p, u32 t) const { decommit::Strided s; s.p = single_scratch + ((size_t)p * 4 + t) * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq(); s.stride = 1; return s; }
+    HDM decommit::Strided scratch_pair(u32 p, u32 f) const { decommit::Strided s; s.p = pair_scratch + ((size_t)p * shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq(); s.stride = 1; return s; }
+#endif
     HDM u32 *q4(u32 *base, u32 p, u32 a, u32 na, u32 i) const { return base + (((size_t)p * na + a) * nq() + i) * 4; }
 };
 
@@ -134,7 +144,7 @@ HD void stage_single_tree(const Workspace &ws, u32 p, u32 t) {
     u32 perms = 0;
     bool ok = decommit::single_tree(sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
                                     w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
-                                    ws.single_scratch + ((size_t)p * 4 + t) * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq, &perms);
+                                    ws.scratch_single(p, t), &perms);
     VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
     if (!ok) fail_shared(&dt, proof::ST_MERKLE);
 }
@@ -287,22 +297,19 @@ HD void stage_folds(const Workspace &ws, u32 p) {
     if (!inner_ok) fail_shared(&dt, proof::ST_FRI_INNER);
     // last layer
     bool last_ok = true;
-    qm31_t *buf = (qm31_t *)(ws.pair_scratch + (size_t)p * ws.shape.n_fri_trees() * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq);
+    const u32 fold_cap = d.log_last ? (1u << (d.log_last - 1)) : 1u;
+    qm31_t *buf = (qm31_t *)(ws.fold_buf + (size_t)p * fold_cap * 4);
     for (u32 i = 0; i < nq; i++) {
         const cpoint_t ab = fri::absolute_point(log_size, fri::position(d, dt.fs.raw_queries[i], log_size));
         const u32 x = m31::subc(m31::mulc(ab.x, ab.x), m31::mulc(ab.y, ab.y));
-        // the scratch of the FRI trees is free until stage 5 runs; it holds the 2^log_last fold buffer (<= 4096 QM31)
         qm31_t ev;
         if (d.log_last == 0) ev = fs::qload(w + d.last_coeffs);
         else {
             u32 dbl[16];
             dbl[0] = x;
             for (u32 k = 1; k < d.log_last; k++) { u32 sq = m31::mulc(dbl[k - 1], dbl[k - 1]); dbl[k] = m31::subc(m31::addc(sq, sq), 1); }
-            // fold without a buffer larger than the scratch allows: recursive halves evaluated iteratively per level
             u32 n = 1u << d.log_last;
-            const u32 cap = (u32)((size_t)ws.shape.n_fri_trees() * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq / 4);
-            if (n / 2 > cap) { last_ok = false; ev = qm31::zero(); }
-            else {
+            {
                 n >>= 1;
                 for (u32 k = 0; k < n; k++)
                     buf[k] = fs::qadd(fs::qload(w + d.last_coeffs + 8 * k), qm31::mul_m31(fs::qload(w + d.last_coeffs + 8 * k + 4), dbl[d.log_last - 1]));
@@ -333,7 +340,7 @@ HD void stage_pair_tree(const Workspace &ws, u32 p, u32 f) {
     const u32 *root = w + (f ? d.in_commitment[f - 1] : d.fl_commitment);
     u32 *hint = ws.hint_of(p, f, 0);
     // pair_tree writes packed per-query arrays; give it strided views by running it on a packed scratch tail and spreading
-    u32 *scratch = ws.pair_scratch + ((size_t)p * ws.shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq;
+    const decommit::Strided scratch = ws.scratch_pair(p, f);
     u32 perms = 0;
     // packed outputs live at the start of the hint block of this tree (nq * PAIR_HINT_WORDS words available)
     u32 *self_vals = hint, *sib_vals = hint + nq * decommit::MAX_DATA_LAYERS * 4, *sib_hashes = sib_vals + nq * decommit::MAX_DATA_LAYERS * 4;
@@ -411,6 +418,7 @@ inline size_t carve(Workspace &ws, uint8_t *base) {
     ws.n_fri_vals = c.take<u32>(n * nf);
     ws.pair_hints = c.take<u32>(n * nf * nq * PAIR_HINT_WORDS);
     ws.pair_scratch = c.take<u32>(n * nf * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq);
+    ws.fold_buf = c.take<u32>(n * (ws.shape.log_last ? ((size_t)1 << (ws.shape.log_last - 1)) : 1) * 4);
     return (c.at + 255) & ~(size_t)255;
 }
 

@@ -14,56 +14,74 @@ using verify::Workspace;
 namespace {
 constexpr int kT = 64;
 
-__global__ void __launch_bounds__(kT) k_fiat_shamir(const Workspace ws) {
-    u32 p = blockIdx.x * kT + threadIdx.x;
-    if (p < ws.n_proofs) verify::stage_fiat_shamir(ws, p);
-}
-__global__ void __launch_bounds__(kT) k_single_tree(const Workspace ws) {
+// every kernel covers the proofs [p0, p0 + pn) so that a batch can be cut into slices that run on separate streams
+__global__ void __launch_bounds__(kT) k_fiat_shamir(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    if (idx < ws.n_proofs * 4) verify::stage_single_tree(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+    if (idx < pn) verify::stage_fiat_shamir(ws, p0 + idx);
 }
-__global__ void __launch_bounds__(kT) k_group(const Workspace ws) {
+__global__ void __launch_bounds__(kT) k_single_tree(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    if (idx < ws.n_proofs * fri::MAX_LOGS) verify::stage_group(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+    if (idx < pn * 4) verify::stage_single_tree(ws, p0 + idx % pn, idx / pn);
 }
-__global__ void __launch_bounds__(kT) k_answer(const Workspace ws) {
+__global__ void __launch_bounds__(kT) k_group(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    const u32 per_g = ws.n_proofs * ws.shape.n_queries;
+    if (idx < pn * fri::MAX_LOGS) verify::stage_group(ws, p0 + idx % pn, idx / pn);
+}
+__global__ void __launch_bounds__(kT) k_answer(const Workspace ws, u32 p0, u32 pn) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    const u32 per_g = pn * ws.shape.n_queries;
     if (idx < per_g * fri::MAX_LOGS) {
         u32 g = idx / per_g, r = idx % per_g;
-        verify::stage_answer(ws, r / ws.shape.n_queries, g, r % ws.shape.n_queries);
+        verify::stage_answer(ws, p0 + r / ws.shape.n_queries, g, r % ws.shape.n_queries);
     }
 }
-__global__ void __launch_bounds__(kT) k_folds(const Workspace ws) {
-    u32 p = blockIdx.x * kT + threadIdx.x;
-    if (p < ws.n_proofs) verify::stage_folds(ws, p);
-}
-__global__ void __launch_bounds__(kT) k_pair_tree(const Workspace ws) {
+__global__ void __launch_bounds__(kT) k_folds(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    if (idx < ws.n_proofs * ws.shape.n_fri_trees()) verify::stage_pair_tree(ws, idx % ws.n_proofs, idx / ws.n_proofs);
+    if (idx < pn) verify::stage_folds(ws, p0 + idx);
 }
-__global__ void __launch_bounds__(kT) k_single_path(const Workspace ws) {
+__global__ void __launch_bounds__(kT) k_pair_tree(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    const u32 per_t = ws.n_proofs * ws.shape.n_queries;
+    if (idx < pn * ws.shape.n_fri_trees()) verify::stage_pair_tree(ws, p0 + idx % pn, idx / pn);
+}
+__global__ void __launch_bounds__(kT) k_single_path(const Workspace ws, u32 p0, u32 pn) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    const u32 per_t = pn * ws.shape.n_queries;
     if (idx < per_t * 4) {
         u32 t = idx / per_t, r = idx % per_t;
-        verify::stage_single_path(ws, r / ws.shape.n_queries, t, r % ws.shape.n_queries);
+        verify::stage_single_path(ws, p0 + r / ws.shape.n_queries, t, r % ws.shape.n_queries);
     }
 }
-__global__ void __launch_bounds__(kT) k_pair_path(const Workspace ws) {
+__global__ void __launch_bounds__(kT) k_pair_path(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
-    const u32 per_f = ws.n_proofs * ws.shape.n_queries;
+    const u32 per_f = pn * ws.shape.n_queries;
     if (idx < per_f * ws.shape.n_fri_trees()) {
         u32 f = idx / per_f, r = idx % per_f;
-        verify::stage_pair_path(ws, r / ws.shape.n_queries, f, r % ws.shape.n_queries);
+        verify::stage_pair_path(ws, p0 + r / ws.shape.n_queries, f, r % ws.shape.n_queries);
     }
 }
-__global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, uint8_t *verdict, uint8_t *stage) {
-    u32 p = blockIdx.x * kT + threadIdx.x;
-    if (p >= ws.n_proofs) return;
+__global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, u32 p0, u32 pn, uint8_t *verdict, uint8_t *stage) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx >= pn) return;
+    const u32 p = p0 + idx;
     verify::stage_verdict(ws, p);
     if (verdict) verdict[p] = (uint8_t)ws.detail[p].verdict;
     if (stage) stage[p] = (uint8_t)ws.detail[p].stage;
+}
+
+// stream pool for sliced batches: per slice a main chain and a side stream for the commitment-tree path recomputation
+constexpr int kSlices = 4;
+cudaStream_t g_pool[2 * kSlices] = {nullptr};
+cudaEvent_t g_fork = nullptr, g_tree_done[kSlices] = {nullptr}, g_side_done[kSlices] = {nullptr}, g_join[kSlices] = {nullptr};
+bool pool_init() {
+    if (g_fork) return true;
+    for (int i = 0; i < 2 * kSlices; i++) if (cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < kSlices; i++) {
+        if (cudaEventCreateWithFlags(&g_tree_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&g_side_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    return true;
 }
 
 cudaEvent_t g_ev[STWO_B200_N_STAGE_KERNELS + 1] = {nullptr};
@@ -138,30 +156,61 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
     ws.input_idx = input_idx; ws.input_vals = input_vals; ws.n_inputs = n_inputs;
     if (verify::carve(ws, (uint8_t *)workspace) > workspace_bytes) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = n_proofs, nq = shape->n_queries, nf = ws.shape.n_fri_trees();
-    const bool timed = flags & STWO_B200_VERIFY_TIMED;
-    if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
-    int e = 0;
+    const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees();
+    const bool timed = flags & STWO_B200_VERIFY_TIMED, full = flags & STWO_B200_VERIFY_FULL;
+    g_timed_valid = false;
+    if (timed || n_proofs < 256 || (flags & STWO_B200_VERIFY_ONE_STREAM)) {
+        // one stream, stage after stage (clean per-stage timings; small batches)
+        const u32 n = n_proofs;
+        if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
+        int e = 0;
 #define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
-    MARK(); k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws);
-    MARK(); k_single_tree<<<nblk(n * 4), kT, 0, st>>>(ws);
-    MARK(); k_group<<<nblk(n * fri::MAX_LOGS), kT, 0, st>>>(ws);
-    MARK(); k_answer<<<nblk(n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws);
-    MARK(); k_folds<<<nblk(n), kT, 0, st>>>(ws);
-    MARK(); k_pair_tree<<<nblk(n * nf), kT, 0, st>>>(ws);
-    note_launch(6);
-    MARK();
-    if (flags & STWO_B200_VERIFY_FULL) {
-        k_single_path<<<nblk(n * 4 * nq), kT, 0, st>>>(ws);
+        MARK(); k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_single_tree<<<nblk((size_t)n * 4), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_folds<<<nblk(n), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_pair_tree<<<nblk((size_t)n * nf), kT, 0, st>>>(ws, 0, n);
         MARK();
-        k_pair_path<<<nblk(n * nf * nq), kT, 0, st>>>(ws);
-        note_launch(2);
-    } else MARK();
-    MARK(); k_verdict<<<nblk(n), kT, 0, st>>>(ws, verdict, stage);
-    MARK();
+        if (full) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
+        MARK();
+        if (full) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, st>>>(ws, 0, n);
+        MARK(); k_verdict<<<nblk(n), kT, 0, st>>>(ws, 0, n, verdict, stage);
+        MARK();
 #undef MARK
-    g_timed_valid = timed;
-    note_launch(1);
+        g_timed_valid = timed;
+        note_launch(full ? 9 : 7);
+        return cuda_status(cudaGetLastError());
+    }
+    // sliced: the per-proof and per-tree stages have far fewer threads than the GPU holds, so independent slices of the
+    // batch run concurrently on pooled streams, and the commitment-tree path recomputation runs beside the FRI chain
+    if (!pool_init()) return cuda_status(cudaGetLastError());
+    STWO_CUDA(cudaEventRecord(g_fork, st));
+    for (int sl = 0; sl < kSlices; sl++) {
+        const u32 p0 = (u32)((uint64_t)n_proofs * sl / kSlices), p1 = (u32)((uint64_t)n_proofs * (sl + 1) / kSlices), n = p1 - p0;
+        cudaStream_t a = g_pool[2 * sl], b = g_pool[2 * sl + 1];
+        STWO_CUDA(cudaStreamWaitEvent(a, g_fork, 0));
+        k_fiat_shamir<<<nblk(n), kT, 0, a>>>(ws, p0, n);
+        k_single_tree<<<nblk((size_t)n * 4), kT, 0, a>>>(ws, p0, n);
+        if (full) {
+            STWO_CUDA(cudaEventRecord(g_tree_done[sl], a));
+            STWO_CUDA(cudaStreamWaitEvent(b, g_tree_done[sl], 0));
+            k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, b>>>(ws, p0, n);
+            STWO_CUDA(cudaEventRecord(g_side_done[sl], b));
+        }
+        k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, a>>>(ws, p0, n);
+        k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
+        k_folds<<<nblk(n), kT, 0, a>>>(ws, p0, n);
+        k_pair_tree<<<nblk((size_t)n * nf), kT, 0, a>>>(ws, p0, n);
+        if (full) {
+            k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
+            STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));
+        }
+        k_verdict<<<nblk(n), kT, 0, a>>>(ws, p0, n, verdict, stage);
+        STWO_CUDA(cudaEventRecord(g_join[sl], a));
+        STWO_CUDA(cudaStreamWaitEvent(st, g_join[sl], 0));
+        note_launch(full ? 9 : 7);
+    }
     return cuda_status(cudaGetLastError());
 }
 
