@@ -76,7 +76,8 @@ HD int find(A v, u32 n, u32 x) {
 }
 
 // ---- commitment trees ---------------------------------------------------------------------------------
-constexpr u32 SINGLE_SCRATCH_WORDS_PER_QUERY = 22;
+constexpr u32 SINGLE_SCRATCH_WORDS_PER_QUERY = 16;   // two layers of node hashes
+constexpr u32 SINGLE_IDX_WORDS_PER_QUERY = 6;        // thread-local position / index tables
 
 // Columns live at two layers at most: nA columns at log size hA and nB at hB (the Plonk and the Poseidon
 // component; composition tree: nB = 0).  depth = max(hA, hB) = log size of the leaf layer.
@@ -89,9 +90,10 @@ struct SingleShape {
 // injected layer) to path_cols + i*cpp and its sibling hashes (leaf level first) to path_sib + i*sib_stride.
 // Returns true iff both streams are consumed exactly and the recomputed root equals `root`.
 HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *values, u32 n_values, const u32 *hw, u32 n_hw,
-                    const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, Strided scratch, u32 *perms) {
-    Strided cpos = scratch, chash = cpos.at(nq), ppos = chash.at(8 * nq), phash = ppos.at(nq);
-    Strided sibsrc = phash.at(8 * nq), par = sibsrc.at(nq), colsrc = par.at(nq), qnode = colsrc.at(nq);
+                    const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, Strided scratch, u32 *idx, u32 *perms) {
+    // node hashes live in the (global, strided) scratch; the small position / index tables in thread-local memory
+    Strided chash = scratch, phash = chash.at(8 * nq);
+    u32 *cpos = idx, *ppos = cpos + nq, *sibsrc = ppos + nq, *par = sibsrc + nq, *colsrc = par + nq, *qnode = colsrc + nq;
     const u32 depth = sh.depth;
     for (u32 i = 0; i < nq; i++) cpos[i] = q[i];
     u32 m = sort_unique(cpos, nq);
@@ -150,9 +152,8 @@ HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *valu
             for (u32 c = 0; c < nc; c++) path_cols[i * cpp + colpos + c] = values[src + c];
         }
         colpos += nc;
-        Strided t;
-        t = cpos; cpos = ppos; ppos = t;
-        t = chash; chash = phash; phash = t;
+        u32 *tp = cpos; cpos = ppos; ppos = tp;
+        Strided t = chash; chash = phash; phash = t;
         m = j;
     }
     if (perms) *perms += np;
@@ -161,7 +162,8 @@ HD bool single_tree(const SingleShape &sh, const u32 *q, u32 nq, const u32 *valu
 }
 
 // ---- FRI layer trees (query and sibling both opened; QM31 leaf = 4 words) -------------------------------------
-constexpr u32 PAIR_SCRATCH_WORDS_PER_QUERY = 2 * 44;
+constexpr u32 PAIR_SCRATCH_WORDS_PER_QUERY = 2 * 40;   // five tables of node hashes, 2*nq nodes each
+constexpr u32 PAIR_IDX_WORDS_PER_QUERY = 2 * 4;
 constexpr u32 MAX_DATA_LAYERS = 3;
 
 // data_mask bit h set <=> evaluations are committed at the layer of log size h (bit `depth` always set).
@@ -170,10 +172,10 @@ constexpr u32 MAX_DATA_LAYERS = 3;
 //               sib_hashes [(i*(depth-1) + j)*8], j = depth-1-h for layers h = depth-1 .. 1:
 //               the sibling's hash (plain layers) or the sibling's hash *without* its own evaluation (data layers).
 HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *vals, u32 n_vals, const u32 *hw, u32 n_hw,
-                  const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, Strided scratch, u32 *perms) {
+                  const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, Strided scratch, u32 *idx, u32 *perms) {
     const u32 cap = 2 * nq;
-    Strided qs = scratch, cpos = qs.at(cap), chash = cpos.at(cap), npos = chash.at(8 * cap), nhash = npos.at(cap);
-    Strided ntree = nhash.at(8 * cap), nL = ntree.at(8 * cap), nR = nL.at(8 * cap), nval = nR.at(8 * cap);
+    Strided chash = scratch, nhash = chash.at(8 * cap), ntree = nhash.at(8 * cap), nL = ntree.at(8 * cap), nR = nL.at(8 * cap);
+    u32 *qs = idx, *cpos = qs + cap, *npos = cpos + cap, *nval = npos + cap;
     for (u32 i = 0; i < nq; i++) qs[i] = q[i];
     u32 n = sort_unique(qs, nq);
     u32 cm = 0;                    // child table size

@@ -139,12 +139,12 @@ HD void stage_single_tree(const Workspace &ws, u32 p, u32 t) {
         sh.hA = d.log_plonk; sh.nA = proof::plonk_cols(t); sh.hB = d.log_pos; sh.nB = proof::n_cols(t) - proof::plonk_cols(t);
         sh.depth = sh.hA > sh.hB ? sh.hA : sh.hB;
     } else { sh.hA = d.max_first; sh.nA = 8; sh.hB = 0; sh.nB = 0; sh.depth = d.max_first; }
-    u32 q[proof::MAX_QUERIES];
+    u32 q[proof::MAX_QUERIES], idx[decommit::SINGLE_IDX_WORDS_PER_QUERY * proof::MAX_QUERIES];
     for (u32 i = 0; i < nq; i++) q[i] = fri::position(d, dt.fs.raw_queries[i], sh.depth);
     u32 perms = 0;
     bool ok = decommit::single_tree(sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
                                     w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
-                                    ws.scratch_single(p, t), &perms);
+                                    ws.scratch_single(p, t), idx, &perms);
     VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
     if (!ok) fail_shared(&dt, proof::ST_MERKLE);
 }
@@ -333,7 +333,7 @@ HD void stage_pair_tree(const Workspace &ws, u32 p, u32 f) {
     Detail &dt = ws.detail[p];
     const u32 *w = ws.blob(p);
     const u32 nq = d.n_queries, depth = ws.shape.fri_depth(f);
-    u32 q[proof::MAX_QUERIES];
+    u32 q[proof::MAX_QUERIES], idx[decommit::PAIR_IDX_WORDS_PER_QUERY * proof::MAX_QUERIES];
     for (u32 i = 0; i < nq; i++) q[i] = fri::position(d, dt.fs.raw_queries[i], depth);
     const u32 *hw = w + (f ? d.in_hash_witness[f - 1] : d.fl_hash_witness);
     const u32 n_hw = f ? d.in_n_hash_witness[f - 1] : d.fl_n_hash_witness;
@@ -345,7 +345,7 @@ HD void stage_pair_tree(const Workspace &ws, u32 p, u32 f) {
     // packed outputs live at the start of the hint block of this tree (nq * PAIR_HINT_WORDS words available)
     u32 *self_vals = hint, *sib_vals = hint + nq * decommit::MAX_DATA_LAYERS * 4, *sib_hashes = sib_vals + nq * decommit::MAX_DATA_LAYERS * 4;
     bool ok = decommit::pair_tree(depth, ws.shape.fri_data_mask(f), q, nq, ws.vals_of(p, f), *ws.nvals_of(p, f), hw, n_hw, root,
-                                  self_vals, sib_vals, sib_hashes, scratch, &perms);
+                                  self_vals, sib_vals, sib_hashes, scratch, idx, &perms);
     VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
     if (!ok) fail_shared(&dt, f ? proof::ST_FRI_INNER : proof::ST_FRI_FIRST);
 }
