@@ -129,6 +129,22 @@ int orc_verify_proof(const uint8_t *blob, size_t len,
                      const uint32_t *input_idx, const uint32_t *input_vals /* n x4 */,
                      uint32_t n_inputs, orc_verify_out *out);
 
+/* per-query decommitment hints = the witnesses DecommitmentVar / SinglePairMerkleProofVar allocate
+ * (components/recursive/data_structures/src/lib.rs:287-312,372-398) */
+typedef struct {
+    uint32_t single_depth[4];
+    uint32_t single_ncols[4][33];                               /* columns per layer log size */
+    uint32_t single_cols[4][ORC_MAX_QUERIES][64];               /* leaf layer first, then descending layers */
+    uint32_t single_sib[4][ORC_MAX_QUERIES][32][8];             /* sibling_hashes[i], i = depth - h */
+    uint32_t pair_depth[1 + ORC_MAX_INNER];                     /* 0 = FRI first layer, 1.. = inner layers */
+    uint8_t pair_has_data[1 + ORC_MAX_INNER][33];
+    uint32_t pair_self[1 + ORC_MAX_INNER][ORC_MAX_QUERIES][33][4];
+    uint32_t pair_sib[1 + ORC_MAX_INNER][ORC_MAX_QUERIES][33][4];
+    uint32_t pair_sib_hash[1 + ORC_MAX_INNER][ORC_MAX_QUERIES][32][8];
+} orc_hints;
+int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
+                           uint32_t n_inputs, orc_verify_out *out, orc_hints *hints);
+
 /* independent proofs on n_threads pthreads (CPU baseline); off = n+1 byte offsets; returns permutations executed */
 uint64_t orc_verify_batch_mt(const uint8_t *blobs, const uint64_t *off, uint32_t n, const uint32_t *idx, const uint32_t *vals,
                              uint32_t n_inputs, uint8_t *verdict, uint8_t *stage, unsigned n_threads);

@@ -471,7 +471,8 @@ static int pair_tree_rebuild(uint32_t depth, const uint8_t *has_data, const uint
 static void pair_tree_free(pair_tree *t) { for (int h = 0; h < 33; h++) free(t->layer[h]); }
 
 /* SinglePairMerkleProof::verify on the path extracted for leaf query q; self/sibling values returned per data layer */
-static int pair_path_root(const pair_tree *t, uint32_t q, qm31 *self_vals, qm31 *sib_vals, uint32_t root_out[8], uint64_t *perms) {
+static int pair_path_root(const pair_tree *t, uint32_t q, qm31 *self_vals, qm31 *sib_vals, uint32_t root_out[8], uint64_t *perms,
+                          uint32_t *sib_hash_out /* (depth-1) x 8, SinglePairMerkleProof.sibling_hashes, or NULL */) {
     uint32_t depth = t->depth, cur = q;
     uint32_t self_h[8], sib_h[8];
     pnode *s = pfind(t, depth, cur), *b = pfind(t, depth, cur ^ 1);
@@ -501,10 +502,12 @@ static int pair_path_root(const pair_tree *t, uint32_t q, qm31 *self_vals, qm31 
                 pnode *sb = pfind(t, h, parent ^ 1);
                 if (!sb) return 1;
                 memcpy(sib_h, sb->hash, 32);
+                if (sib_hash_out) memcpy(sib_hash_out + 8 * i, sb->hash, 32);
             } else {
                 /* sibling: its tree hash (hash witness of the per-query proof) combined with its own column hash */
                 uint32_t st[16];
                 memcpy(st, pb->tree_hash, 32);
+                if (sib_hash_out) memcpy(sib_hash_out + 8 * i, pb->tree_hash, 32);
                 orc_hash_column_get_capacity(pb->val, 4, st + 8);
                 orc_poseidon2_permute(st);
                 memcpy(sib_h, st, 32);
@@ -524,6 +527,7 @@ static cpoint absolute_point(uint32_t L, uint32_t q) { return cp_half_odds_at(L,
 /* ---- answers (components/recursive/answer/src) ------------------------------------------ */
 typedef struct { int shift; uint32_t comp_log; qpoint point; uint32_t n; uint32_t col[160]; qm31 val[160]; } sample_batch;
 
+static _Thread_local orc_hints *g_hints;      /* optional sink for the per-query hints (orc_verify_proof_hints) */
 int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
                      uint32_t n_inputs, orc_verify_out *o) {
     static _Thread_local orc_proof P;
@@ -596,6 +600,12 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
             for (uint32_t i = 0; i < nq && !bad; i++) {
                 uint32_t sib[32 * 8];
                 bad = single_path_root(&pt, pos_at[depth][i], path_cols[t][i], sib, o->path_roots[t][i], &o->n_perms_paths);
+                if (g_hints && !bad) {
+                    g_hints->single_depth[t] = depth;
+                    memcpy(g_hints->single_ncols[t], ncl, sizeof ncl);
+                    memcpy(g_hints->single_cols[t][i], path_cols[t][i], sizeof path_cols[t][i]);
+                    memcpy(g_hints->single_sib[t][i], sib, depth * 32);
+                }
                 if (!bad && memcmp(o->path_roots[t][i], p->commitments[t], 32)) bad = 1;
             }
             partial_tree_free(&pt);
@@ -731,7 +741,15 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
         int bad = pair_tree_rebuild(max_first, has_data, pos_at[max_first], nq, vals, nv, &p->first_layer.decommitment,
                                     p->first_layer.commitment, &pt, &o->n_perms_hints);
         for (uint32_t i = 0; i < nq && !bad; i++) {
-            bad = pair_path_root(&pt, pos_at[max_first][i], self_v[i], sib_v[i], o->path_roots[4][i], &o->n_perms_paths);
+            bad = pair_path_root(&pt, pos_at[max_first][i], self_v[i], sib_v[i], o->path_roots[4][i], &o->n_perms_paths,
+                                 g_hints ? g_hints->pair_sib_hash[0][i][0] : NULL);
+            if (g_hints && !bad) {
+                g_hints->pair_depth[0] = max_first;
+                memcpy(g_hints->pair_has_data[0], has_data, 33);
+                for (uint32_t h = 0; h <= max_first; h++) if (has_data[h]) {
+                    memcpy(g_hints->pair_self[0][i][h], self_v[i][h].v, 16); memcpy(g_hints->pair_sib[0][i][h], sib_v[i][h].v, 16);
+                }
+            }
             if (!bad && memcmp(o->path_roots[4][i], p->first_layer.commitment, 32)) bad = 1;
         }
         pair_tree_free(&pt);
@@ -795,7 +813,14 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
             int bad = pair_tree_rebuild(log_size, has_data, pos_at[log_size], nq, vals, nv, &layer->decommitment,
                                         layer->commitment, &pt, &o->n_perms_hints);
             for (uint32_t i = 0; i < nq && !bad; i++) {
-                bad = pair_path_root(&pt, pos_at[log_size][i], self_v[i], sib_v[i], o->path_roots[5 + li][i], &o->n_perms_paths);
+                bad = pair_path_root(&pt, pos_at[log_size][i], self_v[i], sib_v[i], o->path_roots[5 + li][i], &o->n_perms_paths,
+                                     g_hints ? g_hints->pair_sib_hash[1 + li][i][0] : NULL);
+                if (g_hints && !bad) {
+                    g_hints->pair_depth[1 + li] = log_size;
+                    memcpy(g_hints->pair_has_data[1 + li], has_data, 33);
+                    memcpy(g_hints->pair_self[1 + li][i][log_size], self_v[i][log_size].v, 16);
+                    memcpy(g_hints->pair_sib[1 + li][i][log_size], sib_v[i][log_size].v, 16);
+                }
                 if (!bad && memcmp(o->path_roots[5 + li][i], layer->commitment, 32)) bad = 1;
             }
             pair_tree_free(&pt);
@@ -841,6 +866,17 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
     o->verdict = 0; o->stage = ORC_OK;
     return 0;
 #undef FAIL
+}
+
+/* same run, additionally exporting the per-query decommitment hints the verifier circuit takes as witnesses
+ * (components/hints/src/decommit.rs:10-16 SinglePathMerkleProof, folding.rs:21-28 SinglePairMerkleProof) */
+int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
+                           uint32_t n_inputs, orc_verify_out *o, orc_hints *h) {
+    memset(h, 0, sizeof *h);
+    g_hints = h;
+    int r = orc_verify_proof(blob, len, input_idx, input_vals, n_inputs, o);
+    g_hints = NULL;
+    return r;
 }
 
 /* ---- pthread batch driver for the CPU baseline: proofs are independent ----------------------------------- */
