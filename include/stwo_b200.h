@@ -199,6 +199,51 @@ typedef struct {
 int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
                                uint32_t what, void *out, size_t out_bytes, void *stream);
 
+/* ---- K7: constraint-system finalisation loops and trace export (Plonk-with-Poseidon system) -------------------------
+ * The flat image of PlonkWithPoseidonConstraintSystem (constraint_system/src/plonk_with_poseidon.rs:18-41) after
+ * pad(): wiring is shared by every proof of a shape, values (variables, Poseidon flow hashes, swap bits) are per
+ * batch item.  All pointers are DEVICE pointers for the *_dev entry points. */
+typedef struct {
+    uint32_t n_vars, n_rows, n_flow, num_input;      /* n_rows is a power of two >= 16 */
+    const uint32_t *a_wire, *b_wire, *c_wire;        /* n_rows */
+    const uint32_t *poseidon_wire, *enforce_c_m31;   /* n_rows */
+    const uint32_t *op;                              /* n_rows, M31 */
+    const uint32_t *flow_wire;                       /* n_flow x 4  (PoseidonEntry.wire of entries 1..4) */
+    const uint32_t *flow_swap_addr;                  /* n_flow      (SwapOption.addr) */
+} stwo_b200_cs_wiring;
+typedef struct {
+    uint32_t n_batch;
+    const uint32_t *variables;                       /* n_batch x n_vars x 4 */
+    const uint32_t *flow_hash;                       /* n_batch x n_flow x 32  (PoseidonEntry.hash of entries 1..4) */
+    const uint8_t *flow_swap;                        /* n_batch x n_flow       (SwapOption.swap) */
+} stwo_b200_cs_values;
+
+/* check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): first_bad[b] = index of the first row whose
+ * gate c = op(a+b) + (1-op)ab (or whose enforce_c_m31) fails for batch item b, or -1. */
+int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,
+                                           void *stream);
+/* populate_logup_arguments (:382-466): wiring only.  mult_*: n_rows int32 each; scratch: (3 * n_vars + 4) uint32.
+ * status_out[0] != 0 when the reference's assert (a Poseidon wire used more than once) would fire. */
+int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w, int32_t *mult_a, int32_t *mult_b, int32_t *mult_c,
+                                        int32_t *mult_poseidon, uint32_t *scratch, uint32_t *status_out, void *stream);
+/* check_poseidon_invocations (:468-519): first_bad[b] = first flow entry whose wire contents or permutation disagree,
+ * or -1.  Needs mult_poseidon and the scratch of populate_logup. */
+int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
+                                        const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream);
+/* generate_plonk_with_poseidon_circuit (:521-628): preprocessed = 10 columns x n_rows in the order
+ * mult_a, mult_b, mult_c, poseidon_wire, mult_poseidon, enforce_c_m31, a_wire, b_wire, c_wire, op (wiring only, written
+ * once); values = n_batch x 12 columns x n_rows: a_val_0..3, b_val_0..3, c_val_0..3. */
+int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
+                                      const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
+                                      uint32_t *preprocessed, uint32_t *values, void *stream);
+/* Host entry for ONE constraint system (what the finalisation block of every example does:
+ * cs.check_arithmetics(); cs.populate_logup_arguments(); cs.check_poseidon_invocations();
+ * cs.generate_plonk_with_poseidon_circuit()  -- examples/single-proof/src/main.rs:85-90).  Pointers in w / v are HOST
+ * pointers, v->n_batch must be 1.  trace: 22 x n_rows words (10 preprocessed then 12 value columns).
+ * Returns 0 and bad_row = bad_flow = -1 when the system is consistent. */
+int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, uint32_t *trace,
+                              int64_t *bad_row, int64_t *bad_flow);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,138 @@
+// K6: evaluation of the constraint system's `variables[]` for a batch of witness streams.
+//
+// Replaces the value side of every DSL operation of the reference -- the `value` field each *Var computes on the host
+// while it appends rows: primitives/fields/src/{m31,cm31,qm31}.rs (add/mul/neg/inv/decompose), primitives/bits/src/lib.rs:48-82
+// (bit decomposition), primitives/poseidon31/src/lib.rs:282-407 (permutation + PoseidonEntry hashes + SwapOption.swap),
+// constraint_system/src/plonk_with_poseidon.rs:141-281 (variables.push of add/mul/mul_constant/new_m31/new_qm31).
+//
+// A tape instruction defines one variable from earlier ones (or from the item's witness stream).  Device layout is
+// lane-interleaved: element e of batch item b lives at ((b / lanes) * n_elems + e) * lanes + b % lanes, so the 32 lanes
+// of a warp (32 batch items executing the same instruction) touch one contiguous 512-byte (QM31) or 128-byte (word) run.
+// lanes = 1 gives the plain per-item arrays the single-system host entry points use.
+// HD: tests/hostsim runs the very same evaluator on the CPU box.
+#pragma once
+#include "poseidon2.cuh"
+
+namespace tape {
+
+enum : u32 {
+    T_NONE = 0,
+    T_ADD, T_MUL, T_MULC,                       // dst = a + b | a * b | a * imm(b)          (gate outputs)
+    T_INPUT_M31, T_INPUT_QM31,                  // dst = witness stream word(s) at slot a
+    T_INV_M31, T_INV_QM31,                      // dst = 1 / var a                           (M31Var::inv, QM31Var::inv)
+    T_INV_CM31_RE, T_INV_CM31_IM,               // dst = re / im of 1 / (CM31 part of var a) (CM31Var::inv -> new_witness)
+    T_COORD,                                    // dst = coordinate b of var a               (QM31Var::decompose_m31)
+    T_BIT,                                      // dst = bit b of var a                      (BitsVar::from_m31)
+    T_POSEIDON,                                 // permutation record dst                    (Poseidon2HalfVar::permute)
+};
+constexpr u32 NO_VAR = 0xffffffffu;
+
+struct Ins { u32 op, dst, a, b; };
+
+// One Poseidon2 invocation.  A half state is either two QM31 variables (kind 0; the zero half is variables (0, 0)) or
+// eight words of the witness stream (kind 1: Poseidon2HalfVar::new_single_use_witness_only, a Merkle sibling).
+struct Perm {
+    u32 l_kind, l_a, l_b;
+    u32 r_kind, r_a, r_b;
+    u32 swap_var;                               // NO_VAR: never swapped
+    u32 out[4];                                 // variables receiving state[4k .. 4k+4); NO_VAR when the half is ignored
+    u32 reserved;
+};
+
+struct alignas(16) Q4 { u32 x, y, z, w; };
+
+// Where a word of the verifier circuit's witness stream comes from: a section of the proof blob or of the batched
+// verifier's workspace (circuit.cuh resolves it).  section:4 | a:6 (tree / FRI layer) | i:7 (query / column) | k:15 (word)
+enum : u32 {
+    S_STMT0 = 0, S_STMT1, S_COMMITMENT, S_SAMPLED, S_FRI_COMMITMENT, S_LAST_COEFFS, S_POW_LIMB, S_OODS,
+    S_PATH_COL, S_PATH_SIB, S_PAIR_SELF, S_PAIR_SIB, S_PAIR_HASH,
+};
+HD u32 src_pack(u32 section, u32 a, u32 i, u32 k) { return section | (a << 4) | (i << 10) | (k << 17); }
+HD u32 src_section(u32 s) { return s & 15u; }
+HD u32 src_a(u32 s) { return (s >> 4) & 63u; }
+HD u32 src_i(u32 s) { return (s >> 10) & 127u; }
+HD u32 src_k(u32 s) { return s >> 17; }
+
+// One batch item's window into the lane-interleaved arrays.
+struct View {
+    Q4 *vars;                                   // + element * stride
+    const u32 *input;                           // + word * stride
+    u32 *flow_hash;                             // + (entry * 32 + word) * stride     may be null
+    uint8_t *flow_swap;                         // + entry * stride                   may be null
+    u32 stride;
+};
+
+HD qm31_t ldv(const View &v, u32 i) {
+    const Q4 t = v.vars[(size_t)i * v.stride];
+    return qm31::mk(t.x, t.y, t.z, t.w);
+}
+HD void stv(const View &v, u32 i, qm31_t q) {
+    Q4 t; t.x = q.v[0]; t.y = q.v[1]; t.z = q.v[2]; t.w = q.v[3];
+    v.vars[(size_t)i * v.stride] = t;
+}
+HD u32 ldw(const View &v, u32 slot) { return v.input[(size_t)slot * v.stride]; }
+
+// variables 0..3 = 0, 1, i, j (plonk_with_poseidon.rs:63-66)
+HD void prologue(const View &v) {
+    stv(v, 0, qm31::mk(0, 0, 0, 0)); stv(v, 1, qm31::mk(1, 0, 0, 0)); stv(v, 2, qm31::mk(0, 1, 0, 0)); stv(v, 3, qm31::mk(0, 0, 1, 0));
+}
+
+HD void load_half(const View &v, u32 kind, u32 a, u32 b, u32 *h) {
+    if (kind == 0) {
+        const qm31_t l = ldv(v, a), r = ldv(v, b);
+        for (int k = 0; k < 4; k++) { h[k] = l.v[k]; h[4 + k] = r.v[k]; }
+    } else {
+        for (u32 k = 0; k < 8; k++) h[k] = ldw(v, a + k);
+    }
+}
+
+HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
+    u32 st[16], in[16];
+    load_half(v, p.l_kind, p.l_a, p.l_b, in);
+    load_half(v, p.r_kind, p.r_a, p.r_b, in + 8);
+    const bool swap = p.swap_var != NO_VAR && ldv(v, p.swap_var).v[0] != 0;
+    for (int k = 0; k < 8; k++) { st[k] = swap ? in[8 + k] : in[k]; st[8 + k] = swap ? in[k] : in[8 + k]; }
+    if (v.flow_hash) {
+        u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
+        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];          // PoseidonEntry 1, 2: the halves as given
+    }
+    poseidon2::permute<false>(st);
+    if (v.flow_hash) {
+        u32 *fh = v.flow_hash + ((size_t)entry * 32 + 16) * v.stride;
+        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = st[k];          // PoseidonEntry 3, 4: the full output
+    }
+    if (v.flow_swap) v.flow_swap[(size_t)entry * v.stride] = swap ? 1 : 0;
+    for (int k = 0; k < 4; k++)
+        if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(st[4 * k], st[4 * k + 1], st[4 * k + 2], st[4 * k + 3]));
+}
+
+HD void eval(const View &v, const Ins &in, const Perm *perms) {
+    switch (in.op) {
+    case T_ADD: stv(v, in.dst, qm31::add(ldv(v, in.a), ldv(v, in.b))); break;
+    case T_MUL: stv(v, in.dst, qm31::mul(ldv(v, in.a), ldv(v, in.b))); break;
+    case T_MULC: stv(v, in.dst, qm31::mul_m31(ldv(v, in.a), in.b)); break;
+    case T_INPUT_M31: stv(v, in.dst, qm31::from_m31(ldw(v, in.a))); break;
+    case T_INPUT_QM31: stv(v, in.dst, qm31::mk(ldw(v, in.a), ldw(v, in.a + 1), ldw(v, in.a + 2), ldw(v, in.a + 3))); break;
+    case T_INV_M31: stv(v, in.dst, qm31::from_m31(m31::inv(ldv(v, in.a).v[0]))); break;
+    case T_INV_QM31: stv(v, in.dst, qm31::inv(ldv(v, in.a))); break;
+    case T_INV_CM31_RE: stv(v, in.dst, qm31::from_m31(cm31::inv(qm31::lo(ldv(v, in.a))).a)); break;
+    case T_INV_CM31_IM: stv(v, in.dst, qm31::from_m31(cm31::inv(qm31::lo(ldv(v, in.a))).b)); break;
+    case T_COORD: stv(v, in.dst, qm31::from_m31(ldv(v, in.a).v[in.b & 3u])); break;
+    case T_BIT: stv(v, in.dst, qm31::from_m31((ldv(v, in.a).v[0] >> (in.b & 31u)) & 1u)); break;
+    case T_POSEIDON: eval_poseidon(v, perms[in.dst], in.dst); break;
+    default: break;
+    }
+}
+
+// ---- the O(n_rows) loops of the constraint system, per batch item ------------------------------------------------------
+// check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): one row
+HD bool row_ok(const View &v, u32 a, u32 b, u32 c, u32 op, u32 enforce_c_m31, bool op_follows_c) {
+    const qm31_t va = ldv(v, a), vb = ldv(v, b), vc = ldv(v, c);
+    if (op_follows_c) op = vc.v[0];
+    const qm31_t want = qm31::add(qm31::mul_m31(qm31::add(va, vb), op), qm31::mul_m31(qm31::mul(va, vb), m31::subc(1, op)));
+    bool ok = qm31::eq(want, vc);
+    if (enforce_c_m31 && (vc.v[1] | vc.v[2] | vc.v[3])) ok = false;
+    return ok;
+}
+
+}  // namespace tape

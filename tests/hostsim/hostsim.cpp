@@ -65,3 +65,58 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
 }
 void hs_free(void *p) { free(p); }
 }
+
+// ---- circuit recorder + tape evaluator on the host -------------------------------------------------------------------------
+#include "../../recursive-stwo_b200/csrc/circuit.cuh"
+#include "../../recursive-stwo_b200/csrc/dsl/recorded.hpp"
+#include <stdio.h>
+extern "C" {
+using stwo_b200::dsl::RecordedCircuit;
+// shape: 7 words (stwo_b200_proof_shape); returns an owned handle or null (message on stderr)
+void *hs_circuit_record(const u32 *shape, const u32 *input_idx, const u32 *input_vals, u32 n_inputs, u32 multipliers) {
+    try {
+        stwo_b200::dsl::ProofShape s{shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6]};
+        std::vector<stwo_b200::dsl::PublicInput> in;
+        for (u32 k = 0; k < n_inputs; k++) in.push_back({input_idx[k], {{input_vals[4 * k], input_vals[4 * k + 1], input_vals[4 * k + 2], input_vals[4 * k + 3]}}});
+        return stwo_b200::dsl::record_verifier(s, in, multipliers).release();
+    } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record: %s\n", e.what()); return nullptr; }
+}
+void hs_circuit_free(void *h) { delete (RecordedCircuit *)h; }
+// info: n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance
+void hs_circuit_info(void *h, u32 *info) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    const auto &c = *r->cs.p;
+    const u32 v[10] = {c.num_plonk_rows(), c.n_rows_unpadded, c.n_vars, c.num_poseidon_invocations(), c.padded_poseidon_len(), c.n_input_words,
+                       (u32)r->ins.size(), r->n_levels(), c.num_input, r->words_per_instance};
+    memcpy(info, v, sizeof v);
+}
+// what: 0 a_wire 1 b_wire 2 c_wire 3 poseidon_wire 4 enforce_c_m31 5 op 6 op_follows_c 7 flow_wire 8 flow_swap_addr 9 gather 10 level_start
+void hs_circuit_get(void *h, u32 what, u32 *out) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    const auto &c = *r->cs.p;
+    const std::vector<u32> *src[] = {&c.a_wire, &c.b_wire, &c.c_wire, &c.poseidon_wire, &c.enforce_c_m31, &c.op, nullptr, &c.flow_wire,
+                                     &c.flow_swap_addr, &r->gather, &r->level_start};
+    if (what == 6) { for (size_t k = 0; k < c.op_follows_c.size(); k++) out[k] = c.op_follows_c[k]; return; }
+    memcpy(out, src[what]->data(), src[what]->size() * 4);
+}
+// evaluates the tape for every proof of a verified batch (ws_base from hs_verify_batch) in level order, lanes = 1.
+// vars: n x n_vars x 4, flow_hash: n x n_flow x 32, flow_swap: n x n_flow, stream (optional): n x n_input_words.
+// bad_row[p] = first row failing check_arithmetics or -1.
+void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, uint8_t *flow_swap, u32 *stream_out, int64_t *bad_row) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    const auto &c = *r->cs.p;
+    const verify::Workspace &ws = *(const verify::Workspace *)ws_base;
+    std::vector<u32> stream(c.n_input_words);
+    for (u32 p = 0; p < n; p++) {
+        for (u32 k = 0; k < c.n_input_words; k++) stream[k] = circuit::gather_word(ws, p, r->gather[k]);
+        if (stream_out) memcpy(stream_out + (size_t)p * c.n_input_words, stream.data(), stream.size() * 4);
+        tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
+                     flow_swap + (size_t)p * c.num_poseidon_invocations(), 1};
+        tape::prologue(v);
+        for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data());
+        bad_row[p] = -1;
+        for (u32 i = 0; i < c.num_plonk_rows(); i++)
+            if (!tape::row_ok(v, c.a_wire[i], c.b_wire[i], c.c_wire[i], c.op[i], c.enforce_c_m31[i], c.op_follows_c[i] != 0)) { bad_row[p] = i; break; }
+    }
+}
+}
