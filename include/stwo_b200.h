@@ -199,30 +199,58 @@ typedef struct {
 int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
                                uint32_t what, void *out, size_t out_bytes, void *stream);
 
-/* ---- K7: constraint-system finalisation loops and trace export (Plonk-with-Poseidon system) -------------------------
- * The flat image of PlonkWithPoseidonConstraintSystem (constraint_system/src/plonk_with_poseidon.rs:18-41) after
- * pad(): wiring is shared by every proof of a shape, values (variables, Poseidon flow hashes, swap bits) are per
- * batch item.  All pointers are DEVICE pointers for the *_dev entry points. */
+/* ---- K6 / K7: the constraint system on the device ----------------------------------------------------------------------
+ * The flat image of PlonkWithPoseidonConstraintSystem (constraint_system/src/plonk_with_poseidon.rs:18-41) after pad().
+ * Wiring is shared by every batch item of a shape; values (variables, Poseidon flow hashes, swap bits) are per item.
+ * Per-item arrays are LANE-INTERLEAVED: element e of item b lives at ((b / lanes) * n_elems + e) * lanes + b % lanes
+ * (lanes = 32: a warp's 32 items touch one contiguous run; lanes = 1: plain [item][element] arrays).
+ * All pointers are DEVICE pointers for the *_dev entry points. */
 typedef struct {
     uint32_t n_vars, n_rows, n_flow, num_input;      /* n_rows is a power of two >= 16 */
     const uint32_t *a_wire, *b_wire, *c_wire;        /* n_rows */
     const uint32_t *poseidon_wire, *enforce_c_m31;   /* n_rows */
     const uint32_t *op;                              /* n_rows, M31 */
+    const uint8_t *op_follows_c;                     /* n_rows or NULL: rows whose op constant is the selected value, i.e. equals
+                                                        c_val_0 of that item (CirclePointM31Var::select, primitives/circle/src/lib.rs:80-92) */
     const uint32_t *flow_wire;                       /* n_flow x 4  (PoseidonEntry.wire of entries 1..4) */
     const uint32_t *flow_swap_addr;                  /* n_flow      (SwapOption.addr) */
 } stwo_b200_cs_wiring;
 typedef struct {
-    uint32_t n_batch;
-    const uint32_t *variables;                       /* n_batch x n_vars x 4 */
-    const uint32_t *flow_hash;                       /* n_batch x n_flow x 32  (PoseidonEntry.hash of entries 1..4) */
-    const uint8_t *flow_swap;                        /* n_batch x n_flow       (SwapOption.swap) */
+    uint32_t n_batch, lanes;                         /* lanes: 1 or 32 */
+    uint32_t *variables;                             /* n_vars QM31 per item */
+    uint32_t *flow_hash;                             /* n_flow x 32 words per item (PoseidonEntry.hash of entries 1..4) */
+    uint8_t *flow_swap;                              /* n_flow bytes per item (SwapOption.swap) */
 } stwo_b200_cs_values;
+/* The value definitions of a recorded circuit, sorted by dependency level (instructions of a level are independent).
+ * ins: n_ins x {op, dst, a, b} (STWO_B200_T_*); perms: n_perms x 12 words {l_kind, l_a, l_b, r_kind, r_a, r_b, swap_var,
+ * out[4], 0}: half kind 0 = the two QM31 variables (a, b), kind 1 = eight witness-stream words at slot a. */
+typedef struct {
+    uint32_t n_ins, n_perms, n_levels, n_input_words;
+    const uint32_t *ins, *level_start /* n_levels + 1 */, *perms;
+} stwo_b200_cs_tape;
+#define STWO_B200_T_ADD 1
+#define STWO_B200_T_MUL 2
+#define STWO_B200_T_MULC 3
+#define STWO_B200_T_INPUT_M31 4
+#define STWO_B200_T_INPUT_QM31 5
+#define STWO_B200_T_INV_M31 6
+#define STWO_B200_T_INV_QM31 7
+#define STWO_B200_T_INV_CM31_RE 8
+#define STWO_B200_T_INV_CM31_IM 9
+#define STWO_B200_T_COORD 10
+#define STWO_B200_T_BIT 11
+#define STWO_B200_T_POSEIDON 12
 
+/* K6: variables[] (and the Poseidon flow) of every batch item from its witness stream (n_input_words words per item,
+ * lane-interleaved like the values).  Replaces the `value` arithmetic of every DSL call: primitives/fields/src/*.rs,
+ * primitives/bits/src/lib.rs:48-82, primitives/poseidon31/src/lib.rs:282-407, plonk_with_poseidon.rs:141-281. */
+int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
+                                   void *stream);
 /* check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): first_bad[b] = index of the first row whose
  * gate c = op(a+b) + (1-op)ab (or whose enforce_c_m31) fails for batch item b, or -1. */
 int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,
                                            void *stream);
-/* populate_logup_arguments (:382-466): wiring only.  mult_*: n_rows int32 each; scratch: (3 * n_vars + 4) uint32.
+/* populate_logup_arguments (:382-466): wiring only.  mult_*: n_rows int32 each; scratch: (4 * n_vars + 4) uint32.
  * status_out[0] != 0 when the reference's assert (a Poseidon wire used more than once) would fire. */
 int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w, int32_t *mult_a, int32_t *mult_b, int32_t *mult_c,
                                         int32_t *mult_poseidon, uint32_t *scratch, uint32_t *status_out, void *stream);
@@ -230,19 +258,67 @@ int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w, int32_t *m
  * or -1.  Needs mult_poseidon and the scratch of populate_logup. */
 int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
                                         const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream);
-/* generate_plonk_with_poseidon_circuit (:521-628): preprocessed = 10 columns x n_rows in the order
- * mult_a, mult_b, mult_c, poseidon_wire, mult_poseidon, enforce_c_m31, a_wire, b_wire, c_wire, op (wiring only, written
- * once); values = n_batch x 12 columns x n_rows: a_val_0..3, b_val_0..3, c_val_0..3. */
+/* generate_plonk_with_poseidon_circuit (:521-628).  preprocessed (optional): 10 columns x n_rows in the struct-literal
+ * order mult_a, mult_b, mult_c, poseidon_wire, mult_poseidon, enforce_c_m31, a_wire, b_wire, c_wire, op (wiring only;
+ * op holds the shape constant).  values: per item 13 columns x n_rows, plain [item][column][row]: a_val_0..3, b_val_0..3,
+ * c_val_0..3, then the item's op column (differs from the shared one only on op_follows_c rows). */
 int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                       const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
                                       uint32_t *preprocessed, uint32_t *values, void *stream);
-/* Host entry for ONE constraint system (what the finalisation block of every example does:
- * cs.check_arithmetics(); cs.populate_logup_arguments(); cs.check_poseidon_invocations();
+/* Host entry for ONE constraint system whose values were produced on the host (what the finalisation block of every
+ * example does: cs.check_arithmetics(); cs.populate_logup_arguments(); cs.check_poseidon_invocations();
  * cs.generate_plonk_with_poseidon_circuit()  -- examples/single-proof/src/main.rs:85-90).  Pointers in w / v are HOST
- * pointers, v->n_batch must be 1.  trace: 22 x n_rows words (10 preprocessed then 12 value columns).
- * Returns 0 and bad_row = bad_flow = -1 when the system is consistent. */
+ * pointers, v->n_batch and v->lanes must be 1.  trace: 22 x n_rows words (10 preprocessed then 12 value columns, the op
+ * column already per-item).  Returns 0 and bad_row = bad_flow = -1 when the system is consistent. */
 int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, uint32_t *trace,
                               int64_t *bad_row, int64_t *bad_flow);
+
+/* ---- the recursive verifier circuit: recorded once per shape, evaluated per batch ------------------------------------
+ * Recording replaces the *row-appending* side of examples/single-proof/src/main.rs:48-84 /
+ * examples/multi-proofs/src/main.rs:62-135 (PlonkWithPoseidonProofVar::new_witness, FiatShamirResults, CompositionCheck,
+ * AnswerResults, FoldingResults ::compute); it is host logic and needs no device.  multipliers = how many times the
+ * proof is verified inside one constraint system (the `multipliers` of multi-proofs). */
+typedef struct stwo_b200_circuit stwo_b200_circuit;
+typedef struct {
+    uint32_t n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance;
+} stwo_b200_circuit_info;
+int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,
+                                          uint32_t n_inputs, uint32_t multipliers, stwo_b200_circuit **out);
+void stwo_b200_circuit_free(stwo_b200_circuit *c);
+int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b200_circuit_info *out);
+#define STWO_B200_COL_A_WIRE 0
+#define STWO_B200_COL_B_WIRE 1
+#define STWO_B200_COL_C_WIRE 2
+#define STWO_B200_COL_POSEIDON_WIRE 3
+#define STWO_B200_COL_ENFORCE_C_M31 4
+#define STWO_B200_COL_OP 5
+#define STWO_B200_COL_OP_FOLLOWS_C 6
+#define STWO_B200_COL_FLOW_WIRE 7
+#define STWO_B200_COL_FLOW_SWAP_ADDR 8
+#define STWO_B200_COL_LEVEL_START 10
+/* host copy of one recorded column (n_words must match its length) */
+int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, uint32_t *out, size_t n_words);
+
+#define STWO_B200_TRACE_CHECK_ARITHMETICS 1u
+#define STWO_B200_TRACE_CHECK_POSEIDON 2u
+#define STWO_B200_TRACE_TIMED 4u
+/* stage kernels of the trace pass in launch order: gather, eval, check_arithmetics, check_poseidon, export */
+#define STWO_B200_N_TRACE_STAGES 5
+size_t stwo_b200_circuit_workspace_bytes(const stwo_b200_circuit *c, uint32_t n_proofs);
+/* Trace generation for a verified batch: run after stwo_b200_verify_proofs_batch_dev on the same blobs / workspace (the
+ * verifier's workspace holds the hints the circuit takes as witnesses).  values: n_proofs x 13 x n_rows words or NULL;
+ * preprocessed: 10 x n_rows words or NULL; bad_row / bad_flow: n_proofs each or NULL (need the CHECK flags; -1 = ok). */
+int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                          const void *verify_workspace, void *circuit_workspace, size_t circuit_workspace_bytes,
+                                          uint32_t flags, uint32_t *preprocessed, uint32_t *values, int64_t *bad_row, int64_t *bad_flow,
+                                          void *stream);
+int32_t stwo_b200_circuit_stage_ms(float *ms /* [STWO_B200_N_TRACE_STAGES] */);
+#define STWO_B200_CFETCH_VARIABLES 0      /* n_vars x 4 words of proof p */
+#define STWO_B200_CFETCH_FLOW_HASH 1      /* n_flow x 32 words */
+#define STWO_B200_CFETCH_FLOW_SWAP 2      /* n_flow bytes */
+#define STWO_B200_CFETCH_WITNESS 3        /* n_input_words words */
+int32_t stwo_b200_circuit_fetch(const stwo_b200_circuit *c, const void *circuit_workspace, uint32_t n_proofs, uint32_t p, uint32_t what,
+                                void *out, size_t out_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,39 @@ FETCH = {"detail": 0, "domain_points": 1, "answers": 2, "circle_folds": 3, "line
 STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
           9: "unsupported"}
 
+class CsWiring(ctypes.Structure):
+    """stwo_b200_cs_wiring"""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("n_vars", "n_rows", "n_flow", "num_input")] + [
+        (n, ctypes.c_void_p) for n in ("a_wire", "b_wire", "c_wire", "poseidon_wire", "enforce_c_m31", "op", "op_follows_c", "flow_wire",
+                                       "flow_swap_addr")]
+
+
+class CsValues(ctypes.Structure):
+    """stwo_b200_cs_values"""
+    _fields_ = [("n_batch", ctypes.c_uint32), ("lanes", ctypes.c_uint32), ("variables", ctypes.c_void_p), ("flow_hash", ctypes.c_void_p),
+                ("flow_swap", ctypes.c_void_p)]
+
+
+class CsTape(ctypes.Structure):
+    """stwo_b200_cs_tape"""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("n_ins", "n_perms", "n_levels", "n_input_words")] + [
+        (n, ctypes.c_void_p) for n in ("ins", "level_start", "perms")]
+
+
+class CircuitInfo(ctypes.Structure):
+    """stwo_b200_circuit_info"""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("n_rows", "n_rows_unpadded", "n_vars", "n_flow", "n_flow_padded", "n_input_words", "n_ins",
+                                               "n_levels", "num_input", "words_per_instance")]
+
+
+TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED = 1, 2, 4
+TRACE_STAGES = ("gather", "eval", "check_arithmetics", "check_poseidon", "export")
+COLUMNS = {"a_wire": 0, "b_wire": 1, "c_wire": 2, "poseidon_wire": 3, "enforce_c_m31": 4, "op": 5, "op_follows_c": 6, "flow_wire": 7,
+           "flow_swap_addr": 8, "level_start": 10}
+CFETCH = {"variables": 0, "flow_hash": 1, "flow_swap": 2, "witness": 3}
+
 _vp, _u32, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_size_t, ctypes.c_uint64
+_WIR_P, _VAL_P, _TAPE_P, _INFO_P = ctypes.POINTER(CsWiring), ctypes.POINTER(CsValues), ctypes.POINTER(CsTape), ctypes.POINTER(CircuitInfo)
 _SHAPE_P = ctypes.POINTER(PathShape)
 _PSHAPE_P = ctypes.POINTER(ProofShape)
 
@@ -114,6 +146,20 @@ SIGNATURES = {
     "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
     "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
+    "stwo_b200_cs_eval_tape_dev": (_i32, [_TAPE_P, _u32, _vp, _VAL_P, _vp]),
+    "stwo_b200_cs_check_arithmetics_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp]),
+    "stwo_b200_cs_populate_logup_dev": (_i32, [_WIR_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_cs_check_poseidon_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp]),
+    "stwo_b200_cs_export_trace_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_cs_finalize": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp]),
+    "stwo_b200_circuit_record_verifier": (_i32, [_PSHAPE_P, _vp, _vp, _u32, _u32, ctypes.POINTER(_vp)]),
+    "stwo_b200_circuit_free": (None, [_vp]),
+    "stwo_b200_circuit_get_info": (_i32, [_vp, _INFO_P]),
+    "stwo_b200_circuit_get_column": (_i32, [_vp, _u32, _vp, _sz]),
+    "stwo_b200_circuit_workspace_bytes": (_sz, [_vp, _u32]),
+    "stwo_b200_circuit_trace_batch_dev": (_i32, [_vp, _vp, _vp, _u32, _vp, _vp, _sz, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_circuit_stage_ms": (_i32, [_vp]),
+    "stwo_b200_circuit_fetch": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,240 @@
+// The recursive verifier circuit on the device: C ABI of stwo_b200_circuit_* (record once per shape on the host, then per
+// batch: gather the witness streams out of the verifier's workspace -> K6 tape evaluation -> K7 checks and trace export).
+// Replaces the circuit half of examples/single-proof/src/main.rs:48-90 and examples/multi-proofs/src/main.rs:62-139.
+#include "common.cuh"
+#include "circuit.cuh"
+#include "dsl/recorded.hpp"
+#include <string.h>
+
+using namespace stwo_b200;
+using dsl::RecordedCircuit;
+
+struct stwo_b200_circuit {
+    std::unique_ptr<RecordedCircuit> rec;
+    // device image (uploaded on first use)
+    uint8_t *dev = nullptr;
+    stwo_b200_cs_wiring wiring{};
+    stwo_b200_cs_tape tape_{};
+    const u32 *gather = nullptr;
+};
+
+namespace {
+constexpr int kT = 256;
+inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
+
+// witness streams, lane-interleaved over groups of 32 proofs; thread = (word, proof) with the proof fastest (coalesced
+// stores; the loads walk each proof's own blob / workspace rows)
+__global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, const u32 *__restrict__ gather, u32 n_words, u32 *out) {
+    const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
+    const u32 n_groups = (ws.n_proofs + 31) / 32;
+    if (g >= (size_t)n_groups * n_words * 32) return;
+    const u32 lane = (u32)(g % 32);
+    const size_t t = g / 32;
+    const u32 word = (u32)(t % n_words), grp = (u32)(t / n_words), p = grp * 32 + lane;
+    if (p >= ws.n_proofs) return;
+    const bool ok = ws.desc[p].ok != 0;          // a blob that did not parse has no sections: its stream is all zero
+    out[g] = ok ? circuit::gather_word(ws, p, __ldg(gather + word)) : 0u;
+}
+
+struct Carve {
+    u32 *witness, *vars, *flow_hash; uint8_t *flow_swap; int32_t *mult; u32 *scratch, *status;
+    size_t bytes;
+};
+Carve carve(const RecordedCircuit &r, u32 n_proofs, uint8_t *base) {
+    const auto &c = *r.cs.p;
+    const size_t groups = (n_proofs + 31) / 32;
+    size_t at = 0;
+    auto take = [&](size_t bytes) { at = align_up(at, 256); uint8_t *p = base ? base + at : nullptr; at += bytes; return p; };
+    Carve k;
+    k.witness = (u32 *)take(groups * c.n_input_words * 32 * 4);
+    k.vars = (u32 *)take(groups * c.n_vars * 32 * 16);
+    k.flow_hash = (u32 *)take(groups * c.num_poseidon_invocations() * 32 * 32 * 4);
+    k.flow_swap = take(groups * c.num_poseidon_invocations() * 32);
+    k.mult = (int32_t *)take((size_t)4 * c.num_plonk_rows() * 4);
+    k.scratch = (u32 *)take(((size_t)4 * c.n_vars + 4) * 4);
+    k.status = (u32 *)take(256);
+    k.bytes = align_up(at, 256);
+    return k;
+}
+
+int32_t upload(stwo_b200_circuit *c) {
+    if (c->dev) return STWO_B200_OK;
+    const RecordedCircuit &r = *c->rec;
+    const auto &cs = *r.cs.p;
+    const size_t nr = cs.num_plonk_rows(), nf = cs.num_poseidon_invocations();
+    size_t at = 0;
+    auto take = [&](size_t bytes) { at = align_up(at, 256); size_t o = at; at += bytes; return o; };
+    const size_t o_w = take(6 * nr * 4), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
+                 o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4);
+    uint8_t *d = nullptr;
+    STWO_CUDA(cudaMalloc(&d, at));
+    const std::vector<u32> *cols[6] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op};
+    for (int k = 0; k < 6; k++) STWO_CUDA(cudaMemcpy(d + o_w + k * nr * 4, cols[k]->data(), nr * 4, cudaMemcpyHostToDevice));
+    STWO_CUDA(cudaMemcpy(d + o_fol, cs.op_follows_c.data(), nr, cudaMemcpyHostToDevice));
+    if (nf) {
+        STWO_CUDA(cudaMemcpy(d + o_fw, cs.flow_wire.data(), nf * 16, cudaMemcpyHostToDevice));
+        STWO_CUDA(cudaMemcpy(d + o_fa, cs.flow_swap_addr.data(), nf * 4, cudaMemcpyHostToDevice));
+        STWO_CUDA(cudaMemcpy(d + o_perm, cs.perms.data(), cs.perms.size() * sizeof(tape::Perm), cudaMemcpyHostToDevice));
+    }
+    STWO_CUDA(cudaMemcpy(d + o_ins, r.ins.data(), r.ins.size() * 16, cudaMemcpyHostToDevice));
+    STWO_CUDA(cudaMemcpy(d + o_lvl, r.level_start.data(), r.level_start.size() * 4, cudaMemcpyHostToDevice));
+    if (!r.gather.empty()) STWO_CUDA(cudaMemcpy(d + o_g, r.gather.data(), r.gather.size() * 4, cudaMemcpyHostToDevice));
+    const u32 *w = (const u32 *)(d + o_w);
+    c->wiring = {cs.n_vars, (u32)nr, (u32)nf, cs.num_input, w, w + nr, w + 2 * nr, w + 3 * nr, w + 4 * nr, w + 5 * nr, d + o_fol,
+                 (const u32 *)(d + o_fw), (const u32 *)(d + o_fa)};
+    c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
+                (const u32 *)(d + o_perm)};
+    c->gather = (const u32 *)(d + o_g);
+    c->dev = d;
+    return STWO_B200_OK;
+}
+
+cudaEvent_t g_ev[STWO_B200_N_TRACE_STAGES + 1] = {nullptr};
+bool g_timed_valid = false;
+}  // namespace
+
+static_assert(sizeof(dsl::ProofShape) == sizeof(stwo_b200_proof_shape), "shape mirrors");
+
+extern "C" int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,
+                                                     uint32_t n_inputs, uint32_t multipliers, stwo_b200_circuit **out) {
+    if (!shape || !out || multipliers == 0 || (n_inputs && (!input_idx || !input_vals))) return STWO_B200_E_BAD_ARG;
+    if (shape->n_queries == 0 || shape->n_queries > proof::MAX_QUERIES || shape->n_inner >= proof::MAX_INNER || shape->log_last > 12 ||
+        shape->pow_bits >= 32 || !shape->log_size_plonk || !shape->log_size_poseidon)
+        return STWO_B200_E_SHAPE;
+    verify::Shape v;
+    memcpy(&v, shape, sizeof v);
+    if (v.max_first() > 29 || v.log_plonk() > v.max_first() || v.log_pos() > v.max_first() || v.max_first() <= shape->log_last + shape->log_blowup)
+        return STWO_B200_E_SHAPE;
+    try {
+        dsl::ProofShape s;
+        memcpy(&s, shape, sizeof s);
+        std::vector<dsl::PublicInput> in;
+        for (u32 k = 0; k < n_inputs; k++)
+            in.push_back({input_idx[k], {{input_vals[4 * k], input_vals[4 * k + 1], input_vals[4 * k + 2], input_vals[4 * k + 3]}}});
+        stwo_b200_circuit *c = new stwo_b200_circuit();
+        c->rec = dsl::record_verifier(s, in, multipliers);
+        *out = c;
+        return STWO_B200_OK;
+    } catch (const std::exception &) { return STWO_B200_E_SHAPE; }
+}
+extern "C" void stwo_b200_circuit_free(stwo_b200_circuit *c) {
+    if (!c) return;
+    if (c->dev) cudaFree(c->dev);
+    delete c;
+}
+extern "C" int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b200_circuit_info *out) {
+    if (!c || !out) return STWO_B200_E_BAD_ARG;
+    const auto &cs = *c->rec->cs.p;
+    *out = {cs.num_plonk_rows(), cs.n_rows_unpadded, cs.n_vars, cs.num_poseidon_invocations(), cs.padded_poseidon_len(), cs.n_input_words,
+            (u32)c->rec->ins.size(), c->rec->n_levels(), cs.num_input, c->rec->words_per_instance};
+    return STWO_B200_OK;
+}
+extern "C" int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, uint32_t *out, size_t n_words) {
+    if (!c || !out) return STWO_B200_E_BAD_ARG;
+    const auto &cs = *c->rec->cs.p;
+    const std::vector<u32> *src = nullptr;
+    switch (what) {
+        case STWO_B200_COL_A_WIRE: src = &cs.a_wire; break;
+        case STWO_B200_COL_B_WIRE: src = &cs.b_wire; break;
+        case STWO_B200_COL_C_WIRE: src = &cs.c_wire; break;
+        case STWO_B200_COL_POSEIDON_WIRE: src = &cs.poseidon_wire; break;
+        case STWO_B200_COL_ENFORCE_C_M31: src = &cs.enforce_c_m31; break;
+        case STWO_B200_COL_OP: src = &cs.op; break;
+        case STWO_B200_COL_FLOW_WIRE: src = &cs.flow_wire; break;
+        case STWO_B200_COL_FLOW_SWAP_ADDR: src = &cs.flow_swap_addr; break;
+        case STWO_B200_COL_LEVEL_START: src = &c->rec->level_start; break;
+        case STWO_B200_COL_OP_FOLLOWS_C:
+            if (n_words != cs.op_follows_c.size()) return STWO_B200_E_BAD_ARG;
+            for (size_t k = 0; k < n_words; k++) out[k] = cs.op_follows_c[k];
+            return STWO_B200_OK;
+        default: return STWO_B200_E_BAD_ARG;
+    }
+    if (n_words != src->size()) return STWO_B200_E_BAD_ARG;
+    memcpy(out, src->data(), n_words * 4);
+    return STWO_B200_OK;
+}
+extern "C" size_t stwo_b200_circuit_workspace_bytes(const stwo_b200_circuit *c, uint32_t n_proofs) {
+    if (!c || !n_proofs) return 0;
+    return carve(*c->rec, n_proofs, nullptr).bytes;
+}
+
+extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                                     const void *verify_workspace, void *circuit_workspace, size_t circuit_workspace_bytes,
+                                                     uint32_t flags, uint32_t *preprocessed, uint32_t *values, int64_t *bad_row, int64_t *bad_flow,
+                                                     void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!c || !blobs || !blob_off || !verify_workspace || !circuit_workspace || !n_proofs) return STWO_B200_E_BAD_ARG;
+    if ((flags & STWO_B200_TRACE_CHECK_ARITHMETICS) && !bad_row) return STWO_B200_E_BAD_ARG;
+    if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && !bad_flow) return STWO_B200_E_BAD_ARG;
+    const RecordedCircuit &r = *c->rec;
+    const Carve k = carve(r, n_proofs, (uint8_t *)circuit_workspace);
+    if (k.bytes > circuit_workspace_bytes) return STWO_B200_E_BAD_ARG;
+    int32_t rc = upload(c);
+    if (rc) return rc;
+    verify::Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, &r.shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs; ws.blobs = blobs; ws.blob_off = blob_off;
+    verify::carve(ws, (uint8_t *)const_cast<void *>(verify_workspace));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool timed = flags & STWO_B200_TRACE_TIMED;
+    g_timed_valid = false;
+    if (timed && !g_ev[0]) for (auto &e : g_ev) STWO_CUDA(cudaEventCreate(&e));
+    int e = 0;
+#define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
+    const u32 nw = c->tape_.n_input_words;
+    const size_t groups = (n_proofs + 31) / 32;
+    MARK();
+    k_gather_witness<<<nblk(groups * nw * 32), kT, 0, st>>>(ws, c->gather, nw, k.witness);
+    note_launch(1);
+    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap};
+    MARK();
+    if ((rc = stwo_b200_cs_eval_tape_dev(&c->tape_, c->wiring.n_vars, k.witness, &v, st))) return rc;
+    MARK();
+    if (flags & STWO_B200_TRACE_CHECK_ARITHMETICS)
+        if ((rc = stwo_b200_cs_check_arithmetics_dev(&c->wiring, &v, bad_row, st))) return rc;
+    MARK();
+    const size_t nr = c->wiring.n_rows;
+    const bool need_mult = preprocessed || (flags & STWO_B200_TRACE_CHECK_POSEIDON);
+    if (need_mult)
+        if ((rc = stwo_b200_cs_populate_logup_dev(&c->wiring, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, k.scratch, k.status, st))) return rc;
+    if (flags & STWO_B200_TRACE_CHECK_POSEIDON)
+        if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, st))) return rc;
+    MARK();
+    if (preprocessed || values)
+        if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, preprocessed, values, st))) return rc;
+    MARK();
+#undef MARK
+    g_timed_valid = timed;
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int32_t stwo_b200_circuit_stage_ms(float *ms) {
+    STWO_CHECK_DEVICE();
+    if (!ms || !g_timed_valid) return STWO_B200_E_BAD_ARG;
+    STWO_CUDA(cudaEventSynchronize(g_ev[STWO_B200_N_TRACE_STAGES]));
+    for (int i = 0; i < STWO_B200_N_TRACE_STAGES; i++) STWO_CUDA(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
+    return STWO_B200_OK;
+}
+
+extern "C" int32_t stwo_b200_circuit_fetch(const stwo_b200_circuit *c, const void *circuit_workspace, uint32_t n_proofs, uint32_t p, uint32_t what,
+                                           void *out, size_t out_bytes, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!c || !circuit_workspace || p >= n_proofs || !out) return STWO_B200_E_BAD_ARG;
+    const auto &cs = *c->rec->cs.p;
+    const Carve k = carve(*c->rec, n_proofs, (uint8_t *)const_cast<void *>(circuit_workspace));
+    const size_t grp = p / 32, lane = p % 32;
+    const uint8_t *src; size_t elem, n;
+    switch (what) {
+        case STWO_B200_CFETCH_VARIABLES: elem = 16; n = cs.n_vars; src = (const uint8_t *)k.vars; break;
+        case STWO_B200_CFETCH_FLOW_HASH: elem = 4; n = (size_t)cs.num_poseidon_invocations() * 32; src = (const uint8_t *)k.flow_hash; break;
+        case STWO_B200_CFETCH_FLOW_SWAP: elem = 1; n = cs.num_poseidon_invocations(); src = k.flow_swap; break;
+        case STWO_B200_CFETCH_WITNESS: elem = 4; n = cs.n_input_words; src = (const uint8_t *)k.witness; break;
+        default: return STWO_B200_E_BAD_ARG;
+    }
+    if (out_bytes < n * elem) return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    // de-interleave one lane: a strided 2-D copy
+    STWO_CUDA(cudaMemcpy2DAsync(out, elem, src + (grp * n * 32 + lane) * elem, 32 * elem, elem, n, cudaMemcpyDeviceToHost, st));
+    return cuda_status(cudaStreamSynchronize(st));
+}

@@ -1,37 +1,78 @@
-// K7: the O(n_rows) finalisation loops of the Plonk-with-Poseidon constraint system and the trace export.
-// HBM-bound: per row 6 x 4 B of wiring in, three random 16-B gathers, 12 (+10 once) coalesced 4-B column stores.
+// K6 (tape evaluation) and K7 (the O(n_rows) finalisation loops + trace export) of the Plonk-with-Poseidon constraint
+// system, for batches of items that share one recorded wiring.
 //   constraint_system/src/plonk_with_poseidon.rs:337-380  check_arithmetics
 //   :382-466 populate_logup_arguments   :468-519 check_poseidon_invocations   :521-628 generate_plonk_with_poseidon_circuit
+// Bounds: K6 is integer-issue bound (it executes the circuit's Poseidon2 permutations, one lane per item); K7 export is
+// HBM bound: per (row, item) three 16-byte variable reads + thirteen 4-byte column writes = 100 B.
+// Layout: per-item arrays are lane-interleaved (tape.cuh) so a warp = 32 items touches contiguous runs.
 #include "common.cuh"
-#include "poseidon2.cuh"
+#include "tape.cuh"
 
 using namespace stwo_b200;
 
 namespace {
 constexpr int kT = 256;
-inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
+inline unsigned nblk(size_t n, int t = kT) { return (unsigned)((n + t - 1) / t); }
 
-__device__ __forceinline__ qm31_t ldq(const u32 *vars, u32 idx) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(vars) + idx);
-    return qm31::mk(t.x, t.y, t.z, t.w);
+struct Batch {                       // stwo_b200_cs_values + sizes, passed by value to the kernels
+    tape::Q4 *vars; u32 *flow_hash; uint8_t *flow_swap;
+    u32 n_batch, lanes, n_vars, n_flow;
+    __device__ __forceinline__ tape::View view(u32 item, const u32 *input, u32 n_input_words) const {
+        const size_t g = item / lanes, l = item % lanes;
+        tape::View v;
+        v.vars = vars + g * n_vars * lanes + l;
+        v.input = input ? input + g * n_input_words * lanes + l : nullptr;
+        v.flow_hash = flow_hash ? flow_hash + g * n_flow * 32 * lanes + l : nullptr;
+        v.flow_swap = flow_swap ? flow_swap + g * n_flow * lanes + l : nullptr;
+        v.stride = lanes;
+        return v;
+    }
+};
+
+// ---- K6 -------------------------------------------------------------------------------------------------------------------
+// One CTA per group of `lanes` items.  Thread t works for item t % lanes in instruction slot t / lanes: with lanes = 32 a
+// warp executes one instruction for 32 items (uniform control flow, coalesced variable traffic) and the CTA's warps share
+// the instructions of a level; a barrier separates levels.  Instruction words are warp-uniform broadcast loads.
+constexpr int kEvalThreads = 1024;
+__global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
+                                                            const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words) {
+    const u32 lane = threadIdx.x % b.lanes, slot = threadIdx.x / b.lanes, n_slots = kEvalThreads / b.lanes;
+    const u32 item = blockIdx.x * b.lanes + lane;
+    const bool live = item < b.n_batch;
+    const tape::View v = b.view(live ? item : 0, input, n_input_words);
+    if (live && slot == 0) tape::prologue(v);
+    __syncthreads();
+    for (u32 l = 0; l < n_levels; l++) {
+        const u32 lo = __ldg(level_start + l), hi = __ldg(level_start + l + 1);
+        if (live)
+            for (u32 k = lo + slot; k < hi; k += n_slots) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
+                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                tape::eval(v, in, perms);
+            }
+        __syncthreads();
+    }
 }
 
-__global__ void __launch_bounds__(kT) k_cs_check_arith(stwo_b200_cs_wiring w, const u32 *variables, u32 n_batch,
-                                                       unsigned long long *first_bad) {
+// ---- K7: check_arithmetics ---------------------------------------------------------------------------------------------------
+// thread = (row, item) with the item fastest: a warp checks one row for 32 items
+__global__ void __launch_bounds__(kT) k_cs_check_arith(stwo_b200_cs_wiring w, Batch b, unsigned long long *first_bad) {
     const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
-    if (g >= (size_t)w.n_rows * n_batch) return;
-    const u32 b = (u32)(g / w.n_rows), i = (u32)(g % w.n_rows);
-    const u32 *vars = variables + (size_t)b * w.n_vars * 4;
-    const qm31_t a = ldq(vars, w.a_wire[i]), bb = ldq(vars, w.b_wire[i]), c = ldq(vars, w.c_wire[i]);
-    const u32 op = w.op[i];
-    // c == op*(a+b) + (1-op)*a*b
-    const qm31_t lhs = qm31::add(qm31::mul_m31(qm31::add(a, bb), op), qm31::mul_m31(qm31::mul(a, bb), m31::subc(1, op)));
-    bool ok = qm31::eq(lhs, c);
-    if (w.enforce_c_m31[i] && (c.v[1] | c.v[2] | c.v[3])) ok = false;
-    if (!ok) atomicMin(first_bad + b, (unsigned long long)i);
+    const u32 padded = (b.n_batch + b.lanes - 1) / b.lanes * b.lanes;
+    if (g >= (size_t)w.n_rows * padded) return;
+    // order: group-major, then row, then lane -> consecutive threads share a row and a group
+    const u32 lane = (u32)(g % b.lanes);
+    const size_t t = g / b.lanes;
+    const u32 row = (u32)(t % w.n_rows), grp = (u32)(t / w.n_rows), item = grp * b.lanes + lane;
+    if (item >= b.n_batch) return;
+    const tape::View v = b.view(item, nullptr, 0);
+    const bool follows = w.op_follows_c && w.op_follows_c[row];
+    if (!tape::row_ok(v, __ldg(w.a_wire + row), __ldg(w.b_wire + row), __ldg(w.c_wire + row), __ldg(w.op + row), __ldg(w.enforce_c_m31 + row), follows))
+        atomicMin(first_bad + item, (unsigned long long)row);
 }
 
-// scratch layout: counts[n_vars] | first_key[n_vars] | first_prow[n_vars] | mpv aliases nothing: kept in counts2
+// ---- K7: populate_logup_arguments (wiring only) ------------------------------------------------------------------------------
+// scratch layout: counts[n_vars] | first_key[n_vars] | first_prow[n_vars] | mult_poseidon_vars[n_vars]
 __global__ void __launch_bounds__(kT) k_cs_count(stwo_b200_cs_wiring w, u32 *counts, u32 *first_key, u32 *first_prow, u32 *mpv) {
     const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
     if (g < w.n_rows) {
@@ -66,33 +107,42 @@ __global__ void __launch_bounds__(kT) k_cs_mult(stwo_b200_cs_wiring w, const u32
     mult_poseidon[i] = mp;
 }
 
-__global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w, const u32 *variables, const u32 *flow_hash,
-                                                           const uint8_t *flow_swap, u32 n_batch, const int32_t *mult_poseidon,
+// ---- K7: check_poseidon_invocations ----------------------------------------------------------------------------------------
+// thread = (flow entry, item), item fastest
+__global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
                                                            const u32 *first_prow, unsigned long long *first_bad) {
     const size_t g = blockIdx.x * (size_t)128 + threadIdx.x;
-    if (g >= (size_t)w.n_flow * n_batch) return;
-    const u32 b = (u32)(g / w.n_flow), e = (u32)(g % w.n_flow);
-    const u32 *vars = variables + (size_t)b * w.n_vars * 4;
-    const u32 *h = flow_hash + ((size_t)b * w.n_flow + e) * 32;
+    const u32 padded = (b.n_batch + b.lanes - 1) / b.lanes * b.lanes;
+    if (g >= (size_t)w.n_flow * padded) return;
+    const u32 lane = (u32)(g % b.lanes);
+    const size_t t = g / b.lanes;
+    const u32 e = (u32)(t % w.n_flow), grp = (u32)(t / w.n_flow), item = grp * b.lanes + lane;
+    if (item >= b.n_batch) return;
+    const tape::View v = b.view(item, nullptr, 0);
+    const u32 *h = v.flow_hash + (size_t)e * 32 * v.stride;
+    u32 hh[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) hh[k] = h[(size_t)k * v.stride];
     bool ok = true;
     for (int k = 0; k < 4; k++) {
         const u32 wire = w.flow_wire[4 * e + k];
         if (!wire) continue;
         const u32 row = first_prow[wire];
         if (row >= w.n_rows || mult_poseidon[row] == 0) { ok = false; continue; }    // map.get(..).unwrap() would panic
-        const qm31_t l = ldq(vars, w.a_wire[row]), r = ldq(vars, w.b_wire[row]);
-        for (int j = 0; j < 4; j++) ok &= (l.v[j] == h[8 * k + j]) & (r.v[j] == h[8 * k + 4 + j]);
+        const qm31_t l = tape::ldv(v, w.a_wire[row]), r = tape::ldv(v, w.b_wire[row]);
+        for (int j = 0; j < 4; j++) ok &= (l.v[j] == hh[8 * k + j]) & (r.v[j] == hh[8 * k + 4 + j]);
     }
     u32 st[16];
-    const bool swap = flow_swap[(size_t)b * w.n_flow + e] != 0;
+    const bool swap = v.flow_swap[(size_t)e * v.stride] != 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { st[j] = h[(swap ? 8 : 0) + j]; st[8 + j] = h[(swap ? 0 : 8) + j]; }
+    for (int j = 0; j < 8; j++) { st[j] = hh[(swap ? 8 : 0) + j]; st[8 + j] = hh[(swap ? 0 : 8) + j]; }
     poseidon2::permute<false>(st);
 #pragma unroll
-    for (int j = 0; j < 16; j++) ok &= st[j] == h[16 + j];
-    if (!ok) atomicMin(first_bad + b, (unsigned long long)e);
+    for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
+    if (!ok) atomicMin(first_bad + item, (unsigned long long)e);
 }
 
+// ---- K7: trace export ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 m31_of_i32(int32_t v) { return v < 0 ? M31_P - (u32)(-v) : (u32)v; }
 
 __global__ void __launch_bounds__(kT) k_cs_export_pre(stwo_b200_cs_wiring w, const int32_t *mult_a, const int32_t *mult_b,
@@ -104,16 +154,50 @@ __global__ void __launch_bounds__(kT) k_cs_export_pre(stwo_b200_cs_wiring w, con
     pre[3 * n + i] = w.poseidon_wire[i]; pre[4 * n + i] = (u32)mult_poseidon[i]; pre[5 * n + i] = w.enforce_c_m31[i];
     pre[6 * n + i] = w.a_wire[i]; pre[7 * n + i] = w.b_wire[i]; pre[8 * n + i] = w.c_wire[i]; pre[9 * n + i] = w.op[i];
 }
-__global__ void __launch_bounds__(kT) k_cs_export_vals(stwo_b200_cs_wiring w, const u32 *variables, u32 n_batch, u32 *vals) {
+
+constexpr int kCols = 13;            // a_val_0..3, b_val_0..3, c_val_0..3, op
+// lanes = 1: thread per (item, row); random 16-byte gathers, coalesced column stores
+__global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring w, Batch b, u32 *vals) {
     const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
-    if (g >= (size_t)w.n_rows * n_batch) return;
-    const u32 b = (u32)(g / w.n_rows), i = (u32)(g % w.n_rows);
-    const u32 *vars = variables + (size_t)b * w.n_vars * 4;
+    if (g >= (size_t)w.n_rows * b.n_batch) return;
+    const u32 item = (u32)(g / w.n_rows), i = (u32)(g % w.n_rows);
+    const tape::View v = b.view(item, nullptr, 0);
     const size_t n = w.n_rows;
-    u32 *o = vals + (size_t)b * 12 * n + i;
-    const qm31_t a = ldq(vars, w.a_wire[i]), bb = ldq(vars, w.b_wire[i]), c = ldq(vars, w.c_wire[i]);
+    u32 *o = vals + (size_t)item * kCols * n + i;
+    const qm31_t a = tape::ldv(v, w.a_wire[i]), bb = tape::ldv(v, w.b_wire[i]), c = tape::ldv(v, w.c_wire[i]);
 #pragma unroll
     for (int k = 0; k < 4; k++) { o[k * n] = a.v[k]; o[(4 + k) * n] = bb.v[k]; o[(8 + k) * n] = c.v[k]; }
+    o[12 * n] = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : w.op[i];
+}
+// lanes = 32: a CTA transposes a tile of 32 rows x 32 items through shared memory.  Load phase: a warp reads one row's
+// three variables for 32 items (3 x 512 contiguous bytes).  Store phase: a warp writes 32 consecutive rows of one
+// (item, column) = one 128-byte line.
+constexpr int kTileRows = 32;
+__global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring w, Batch b, u32 *vals) {
+    extern __shared__ u32 tile[];                        // [kCols][32 items][33]
+    const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32, n_warps = kT / 32;
+    const u32 row0 = blockIdx.x * kTileRows, grp = blockIdx.y;
+    const u32 item = grp * 32 + lane;
+    if (item < b.n_batch) {
+        const tape::View v = b.view(item, nullptr, 0);
+        for (u32 r = warp; r < kTileRows; r += n_warps) {
+            const u32 i = row0 + r;
+            const qm31_t a = tape::ldv(v, __ldg(w.a_wire + i)), bb = tape::ldv(v, __ldg(w.b_wire + i)), c = tape::ldv(v, __ldg(w.c_wire + i));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                tile[((0 + k) * 32 + lane) * 33 + r] = a.v[k];
+                tile[((4 + k) * 32 + lane) * 33 + r] = bb.v[k];
+                tile[((8 + k) * 32 + lane) * 33 + r] = c.v[k];
+            }
+            tile[(12 * 32 + lane) * 33 + r] = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
+        }
+    }
+    __syncthreads();
+    const size_t n = w.n_rows;
+    for (u32 pair = warp; pair < 32 * kCols; pair += n_warps) {
+        const u32 it = pair / kCols, col = pair % kCols;
+        if (grp * 32 + it < b.n_batch) vals[((size_t)(grp * 32 + it) * kCols + col) * n + row0 + lane] = tile[(col * 32 + it) * 33 + lane];
+    }
 }
 __global__ void k_fill64(unsigned long long *p, size_t n, unsigned long long v) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -123,15 +207,39 @@ bool wiring_ok(const stwo_b200_cs_wiring *w) {
     return w && w->n_rows >= 16 && (w->n_rows & (w->n_rows - 1)) == 0 && w->n_vars >= 4 && w->a_wire && w->b_wire && w->c_wire &&
            w->poseidon_wire && w->enforce_c_m31 && w->op && (w->n_flow == 0 || (w->flow_wire && w->flow_swap_addr));
 }
+bool values_ok(const stwo_b200_cs_values *v) { return v && v->n_batch && (v->lanes == 1 || v->lanes == 32) && v->variables; }
+Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
+    Batch b;
+    b.vars = reinterpret_cast<tape::Q4 *>(v->variables); b.flow_hash = v->flow_hash; b.flow_swap = v->flow_swap;
+    b.n_batch = v->n_batch; b.lanes = v->lanes; b.n_vars = n_vars; b.n_flow = n_flow;
+    return b;
+}
 }  // namespace
 
+static_assert(sizeof(tape::Perm) == 48 && sizeof(tape::Ins) == 16, "tape records mirror the C ABI");
+static_assert(tape::T_POSEIDON == STWO_B200_T_POSEIDON && tape::T_ADD == STWO_B200_T_ADD && tape::T_BIT == STWO_B200_T_BIT, "opcodes mirror the C ABI");
+
+extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
+                                              void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!t || !values_ok(v) || n_vars < 4 || !t->ins || !t->level_start || (t->n_perms && !t->perms) || (t->n_input_words && !witness))
+        return STWO_B200_E_BAD_ARG;
+    const Batch b = batch_of(v, n_vars, t->n_perms);
+    const u32 n_groups = (v->n_batch + v->lanes - 1) / v->lanes;
+    k_tape_eval<<<n_groups, kEvalThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const tape::Ins *>(t->ins), t->level_start, t->n_levels,
+                                                                     reinterpret_cast<const tape::Perm *>(t->perms), b, witness, t->n_input_words);
+    note_launch(1);
+    return cuda_status(cudaGetLastError());
+}
 extern "C" int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,
                                                       void *stream) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(w) || !v || !v->variables || !first_bad || v->n_batch == 0) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(w) || !values_ok(v) || !first_bad) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const Batch b = batch_of(v, w->n_vars, w->n_flow);
+    const size_t padded = (size_t)(v->n_batch + v->lanes - 1) / v->lanes * v->lanes;
     k_fill64<<<nblk(v->n_batch), kT, 0, st>>>((unsigned long long *)first_bad, v->n_batch, ~0ull);
-    k_cs_check_arith<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, v->variables, v->n_batch, (unsigned long long *)first_bad);
+    k_cs_check_arith<<<nblk((size_t)w->n_rows * padded), kT, 0, st>>>(*w, b, (unsigned long long *)first_bad);
     note_launch(2);
     return cuda_status(cudaGetLastError());
 }
@@ -157,14 +265,16 @@ extern "C" int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w,
 extern "C" int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
                                                    const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(w) || !v || !v->variables || !first_bad || !mult_poseidon || !scratch || v->n_batch == 0) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(w) || !values_ok(v) || !first_bad || !mult_poseidon || !scratch) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     k_fill64<<<nblk(v->n_batch), kT, 0, st>>>((unsigned long long *)first_bad, v->n_batch, ~0ull);
     note_launch(1);
     if (w->n_flow) {
         if (!v->flow_hash || !v->flow_swap) return STWO_B200_E_BAD_ARG;
-        k_cs_check_poseidon<<<(unsigned)(((size_t)w->n_flow * v->n_batch + 127) / 128), 128, 0, st>>>(
-            *w, v->variables, v->flow_hash, v->flow_swap, v->n_batch, mult_poseidon, scratch + 2 * (size_t)w->n_vars, (unsigned long long *)first_bad);
+        const Batch b = batch_of(v, w->n_vars, w->n_flow);
+        const size_t padded = (size_t)(v->n_batch + v->lanes - 1) / v->lanes * v->lanes;
+        k_cs_check_poseidon<<<nblk((size_t)w->n_flow * padded, 128), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
+                                                                                  (unsigned long long *)first_bad);
         note_launch(1);
     }
     return cuda_status(cudaGetLastError());
@@ -173,28 +283,41 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
                                                  const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
                                                  uint32_t *preprocessed, uint32_t *values, void *stream) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(w) || !v || !v->variables || v->n_batch == 0 || !values) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(w) || !values_ok(v) || (!values && !preprocessed)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (preprocessed) {
         if (!mult_a || !mult_b || !mult_c || !mult_poseidon) return STWO_B200_E_BAD_ARG;
         k_cs_export_pre<<<nblk(w->n_rows), kT, 0, st>>>(*w, mult_a, mult_b, mult_c, mult_poseidon, preprocessed);
         note_launch(1);
     }
-    k_cs_export_vals<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, v->variables, v->n_batch, values);
-    note_launch(1);
+    if (values) {
+        const Batch b = batch_of(v, w->n_vars, w->n_flow);
+        if (v->lanes == 1) k_cs_export_vals_plain<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, b, values);
+        else {
+            const size_t smem = (size_t)kCols * 32 * 33 * 4;
+            static bool attr_set = false;
+            if (!attr_set) {
+                STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            dim3 grid(w->n_rows / kTileRows, (v->n_batch + 31) / 32);
+            k_cs_export_vals_tiled<<<grid, kT, smem, st>>>(*w, b, values);
+        }
+        note_launch(1);
+    }
     return cuda_status(cudaGetLastError());
 }
 
 extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const stwo_b200_cs_values *hv, uint32_t *trace,
                                          int64_t *bad_row, int64_t *bad_flow) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(hw) || !hv || hv->n_batch != 1 || !hv->variables || !trace || !bad_row || !bad_flow) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(hw) || !hv || hv->n_batch != 1 || hv->lanes != 1 || !hv->variables || !trace || !bad_row || !bad_flow) return STWO_B200_E_BAD_ARG;
     const size_t nr = hw->n_rows, nv = hw->n_vars, nf = hw->n_flow;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_wires = take(6 * nr * 4), o_fw = take(nf * 4 * 4 + 4), o_fa = take(nf * 4 + 4), o_vars = take(nv * 16),
+    const size_t o_wires = take(6 * nr * 4), o_follow = take(nr), o_fw = take(nf * 4 * 4 + 4), o_fa = take(nf * 4 + 4), o_vars = take(nv * 16),
                  o_fh = take(nf * 128 + 4), o_fs = take(nf + 4), o_mult = take(4 * nr * 4), o_scr = take((4 * nv + 4) * 4),
-                 o_bad = take(16), o_stat = take(4), o_trace = take(22 * nr * 4);
+                 o_bad = take(16), o_stat = take(4), o_pre = take(10 * nr * 4), o_vals = take(kCols * nr * 4);
     int32_t rc = stage_reserve(off);
     if (rc) return rc;
     cudaStream_t st = stage_stream();
@@ -202,30 +325,35 @@ extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const st
     u32 *dw = (u32 *)(d + o_wires);
     const u32 *srcs[6] = {hw->a_wire, hw->b_wire, hw->c_wire, hw->poseidon_wire, hw->enforce_c_m31, hw->op};
     for (int k = 0; k < 6; k++) STWO_CUDA(cudaMemcpyAsync(dw + k * nr, srcs[k], nr * 4, cudaMemcpyHostToDevice, st));
+    if (hw->op_follows_c) STWO_CUDA(cudaMemcpyAsync(d + o_follow, hw->op_follows_c, nr, cudaMemcpyHostToDevice, st));
     if (nf) {
+        if (!hv->flow_hash || !hv->flow_swap) return STWO_B200_E_BAD_ARG;
         STWO_CUDA(cudaMemcpyAsync(d + o_fw, hw->flow_wire, nf * 16, cudaMemcpyHostToDevice, st));
         STWO_CUDA(cudaMemcpyAsync(d + o_fa, hw->flow_swap_addr, nf * 4, cudaMemcpyHostToDevice, st));
-        if (!hv->flow_hash || !hv->flow_swap) return STWO_B200_E_BAD_ARG;
         STWO_CUDA(cudaMemcpyAsync(d + o_fh, hv->flow_hash, nf * 128, cudaMemcpyHostToDevice, st));
         STWO_CUDA(cudaMemcpyAsync(d + o_fs, hv->flow_swap, nf, cudaMemcpyHostToDevice, st));
     }
     STWO_CUDA(cudaMemcpyAsync(d + o_vars, hv->variables, nv * 16, cudaMemcpyHostToDevice, st));
     stwo_b200_cs_wiring w = *hw;
     w.a_wire = dw; w.b_wire = dw + nr; w.c_wire = dw + 2 * nr; w.poseidon_wire = dw + 3 * nr; w.enforce_c_m31 = dw + 4 * nr; w.op = dw + 5 * nr;
+    w.op_follows_c = hw->op_follows_c ? d + o_follow : nullptr;
     w.flow_wire = (u32 *)(d + o_fw); w.flow_swap_addr = (u32 *)(d + o_fa);
-    stwo_b200_cs_values v = {1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs};
+    stwo_b200_cs_values v = {1, 1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs};
     int32_t *m = (int32_t *)(d + o_mult);
     int64_t *bad = (int64_t *)(d + o_bad);
-    u32 *scr = (u32 *)(d + o_scr), *stat = (u32 *)(d + o_stat), *tr = (u32 *)(d + o_trace);
+    u32 *scr = (u32 *)(d + o_scr), *stat = (u32 *)(d + o_stat), *pre = (u32 *)(d + o_pre), *vals = (u32 *)(d + o_vals);
     if ((rc = stwo_b200_cs_check_arithmetics_dev(&w, &v, bad, st))) return rc;
     if ((rc = stwo_b200_cs_populate_logup_dev(&w, m, m + nr, m + 2 * nr, m + 3 * nr, scr, stat, st))) return rc;
     if ((rc = stwo_b200_cs_check_poseidon_dev(&w, &v, m + 3 * nr, scr, bad + 1, st))) return rc;
-    if ((rc = stwo_b200_cs_export_trace_dev(&w, &v, m, m + nr, m + 2 * nr, m + 3 * nr, tr, tr + 10 * nr, st))) return rc;
+    if ((rc = stwo_b200_cs_export_trace_dev(&w, &v, m, m + nr, m + 2 * nr, m + 3 * nr, pre, vals, st))) return rc;
     int64_t hb[2];
     u32 hstat = 0;
     STWO_CUDA(cudaMemcpyAsync(hb, bad, 16, cudaMemcpyDeviceToHost, st));
     STWO_CUDA(cudaMemcpyAsync(&hstat, stat, 4, cudaMemcpyDeviceToHost, st));
-    STWO_CUDA(cudaMemcpyAsync(trace, tr, 22 * nr * 4, cudaMemcpyDeviceToHost, st));
+    // 22 columns: 9 shared preprocessed + the item's op column, then the 12 value columns
+    STWO_CUDA(cudaMemcpyAsync(trace, pre, 9 * nr * 4, cudaMemcpyDeviceToHost, st));
+    STWO_CUDA(cudaMemcpyAsync(trace + 9 * nr, vals + 12 * nr, nr * 4, cudaMemcpyDeviceToHost, st));
+    STWO_CUDA(cudaMemcpyAsync(trace + 10 * nr, vals, 12 * nr * 4, cudaMemcpyDeviceToHost, st));
     STWO_CUDA(cudaStreamSynchronize(st));
     *bad_row = hb[0]; *bad_flow = hb[1];
     if (hstat) *bad_flow = -2;     // a Poseidon wire is referenced by more than one row (reference: assert_eq!(counts[..], 1))

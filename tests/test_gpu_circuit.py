@@ -1,0 +1,104 @@
+"""GPU tier: trace generation of the recursive verifier circuit through the C ABI (gather -> K6 tape evaluation -> K7 checks
+and export), bit-exact against the oracle's circuit DSL: variables[], Poseidon flow, the 22 trace columns (golden digests of
+tests/golden/trace_digests.json), check_arithmetics / check_poseidon_invocations verdicts on accepted and tampered proofs."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from circuit_common import D, oracle_circuit
+
+pytestmark = pytest.mark.gpu
+GOLD = {g["src"]: g for g in json.load(open(os.path.join(O.ROOT, "tests", "golden", "trace_digests.json")))["chain"]}
+
+
+def _inputs(pkg, name):
+    return pkg.INPUTS_SINGLE if name.startswith("small") else pkg.INPUTS_RECURSIVE
+
+
+@pytest.mark.parametrize("name", ["small_proof.bin", "level13-1.bin", "level7-1.bin", "level9-1.bin", "level11-1.bin"])
+def test_trace_matches_oracle_and_golden(pkg, gpu, orc, name):
+    cs, out = oracle_circuit(name, 1)
+    blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+    n = 40                                           # more than one lane group, ragged tail
+    vb = pkg.VerifyBatch([blob] * n, inputs=_inputs(pkg, name))
+    verdict, _ = vb.run(full=True)
+    assert not verdict.cpu().numpy().any()
+    circ = pkg.VerifierCircuit(vb.shape, inputs=_inputs(pkg, name))
+    r = circ.trace(vb, check=True, export=True)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    want = np.array(cs.variables, dtype=np.uint32)
+    wire, addr, wh, wsw = cs.flow_arrays()
+    for p in (0, 31, 32, n - 1):
+        assert np.array_equal(circ.fetch(p, "variables"), want)
+        assert np.array_equal(circ.fetch(p, "flow_hash"), wh) and np.array_equal(circ.fetch(p, "flow_swap"), wsw)
+    tr = cs.trace_columns()
+    for p in (0, 33, n - 1):
+        got = pkg.VerifierCircuit.assemble_trace(r["preprocessed"], r["values"][p])
+        bad = np.argwhere(got != tr)
+        assert bad.size == 0, "column %s row %d" % (pkg.circuit.COLUMN_NAMES[bad[0][0]], bad[0][1])
+        assert D.trace_digest(got) == GOLD[name]["trace_sha256"]
+
+
+def test_multipliers(pkg, gpu, orc):
+    """examples/multi-proofs: the same proof verified twice inside one constraint system"""
+    name = "small_proof.bin"
+    cs, _ = oracle_circuit(name, 2)
+    blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+    vb = pkg.VerifyBatch([blob] * 3, inputs=pkg.INPUTS_SINGLE)
+    vb.run(full=True)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE, multipliers=2)
+    r = circ.trace(vb)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    got = pkg.VerifierCircuit.assemble_trace(r["preprocessed"], r["values"][2])
+    assert np.array_equal(got, cs.trace_columns())
+
+
+def test_tampered_proofs_fail_check_arithmetics(pkg, gpu, orc):
+    """a rejected proof leaves an unsatisfied row (the reference would panic inside the DSL); accepted neighbours are unaffected"""
+    name = "small_proof.bin"
+    buf, n = O.load_proof(name)
+    offs = O.proof_offsets(buf, n)
+    blobs, expect_ok = [], []
+    for k, region in enumerate(["sampled0", None, "queried0", "fri_first_witness", None, "last_coeffs", "pow_nonce", None]):
+        b = buf.copy()
+        if region:
+            b[offs[region] + 1] ^= 1 << (k % 7)
+        blobs.append(bytes(b[:n]))
+        expect_ok.append(region is None)
+    vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_SINGLE)
+    verdict, _ = vb.run(full=True)
+    verdict = verdict.cpu().numpy()
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)
+    r = circ.trace(vb, export=False, preprocessed=False)
+    bad_row = r["bad_row"].cpu().numpy()
+    for k, ok in enumerate(expect_ok):
+        assert (verdict[k] == 0) == ok
+        assert (bad_row[k] == -1) == ok, (k, bad_row[k])
+    assert (r["bad_flow"].cpu().numpy() == -1).all()     # the Poseidon flow is self-consistent whatever the proof says
+
+
+def test_cs_finalize_host_entry(pkg, gpu, orc):
+    """stwo_b200_cs_finalize: one constraint system whose values were produced on the host (here: by the oracle)"""
+    cs, _ = oracle_circuit("small_proof.bin", 1)
+    L = pkg._lib
+    cols = {k: np.ascontiguousarray(getattr(cs, k), dtype=np.uint32) for k in ("a_wire", "b_wire", "c_wire", "poseidon_wire", "enforce_c_m31", "op")}
+    wire, addr, wh, wsw = cs.flow_arrays()
+    variables = np.ascontiguousarray(cs.variables, dtype=np.uint32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    w = L.CsWiring(len(cs.variables), len(cs.a_wire), len(cs.flow), cs.num_input, *[vp(cols[k]) for k in cols], None, vp(wire), vp(addr))
+    v = L.CsValues(1, 1, vp(variables), vp(wh), vp(wsw))
+    trace = np.zeros((22, len(cs.a_wire)), dtype=np.uint32)
+    bad_row, bad_flow = ctypes.c_int64(7), ctypes.c_int64(7)
+    L.call("stwo_b200_cs_finalize", ctypes.byref(w), ctypes.byref(v), vp(trace), ctypes.byref(bad_row), ctypes.byref(bad_flow))
+    assert (bad_row.value, bad_flow.value) == (-1, -1)
+    assert np.array_equal(trace, cs.trace_columns())
+    # a corrupted variable and a corrupted flow hash are located
+    row = next(i for i in range(2000, len(cs.a_wire)) if cs.op[i] == 0 and cs.c_wire[i] > 3)
+    variables[cs.c_wire[row], 0] ^= 1
+    wh[17, 20] ^= 1
+    L.call("stwo_b200_cs_finalize", ctypes.byref(w), ctypes.byref(v), vp(trace), ctypes.byref(bad_row), ctypes.byref(bad_flow))
+    assert 0 <= bad_row.value <= row and bad_flow.value == 17
