@@ -6,12 +6,15 @@
 
 Workload (BASELINE.json configs[4], the single-GPU share of it): a batch of
 --proofs replicas per GPU of the reference's own fixture components/test_data/small_proof.bin (shape S:
-pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers), verified natively: transcript + PoW, logup sum,
-OODS, batched Merkle decommitment re-shaped into per-query paths, DEEP answers, circle/line folds, last
-layer, and every per-query authentication path recomputed (what the verifier circuit does).
-One "step" = one batch.  Metric: verified proofs/s over all GPUs; `poseidon31_perms_per_sec` rides along
-(the permutations that batch executed, and the K1 / Merkle-sweep rates of BASELINE configs[2]).
-`value`: blobs already in HBM.  `e2e`: pinned host blobs -> device -> verdicts back on the host, every step.
+pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers).  One "step" = one batch through the whole path:
+  (1) native verification: transcript + PoW, logup sum, OODS, batched Merkle decommitment re-shaped into
+      per-query paths, DEEP answers, circle/line folds, last layer, every per-query authentication path;
+  (2) the verifier circuit's trace: witness streams gathered from (1), variables[] evaluated along the recorded
+      tape (3 481 in-circuit Poseidon2 permutations per proof), check_arithmetics, check_poseidon_invocations,
+      export of the 2^16-row x 13 per-proof trace columns (examples/single-proof/src/main.rs:33-90).
+Metric: verified proofs/s over all GPUs (a proof counts when its verdict is accept AND its circuit checks pass);
+`poseidon31_perms_per_sec` rides along.  `value`: blobs already in HBM.  `e2e`: pinned host blobs -> device ->
+verdicts + check results back on the host, every step (traces stay in HBM for the prover that consumes them).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -94,31 +97,52 @@ def load_fixture():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_verify_rate(n_proofs, seconds, cores):
-    """oracle port (oracle/orc_verify.c) on `cores` pthreads over replicas of the fixture"""
-    import oracle_py as O
-    lib = O.load_oracle()
-    lib.orc_verify_batch_mt.restype = ctypes.c_uint64
-    buf, n = O.load_proof(FIXTURE)
-    blobs = np.tile(buf[:n], n_proofs)
-    off = np.arange(n_proofs + 1, dtype=np.uint64) * n
-    idx = np.array(O.INPUTS_SMALL[0], dtype=np.uint32)
-    vals = np.array(O.INPUTS_SMALL[1], dtype=np.uint32)
-    v = np.zeros(n_proofs, np.uint8)
-    s = np.zeros(n_proofs, np.uint8)
+class CpuPath:
+    """The reference path on the host cores: oracle/orc_verify.c (native verifier) + oracle/orc_tape.c (the circuit's
+    value arithmetic, check_arithmetics, check_poseidon_invocations, value-column export replayed from the value log that
+    oracle/orc_dsl.py records), both on `cores` pthreads over replicas of the fixture."""
 
-    def run():
-        return lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n_proofs, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
+    def __init__(self, n_proofs, cores):
+        import oracle_py as O
+        sys.path.insert(0, O.ORACLE_DIR)
+        import orc_dsl as D
+        self.O, self.n, self.cores = O, n_proofs, cores
+        lib = self.lib = O.load_oracle()
+        lib.orc_verify_batch_mt.restype = ctypes.c_uint64
+        lib.orc_circuit_trace_mt.restype = ctypes.c_int64
+        buf, n = O.load_proof(FIXTURE)
+        self.blobs = np.tile(buf[:n], n_proofs)
+        self.off = np.arange(n_proofs + 1, dtype=np.uint64) * n
+        self.idx = np.array(O.INPUTS_SMALL[0], dtype=np.uint32)
+        self.vals = np.array(O.INPUTS_SMALL[1], dtype=np.uint32)
+        self.v, self.s = np.zeros(n_proofs, np.uint8), np.zeros(n_proofs, np.uint8)
+        cs, _ = D.verifier_circuit(bytes(buf[:n]), D.INPUTS_SINGLE, 1, O.VerifyOut)
+        self.ops, self.perms = D.value_log_arrays(cs)
+        self.wiring = np.ascontiguousarray([cs.a_wire, cs.b_wire, cs.c_wire, cs.poseidon_wire, cs.enforce_c_m31, cs.op], dtype=np.uint32)
+        self.flow_wire = cs.flow_arrays()[0]
+        self.n_vars, self.n_rows, self.circuit_perms = len(cs.variables), len(cs.a_wire), len(cs.flow)
 
-    run()
+    def step(self):
+        """one batch: verify, then the circuit of every proof; returns the permutations executed"""
+        O, lib = self.O, self.lib
+        perms = lib.orc_verify_batch_mt(O.vp(self.blobs), O.vp(self.off), self.n, O.vp(self.idx), O.vp(self.vals), self.idx.size,
+                                        O.vp(self.v), O.vp(self.s), self.cores)
+        bad = lib.orc_circuit_trace_mt(O.vp(self.ops), len(self.ops), O.vp(self.perms), len(self.perms), self.n_vars, O.vp(self.wiring),
+                                       self.n_rows, O.vp(self.flow_wire), self.n, self.cores)
+        assert bad == 0 and not self.v.any()
+        return perms + 2 * self.circuit_perms * self.n          # evaluation + check_poseidon_invocations
+
+
+def cpu_rate(n_proofs, seconds, cores):
+    cpu = CpuPath(n_proofs, cores)
+    cpu.step()
     reps, perms, t0 = 0, 0, time.perf_counter()
     while True:
-        perms += run()
+        perms += cpu.step()
         reps += 1
         if time.perf_counter() - t0 >= seconds:
             break
     dt = time.perf_counter() - t0
-    assert not v.any()
     return reps * n_proofs / dt, perms / dt, reps, dt
 
 
@@ -129,30 +153,22 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n = max(cores * 4, 64)
-    import oracle_py as O
-    lib = O.load_oracle()
-    lib.orc_verify_batch_mt.restype = ctypes.c_uint64
-    buf, ln = O.load_proof(FIXTURE)
-    blobs = np.tile(buf[:ln], n)
-    off = np.arange(n + 1, dtype=np.uint64) * ln
-    idx = np.array(O.INPUTS_SMALL[0], dtype=np.uint32)
-    vals = np.array(O.INPUTS_SMALL[1], dtype=np.uint32)
-    v, s = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    cpu = CpuPath(n, cores)
     perms = 0
     for _ in range(args.warmup):
-        lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
+        cpu.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        perms += lib.orc_verify_batch_mt(O.vp(blobs), O.vp(off), n, O.vp(idx), O.vp(vals), idx.size, O.vp(v), O.vp(s), cores)
+        perms += cpu.step()
     dt = time.perf_counter() - t0
-    assert not v.any()
     val = n * args.steps / dt
-    sample = "%d replicas of %s per step on %d pthreads (the GPU arm's step is %d per GPU)" % (n, FIXTURE, cores, args.proofs)
+    sample = "%d replicas of %s per step on %d pthreads: native verifier + circuit value log replay, checks and export " \
+             "(the GPU arm's step is %d per GPU)" % (n, FIXTURE, cores, args.proofs)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
-        "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full"},
+        "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full+trace"},
         "poseidon31_perms_per_sec": perms / dt,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,24 +240,40 @@ def main():
     n_total = args.proofs * world                       # weak scaling: --proofs per GPU
     lo, hi = sharding.shard_range(n_total, rank, world)
     vb = pkg.VerifyBatch([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
-    ws_mb = vb.ws_bytes >> 20
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)       # recorded once per shape (host)
+    ci = circ.info
+    ws_mb = (vb.ws_bytes + circ.workspace_bytes(hi - lo)) >> 20
     blob_mb = vb.h_words.numel() * 4 >> 20
+    trace_mb = (hi - lo) * 13 * ci.n_rows * 4 >> 20
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def local_step(pre=False):
         v, s = vb.run(full=True)
+        r = circ.trace(vb, check=True, export=True, preprocessed=pre)
+        # a proof counts when the native verdict is accept and both circuit checks pass (plumbing: 3 tiny elementwise ops)
+        bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
+        return torch.where(bad & (v == 0), torch.full_like(v, 1), v), s, r
+
+    def step():
+        v, s, _ = local_step()
         return sharding.gather_verdicts(v, s, n_total)
 
+    _, _, r0 = local_step(pre=True)           # the 10 preprocessed columns depend on the shape only: written once
     for _ in range(warmup):
         v, s = step()
     torch.cuda.synchronize()
     assert int(v.sum().item()) == 0 and v.numel() == n_total, "every replica of the fixture must be accepted"
+    # spot parity inside the bench: the exported trace of one proof against the committed golden digest
+    import hashlib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "trace_digests.json")))["chain"][0]
+    tr = pkg.VerifierCircuit.assemble_trace(r0["preprocessed"], r0["values"][(hi - lo) // 2])
+    assert hashlib.sha256(np.ascontiguousarray(tr, dtype="<u4").tobytes()).hexdigest() == gold["trace_sha256"], "trace differs from the golden"
     dt0 = vb.fetch(0, "detail")
-    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths
+    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths + 2 * ci.n_flow      # + tape evaluation + check_poseidon_invocations
     assert dt0.n_perms_paths == 3481, "permutation count of the per-query paths differs from the reference's (SURVEY App. C)"
 
     # ---- timed region: device-resident ----------------------------------------------------------------
@@ -268,18 +300,18 @@ def main():
     # ---- e2e: pinned host blobs -> device -> verdicts on the host, every step ---------------------------
     def e2e_step():
         vb.upload()
-        v, s = vb.run(full=True)
+        v, s, r = local_step()
         v, s = sharding.gather_verdicts(v, s, n_total)
-        return v.cpu(), s.cpu()
+        return v.cpu(), s.cpu(), r["bad_row"].cpu(), r["bad_flow"].cpu()
 
     for _ in range(2):
-        hv, hs = e2e_step()
-    assert int(hv.sum()) == 0
+        hv, hs, hb, hf = e2e_step()
+    assert int(hv.sum()) == 0 and int((hb != -1).sum()) == 0
     e2e_steps = max(2, args.steps // 2)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        hv, hs = e2e_step()
+        hv, hs, hb, hf = e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -287,7 +319,7 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / float(t_e.item())
     h2d = vb.h_words.numel() * 4 + vb.h_off.numel() * 8
-    d2h = 2 * n_total
+    d2h = 2 * n_total + 16 * (hi - lo)
 
     # ---- stage breakdown + roofline of the dominant kernel (CUDA events between the stage kernels) -------
     pk = peaks()
@@ -297,6 +329,9 @@ def main():
         vb.run(full=True, timed=True)
         for k, t in vb.stage_ms().items():
             acc[k] = acc.get(k, 0.0) + t / reps
+        circ.trace(vb, check=True, export=True, preprocessed=False, timed=True)
+        for k, t in circ.stage_ms().items():
+            acc["trace_" + k] = acc.get("trace_" + k, 0.0) + t / reps
     total_ms = sum(acc.values())
     dom = max(acc, key=acc.get)
     n_local = hi - lo
@@ -304,9 +339,12 @@ def main():
     # permutations each stage kernel executes per proof (counted by the kernels themselves)
     single_paths = sum(pkg.path_perms(pkg.PathShape.make(d, lay)) for d, lay in _tree_shapes(sh)) * sh.n_queries
     pair_paths = pkg.proof_perms(sh) - single_paths
-    perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths}
+    perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths,
+                "trace_eval": ci.n_flow, "trace_check_poseidon": ci.n_flow}
+    kernel_of = {"trace_eval": "k_tape_eval", "trace_check_poseidon": "k_cs_check_poseidon", "trace_export": "k_cs_export_vals_tiled",
+                 "trace_check_arithmetics": "k_cs_check_arith", "trace_gather": "k_gather_witness"}
     hints_total = dt0.n_perms_hints
-    if dom not in perms_of:
+    if dom in ("single_tree", "pair_tree"):
         # the two hint kernels split n_perms_hints; attribute by the per-query path permutations of their trees
         share = single_paths / float(single_paths + pair_paths)
         perms_of["single_tree"], perms_of["pair_tree"] = hints_total * share, hints_total * (1 - share)
@@ -315,7 +353,7 @@ def main():
     achieved = dom_rate * LANE_OPS_PER_PERM / 1e12
     path_bytes = n_local * sh.n_queries * (4 * (64 * 4 + 30 * 32))      # what the path kernels stream per proof (cols + siblings)
     roofline = {
-        "bound": "int32-issue", "kernel": "k_" + dom, "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
+        "bound": "int32-issue", "kernel": kernel_of.get(dom, "k_" + dom), "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
         "perms_per_launch": dom_perms, "launch_ms": acc[dom], "share_of_step": acc[dom] / total_ms, "traffic": None,
         "stage_ms": acc,
@@ -324,6 +362,12 @@ def main():
                 "peak_src": pk["src"], "note": "hashing is integer-bound; HBM figure shown for completeness"},
     }
 
+    # the HBM-bound kernel of the path: trace export, 3 x 16-byte variable reads + 13 x 4-byte column writes per (row, proof)
+    export_bytes = n_local * ci.n_rows * (3 * 16 + 13 * 4)
+    export_gbs = export_bytes / (acc["trace_export"] * 1e-3) / 1e9
+    roofline_export = {"bound": "hbm", "kernel": "k_cs_export_vals_tiled", "achieved": export_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                       "frac": export_gbs / pk["hbm_gbs"], "peak_src": pk["src"], "algorithmic_bytes_per_launch": export_bytes,
+                       "launch_ms": acc["trace_export"], "share_of_step": acc["trace_export"] / total_ms, "traffic": None}
     secondary = {}
     if not args.no_secondary and rank == 0:
         n_states = 1 << 22
@@ -347,24 +391,27 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (M31)", "data": "synthetic",
-            "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full",
+            "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full+trace",
+                       "circuit": {"rows": ci.n_rows, "rows_unpadded": ci.n_rows_unpadded, "variables": ci.n_vars, "poseidon_flow": ci.n_flow,
+                                   "tape_levels": ci.n_levels, "witness_words": ci.n_input_words},
                        "shape": dict(zip(("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last", "n_queries", "n_inner"), sh.key())),
                        "perms_per_proof": perms_per_proof,
-                       "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace per step" % (blob_mb, ws_mb),
+                       "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace + %d MB of trace columns per step" % (blob_mb, ws_mb, trace_mb),
                        "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only"},
             "poseidon31_perms_per_sec": value * perms_per_proof,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t_e.item()) / e2e_steps * 1e3},
             "roofline": roofline,
+            "roofline_export": roofline_export,
             "secondary": secondary,
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            rate, prate, reps_c, dtc = cpu_verify_rate(max(cores * 4, 64), args.cpu_seconds, cores)
+            rate, prate, reps_c, dtc = cpu_rate(max(cores * 4, 64), args.cpu_seconds, cores)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "poseidon31_perms_per_sec": prate,
-                                   "sample": "%d x %d replicas of %s with the oracle port on %d pthreads (%.1f s)" % (
-                                       reps_c, max(cores * 4, 64), FIXTURE, cores, dtc)}
+                                   "sample": "%d x %d replicas of %s with the oracle port (native verifier + circuit value-log replay, checks, "
+                                             "export) on %d pthreads (%.1f s)" % (reps_c, max(cores * 4, 64), FIXTURE, cores, dtc)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -149,6 +149,15 @@ int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *inpu
 uint64_t orc_verify_batch_mt(const uint8_t *blobs, const uint64_t *off, uint32_t n, const uint32_t *idx, const uint32_t *vals,
                              uint32_t n_inputs, uint8_t *verdict, uint8_t *stage, unsigned n_threads);
 
+/* ---- circuit value log replay (oracle/orc_tape.c; the log is recorded by oracle/orc_dsl.py) ---------------------------- */
+void orc_circuit_replay(const uint32_t *ops, uint32_t n_ops, const uint32_t *perms, uint32_t *vars, uint32_t *flow_hash, uint8_t *flow_swap);
+int64_t orc_circuit_check_arithmetics(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars);
+int64_t orc_circuit_check_poseidon(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars, uint32_t n_vars, const uint32_t *flow_wire,
+                                   uint32_t n_flow, const uint32_t *flow_hash, const uint8_t *flow_swap, uint32_t *row_of_wire);
+void orc_circuit_export_values(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars, uint32_t *out);
+int64_t orc_circuit_trace_mt(const uint32_t *ops, uint32_t n_ops, const uint32_t *perms, uint32_t n_perms, uint32_t n_vars,
+                             const uint32_t *wiring, uint32_t n_rows, const uint32_t *flow_wire, uint32_t n, unsigned n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,10 @@ def cp_gen(k):
 
 
 # ---- constraint system (constraint_system/src/plonk_with_poseidon.rs) ------------------------------------------------
+LOG_ADD, LOG_MUL, LOG_MULC, LOG_IN, LOG_INV_M31, LOG_INV_QM31, LOG_CINV_RE, LOG_CINV_IM, LOG_COORD, LOG_BIT, LOG_PERM = range(1, 12)
+NO_VAR = 0xFFFFFFFF
+
+
 class CS:
     def __init__(self):                                                  # :43-99
         self.variables = [Q0, Q1, (0, 1, 0, 0), (0, 0, 1, 0)]
@@ -138,6 +142,10 @@ class CS:
         self.num_input = 3
         self.mult_a = self.mult_b = self.mult_c = self.mult_poseidon = None
         self.n_perm = 0
+        # how every variable got its value, in creation order: [kind, dst, a, b, v0..v3] (orc_tape.c replays it in C as the
+        # CPU baseline of the circuit's value arithmetic).  kinds: LOG_*.
+        self.log = []
+        self.perm_log = []
 
     def _row(self, a, b, c, op, pw=0, enf=0):
         self.a_wire.append(a); self.b_wire.append(b); self.c_wire.append(c)
@@ -154,12 +162,14 @@ class CS:
     def add(self, a, b):                                                 # :141-150
         c = len(self.variables)
         self.variables.append(q_add(self.variables[a], self.variables[b]))
+        self.log.append((LOG_ADD, c, a, b, 0, 0, 0, 0))
         self.insert_gate(a, b, c, 1)
         return c
 
     def mul(self, a, b):                                                 # :173-182
         c = len(self.variables)
         self.variables.append(q_mul(self.variables[a], self.variables[b]))
+        self.log.append((LOG_MUL, c, a, b, 0, 0, 0, 0))
         self.insert_gate(a, b, c, 0)
         return c
 
@@ -167,18 +177,31 @@ class CS:
         k %= P
         c = len(self.variables)
         self.variables.append(q_scale(self.variables[a], k))
+        self.log.append((LOG_MULC, c, a, k, 0, 0, 0, 0))
         self.insert_gate(a, 0, c, k)
         return c
 
     def assemble_poseidon_gate(self, a, b):                              # :152-171
         c = len(self.variables)
         self.variables.append(q_mul(self.variables[a], self.variables[b]))
+        self.log.append((LOG_MUL, c, a, b, 0, 0, 0, 0))
         self._row(a, b, c, 0, pw=c)
         return c
 
-    def new_m31(self, v, mode):                                          # :194-233
+    def _log_def(self, c, src):
+        # src: None = taken from the proof / hint structs, (kind, a, b) = derived from an earlier variable, "perm" = logged by permute
+        if src is None:
+            self.log.append((LOG_IN, c, 0, 0) + tuple(self.variables[c]))
+        elif src != "perm":
+            self.log.append((src[0], c, src[1], src[2], 0, 0, 0, 0))
+
+    def new_m31(self, v, mode, src=None):                                # :194-233
         c = len(self.variables)
         self.variables.append(qm(v))
+        if mode == "constant":
+            self.log.append((LOG_MULC, c, 1, v % P, 0, 0, 0, 0))
+        else:
+            self._log_def(c, src)
         if mode == "input":
             self._row(c, 0, c, 1, enf=1)
             self.num_input += 1
@@ -188,9 +211,11 @@ class CS:
             self._row(1, 0, c, v)
         return c
 
-    def new_qm31(self, v, mode):                                         # :235-281
+    def new_qm31(self, v, mode, src=None):                               # :235-281
         c = len(self.variables)
         self.variables.append(tuple(v))
+        if mode != "constant":
+            self._log_def(c, src)
         if mode == "input":
             self._row(c, 0, c, 1, enf=1)
             self.num_input += 1
@@ -204,6 +229,7 @@ class CS:
             t = self.mul(si, 2)
             t = self.add(sr, t)
             b = self.mul(t, 3)
+            self.log.append((LOG_ADD, c, a, b, 0, 0, 0, 0))
             self._row(a, b, c, 1)
         return c
 
@@ -365,8 +391,8 @@ def qm31_one(cs):
     return V(cs, Q1, 1, 2)
 
 
-def m31_witness(cs, v):
-    return V(cs, qm(v), cs.new_m31(v % P, "witness"), 0)
+def m31_witness(cs, v, src=None):
+    return V(cs, qm(v), cs.new_m31(v % P, "witness", src), 0)
 
 
 def m31_constant(cs, v):                                                 # m31.rs:33-59
@@ -384,23 +410,23 @@ def m31_constant(cs, v):                                                 # m31.r
 
 
 def m31_inv(x):                                                          # m31.rs:136-143
-    r = m31_witness(x.cs, m_inv(x.value[0]))
+    r = m31_witness(x.cs, m_inv(x.value[0]), (LOG_INV_M31, x.variable, 0))
     x.cs.insert_gate(x.variable, r.variable, 1, 0)
     return r
 
 
-def cm31_witness(cs, v):                                                 # cm31.rs:27-37
-    re = m31_witness(cs, v[0])
-    im = m31_witness(cs, v[1])
+def cm31_witness(cs, v, src=(None, None)):                               # cm31.rs:27-37
+    re = m31_witness(cs, v[0], src[0])
+    im = m31_witness(cs, v[1], src[1])
     return V(cs, (v[0] % P, v[1] % P, 0, 0), cs.add(re.variable, cs.mul(im.variable, 2)), 1)
 
 
 def cm31_inv(x):                                                         # cm31.rs:238-243 (no constraint row!)
-    return cm31_witness(x.cs, c_inv(x.value[0:2]))
+    return cm31_witness(x.cs, c_inv(x.value[0:2]), ((LOG_CINV_RE, x.variable, 0), (LOG_CINV_IM, x.variable, 0)))
 
 
-def qm31_witness(cs, v):
-    return V(cs, tuple(v), cs.new_qm31(v, "witness"), 2)
+def qm31_witness(cs, v, src=None):
+    return V(cs, tuple(v), cs.new_qm31(v, "witness", src), 2)
 
 
 def qm31_constant(cs, v):                                                # qm31.rs:35-73
@@ -430,7 +456,7 @@ def qm31_from_m31(a0, a1, a2, a3):                                       # qm31.
 
 def qm31_decompose_m31(x):                                               # qm31.rs:258-272
     cs = x.cs
-    a = [m31_witness(cs, x.value[k]) for k in range(4)]
+    a = [m31_witness(cs, x.value[k], (LOG_COORD, x.variable, k)) for k in range(4)]
     l = cs.add(a[0].variable, cs.mul(a[1].variable, 2))
     r = cs.mul(cs.add(a[2].variable, cs.mul(a[3].variable, 2)), 3)
     cs.insert_gate(l, r, x.variable, 1)
@@ -445,7 +471,7 @@ def qm31_decompose_cm31(x):                                              # qm31.
 
 
 def qm31_inv(x):                                                         # qm31.rs:352-359
-    r = qm31_witness(x.cs, q_inv(x.value))
+    r = qm31_witness(x.cs, q_inv(x.value), (LOG_INV_QM31, x.variable, 0))
     x.cs.insert_gate(x.variable, r.variable, 1, 0)
     return r
 
@@ -467,10 +493,10 @@ class Bits:
         self.cs, self.value, self.variables = cs, list(value), list(variables)
 
     @staticmethod
-    def new_witness(cs, bools):                                          # :25-43
+    def new_witness(cs, bools, of=None):                                 # :25-43
         variables = []
-        for b in bools:
-            bit = cs.new_qm31(Q1 if b else Q0, "witness")
+        for k, b in enumerate(bools):
+            bit = cs.new_qm31(Q1 if b else Q0, "witness", None if of is None else (LOG_BIT, of, k))
             variables.append(bit)
             minus_one = m31_constant(cs, P - 1)
             bm1 = cs.add(bit, minus_one.variable)
@@ -482,7 +508,7 @@ class Bits:
         cs = v.cs
         cur = v.value[0]
         bools = [(cur >> k) & 1 != 0 for k in range(l)]
-        res = Bits.new_witness(cs, bools)
+        res = Bits.new_witness(cs, bools, v.variable)
         rec = V(cs, qm(1 if res.value[0] else 0), res.variables[0], 0)
         for i in range(1, l):
             t = V(cs, qm(1 if res.value[i] else 0), res.variables[i], 0).mul_constant_m31(1 << i)
@@ -539,9 +565,9 @@ class Half:
         return Half(cs, list(a.value) + list(b.value), a.variable, b.variable, sel)
 
     @staticmethod
-    def new_witness(cs, value):                                          # :146-166 (QM31 witnesses cost no rows)
-        left = qm31_witness(cs, value[0:4])
-        right = qm31_witness(cs, value[4:8])
+    def new_witness(cs, value, src=None):                                # :146-166 (QM31 witnesses cost no rows)
+        left = qm31_witness(cs, value[0:4], src)
+        right = qm31_witness(cs, value[4:8], src)
         sel = cs.assemble_poseidon_gate(left.variable, right.variable)
         return Half(cs, value, left.variable, right.variable, sel)
 
@@ -565,12 +591,24 @@ def permute(left, right, ignore_left, ignore_right, is_swap=None):       # posei
     state = (right.value + left.value) if swap else (left.value + right.value)
     state = poseidon2_permute(state)
     cs.n_perm += 1
-    outs = []
+    # value log: a half is two variables, or a literal (a sibling hash that exists only as a value)
+    rec = []
+    for h in (left, right):
+        if h.sel_value == 0 and (h.left_variable, h.right_variable) == (0, 0) and any(h.value):
+            rec += [1, 0, 0]
+        else:
+            rec += [0, h.left_variable, h.right_variable]
+    rec.append(is_swap[1] if is_swap is not None else NO_VAR)
+    cs.log.append((LOG_PERM, len(cs.perm_log), 0, 0, 0, 0, 0, 0))
+    outs, out_vars = [], []
     for ignore, half in ((ignore_left, state[0:8]), (ignore_right, state[8:16])):
         if ignore:
             outs.append(Half(cs, half, 0, 0, 0))
+            out_vars += [NO_VAR, NO_VAR]
         else:
-            outs.append(Half.new_witness(cs, half))
+            outs.append(Half.new_witness(cs, half, "perm"))
+            out_vars += [outs[-1].left_variable, outs[-1].right_variable]
+    cs.perm_log.append(rec + out_vars + [0] * 5 + list(left.value) + list(right.value))
     e = [(h.sel_value, list(h.value)) for h in (left, right, outs[0], outs[1])]
     cs.invoke_poseidon_accelerator(e[0], e[1], e[2], e[3], (is_swap[1], bool(is_swap[0])) if is_swap is not None else (0, False))
     return outs[0], outs[1]
@@ -1464,6 +1502,11 @@ def verifier_circuit(blob, inputs, multipliers=1, verify_out_cls=None, finalize=
         bad = cs.check_poseidon_invocations()
         assert bad < 0, "check_poseidon_invocations fails at entry %d" % bad
     return cs, out
+
+
+def value_log_arrays(cs):
+    """(ops [n, 8], perms [m, 32]) uint32: the value log in the layout oracle/orc_tape.c replays"""
+    return np.array(cs.log, dtype=np.uint32).reshape(-1, 8), np.array(cs.perm_log, dtype=np.uint32).reshape(-1, 32)
 
 
 def trace_digest(cols):
