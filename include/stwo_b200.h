@@ -261,10 +261,12 @@ int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo
 /* generate_plonk_with_poseidon_circuit (:521-628).  preprocessed (optional): 10 columns x n_rows in the struct-literal
  * order mult_a, mult_b, mult_c, poseidon_wire, mult_poseidon, enforce_c_m31, a_wire, b_wire, c_wire, op (wiring only;
  * op holds the shape constant).  values: per item 13 columns x n_rows, plain [item][column][row]: a_val_0..3, b_val_0..3,
- * c_val_0..3, then the item's op column (differs from the shared one only on op_follows_c rows). */
+ * c_val_0..3, then the item's op column (differs from the shared one only on op_follows_c rows).
+ * first_bad (optional, needs values): fuses check_arithmetics into the export pass -- the row's three variables are in
+ * registers anyway, which saves a full read of variables[]; same result as stwo_b200_cs_check_arithmetics_dev. */
 int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                       const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
-                                      uint32_t *preprocessed, uint32_t *values, void *stream);
+                                      uint32_t *preprocessed, uint32_t *values, int64_t *first_bad, void *stream);
 /* Host entry for ONE constraint system whose values were produced on the host (what the finalisation block of every
  * example does: cs.check_arithmetics(); cs.populate_logup_arguments(); cs.check_poseidon_invocations();
  * cs.generate_plonk_with_poseidon_circuit()  -- examples/single-proof/src/main.rs:85-90).  Pointers in w / v are HOST

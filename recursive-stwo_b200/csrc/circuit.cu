@@ -191,7 +191,9 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
     MARK();
     if ((rc = stwo_b200_cs_eval_tape_dev(&c->tape_, c->wiring.n_vars, k.witness, &v, st))) return rc;
     MARK();
-    if (flags & STWO_B200_TRACE_CHECK_ARITHMETICS)
+    // check_arithmetics rides on the export pass when the value columns are written anyway
+    const bool fuse_check = (flags & STWO_B200_TRACE_CHECK_ARITHMETICS) && values;
+    if ((flags & STWO_B200_TRACE_CHECK_ARITHMETICS) && !fuse_check)
         if ((rc = stwo_b200_cs_check_arithmetics_dev(&c->wiring, &v, bad_row, st))) return rc;
     MARK();
     const size_t nr = c->wiring.n_rows;
@@ -202,7 +204,8 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, st))) return rc;
     MARK();
     if (preprocessed || values)
-        if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, preprocessed, values, st))) return rc;
+        if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, preprocessed, values,
+                                                fuse_check ? bad_row : nullptr, st))) return rc;
     MARK();
 #undef MARK
     g_timed_valid = timed;

@@ -7,6 +7,7 @@
 // Layout: per-item arrays are lane-interleaved (tape.cuh) so a warp = 32 items touches contiguous runs.
 #include "common.cuh"
 #include "tape.cuh"
+#include <stdlib.h>
 
 using namespace stwo_b200;
 
@@ -51,6 +52,50 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__r
                 tape::eval(v, in, perms);
             }
         __syncthreads();
+    }
+}
+
+// Grid-wide variant for lanes = 32: the (group, instruction) pairs of a level are spread over every warp of a co-resident
+// grid (one CTA per SM, cooperative launch) and a grid barrier separates levels.  A level that holds one permutation per
+// group (the transcript chain) then keeps n_groups warps on n_groups different SMs busy instead of one warp per CTA, and
+// a batch smaller than 32 x #SM items still uses the whole GPU.
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned n_ctas, unsigned &phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        phase += 1;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = phase * n_ctas;
+        unsigned seen;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+    }
+    __syncthreads();
+}
+template <bool UNROLLED>
+__global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
+                                                                 const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
+                                                                 unsigned *barrier) {
+    const u32 lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const u32 n_groups = (b.n_batch + 31) / 32, n_warps = gridDim.x * (kEvalThreads / 32);
+    const u32 gw = warp * gridDim.x + blockIdx.x;            // consecutive work items land on different SMs
+    unsigned phase = 0;
+    for (u32 g = gw; g < n_groups; g += n_warps)
+        if (g * 32 + lane < b.n_batch) tape::prologue(b.view(g * 32 + lane, input, n_input_words));
+    grid_barrier(barrier, gridDim.x, phase);
+    for (u32 l = 0; l < n_levels; l++) {
+        const u32 lo = __ldg(level_start + l), hi = __ldg(level_start + l + 1);
+        const u32 n_items = (hi - lo) * n_groups;
+        for (u32 t = gw; t < n_items; t += n_warps) {
+            // group fastest: a warp's successive items (stride n_warps) walk through different instructions of the level, so
+            // permutations and cheap gates mix evenly; the groups of a one-instruction level land on different SMs
+            const u32 k = lo + t / n_groups, item = (t % n_groups) * 32 + lane;
+            if (item < b.n_batch) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
+                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms);
+            }
+        }
+        grid_barrier(barrier, gridDim.x, phase);
     }
 }
 
@@ -157,7 +202,7 @@ __global__ void __launch_bounds__(kT) k_cs_export_pre(stwo_b200_cs_wiring w, con
 
 constexpr int kCols = 13;            // a_val_0..3, b_val_0..3, c_val_0..3, op
 // lanes = 1: thread per (item, row); random 16-byte gathers, coalesced column stores
-__global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring w, Batch b, u32 *vals) {
+__global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring w, Batch b, u32 *vals, unsigned long long *first_bad) {
     const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
     if (g >= (size_t)w.n_rows * b.n_batch) return;
     const u32 item = (u32)(g / w.n_rows), i = (u32)(g % w.n_rows);
@@ -167,13 +212,16 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring
     const qm31_t a = tape::ldv(v, w.a_wire[i]), bb = tape::ldv(v, w.b_wire[i]), c = tape::ldv(v, w.c_wire[i]);
 #pragma unroll
     for (int k = 0; k < 4; k++) { o[k * n] = a.v[k]; o[(4 + k) * n] = bb.v[k]; o[(8 + k) * n] = c.v[k]; }
-    o[12 * n] = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : w.op[i];
+    const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : w.op[i];
+    o[12 * n] = op;
+    if (first_bad && !tape::gate_ok(a, bb, c, op, w.enforce_c_m31[i])) atomicMin(first_bad + item, (unsigned long long)i);
 }
 // lanes = 32: a CTA transposes a tile of 32 rows x 32 items through shared memory.  Load phase: a warp reads one row's
 // three variables for 32 items (3 x 512 contiguous bytes).  Store phase: a warp writes 32 consecutive rows of one
 // (item, column) = one 128-byte line.
 constexpr int kTileRows = 32;
-__global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring w, Batch b, u32 *vals) {
+// first_bad != nullptr fuses check_arithmetics into the pass (the three variables of the row are in registers anyway).
+__global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring w, Batch b, u32 *vals, unsigned long long *first_bad) {
     extern __shared__ u32 tile[];                        // [kCols][32 items][33]
     const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32, n_warps = kT / 32;
     const u32 row0 = blockIdx.x * kTileRows, grp = blockIdx.y;
@@ -189,7 +237,9 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring
                 tile[((4 + k) * 32 + lane) * 33 + r] = bb.v[k];
                 tile[((8 + k) * 32 + lane) * 33 + r] = c.v[k];
             }
-            tile[(12 * 32 + lane) * 33 + r] = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
+            const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
+            tile[(12 * 32 + lane) * 33 + r] = op;
+            if (first_bad && !tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i))) atomicMin(first_bad + item, (unsigned long long)i);
         }
     }
     __syncthreads();
@@ -224,10 +274,38 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     STWO_CHECK_DEVICE();
     if (!t || !values_ok(v) || n_vars < 4 || !t->ins || !t->level_start || (t->n_perms && !t->perms) || (t->n_input_words && !witness))
         return STWO_B200_E_BAD_ARG;
-    const Batch b = batch_of(v, n_vars, t->n_perms);
+    Batch b = batch_of(v, n_vars, t->n_perms);
     const u32 n_groups = (v->n_batch + v->lanes - 1) / v->lanes;
-    k_tape_eval<<<n_groups, kEvalThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const tape::Ins *>(t->ins), t->level_start, t->n_levels,
-                                                                     reinterpret_cast<const tape::Perm *>(t->perms), b, witness, t->n_input_words);
+    cudaStream_t st = (cudaStream_t)stream;
+    const tape::Ins *ins = reinterpret_cast<const tape::Ins *>(t->ins);
+    const tape::Perm *perms = reinterpret_cast<const tape::Perm *>(t->perms);
+    const u32 *level_start = t->level_start;
+    u32 n_levels = t->n_levels, n_input_words = t->n_input_words;
+    // grid-wide levels while the batch has fewer lane groups than a few waves of SMs; CTA-local levels beyond that
+    static int n_sm = 0, coop = 0, grid_mode = -1, unrolled = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        const char *e = getenv("STWO_B200_EVAL_MODE");        // "cta" / "grid": force one kernel (profiling)
+        if (e) grid_mode = e[0] == 'g' ? 1 : 0;
+        e = getenv("STWO_B200_EVAL_UNROLLED");                // "1": fully unrolled permutation inside the grid kernel (profiling)
+        if (e) unrolled = e[0] == '1';
+    }
+    const bool use_grid = v->lanes == 32 && coop && (grid_mode == 1 || (grid_mode < 0 && n_groups <= 8u * (u32)n_sm));
+    if (use_grid) {
+        static unsigned *barriers = nullptr;
+        static unsigned next = 0;
+        if (!barriers) STWO_CUDA(cudaMalloc(&barriers, 64 * sizeof(unsigned)));
+        unsigned *bar = barriers + (next++ % 64);
+        STWO_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        void *args[] = {(void *)&ins, (void *)&level_start, (void *)&n_levels, (void *)&perms, (void *)&b, (void *)&witness, (void *)&n_input_words, (void *)&bar};
+        const void *fn = unrolled ? (const void *)k_tape_eval_grid<true> : (const void *)k_tape_eval_grid<false>;
+        STWO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)n_sm), dim3(kEvalThreads), args, 0, st));
+    } else {
+        k_tape_eval<<<n_groups, kEvalThreads, 0, st>>>(ins, level_start, n_levels, perms, b, witness, n_input_words);
+    }
     note_launch(1);
     return cuda_status(cudaGetLastError());
 }
@@ -281,7 +359,7 @@ extern "C" int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w,
 }
 extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                                  const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
-                                                 uint32_t *preprocessed, uint32_t *values, void *stream) {
+                                                 uint32_t *preprocessed, uint32_t *values, int64_t *first_bad, void *stream) {
     STWO_CHECK_DEVICE();
     if (!wiring_ok(w) || !values_ok(v) || (!values && !preprocessed)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -290,9 +368,12 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
         k_cs_export_pre<<<nblk(w->n_rows), kT, 0, st>>>(*w, mult_a, mult_b, mult_c, mult_poseidon, preprocessed);
         note_launch(1);
     }
+    if (first_bad && !values) return STWO_B200_E_BAD_ARG;
     if (values) {
         const Batch b = batch_of(v, w->n_vars, w->n_flow);
-        if (v->lanes == 1) k_cs_export_vals_plain<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, b, values);
+        unsigned long long *fb = (unsigned long long *)first_bad;
+        if (fb) { k_fill64<<<nblk(v->n_batch), kT, 0, st>>>(fb, v->n_batch, ~0ull); note_launch(1); }
+        if (v->lanes == 1) k_cs_export_vals_plain<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, b, values, fb);
         else {
             const size_t smem = (size_t)kCols * 32 * 33 * 4;
             static bool attr_set = false;
@@ -301,7 +382,7 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
                 attr_set = true;
             }
             dim3 grid(w->n_rows / kTileRows, (v->n_batch + 31) / 32);
-            k_cs_export_vals_tiled<<<grid, kT, smem, st>>>(*w, b, values);
+            k_cs_export_vals_tiled<<<grid, kT, smem, st>>>(*w, b, values, fb);
         }
         note_launch(1);
     }
@@ -345,7 +426,7 @@ extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const st
     if ((rc = stwo_b200_cs_check_arithmetics_dev(&w, &v, bad, st))) return rc;
     if ((rc = stwo_b200_cs_populate_logup_dev(&w, m, m + nr, m + 2 * nr, m + 3 * nr, scr, stat, st))) return rc;
     if ((rc = stwo_b200_cs_check_poseidon_dev(&w, &v, m + 3 * nr, scr, bad + 1, st))) return rc;
-    if ((rc = stwo_b200_cs_export_trace_dev(&w, &v, m, m + nr, m + 2 * nr, m + 3 * nr, pre, vals, st))) return rc;
+    if ((rc = stwo_b200_cs_export_trace_dev(&w, &v, m, m + nr, m + 2 * nr, m + 3 * nr, pre, vals, nullptr, st))) return rc;
     int64_t hb[2];
     u32 hstat = 0;
     STWO_CUDA(cudaMemcpyAsync(hb, bad, 16, cudaMemcpyDeviceToHost, st));

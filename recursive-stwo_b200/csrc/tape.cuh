@@ -86,6 +86,7 @@ HD void load_half(const View &v, u32 kind, u32 a, u32 b, u32 *h) {
     }
 }
 
+template <bool UNROLLED>
 HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
     u32 st[16], in[16];
     load_half(v, p.l_kind, p.l_a, p.l_b, in);
@@ -96,7 +97,7 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];          // PoseidonEntry 1, 2: the halves as given
     }
-    poseidon2::permute<false>(st);
+    poseidon2::permute<UNROLLED>(st);
     if (v.flow_hash) {
         u32 *fh = v.flow_hash + ((size_t)entry * 32 + 16) * v.stride;
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = st[k];          // PoseidonEntry 3, 4: the full output
@@ -106,6 +107,7 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(st[4 * k], st[4 * k + 1], st[4 * k + 2], st[4 * k + 3]));
 }
 
+template <bool UNROLLED = false>
 HD void eval(const View &v, const Ins &in, const Perm *perms) {
     switch (in.op) {
     case T_ADD: stv(v, in.dst, qm31::add(ldv(v, in.a), ldv(v, in.b))); break;
@@ -119,20 +121,22 @@ HD void eval(const View &v, const Ins &in, const Perm *perms) {
     case T_INV_CM31_IM: stv(v, in.dst, qm31::from_m31(cm31::inv(qm31::lo(ldv(v, in.a))).b)); break;
     case T_COORD: stv(v, in.dst, qm31::from_m31(ldv(v, in.a).v[in.b & 3u])); break;
     case T_BIT: stv(v, in.dst, qm31::from_m31((ldv(v, in.a).v[0] >> (in.b & 31u)) & 1u)); break;
-    case T_POSEIDON: eval_poseidon(v, perms[in.dst], in.dst); break;
+    case T_POSEIDON: eval_poseidon<UNROLLED>(v, perms[in.dst], in.dst); break;
     default: break;
     }
 }
 
 // ---- the O(n_rows) loops of the constraint system, per batch item ------------------------------------------------------
 // check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): one row
-HD bool row_ok(const View &v, u32 a, u32 b, u32 c, u32 op, u32 enforce_c_m31, bool op_follows_c) {
-    const qm31_t va = ldv(v, a), vb = ldv(v, b), vc = ldv(v, c);
-    if (op_follows_c) op = vc.v[0];
+HD bool gate_ok(qm31_t va, qm31_t vb, qm31_t vc, u32 op, u32 enforce_c_m31) {
     const qm31_t want = qm31::add(qm31::mul_m31(qm31::add(va, vb), op), qm31::mul_m31(qm31::mul(va, vb), m31::subc(1, op)));
     bool ok = qm31::eq(want, vc);
     if (enforce_c_m31 && (vc.v[1] | vc.v[2] | vc.v[3])) ok = false;
     return ok;
+}
+HD bool row_ok(const View &v, u32 a, u32 b, u32 c, u32 op, u32 enforce_c_m31, bool op_follows_c) {
+    const qm31_t va = ldv(v, a), vb = ldv(v, b), vc = ldv(v, c);
+    return gate_ok(va, vb, vc, op_follows_c ? vc.v[0] : op, enforce_c_m31);
 }
 
 }  // namespace tape

@@ -120,3 +120,11 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
     }
 }
 }
+extern "C" void hs_circuit_level_perms(void *h, u32 *perms_per_level) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    for (u32 l = 0; l < r->n_levels(); l++) {
+        u32 n = 0;
+        for (u32 k = r->level_start[l]; k < r->level_start[l + 1]; k++) n += r->ins[k].op == tape::T_POSEIDON;
+        perms_per_level[l] = n;
+    }
+}
