@@ -152,6 +152,7 @@ uint64_t orc_verify_batch_mt(const uint8_t *blobs, const uint64_t *off, uint32_t
 /* ---- circuit value log replay (oracle/orc_tape.c; the log is recorded by oracle/orc_dsl.py) ---------------------------- */
 void orc_circuit_replay(const uint32_t *ops, uint32_t n_ops, const uint32_t *perms, uint32_t *vars, uint32_t *flow_hash, uint8_t *flow_swap);
 int64_t orc_circuit_check_arithmetics(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars);
+int64_t orc_circuit_check_arithmetics_without(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars);
 int64_t orc_circuit_check_poseidon(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars, uint32_t n_vars, const uint32_t *flow_wire,
                                    uint32_t n_flow, const uint32_t *flow_hash, const uint8_t *flow_swap, uint32_t *row_of_wire);
 void orc_circuit_export_values(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars, uint32_t *out);

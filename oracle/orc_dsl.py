@@ -133,6 +133,8 @@ NO_VAR = 0xFFFFFFFF
 
 
 class CS:
+    kind = "with"                                                        # ConstraintSystemType::PlonkWithPoseidon
+
     def __init__(self):                                                  # :43-99
         self.variables = [Q0, Q1, (0, 1, 0, 0), (0, 0, 1, 0)]
         self.cache = {}
@@ -331,6 +333,191 @@ class CS:
                 wire[i, k] = f[k][0]; h[i, 8 * k:8 * k + 8] = f[k][1]
             addr[i], sw[i] = f[4][0], 1 if f[4][1] else 0
         return wire, addr, h, sw
+
+
+def _poseidon2_constants():
+    """round constants out of include/stwo_b200_poseidon2_constants.h (= primitives/poseidon31/src/parameters.rs:6-190)"""
+    import re
+    txt = open(os.path.join(_HERE, "..", "include", "stwo_b200_poseidon2_constants.h")).read()
+    out = {}
+    for name in ("DIAG16", "RC_FIRST", "RC_PARTIAL", "RC_LAST"):
+        body = re.search(r"#define STWO_P2_%s \{(.*?)\}" % name, txt, re.S).group(1)
+        out[name] = [int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)u", body)]
+    return out
+
+
+_P2 = None
+
+
+def p2_constants():
+    global _P2
+    if _P2 is None:
+        _P2 = _poseidon2_constants()
+    return _P2
+
+
+LOG_M4, LOG_POW5M4, LOG_HADAMARD, LOG_GRANDSUM, LOG_POW4 = range(12, 17)
+
+
+def _m4(x):
+    t0 = (x[0] + x[1]) % P
+    t1 = (x[2] + x[3]) % P
+    t2 = (2 * x[1] + t1) % P
+    t3 = (2 * x[3] + t0) % P
+    t4 = (4 * t1 + t3) % P
+    t5 = (4 * t0 + t2) % P
+    return ((t3 + t5) % P, t5, (t2 + t4) % P, t4)
+
+
+def _had(a, b):
+    return tuple(a[k] * b[k] % P for k in range(4))
+
+
+class CSWithout(CS):
+    """constraint_system/src/plonk_without_poseidon.rs: rows carry four selectors (op1..op4) and five more gate kinds"""
+    kind = "without"
+
+    def __init__(self):                                                  # :33-90
+        CS.__init__(self)
+        self.op1, self.op2, self.op3, self.op4 = [1] * 4, [0] * 4, [0] * 4, [0] * 4
+        self.op = self.op1                                               # the arithmetic selector
+        del self.poseidon_wire, self.enforce_c_m31
+
+    def _row(self, a, b, c, op1, op2=0, op3=0, op4=0):
+        self.a_wire.append(a); self.b_wire.append(b); self.c_wire.append(c)
+        self.op1.append(op1 % P); self.op2.append(op2); self.op3.append(op3); self.op4.append(op4)
+
+    def _gate(self, kind, a, b, value, sel):
+        c = len(self.variables)
+        self.variables.append(value)
+        self.log.append((kind, c, a, b, 0, 0, 0, 0))
+        self._row(a, b, c, *sel)
+        return c
+
+    def do_m4_gate(self, a, b):                                          # :108-139 (b is not used by the value)
+        return self._gate(LOG_M4, a, b, _m4(self.variables[a]), (1, 0, 1, 0))
+
+    def do_pow5m4_gate(self, a, b):                                      # :140-173
+        return self._gate(LOG_POW5M4, a, b, _m4(_had(self.variables[a], self.variables[b])), (1, 1, 1, 0))
+
+    def do_pow5_gate(self, a, b):                                        # :174-198
+        return self._gate(LOG_HADAMARD, a, b, _had(self.variables[a], self.variables[b]), (1, 1, 0, 1))
+
+    def do_hadamard(self, a, b):                                         # :199-223
+        return self._gate(LOG_HADAMARD, a, b, _had(self.variables[a], self.variables[b]), (1, 0, 0, 1))
+
+    def do_grandsum_gate(self, a, b):                                    # :224-245
+        s = (sum(self.variables[a]) + sum(self.variables[b])) % P
+        return self._gate(LOG_GRANDSUM, a, b, (s, s, s, s), (1, 0, 1, 1))
+
+    def assemble_poseidon_gate(self, a, b):
+        raise NotImplementedError("unimplemented!() in the reference (constraint_system/src/lib.rs:267-277)")
+
+    def new_m31(self, v, mode, src=None):                                # :290-334
+        c = len(self.variables)
+        self.variables.append(qm(v))
+        if mode == "constant":
+            self.log.append((LOG_MULC, c, 1, v % P, 0, 0, 0, 0))
+            self._row(1, 0, c, v)
+        else:
+            self._log_def(c, src)
+            self._row(c, 1, c, 1, 0, 0, 1)                               # hadamard with variable 1 forces an M31
+            if mode == "input":
+                self.num_input += 1
+        return c
+
+    def new_qm31(self, v, mode, src=None):                               # :335-391
+        c = len(self.variables)
+        self.variables.append(tuple(v))
+        if mode == "constant":
+            fr, fi = self.new_m31(v[0], "constant"), self.new_m31(v[1], "constant")
+            sr, si = self.new_m31(v[2], "constant"), self.new_m31(v[3], "constant")
+            t = self.mul(fi, 2)
+            a = self.add(fr, t)
+            t = self.mul(si, 2)
+            t = self.add(sr, t)
+            b = self.mul(t, 3)
+            self.log.append((LOG_ADD, c, a, b, 0, 0, 0, 0))
+            self._row(a, b, c, 1)
+        else:
+            self._log_def(c, src)
+            self._row(c, 0, c, 1)
+            if mode == "input":
+                self.num_input += 1
+        return c
+
+    def pad(self):                                                       # :392-409
+        self.n_rows_unpadded, self.n_flow_unpadded, self.n_flow_padded = len(self.a_wire), 0, 0
+        n = len(self.a_wire)
+        for _ in range(n, 1 << (n - 1).bit_length()):
+            self._row(0, 0, 0, 1)
+
+    def check_arithmetics(self):                                         # :410-599
+        v = self.variables
+        for i in range(len(self.a_wire)):
+            a, b, c = v[self.a_wire[i]], v[self.b_wire[i]], v[self.c_wire[i]]
+            op1, sel = self.op1[i], (self.op2[i], self.op3[i], self.op4[i])
+            pow4 = tuple(pow(x, 4, P) for x in a)
+            had = _had(a, b)
+            if sel == (0, 0, 0):
+                want = q_add(q_scale(q_add(a, b), op1), q_scale(q_mul(a, b), (1 - op1) % P))
+            elif sel == (0, 0, 1):
+                want = had
+            elif sel == (1, 1, 0):
+                want = _m4(had)
+                if b != pow4:
+                    return i
+            elif sel == (1, 0, 1):
+                want = had
+                if b != pow4:
+                    return i
+            elif sel == (0, 1, 0):
+                want = _m4(had)
+            elif sel == (0, 1, 1):
+                s = (sum(a) + sum(b)) % P
+                want = (s, s, s, s)
+            else:
+                return i
+            if sel != (0, 0, 0) and op1 != 1:
+                return i
+            if want != c:
+                return i
+        return -1
+
+    def populate_logup_arguments(self):                                  # :600-632
+        nv, nr = len(self.variables), len(self.a_wire)
+        counts = [0] * nv
+        for i in range(nr):
+            counts[self.a_wire[i]] += 1; counts[self.b_wire[i]] += 1; counts[self.c_wire[i]] += 1
+        for i in range(self.num_input):
+            counts[i + 1] += 1
+        seen = [False] * nv
+        mc = []
+        for i in range(nr):
+            w = self.c_wire[i]
+            if not seen[w]:
+                mc.append(-(counts[w] - 1))
+                seen[w] = True
+            else:
+                mc.append(1)
+        self.mult_c = mc
+
+    def check_poseidon_invocations(self):
+        return -1                                                        # unimplemented!() for this system: nothing to check
+
+    def trace_columns(self):
+        """generate_plonk_without_poseidon_circuit (:633-713): uint32 [20, n_rows]: mult_c, a_wire, b_wire, c_wire, op1..op4,
+        a_val_0..3, b_val_0..3, c_val_0..3"""
+        n = len(self.a_wire)
+        out = np.zeros((20, n), dtype=np.uint32)
+        out[0] = np.array([x % P for x in self.mult_c], dtype=np.uint32)
+        out[1] = self.a_wire; out[2] = self.b_wire; out[3] = self.c_wire
+        out[4] = self.op1; out[5] = self.op2; out[6] = self.op3; out[7] = self.op4
+        va = np.array(self.variables, dtype=np.uint32)
+        out[8:12] = va[np.array(self.a_wire)].T
+        out[12:16] = va[np.array(self.b_wire)].T
+        out[16:20] = va[np.array(self.c_wire)].T
+        return out
 
 
 # ---- variables: one class, value = QM31 4-tuple; the m31_/cm31_/qm31_ prefix says which reference impl a helper follows ----
@@ -547,32 +734,50 @@ class Half:
         self.cs, self.value, self.left_variable, self.right_variable, self.sel_value = cs, list(value), l, r, sel
 
     @staticmethod
-    def single_use_witness_only(cs, value):                              # :51-60
+    def single_use_witness_only(cs, value):                              # :51-74
+        if cs.kind == "without":
+            return HalfE(cs, [qm31_witness(cs, value[0:4]), qm31_witness(cs, value[4:8])])
         return Half(cs, value, 0, 0, 0)
 
     @staticmethod
-    def from_m31(s):                                                     # :76-97
+    def from_m31(s):                                                     # :76-105
         cs = s[0].cs
         left = qm31_from_m31(s[0], s[1], s[2], s[3])
         right = qm31_from_m31(s[4], s[5], s[6], s[7])
+        if cs.kind == "without":
+            return HalfE(cs, [left, right])
         sel = cs.assemble_poseidon_gate(left.variable, right.variable)
         return Half(cs, [x.value[0] for x in s], left.variable, right.variable, sel)
 
     @staticmethod
-    def from_qm31(a, b):                                                 # :107-124
+    def from_qm31(a, b):                                                 # :107-131
         cs = a.cs
+        if cs.kind == "without":
+            return HalfE(cs, [a, b])
         sel = cs.assemble_poseidon_gate(a.variable, b.variable)
         return Half(cs, list(a.value) + list(b.value), a.variable, b.variable, sel)
+
+    @staticmethod
+    def new_variables(cs, value, mode):                                  # :142-188
+        mk = {"witness": qm31_witness, "input": qm31_input}[mode]
+        left, right = mk(cs, value[0:4]), mk(cs, value[4:8])
+        if cs.kind == "without":
+            return HalfE(cs, [left, right])
+        return Half(cs, value, left.variable, right.variable, cs.assemble_poseidon_gate(left.variable, right.variable))
 
     @staticmethod
     def new_witness(cs, value, src=None):                                # :146-166 (QM31 witnesses cost no rows)
         left = qm31_witness(cs, value[0:4], src)
         right = qm31_witness(cs, value[4:8], src)
+        if cs.kind == "without":
+            return HalfE(cs, [left, right])
         sel = cs.assemble_poseidon_gate(left.variable, right.variable)
         return Half(cs, value, left.variable, right.variable, sel)
 
     @staticmethod
     def zero(cs):                                                        # :191-218
+        if cs.kind == "without":
+            return HalfE(cs, [qm31_zero(cs), qm31_zero(cs)])
         if "poseidon2 zero_half" not in cs.cache:
             cs.cache["poseidon2 zero_half"] = cs.assemble_poseidon_gate(0, 0)
         return Half(cs, [0] * 8, 0, 0, cs.cache["poseidon2 zero_half"])
@@ -585,7 +790,116 @@ class Half:
         self.cs.insert_gate(self.right_variable, 0, o.right_variable, 1)
 
 
+class HalfE:
+    """Poseidon2HalfEmulatedVar (poseidon31/src/lib.rs:30-34): two QM31 limbs"""
+    __slots__ = ("cs", "elems")
+
+    def __init__(self, cs, elems):
+        self.cs, self.elems = cs, list(elems)
+
+    @property
+    def value(self):
+        return list(self.elems[0].value) + list(self.elems[1].value)
+
+    def to_qm31(self):
+        return list(self.elems)
+
+    def equalverify(self, o):
+        for a, b in zip(self.elems, o.elems):
+            a.equalverify(b)
+
+
+def qm31_input(cs, v):
+    return V(cs, tuple(v), cs.new_qm31(v, "input"), 2)
+
+
+def m31_input(cs, v):
+    return V(cs, qm(v), cs.new_m31(v % P, "input"), 0)
+
+
+def _e_m4(x):                                                            # emulated.rs:12-22
+    cs = x.cs
+    k = qm31_constant(cs, (1, 1, 1, 1))
+    var = cs.do_m4_gate(x.variable, k.variable)
+    return V(cs, cs.variables[var], var, 2)
+
+
+def _e_mds16(st):                                                        # emulated.rs:24-35
+    p = [_e_m4(x) for x in st]
+    t = p[0] + p[1]
+    t = t + p[2]
+    t = t + p[3]
+    return [p[0] + t, p[1] + t, p[2] + t, p[3] + t]
+
+
+def _pow4_witness(cs, var):
+    b = tuple(pow(x, 4, P) for x in cs.variables[var])
+    return qm31_witness(cs, b, (LOG_POW4, var, 0))
+
+
+def _e_pow5m4(x):                                                        # emulated.rs:37-61
+    cs = x.cs
+    b = _pow4_witness(cs, x.variable)
+    var = cs.do_pow5m4_gate(x.variable, b.variable)
+    return V(cs, cs.variables[var], var, 2)
+
+
+def _e_pow5(cs, var):                                                    # emulated.rs:63-78
+    b = _pow4_witness(cs, var)
+    return cs.do_pow5_gate(var, b.variable)
+
+
+def poseidon_permute_emulated(left, right, is_swap=None):                # emulated.rs:80-221
+    cs = left.cs
+    K = p2_constants()
+    if is_swap is not None:
+        bit = V(cs, qm(1 if is_swap[0] else 0), is_swap[1], 0)
+        rml = [right.elems[i] - left.elems[i] for i in range(2)]
+        rmlb = [rml[i] * bit for i in range(2)]
+        nl = [rmlb[i] + left.elems[i] for i in range(2)]
+        nr = [right.elems[i] - rmlb[i] for i in range(2)]
+    else:
+        nl, nr = list(left.elems), list(right.elems)
+    st = [nl[0], nl[1], nr[0], nr[1]]
+    st = _e_mds16(st)
+
+    def full_rounds(st, rc):
+        for r in range(4):
+            for i in range(4):
+                st[i] = st[i] + qm31_constant(cs, tuple(rc[16 * r + 4 * i:16 * r + 4 * i + 4]))
+            for i in range(4):
+                st[i] = _e_pow5m4(st[i])
+            t = st[0] + st[1]
+            t = t + st[2]
+            t = t + st[3]
+            st = [st[0] + t, st[1] + t, st[2] + t, st[3] + t]
+        return st
+    st = full_rounds(st, K["RC_FIRST"])
+    for r in range(14):
+        first_only = cs.do_hadamard(st[0].variable, 1)
+        k = qm31_constant(cs, (0, 1, 1, 1))
+        without_first = cs.do_hadamard(st[0].variable, k.variable)
+        k = m31_constant(cs, K["RC_PARTIAL"][r])
+        first_only = cs.add(first_only, k.variable)
+        first_only = _e_pow5(cs, first_only)
+        tmp = cs.add(first_only, without_first)
+        st[0] = V(cs, cs.variables[tmp], tmp, 2)
+        s1 = cs.do_grandsum_gate(st[0].variable, st[1].variable)
+        s2 = cs.do_grandsum_gate(st[2].variable, st[3].variable)
+        total = cs.add(s1, s2)
+        for i in range(4):
+            k = qm31_constant(cs, tuple(K["DIAG16"][4 * i:4 * i + 4]))
+            v = cs.do_hadamard(st[i].variable, k.variable)
+            v = cs.add(total, v)
+            st[i] = V(cs, cs.variables[v], v, 2)
+    st = full_rounds(st, K["RC_LAST"])
+    cs.n_perm += 1
+    return HalfE(cs, [st[0], st[1]]), HalfE(cs, [st[2], st[3]])
+
+
 def permute(left, right, ignore_left, ignore_right, is_swap=None):       # poseidon31/src/lib.rs:282-407
+    if isinstance(left, HalfE):
+        return poseidon_permute_emulated(left, right, is_swap)
     cs = left.cs
     swap = is_swap is not None and is_swap[0]
     state = (right.value + left.value) if swap else (left.value + right.value)
@@ -1311,7 +1625,7 @@ class PairVar:
         self_hash.equalverify(root)
 
 
-def answers(cs, pv, shape, fs, hints, oods_witness):
+def answers(cs, pv, shape, fs, hints, oods_witness, last_decommit=None):
     """AnswerResults::compute (components/recursive/answer/src/lib.rs:34-354)"""
     nq = shape.n_queries
     # shifted mask points: shift sets in first-appearance order (0, -1); Plonk before Poseidon (see module docstring)
@@ -1336,25 +1650,28 @@ def answers(cs, pv, shape, fs, hints, oods_witness):
                     key = "zero" if s == 0 else (s, comp_log)            # ShiftIndex::from_shift
                     entries.append((key, shifted[(comp, s)], v))
             samples.append((shape.column_log_sizes[t][c], entries))
-    lo = shape.log_last + shape.blowup + 1
+    lo = (shape.blowup + 1) if last_decommit is not None else (shape.log_last + shape.blowup + 1)
     qpos = query_positions_per_log_size(lo, shape.max_first, fs["raw_queries"])
     if len({q.bits.get_value() for q in qpos[shape.max_first]}) != nq:
         raise NotImplementedError("duplicated queries at the largest size (answer/src/lib.rs:190-195)")
-    # DecommitmentVar::new: per tree, per query: sibling hashes (values only), column witnesses in ascending layer order
     tree_depth = [max(shape.log_plonk, shape.log_poseidon) + shape.blowup] * 3 + [shape.max_first]
-    dec = []
-    for t in range(4):
-        per_q = []
-        for i in range(nq):
-            sp = SinglePath(hints, t, i, qpos[tree_depth[t]][i].bits.get_value())
-            sib = [Half.single_use_witness_only(cs, s) for s in sp.sibling_hashes]
-            cols = {k: [m31_witness(cs, v) for v in vs] for k, vs in sorted(sp.columns.items())}
-            per_q.append((sp, sib, cols))
-        dec.append(per_q)
-    for t in range(4):
-        for i in range(nq):
-            sp, sib, cols = dec[t][i]
-            single_path_verify(cs, sp, sib, cols, pv.commitments[t], qpos[tree_depth[t]][i].bits)
+    if last_decommit is not None:
+        dec = last_decommit(tree_depth, qpos)                            # LastDecommitVar::compute
+    else:
+        # DecommitmentVar::new: per tree, per query: sibling hashes (values only), column witnesses in ascending layer order
+        dec = []
+        for t in range(4):
+            per_q = []
+            for i in range(nq):
+                sp = SinglePath(hints, t, i, qpos[tree_depth[t]][i].bits.get_value())
+                sib = [Half.single_use_witness_only(cs, s) for s in sp.sibling_hashes]
+                cols = {k: [m31_witness(cs, v) for v in vs] for k, vs in sorted(sp.columns.items())}
+                per_q.append((sp, sib, cols))
+            dec.append(per_q)
+        for t in range(4):
+            for i in range(nq):
+                sp, sib, cols = dec[t][i]
+                single_path_verify(cs, sp, sib, cols, pv.commitments[t], qpos[tree_depth[t]][i].bits)
     queried = {}
     for L in shape.all_log_sizes:
         queried[L] = [[v for t in range(4) for v in dec[t][i][2].get(L, [])] for i in range(nq)]
@@ -1501,6 +1818,179 @@ def verifier_circuit(blob, inputs, multipliers=1, verify_out_cls=None, finalize=
         cs.populate_logup_arguments()
         bad = cs.check_poseidon_invocations()
         assert bad < 0, "check_poseidon_invocations fails at entry %d" % bad
+    return cs, out
+
+
+# ---- the last-layer circuit (components/last/*, examples/last-layer/src/main.rs:26-94) --------------------------------
+def native_hash_rate(words):
+    """Poseidon31MerkleHasher::hash_column_get_capacity then permute_get_rate([0; 8] || capacity)
+    (last/fiat_shamir/src/lib.rs:46-54, last/answer/src/data_structures/merkle_proofs.rs:190-195)"""
+    arr = np.ascontiguousarray(words, dtype=np.uint32)
+    cap = np.zeros(8, dtype=np.uint32)
+    _orc().orc_hash_column_get_capacity(arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arr.size), cap.ctypes.data_as(ctypes.c_void_p))
+    return poseidon2_permute([0] * 8 + [int(x) for x in cap])[0:8]
+
+
+def pack_columns(values):
+    """LastSinglePathMerkleProofInput::from_proof (merkle_proofs.rs:170-206): <= 4 values one QM31, <= 8 two, else their hash"""
+    if len(values) <= 4:
+        v = list(values) + [0] * (4 - len(values))
+        return [tuple(v)]
+    if len(values) <= 8:
+        v = list(values) + [0] * (8 - len(values))
+        return [tuple(v[0:4]), tuple(v[4:8])]
+    h = native_hash_rate(values)
+    return [tuple(h[0:4]), tuple(h[4:8])]
+
+
+def last_layer_circuit(blob, verify_out_cls, finalize=True):
+    """examples/last-layer/src/main.rs:26-97 on a Poseidon31 proof (the hybrid SHA-256 channel of hybrid_hash.bin is
+    parity-unpinned; the circuit itself never replays the channel -- every Fiat-Shamir value is a public input)."""
+    p = parse_proof(blob)
+    shape = Shape(p)
+    out, hints = compute_hints(blob, ([i for i, _ in INPUTS_RECURSIVE], [list(v) for _, v in INPUTS_RECURSIVE]), verify_out_cls)
+    assert out.verdict == 0
+    nq = shape.n_queries
+    cs = CSWithout()
+    tree_depth = [max(shape.log_plonk, shape.log_poseidon) + shape.blowup] * 3 + [shape.max_first]
+    pos_max = [int(out.query_pos[0][i]) for i in range(nq)]
+    # ---- public inputs, in the order of main.rs:62-69 --------------------------------------------------------------
+    flat_words = [w for tree in p.sampled_values for col in tree for v in col for w in v]
+    inp = {}
+    inp["t"] = qm31_input(cs, tuple(out.oods_t))                        # LastFiatShamirInputVar (last/fiat_shamir/src/lib.rs:104-150)
+    inp["sampled_values_hash"] = Half.new_variables(cs, native_hash_rate(flat_words), "input")
+    inp["plonk_total_sum"] = qm31_input(cs, p.plonk_total_sum)
+    inp["poseidon_total_sum"] = qm31_input(cs, p.poseidon_total_sum)
+    inp["z"] = qm31_input(cs, tuple(out.z))
+    inp["alpha"] = qm31_input(cs, tuple(out.alpha))
+    inp["random_coeff"] = qm31_input(cs, tuple(out.random_coeff))
+    inp["after"] = qm31_input(cs, tuple(out.after_coeff))
+    inp["packed_queries"] = [qm31_input(cs, tuple((pos_max[k:k + 4] + [0, 0, 0])[:4])) for k in range(0, nq, 4)]
+    inp["fri_alphas"] = [qm31_input(cs, tuple(out.fri_alphas[k])) for k in range(len(p.inner_layers) + 1)]
+    paths = [[SinglePath(hints, t, i, None) for i in range(nq)] for t in range(4)]
+    dec_in = [[{k: [qm31_input(cs, q) for q in pack_columns(vs)] for k, vs in sorted(paths[t][i].columns.items())} for i in range(nq)]
+              for t in range(4)]                                         # LastDecommitInputVar
+    pairs0 = [SinglePair(hints, 0, i, None) for i in range(nq)]
+
+    def pair_input(sp):
+        self_c = {k: qm31_input(cs, v) for k, v in sorted(sp.self_columns.items())}
+        sib_c = {k: qm31_input(cs, v) for k, v in sorted(sp.siblings_columns.items())}
+        return self_c, sib_c
+    first_in = [pair_input(sp) for sp in pairs0]                         # LastFirstLayerInputVar
+    inner_in = {}                                                        # LastInnerLayersInputVar: BTreeMap, ascending log size
+    n_inner = len(p.inner_layers)
+    for li in range(n_inner - 1, -1, -1):
+        inner_in[shape.max_first - 1 - li] = [pair_input(SinglePair(hints, 1 + li, k, None)) for k in range(nq)]
+    n_public = cs.num_input
+    # ---- LastPlonkWithPoseidonProofVar::new_witness (last/data_structures/src/lib.rs:28-82) ---------------------------
+    class PV:
+        pass
+    pv = PV()
+    pv.p = p
+    pv.log_size_plonk = m31_witness(cs, p.log_size_plonk)
+    pv.log_size_poseidon = m31_witness(cs, p.log_size_poseidon)
+    pv.plonk_total_sum = qm31_witness(cs, p.plonk_total_sum)
+    pv.poseidon_total_sum = qm31_witness(cs, p.poseidon_total_sum)
+    pv.sampled_values = [[[qm31_witness(cs, v) for v in col] for col in tree] for tree in p.sampled_values]
+    pv.last_poly = [qm31_witness(cs, c) for c in p.last_coeffs]
+    marks = [("alloc", len(cs.a_wire))]
+    # ---- LastFiatShamirResults::compute (last/fiat_shamir/src/lib.rs:164-216) ---------------------------------------------
+    oods_point = PointQM31.from_t(inp["t"])
+    flat = [v for tree in pv.sampled_values for col in tree for v in col]
+    hash_qm31_columns_get_rate(flat).equalverify(inp["sampled_values_hash"])
+    z, alpha = inp["z"], inp["alpha"]
+    alpha_powers = [qm31_one(cs), alpha, alpha * alpha]
+    queries = []
+    for packed in inp["packed_queries"]:
+        queries += qm31_decompose_m31(packed)
+    queries = queries[:nq]
+    input_sum = qm31_zero(cs)
+    s1 = (qm31_one(cs) + alpha) - z
+    input_sum = input_sum + qm31_inv(s1)
+    alpha_two = alpha + alpha
+    s2 = (V(cs, (0, 1, 0, 0), 2, 2) + alpha_two) - z
+    input_sum = input_sum + qm31_inv(s2)
+    alpha_three = alpha_two + alpha
+    s3 = (V(cs, (0, 0, 1, 0), 3, 2) + alpha_three) - z
+    input_sum = input_sum + qm31_inv(s3)
+    ((input_sum + inp["poseidon_total_sum"]) + inp["plonk_total_sum"]).equalverify(qm31_zero(cs))
+    fs = dict(z=z, alpha=alpha, alpha_powers=alpha_powers, random_coeff=inp["random_coeff"], after=inp["after"], oods_point=oods_point,
+              raw_queries=queries, fri_alphas=inp["fri_alphas"])
+    marks.append(("fiat_shamir", len(cs.a_wire)))
+
+    # ---- LastAnswerResults::compute (last/answer/src/lib.rs:30-262) ----------------------------------------------------------
+    def last_decommit(depths, qpos):
+        """LastDecommitVar::compute / LastSinglePathMerkleProofVar::from_proof_and_input (merkle_proofs.rs:114-160)"""
+        dec = []
+        for t in range(4):
+            per_q = []
+            for i in range(nq):
+                cols = {}
+                for L, vs in sorted(paths[t][i].columns.items()):
+                    vars_ = [m31_witness(cs, v) for v in vs]
+                    packed = dec_in[t][i][L]
+                    if len(vars_) <= 8:
+                        for k in range(0, len(vars_), 4):
+                            d = qm31_decompose_m31(packed[k // 4])
+                            for l, r in zip(vars_[k:k + 4], d):
+                                l.equalverify(r)
+                    else:
+                        h = hash_m31_columns_get_rate(vars_).to_qm31()
+                        h[0].equalverify(packed[0])
+                        h[1].equalverify(packed[1])
+                    cols[L] = vars_
+                per_q.append((None, None, cols))
+            dec.append(per_q)
+        return dec
+    ans = answers(cs, pv, shape, fs, hints, oods_point, last_decommit)
+    marks.append(("answer", len(cs.a_wire)))
+    # ---- LastFoldingResults::compute (last/folding/src/lib.rs:14-161) ----------------------------------------------------
+    qpos = ans["qpos"]
+    for L in sorted(shape.all_log_sizes, reverse=True):
+        for i in range(nq):
+            first_in[i][0][L].equalverify(ans["fri_answers"][L][i])
+    folded_results = {}
+    for L in shape.all_log_sizes:
+        res = []
+        for (self_c, sib_c), q in zip(first_in, qpos[L]):
+            point = q.point.double()
+            y_inv = m31_inv(point.y)
+            l, r = qm31_swap(self_c[L], sib_c[L], q.bits.value[0], q.bits.variables[0])
+            nl = l + r
+            nr = (l - r) * y_inv
+            res.append(nl + (nr * fs["fri_alphas"][shape.max_first - L]))
+        folded_results[L] = res
+    log_size = shape.max_first
+    folded = [qm31_zero(cs) for _ in range(nq)]
+    for i in range(n_inner):
+        if log_size in folded_results:
+            a = fs["fri_alphas"][i]
+            a = a * a
+            folded = [(a * v) + b for v, b in zip(folded, folded_results[log_size])]
+        log_size -= 1
+        new_folded = []
+        for k in range(nq):
+            q = qpos[log_size][k]
+            self_c, sib_c = inner_in[log_size][k]
+            folded[k].equalverify(self_c[log_size])
+            x_inv = m31_inv(q.point.x)
+            l, r = qm31_swap(self_c[log_size], sib_c[log_size], q.bits.value[0], q.bits.variables[0])
+            nl = l + r
+            nr = (l - r) * x_inv
+            new_folded.append(nl + (nr * fs["fri_alphas"][i + 1]))
+        folded = new_folded
+    for q, v in zip(qpos[log_size], folded):
+        if len(pv.last_poly) == 1:
+            v.equalverify(pv.last_poly[0])
+        else:
+            v.equalverify(line_poly_eval_at_point(cs, pv.last_poly, q.get_next_point_x()))
+    marks.append(("folding", len(cs.a_wire)))
+    cs.marks, cs.n_public_inputs = marks, n_public
+    if finalize:
+        cs.pad()
+        bad = cs.check_arithmetics()
+        assert bad < 0, "check_arithmetics fails at row %d" % bad
+        cs.populate_logup_arguments()
     return cs, out
 
 

@@ -14,9 +14,23 @@
 #include <string.h>
 #include "orc.h"
 
-enum { LOG_ADD = 1, LOG_MUL, LOG_MULC, LOG_IN, LOG_INV_M31, LOG_INV_QM31, LOG_CINV_RE, LOG_CINV_IM, LOG_COORD, LOG_BIT, LOG_PERM };
+enum { LOG_ADD = 1, LOG_MUL, LOG_MULC, LOG_IN, LOG_INV_M31, LOG_INV_QM31, LOG_CINV_RE, LOG_CINV_IM, LOG_COORD, LOG_BIT, LOG_PERM,
+       LOG_M4, LOG_POW5M4, LOG_HADAMARD, LOG_GRANDSUM, LOG_POW4 };   /* the last five: constraint_system/src/plonk_without_poseidon.rs:108-245 */
 #define NO_VAR 0xffffffffu
 
+/* the M4 MDS block on the four coordinates (plonk_without_poseidon.rs:115-125) */
+static qm31 q_m4(qm31 x) {
+    m31 t0 = m31_add(x.v[0], x.v[1]), t1 = m31_add(x.v[2], x.v[3]);
+    m31 t2 = m31_add(m31_dbl(x.v[1]), t1), t3 = m31_add(m31_dbl(x.v[3]), t0);
+    m31 t4 = m31_add(m31_dbl(m31_dbl(t1)), t3), t5 = m31_add(m31_dbl(m31_dbl(t0)), t2);
+    return qm31_mk(m31_add(t3, t5), t5, m31_add(t2, t4), t4);
+}
+static qm31 q_had(qm31 a, qm31 b) { return qm31_mk(m31_mul(a.v[0], b.v[0]), m31_mul(a.v[1], b.v[1]), m31_mul(a.v[2], b.v[2]), m31_mul(a.v[3], b.v[3])); }
+static qm31 q_pow4(qm31 a) { qm31 s = q_had(a, a); return q_had(s, s); }
+static qm31 q_grandsum(qm31 a, qm31 b) {
+    m31 s = m31_add(m31_add(m31_add(a.v[0], a.v[1]), m31_add(a.v[2], a.v[3])), m31_add(m31_add(b.v[0], b.v[1]), m31_add(b.v[2], b.v[3])));
+    return qm31_mk(s, s, s, s);
+}
 static qm31 ldq(const uint32_t *vars, uint32_t i) { return qm31_mk(vars[4 * i], vars[4 * i + 1], vars[4 * i + 2], vars[4 * i + 3]); }
 static void stq(uint32_t *vars, uint32_t i, qm31 q) { memcpy(vars + 4 * i, q.v, 16); }
 
@@ -38,6 +52,11 @@ void orc_circuit_replay(const uint32_t *ops, uint32_t n_ops, const uint32_t *per
         case LOG_CINV_IM: stq(vars, dst, qm31_from_m31(cm31_inv(qm31_lo(ldq(vars, a))).b)); break;
         case LOG_COORD: stq(vars, dst, qm31_from_m31(vars[4 * a + b])); break;
         case LOG_BIT: stq(vars, dst, qm31_from_m31((vars[4 * a] >> b) & 1u)); break;
+        case LOG_M4: stq(vars, dst, q_m4(ldq(vars, a))); break;
+        case LOG_POW5M4: stq(vars, dst, q_m4(q_had(ldq(vars, a), ldq(vars, b)))); break;
+        case LOG_HADAMARD: stq(vars, dst, q_had(ldq(vars, a), ldq(vars, b))); break;
+        case LOG_GRANDSUM: stq(vars, dst, q_grandsum(ldq(vars, a), ldq(vars, b))); break;
+        case LOG_POW4: stq(vars, dst, q_pow4(ldq(vars, a))); break;
         case LOG_PERM: {
             const uint32_t *p = perms + 32 * dst;
             uint32_t in[16], st[16];
@@ -67,6 +86,30 @@ int64_t orc_circuit_check_arithmetics(const uint32_t *wiring, uint32_t n_rows, c
         const qm31 want = qm31_add(qm31_mul_m31(qm31_add(a, b), op[i]), qm31_mul_m31(qm31_mul(a, b), m31_sub(1, op[i])));
         if (!qm31_eq(want, c)) return i;
         if (enf[i] && (c.v[1] | c.v[2] | c.v[3])) return i;
+    }
+    return -1;
+}
+
+/* Plonk-without-Poseidon system (plonk_without_poseidon.rs:410-599): wiring = 7 x n_rows words (a_wire, b_wire, c_wire, op1..op4) */
+int64_t orc_circuit_check_arithmetics_without(const uint32_t *wiring, uint32_t n_rows, const uint32_t *vars) {
+    const uint32_t *aw = wiring, *bw = wiring + n_rows, *cw = wiring + 2 * (size_t)n_rows, *op1 = wiring + 3 * (size_t)n_rows,
+                   *op2 = wiring + 4 * (size_t)n_rows, *op3 = wiring + 5 * (size_t)n_rows, *op4 = wiring + 6 * (size_t)n_rows;
+    for (uint32_t i = 0; i < n_rows; i++) {
+        const qm31 a = ldq(vars, aw[i]), b = ldq(vars, bw[i]), c = ldq(vars, cw[i]);
+        const uint32_t sel = op2[i] * 4 + op3[i] * 2 + op4[i];
+        qm31 want;
+        if (op2[i] > 1 || op3[i] > 1 || op4[i] > 1) return i;
+        if (sel && op1[i] != 1) return i;
+        switch (sel) {
+        case 0: want = qm31_add(qm31_mul_m31(qm31_add(a, b), op1[i]), qm31_mul_m31(qm31_mul(a, b), m31_sub(1, op1[i]))); break;
+        case 1: want = q_had(a, b); break;                              /* hadamard */
+        case 6: want = q_m4(q_had(a, b)); if (!qm31_eq(b, q_pow4(a))) return i; break;   /* pow5m4 */
+        case 5: want = q_had(a, b); if (!qm31_eq(b, q_pow4(a))) return i; break;         /* pow5 */
+        case 2: want = q_m4(q_had(a, b)); break;                        /* m4 (b = (1,1,1,1)) */
+        case 3: want = q_grandsum(a, b); break;
+        default: return i;
+        }
+        if (!qm31_eq(want, c)) return i;
     }
     return -1;
 }

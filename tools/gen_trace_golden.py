@@ -32,5 +32,12 @@ for src, mult, nxt in CHAIN:
                 "trace_sha256": D.trace_digest(cs.trace_columns()), "flow_hash_sha256": D.trace_digest(h),
                 "flow_wire_sha256": D.trace_digest(wire)})
     print(out[-1])
-json.dump({"generator": "tools/gen_trace_golden.py", "rows_per_permutation": 6, "chain": out},
+last = []
+for name in ["level13-1.bin", "level12-1.bin", "level10-1.bin"]:
+    blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+    cs, vo = D.last_layer_circuit(blob, O.VerifyOut)
+    last.append({"src": name, "rows": cs.n_rows_unpadded, "log_rows": len(cs.a_wire).bit_length() - 1, "vars": len(cs.variables),
+                 "public_inputs": cs.num_input, "emulated_permutations": cs.n_perm, "trace_sha256": D.trace_digest(cs.trace_columns())})
+    print(last[-1])
+json.dump({"generator": "tools/gen_trace_golden.py", "rows_per_permutation": 6, "chain": out, "last_layer": last},
           open(os.path.join(ROOT, "tests", "golden", "trace_digests.json"), "w"), indent=1)
