@@ -20,6 +20,7 @@ namespace stwo_b200 {
 namespace dsl {
 
 enum class AllocationMode { PublicInput, Witness, Constant };    // constraint_system/src/var.rs:13-18
+enum class ConstraintSystemType { PlonkWithPoseidon, PlonkWithoutPoseidon };   // constraint_system/src/lib.rs:24-28
 
 struct QM31Const { u32 v[4]; };
 
@@ -42,8 +43,11 @@ struct SwapOption { u32 addr; bool has_swap; };
 
 class ConstraintSystem {
 public:
-    // wiring (shared by every batch item of the shape)
-    std::vector<u32> a_wire, b_wire, c_wire, poseidon_wire, enforce_c_m31, op;
+    ConstraintSystemType type = ConstraintSystemType::PlonkWithPoseidon;
+    bool without() const { return type == ConstraintSystemType::PlonkWithoutPoseidon; }
+    // wiring (shared by every batch item of the shape).  Plonk-without-Poseidon (plonk_without_poseidon.rs:12-25): `op` is
+    // op1 and op2..op4 select the gate; poseidon_wire / enforce_c_m31 stay zero.
+    std::vector<u32> a_wire, b_wire, c_wire, poseidon_wire, enforce_c_m31, op, op2, op3, op4;
     std::vector<uint8_t> op_follows_c;              // rows whose op constant is the selected VALUE (circle/src/lib.rs:80-92)
     std::vector<u32> flow_wire;                     // n_flow x 4
     std::vector<u32> flow_swap_addr;                // n_flow
@@ -55,7 +59,7 @@ public:
     u32 n_rows_unpadded = 0, n_flow_unpadded = 0;
     std::unordered_map<std::string, u32> cache;
 
-    ConstraintSystem() {                            // plonk_with_poseidon.rs:43-99
+    explicit ConstraintSystem(ConstraintSystemType t = ConstraintSystemType::PlonkWithPoseidon) : type(t) {   // plonk_with_poseidon.rs:43-99
         n_vars = 4;                                 // 0, 1, i, j: written by the evaluator's prologue
         for (u32 k = 0; k < 4; k++) row(k, 0, k, 1);
     }
@@ -64,8 +68,23 @@ public:
         if (padded) throw std::logic_error("constraint system already padded");
         a_wire.push_back(a); b_wire.push_back(b); c_wire.push_back(c);
         poseidon_wire.push_back(pw); enforce_c_m31.push_back(enf); op.push_back(op_ % M31_P);
+        op2.push_back(0); op3.push_back(0); op4.push_back(0);
         op_follows_c.push_back(follows ? 1 : 0);
     }
+    // a row of one of the five special gates of the Plonk-without-Poseidon system: selectors (1, s2, s3, s4)
+    u32 special_gate(u32 tape_op, u32 a, u32 b, u32 s2, u32 s3, u32 s4) {
+        if (!without()) throw std::logic_error("unimplemented!() for the Plonk-with-Poseidon system (constraint_system/src/lib.rs:114-152)");
+        is_program_started = true;
+        const u32 c = fresh(tape_op, a, b);
+        row(a, b, c, 1);
+        op2.back() = s2; op3.back() = s3; op4.back() = s4;
+        return c;
+    }
+    u32 do_m4_gate(u32 a, u32 b) { return special_gate(tape::T_M4, a, b, 0, 1, 0); }             // plonk_without_poseidon.rs:108-139
+    u32 do_pow5m4_gate(u32 a, u32 b) { return special_gate(tape::T_POW5M4, a, b, 1, 1, 0); }     // :140-173
+    u32 do_pow5_gate(u32 a, u32 b) { return special_gate(tape::T_HADAMARD, a, b, 1, 0, 1); }     // :174-198
+    u32 do_hadamard(u32 a, u32 b) { return special_gate(tape::T_HADAMARD, a, b, 0, 0, 1); }      // :199-223
+    u32 do_grandsum_gate(u32 a, u32 b) { return special_gate(tape::T_GRANDSUM, a, b, 0, 1, 1); } // :224-245
     u32 fresh(u32 op_, u32 a, u32 b) {
         const u32 c = n_vars++;
         if (op_ != tape::T_NONE) tape_.push_back({op_, c, a, b});
@@ -87,6 +106,7 @@ public:
         return c;
     }
     u32 assemble_poseidon_gate(u32 a, u32 b) {                       // :152-171
+        if (without()) throw std::logic_error("unimplemented!() for the Plonk-without-Poseidon system (constraint_system/src/lib.rs:267-277)");
         const u32 c = fresh(tape::T_MUL, a, b);
         is_program_started = true;
         row(a, b, c, 0, c);
@@ -105,17 +125,21 @@ public:
             num_input += 1;
         } else is_program_started = true;
         const u32 c = fresh(d.op, d.a, d.b);
-        row(c, 0, c, 1, 0, 1);
+        if (without()) { row(c, 1, c, 1); op4.back() = 1; }          // hadamard with variable 1 (plonk_without_poseidon.rs:294-318)
+        else row(c, 0, c, 1, 0, 1);
         return c;
     }
-    u32 new_qm31(const Def &d, AllocationMode mode) {                // :235-255
+    u32 new_qm31(const Def &d, AllocationMode mode) {                // :235-255; plonk_without_poseidon.rs:335-363
         if (mode == AllocationMode::Constant) throw std::logic_error("constants carry a value, not a definition");
         const u32 c = fresh(d.op, d.a, d.b);
         if (mode == AllocationMode::PublicInput) {
             if (is_program_started) throw std::logic_error("public inputs must be allocated first");
-            row(c, 0, c, 1, 0, 1);
+            if (without()) row(c, 0, c, 1); else row(c, 0, c, 1, 0, 1);
             num_input += 1;
-        } else is_program_started = true;
+        } else {
+            is_program_started = true;
+            if (without()) row(c, 0, c, 1);                          // a QM31 witness costs a row in this system
+        }
         return c;
     }
     u32 new_qm31_constant(const QM31Const &v) {                      // :256-277
@@ -163,6 +187,10 @@ public:
 struct ConstraintSystemRef {
     std::shared_ptr<ConstraintSystem> p;
     static ConstraintSystemRef new_plonk_with_poseidon_ref() { return {std::make_shared<ConstraintSystem>()}; }
+    static ConstraintSystemRef new_plonk_without_poseidon_ref() {
+        return {std::make_shared<ConstraintSystem>(ConstraintSystemType::PlonkWithoutPoseidon)};
+    }
+    ConstraintSystemType get_type() const { return p->type; }
     ConstraintSystem *operator->() const { return p.get(); }
     bool operator==(const ConstraintSystemRef &o) const { return p == o.p; }
     const ConstraintSystemRef &and_(const ConstraintSystemRef &o) const {

@@ -11,6 +11,7 @@
 #include <map>
 
 #include "fields.hpp"
+#include "../../../include/stwo_b200_poseidon2_constants.h"
 
 namespace stwo_b200 {
 namespace dsl {
@@ -63,6 +64,17 @@ struct IsSwap { bool some; u32 bit_variable; };
 inline IsSwap no_swap() { return {false, 0}; }
 inline IsSwap swap_by(u32 bit_variable) { return {true, bit_variable}; }
 
+// round constants as shape constants of the emulated permutation (primitives/poseidon31/src/parameters.rs:6-190)
+namespace p2k {
+static const u32 DIAG16[16] = STWO_P2_DIAG16;
+static const u32 RC_FIRST[64] = STWO_P2_RC_FIRST;
+static const u32 RC_PARTIAL[14] = STWO_P2_RC_PARTIAL;
+static const u32 RC_LAST[64] = STWO_P2_RC_LAST;
+}  // namespace p2k
+
+// Native (Plonk-with-Poseidon: an accelerator flow entry) or emulated (Plonk-without-Poseidon: two QM31 limbs and ~401
+// rows of m4 / pow5m4 / pow5 / hadamard / grandsum gates per permutation), chosen by the constraint system's type like the
+// reference's enum Poseidon2HalfVar { Native, Emulated } (primitives/poseidon31/src/lib.rs:16-34).
 struct Poseidon2HalfVar {
     enum Kind { Variables, InputWords, Ignored };
     ConstraintSystemRef cs;
@@ -72,20 +84,24 @@ struct Poseidon2HalfVar {
 
     // a Merkle sibling: value only, no variables, usable once (:51-60)
     static Poseidon2HalfVar new_single_use_witness_only(const ConstraintSystemRef &cs, u32 input_slot) {
+        if (cs->without()) return new_variables(cs, input_slot, AllocationMode::Witness);
         Poseidon2HalfVar h; h.cs = cs; h.kind = InputWords; h.input_slot = input_slot; return h;
     }
-    static Poseidon2HalfVar from_m31(const M31Var *s) {                                   // :76-97
+    static Poseidon2HalfVar from_m31(const M31Var *s) {                                   // :76-105
         const QM31Var left = QM31Var::from_m31(s[0], s[1], s[2], s[3]);
         const QM31Var right = QM31Var::from_m31(s[4], s[5], s[6], s[7]);
         return assemble(left.cs, left.variable, right.variable);
     }
-    static Poseidon2HalfVar from_qm31(const QM31Var &a, const QM31Var &b) { return assemble(a.cs.and_(b.cs), a.variable, b.variable); }   // :107-124
-    // AllocVar::new_variables(Witness): two QM31 witnesses (no rows) + the assembling row (:146-166)
-    static Poseidon2HalfVar new_witness(const ConstraintSystemRef &cs, u32 input_slot) {
-        const QM31Var l = QM31Var::new_witness(cs, Def::input_qm31(input_slot)), r = QM31Var::new_witness(cs, Def::input_qm31(input_slot + 4));
-        return assemble(cs, l.variable, r.variable);
+    static Poseidon2HalfVar from_qm31(const QM31Var &a, const QM31Var &b) { return assemble(a.cs.and_(b.cs), a.variable, b.variable); }   // :107-131
+    // AllocVar::new_variables: two QM31 variables (+ the assembling row in the native case) (:142-188)
+    static Poseidon2HalfVar new_variables(const ConstraintSystemRef &cs, u32 input_slot, AllocationMode mode) {
+        const u32 l = cs->new_qm31(Def::input_qm31(input_slot), mode), r = cs->new_qm31(Def::input_qm31(input_slot + 4), mode);
+        return assemble(cs, l, r);
     }
+    static Poseidon2HalfVar new_witness(const ConstraintSystemRef &cs, u32 input_slot) { return new_variables(cs, input_slot, AllocationMode::Witness); }
+    static Poseidon2HalfVar new_public_input(const ConstraintSystemRef &cs, u32 input_slot) { return new_variables(cs, input_slot, AllocationMode::PublicInput); }
     static Poseidon2HalfVar zero(const ConstraintSystemRef &cs) {                         // :191-218
+        if (cs->without()) { Poseidon2HalfVar h; h.cs = cs; return h; }
         u32 sel;
         if (!cs.get_cache("poseidon2 zero_half", sel)) {
             sel = cs->assemble_poseidon_gate(0, 0);
@@ -106,6 +122,7 @@ struct Poseidon2HalfVar {
     static std::pair<Poseidon2HalfVar, Poseidon2HalfVar> permute(const Poseidon2HalfVar &left, const Poseidon2HalfVar &right,
                                                                  bool ignore_left_result, bool ignore_right_result, IsSwap is_swap) {
         const ConstraintSystemRef &cs = left.cs.and_(right.cs);
+        if (cs->without()) return poseidon_permute_emulated(left, right, is_swap);
         tape::Perm p{};
         left.describe(p.l_kind, p.l_a, p.l_b);
         right.describe(p.r_kind, p.r_a, p.r_b);
@@ -133,10 +150,91 @@ struct Poseidon2HalfVar {
     static Poseidon2HalfVar swap_permute_get_rate(const Poseidon2HalfVar &l, const Poseidon2HalfVar &r, IsSwap s) { return permute(l, r, false, true, s).first; }
     static Poseidon2HalfVar swap_permute_get_capacity(const Poseidon2HalfVar &l, const Poseidon2HalfVar &r, IsSwap s) { return permute(l, r, true, false, s).second; }
 
+    // ---- primitives/poseidon31/src/emulated.rs:12-221 -----------------------------------------------------------------
+    static QM31Var apply_4x4_mds_matrix(const QM31Var &x) {
+        const QM31Var constant = QM31Var::new_constant(x.cs, {{1, 1, 1, 1}});
+        return {x.cs, x.cs->do_m4_gate(x.variable, constant.variable)};
+    }
+    static void apply_16x16_mds_matrix(QM31Var *state) {
+        const QM31Var p1 = apply_4x4_mds_matrix(state[0]), p2 = apply_4x4_mds_matrix(state[1]);
+        const QM31Var p3 = apply_4x4_mds_matrix(state[2]), p4 = apply_4x4_mds_matrix(state[3]);
+        QM31Var t = p1 + p2;
+        t = t + p3;
+        t = t + p4;
+        state[0] = p1 + t; state[1] = p2 + t; state[2] = p3 + t; state[3] = p4 + t;
+    }
+    static QM31Var pow4_witness(const ConstraintSystemRef &cs, u32 variable) { return QM31Var::new_witness(cs, {tape::T_POW4, variable, 0}); }
+    static QM31Var pow5m4(const QM31Var &x) {
+        const QM31Var b = pow4_witness(x.cs, x.variable);
+        return {x.cs, x.cs->do_pow5m4_gate(x.variable, b.variable)};
+    }
+    static u32 pow5(const ConstraintSystemRef &cs, u32 variable) {
+        const QM31Var b = pow4_witness(cs, variable);
+        return cs->do_pow5_gate(variable, b.variable);
+    }
+    static void full_rounds(const ConstraintSystemRef &cs, QM31Var *state, const u32 *rc) {
+        for (u32 r = 0; r < 4; r++) {
+            for (u32 i = 0; i < 4; i++) {
+                const u32 *k = rc + 16 * r + 4 * i;
+                const QM31Var c = QM31Var::new_constant(cs, {{k[0], k[1], k[2], k[3]}});
+                state[i] = state[i] + c;
+            }
+            for (u32 i = 0; i < 4; i++) state[i] = pow5m4(state[i]);
+            QM31Var t = state[0] + state[1];
+            t = t + state[2];
+            t = t + state[3];
+            const QM31Var s0 = state[0] + t, s1 = state[1] + t, s2 = state[2] + t, s3 = state[3] + t;
+            state[0] = s0; state[1] = s1; state[2] = s2; state[3] = s3;
+        }
+    }
+    static std::pair<Poseidon2HalfVar, Poseidon2HalfVar> poseidon_permute_emulated(const Poseidon2HalfVar &left, const Poseidon2HalfVar &right,
+                                                                                   IsSwap is_swap) {
+        const ConstraintSystemRef &cs = left.cs;
+        QM31Var le[2] = {QM31Var(cs, left.left_variable), QM31Var(cs, left.right_variable)};
+        QM31Var re[2] = {QM31Var(cs, right.left_variable), QM31Var(cs, right.right_variable)};
+        QM31Var state[4];
+        if (is_swap.some) {
+            // (right - left) * bit + left
+            const M31Var bit_var(cs, is_swap.bit_variable);
+            const QM31Var d0 = re[0] - le[0], d1 = re[1] - le[1];
+            const QM31Var db0 = d0 * bit_var, db1 = d1 * bit_var;
+            const QM31Var nl0 = db0 + le[0], nl1 = db1 + le[1];
+            const QM31Var nr0 = re[0] - db0, nr1 = re[1] - db1;
+            state[0] = nl0; state[1] = nl1; state[2] = nr0; state[3] = nr1;
+        } else { state[0] = le[0]; state[1] = le[1]; state[2] = re[0]; state[3] = re[1]; }
+        apply_16x16_mds_matrix(state);
+        full_rounds(cs, state, p2k::RC_FIRST);
+        for (u32 r = 0; r < 14; r++) {
+            u32 first_limb_with_first_only = cs->do_hadamard(state[0].variable, 1);
+            const QM31Var mask = QM31Var::new_constant(cs, {{0, 1, 1, 1}});
+            const u32 first_limb_without_first = cs->do_hadamard(state[0].variable, mask.variable);
+            const M31Var rc = M31Var::new_constant(cs, p2k::RC_PARTIAL[r]);
+            first_limb_with_first_only = cs->add(first_limb_with_first_only, rc.variable);
+            first_limb_with_first_only = pow5(cs, first_limb_with_first_only);
+            state[0] = QM31Var(cs, cs->add(first_limb_with_first_only, first_limb_without_first));
+            const u32 sum_1 = cs->do_grandsum_gate(state[0].variable, state[1].variable);
+            const u32 sum_2 = cs->do_grandsum_gate(state[2].variable, state[3].variable);
+            const u32 sum = cs->add(sum_1, sum_2);
+            for (u32 i = 0; i < 4; i++) {
+                const u32 *k = p2k::DIAG16 + 4 * i;
+                const QM31Var diag = QM31Var::new_constant(cs, {{k[0], k[1], k[2], k[3]}});
+                u32 v = cs->do_hadamard(state[i].variable, diag.variable);
+                v = cs->add(sum, v);
+                state[i] = QM31Var(cs, v);
+            }
+        }
+        full_rounds(cs, state, p2k::RC_LAST);
+        Poseidon2HalfVar out_left, out_right;
+        out_left.cs = out_right.cs = cs;
+        out_left.left_variable = state[0].variable; out_left.right_variable = state[1].variable;
+        out_right.left_variable = state[2].variable; out_right.right_variable = state[3].variable;
+        return {out_left, out_right};
+    }
+
 private:
     static Poseidon2HalfVar assemble(const ConstraintSystemRef &cs, u32 l, u32 r) {
         Poseidon2HalfVar h; h.cs = cs; h.left_variable = l; h.right_variable = r;
-        h.sel_value = cs->assemble_poseidon_gate(l, r);
+        if (!cs->without()) h.sel_value = cs->assemble_poseidon_gate(l, r);      // the emulated half is just its two limbs
         return h;
     }
     void describe(u32 &kind_, u32 &a, u32 &b) const {

@@ -1,7 +1,7 @@
 // A recorded circuit in the flat form the device consumes: wiring columns, the levelised tape, permutation records
 // and (for the verifier circuit) the witness-stream gather table.  Host only; built once per shape.
 #pragma once
-#include "recursive_verifier.hpp"
+#include "last_layer.hpp"
 
 namespace stwo_b200 {
 namespace dsl {
@@ -11,6 +11,8 @@ struct RecordedCircuit {
     std::vector<u32> gather;
     u32 words_per_instance = 0, multipliers = 1;
     ProofShape shape{};
+    std::vector<ExtraHashJob> jobs;        // last-layer circuit: public-input hashes computed on the device before the gather
+    u32 n_extra_words = 0;
     // tape sorted by dependency level: instructions of one level are independent of each other
     std::vector<tape::Ins> ins;
     std::vector<u32> level_start;          // n_levels + 1
@@ -25,9 +27,10 @@ struct RecordedCircuit {
             const tape::Ins &in = c.tape_[k];
             u32 l = 0;
             switch (in.op) {
-            case tape::T_ADD: case tape::T_MUL: l = std::max(lv(in.a), lv(in.b)); break;
+            case tape::T_ADD: case tape::T_MUL: case tape::T_POW5M4: case tape::T_HADAMARD: case tape::T_GRANDSUM:
+                l = std::max(lv(in.a), lv(in.b)); break;
             case tape::T_MULC: case tape::T_INV_M31: case tape::T_INV_QM31: case tape::T_INV_CM31_RE: case tape::T_INV_CM31_IM:
-            case tape::T_COORD: case tape::T_BIT: l = lv(in.a); break;
+            case tape::T_COORD: case tape::T_BIT: case tape::T_M4: case tape::T_POW4: l = lv(in.a); break;
             case tape::T_POSEIDON: {
                 const tape::Perm &p = c.perms[in.dst];
                 if (p.l_kind == 0) l = std::max(l, std::max(lv(p.l_a), lv(p.l_b)));
@@ -60,6 +63,16 @@ inline std::unique_ptr<RecordedCircuit> record_verifier(const ProofShape &shape,
     std::unique_ptr<RecordedCircuit> r(new RecordedCircuit());
     r->cs = vc.cs; r->gather = std::move(vc.gather); r->words_per_instance = vc.words_per_instance;
     r->multipliers = multipliers; r->shape = shape;
+    r->levelise();
+    return r;
+}
+
+inline std::unique_ptr<RecordedCircuit> record_last_layer(const ProofShape &shape) {
+    LastLayerCircuit lc = record_last_layer_circuit(shape);
+    std::unique_ptr<RecordedCircuit> r(new RecordedCircuit());
+    r->cs = lc.cs; r->gather = std::move(lc.gather); r->words_per_instance = lc.cs->n_input_words;
+    r->multipliers = 1; r->shape = shape;
+    r->jobs = std::move(lc.jobs); r->n_extra_words = lc.n_extra_words;
     r->levelise();
     return r;
 }

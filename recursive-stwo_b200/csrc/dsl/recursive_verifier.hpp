@@ -13,6 +13,8 @@
 // gather word (tape::Src) that names a section of the proof blob or of the batched verifier's workspace (verify.cuh),
 // which already holds every hint (per-query Merkle paths, pair openings, OODS point).
 #pragma once
+#include <functional>
+
 #include "gadgets.hpp"
 
 namespace stwo_b200 {
@@ -461,14 +463,10 @@ struct SinglePathMerkleProofVar {
     std::vector<HashVar> sibling_hashes;
     std::map<u32, std::vector<M31Var>> columns;
 
-    // hint layout of the batched verifier: cols_of(p, t, i) = leaf layer first then the smaller layer; sib_of = 8 words per level
-    static SinglePathMerkleProofVar new_(WitnessStream &w, const ShapeFacts &f, u32 t, u32 i) {
-        const ConstraintSystemRef &cs = w.cs;
-        SinglePathMerkleProofVar v;
-        v.depth = f.tree_depth(t);
-        for (u32 k = 0; k < v.depth; k++) v.sibling_hashes.push_back(HashVar::new_single_use_witness_only(cs, w.take(tape::S_PATH_SIB, t, i, 8 * k, 8)));
-        // columns per layer, ascending layer order (BTreeMap iteration); offset inside the hint = descending layer order
-        std::map<u32, std::pair<u32, u32>> layers;                    // log size -> (offset in cols_of, count)
+    // columns per layer, ascending layer order (BTreeMap iteration): log size -> (offset in cols_of, count); the hint holds
+    // the layers in descending order
+    static std::map<u32, std::pair<u32, u32>> layer_layout(const ShapeFacts &f, u32 t) {
+        std::map<u32, std::pair<u32, u32>> layers;
         if (t == 3) layers[f.max_first] = {0, 8};
         else {
             const u32 np = ShapeFacts::plonk_cols(t), ns = ShapeFacts::n_cols(t) - np;
@@ -476,7 +474,15 @@ struct SinglePathMerkleProofVar {
             else if (f.log_plonk > f.log_pos) { layers[f.log_plonk] = {0, np}; layers[f.log_pos] = {np, ns}; }
             else { layers[f.log_pos] = {0, ns}; layers[f.log_plonk] = {ns, np}; }
         }
-        for (const auto &l : layers) {
+        return layers;
+    }
+    // hint layout of the batched verifier: cols_of(p, t, i) = leaf layer first then the smaller layer; sib_of = 8 words per level
+    static SinglePathMerkleProofVar new_(WitnessStream &w, const ShapeFacts &f, u32 t, u32 i) {
+        const ConstraintSystemRef &cs = w.cs;
+        SinglePathMerkleProofVar v;
+        v.depth = f.tree_depth(t);
+        for (u32 k = 0; k < v.depth; k++) v.sibling_hashes.push_back(HashVar::new_single_use_witness_only(cs, w.take(tape::S_PATH_SIB, t, i, 8 * k, 8)));
+        for (const auto &l : layer_layout(f, t)) {
             std::vector<M31Var> col;
             for (u32 k = 0; k < l.second.second; k++) col.push_back(M31Var::new_witness(cs, Def::input_m31(w.take(tape::S_PATH_COL, t, i, l.second.first + k, 1))));
             v.columns[l.first] = col;
@@ -551,8 +557,33 @@ struct AnswerResults {
 
     static std::array<CM31Var, 2> dec(const QM31Var &q) { return q.decompose_cm31(); }
 
+    using SampledValues = std::vector<std::vector<std::vector<QM31Var>>>;
+    using Columns = std::map<u32, std::vector<M31Var>>;                                  // layer log size -> opened column values
+    // decommit(query positions) -> [tree][query] columns: DecommitmentVar::new + verify in the recursive circuit,
+    // LastDecommitVar::compute in the last-layer circuit
+    using DecommitFn = std::function<std::vector<std::vector<Columns>>(const QueryPositionsPerLogSizeVar &)>;
+
     static AnswerResults compute(WitnessStream &w, const CirclePointQM31Var &oods_point, const ShapeFacts &f, const FiatShamirResults &fs,
                                  const PlonkWithPoseidonProofVar &proof) {               // answer/src/lib.rs:34-354
+        const u32 nq = f.s.n_queries;
+        return compute_with(w, oods_point, f, fs.raw_queries, fs.after_sampled_values_random_coeff, proof.sampled_values,
+                            f.s.log_last + f.s.log_blowup + 1, [&](const QueryPositionsPerLogSizeVar &qp) {
+            // DecommitmentVar::new, then the four verify loops (:201-247)
+            std::vector<std::vector<SinglePathMerkleProofVar>> dec_proofs(4);
+            for (u32 t = 0; t < 4; t++)
+                for (u32 i = 0; i < nq; i++) dec_proofs[t].push_back(SinglePathMerkleProofVar::new_(w, f, t, i));
+            std::vector<std::vector<Columns>> cols(4);
+            for (u32 t = 0; t < 4; t++)
+                for (u32 i = 0; i < nq; i++) {
+                    dec_proofs[t][i].verify(proof.commitments[t], qp[f.tree_depth(t)][i].bits);
+                    cols[t].push_back(dec_proofs[t][i].columns);
+                }
+            return cols;
+        });
+    }
+    static AnswerResults compute_with(WitnessStream &w, const CirclePointQM31Var &oods_point, const ShapeFacts &f, const std::vector<M31Var> &raw_queries,
+                                      const QM31Var &after_sampled_values_random_coeff, const SampledValues &sampled_values, u32 min_degree,
+                                      const DecommitFn &decommit) {
         const ConstraintSystemRef &cs = w.cs;
         const u32 nq = f.s.n_queries;
         // The reference iterates a HashSet of mask shifts here, i.e. in a per-process random order; this build fixes
@@ -568,7 +599,7 @@ struct AnswerResults {
         for (u32 t = 0; t < 4; t++)
             for (u32 c = 0; c < ShapeFacts::n_cols(t); c++) {
                 std::vector<PointSampleVar> e;
-                const auto &col = proof.sampled_values[t][c];
+                const auto &col = sampled_values[t][c];
                 if (t == 0 || t == 3) e.push_back({0, &oods_point, col[0]});              // mask_points[PREPROCESSED] / composition
                 else {
                     const u32 comp = c < ShapeFacts::plonk_cols(t) ? 0 : 1;
@@ -582,22 +613,17 @@ struct AnswerResults {
                 samples.push_back({f.column_log_size(t, c), e});
             }
         AnswerResults r;
-        r.query_positions_per_log_size.reset(new QueryPositionsPerLogSizeVar(f.s.log_last + f.s.log_blowup + 1, f.max_first, fs.raw_queries));
+        r.query_positions_per_log_size.reset(new QueryPositionsPerLogSizeVar(min_degree, f.max_first, raw_queries));
         const QueryPositionsPerLogSizeVar &qp = *r.query_positions_per_log_size;
-        // DecommitmentVar::new, then the four verify loops (:201-247)
-        std::vector<std::vector<SinglePathMerkleProofVar>> dec_proofs(4);
-        for (u32 t = 0; t < 4; t++)
-            for (u32 i = 0; i < nq; i++) dec_proofs[t].push_back(SinglePathMerkleProofVar::new_(w, f, t, i));
-        for (u32 t = 0; t < 4; t++)
-            for (u32 i = 0; i < nq; i++) dec_proofs[t][i].verify(proof.commitments[t], qp[f.tree_depth(t)][i].bits);
+        const std::vector<std::vector<Columns>> dec_cols = decommit(qp);
         std::vector<u32> desc(f.all_log_sizes.rbegin(), f.all_log_sizes.rend());
         for (u32 L : desc) {
             // queried values of this size: the four trees in order (:249-283)
             std::vector<std::vector<M31Var>> queried(nq);
             for (u32 i = 0; i < nq; i++)
                 for (u32 t = 0; t < 4; t++) {
-                    auto it = dec_proofs[t][i].columns.find(L);
-                    if (it != dec_proofs[t][i].columns.end()) queried[i].insert(queried[i].end(), it->second.begin(), it->second.end());
+                    auto it = dec_cols[t][i].find(L);
+                    if (it != dec_cols[t][i].end()) queried[i].insert(queried[i].end(), it->second.begin(), it->second.end());
                 }
             // ColumnSampleBatchVar::new_vec: group by shift in first-seen order (answer/src/data_structures.rs:42-64)
             std::vector<long> order;
@@ -629,7 +655,7 @@ struct AnswerResults {
                     const QM31Var cb = alpha * bb;
                     const QM31Var cc = alpha * y[1];
                     lc.push_back({ca, cb, cc});
-                    alpha = alpha * fs.after_sampled_values_random_coeff;
+                    alpha = alpha * after_sampled_values_random_coeff;
                 }
                 line_coeffs.push_back(lc);
             }

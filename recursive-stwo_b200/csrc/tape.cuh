@@ -24,6 +24,12 @@ enum : u32 {
     T_COORD,                                    // dst = coordinate b of var a               (QM31Var::decompose_m31)
     T_BIT,                                      // dst = bit b of var a                      (BitsVar::from_m31)
     T_POSEIDON,                                 // permutation record dst                    (Poseidon2HalfVar::permute)
+    // gates of the Plonk-without-Poseidon system (constraint_system/src/plonk_without_poseidon.rs:108-245)
+    T_M4,                                       // dst = M4 MDS block on the coordinates of a
+    T_POW5M4,                                   // dst = M4(a (.) b)          (b = a^4 coordinate-wise)
+    T_HADAMARD,                                 // dst = a (.) b              (do_hadamard, do_pow5_gate)
+    T_GRANDSUM,                                 // dst = (s, s, s, s), s = sum of the 8 coordinates of a and b
+    T_POW4,                                     // dst = a^4 coordinate-wise  (the witness of pow5m4 / pow5, emulated.rs:37-78)
 };
 constexpr u32 NO_VAR = 0xffffffffu;
 
@@ -46,7 +52,12 @@ struct alignas(16) Q4 { u32 x, y, z, w; };
 enum : u32 {
     S_STMT0 = 0, S_STMT1, S_COMMITMENT, S_SAMPLED, S_FRI_COMMITMENT, S_LAST_COEFFS, S_POW_LIMB, S_OODS,
     S_PATH_COL, S_PATH_SIB, S_PAIR_SELF, S_PAIR_SIB, S_PAIR_HASH,
+    S_FS,        // Fiat-Shamir outputs of the native verifier: k < FS_QUERY_BASE: word k of {oods_t, z, alpha, random_coeff,
+                 // after_sampled_values_random_coeff, fri_alphas[..]}; FS_QUERY_BASE + i: position of query i at the largest
+                 // log size; FS_ZERO: the constant 0 (padding of packed public inputs)
+    S_EXTRA,     // word k of the per-proof public-input hashes the last-layer circuit takes (circuit.cuh, k_last_extra)
 };
+constexpr u32 FS_QUERY_BASE = 1024, FS_ZERO = 4095;
 HD u32 src_pack(u32 section, u32 a, u32 i, u32 k) { return section | (a << 4) | (i << 10) | (k << 17); }
 HD u32 src_section(u32 s) { return s & 15u; }
 HD u32 src_a(u32 s) { return (s >> 4) & 63u; }
@@ -71,6 +82,21 @@ HD void stv(const View &v, u32 i, qm31_t q) {
     v.vars[(size_t)i * v.stride] = t;
 }
 HD u32 ldw(const View &v, u32 slot) { return v.input[(size_t)slot * v.stride]; }
+
+// ---- coordinate-wise gates of the Plonk-without-Poseidon system -----------------------------------------------------------
+HD qm31_t q_m4(qm31_t x) {                      // plonk_without_poseidon.rs:115-125
+    const u32 t0 = m31::addc(x.v[0], x.v[1]), t1 = m31::addc(x.v[2], x.v[3]);
+    const u32 t2 = m31::addc(m31::addc(x.v[1], x.v[1]), t1), t3 = m31::addc(m31::addc(x.v[3], x.v[3]), t0);
+    const u32 t1x2 = m31::addc(t1, t1), t0x2 = m31::addc(t0, t0);
+    const u32 t4 = m31::addc(m31::addc(t1x2, t1x2), t3), t5 = m31::addc(m31::addc(t0x2, t0x2), t2);
+    return qm31::mk(m31::addc(t3, t5), t5, m31::addc(t2, t4), t4);
+}
+HD qm31_t q_had(qm31_t a, qm31_t b) { return qm31::mk(m31::mulc(a.v[0], b.v[0]), m31::mulc(a.v[1], b.v[1]), m31::mulc(a.v[2], b.v[2]), m31::mulc(a.v[3], b.v[3])); }
+HD qm31_t q_pow4(qm31_t a) { const qm31_t s = q_had(a, a); return q_had(s, s); }
+HD qm31_t q_grandsum(qm31_t a, qm31_t b) {
+    const u32 s = m31::addc(m31::addc(m31::addc(a.v[0], a.v[1]), m31::addc(a.v[2], a.v[3])), m31::addc(m31::addc(b.v[0], b.v[1]), m31::addc(b.v[2], b.v[3])));
+    return qm31::mk(s, s, s, s);
+}
 
 // variables 0..3 = 0, 1, i, j (plonk_with_poseidon.rs:63-66)
 HD void prologue(const View &v) {
@@ -122,6 +148,11 @@ HD void eval(const View &v, const Ins &in, const Perm *perms) {
     case T_COORD: stv(v, in.dst, qm31::from_m31(ldv(v, in.a).v[in.b & 3u])); break;
     case T_BIT: stv(v, in.dst, qm31::from_m31((ldv(v, in.a).v[0] >> (in.b & 31u)) & 1u)); break;
     case T_POSEIDON: eval_poseidon<UNROLLED>(v, perms[in.dst], in.dst); break;
+    case T_M4: stv(v, in.dst, q_m4(ldv(v, in.a))); break;
+    case T_POW5M4: stv(v, in.dst, q_m4(q_had(ldv(v, in.a), ldv(v, in.b)))); break;
+    case T_HADAMARD: stv(v, in.dst, q_had(ldv(v, in.a), ldv(v, in.b))); break;
+    case T_GRANDSUM: stv(v, in.dst, q_grandsum(ldv(v, in.a), ldv(v, in.b))); break;
+    case T_POW4: stv(v, in.dst, q_pow4(ldv(v, in.a))); break;
     default: break;
     }
 }
@@ -133,6 +164,21 @@ HD bool gate_ok(qm31_t va, qm31_t vb, qm31_t vc, u32 op, u32 enforce_c_m31) {
     bool ok = qm31::eq(want, vc);
     if (enforce_c_m31 && (vc.v[1] | vc.v[2] | vc.v[3])) ok = false;
     return ok;
+}
+// check_arithmetics of the Plonk-without-Poseidon system (plonk_without_poseidon.rs:410-599): the selectors pick one of six gates
+HD bool gate_ok_without(qm31_t a, qm31_t b, qm31_t c, u32 op1, u32 op2, u32 op3, u32 op4) {
+    if (op2 > 1 || op3 > 1 || op4 > 1) return false;
+    const u32 sel = op2 * 4 + op3 * 2 + op4;
+    if (sel && op1 != 1) return false;
+    switch (sel) {
+    case 0: return qm31::eq(c, qm31::add(qm31::mul_m31(qm31::add(a, b), op1), qm31::mul_m31(qm31::mul(a, b), m31::subc(1, op1))));
+    case 1: return qm31::eq(c, q_had(a, b));                                         // hadamard
+    case 2: return qm31::eq(c, q_m4(q_had(a, b)));                                   // m4
+    case 3: return qm31::eq(c, q_grandsum(a, b));                                    // grand sum
+    case 5: return qm31::eq(c, q_had(a, b)) && qm31::eq(b, q_pow4(a));               // pow5
+    case 6: return qm31::eq(c, q_m4(q_had(a, b))) && qm31::eq(b, q_pow4(a));         // pow5m4
+    default: return false;
+    }
 }
 HD bool row_ok(const View &v, u32 a, u32 b, u32 c, u32 op, u32 enforce_c_m31, bool op_follows_c) {
     const qm31_t va = ldv(v, a), vb = ldv(v, b), vc = ldv(v, c);

@@ -22,6 +22,34 @@ def oracle_circuit(name, multipliers=1):
     return _cache[key]
 
 
+_cache_last = {}
+
+
+def oracle_last_circuit(name):
+    """(CSWithout, VerifyOut) of the oracle's last-layer circuit for a Poseidon31 fixture"""
+    if name not in _cache_last:
+        blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+        _cache_last[name] = D.last_layer_circuit(blob, O.VerifyOut)
+    return _cache_last[name]
+
+
+def compare_wiring_without(cs, info, get):
+    """the Plonk-without-Poseidon flavour of compare_wiring: a/b/c wires and the four selectors"""
+    n_rows = len(cs.a_wire)
+    assert (info["n_rows"], info["n_rows_unpadded"], info["n_vars"], info["num_input"], info["n_flow"]) == (
+        n_rows, cs.n_rows_unpadded, len(cs.variables), cs.num_input, 0)
+    follows = get(6, n_rows).astype(bool)
+    for what, name in ((0, "a_wire"), (1, "b_wire"), (2, "c_wire"), (5, "op1"), (11, "op2"), (12, "op3"), (13, "op4")):
+        got, want = get(what, n_rows), np.array(getattr(cs, name), dtype=np.uint32)
+        if name == "op1":
+            c_val = np.array(cs.variables, dtype=np.uint32)[np.array(cs.c_wire)][:, 0]
+            assert np.array_equal(want[follows], c_val[follows])
+            got, want = got[~follows], want[~follows]
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, "%s differs first at row %d: %d != %d" % (name, bad[0], got[bad[0]], want[bad[0]])
+    return follows
+
+
 WIRING = ("a_wire", "b_wire", "c_wire", "poseidon_wire", "enforce_c_m31", "op")
 
 

@@ -81,6 +81,12 @@ void *hs_circuit_record(const u32 *shape, const u32 *input_idx, const u32 *input
         return stwo_b200::dsl::record_verifier(s, in, multipliers).release();
     } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record: %s\n", e.what()); return nullptr; }
 }
+void *hs_circuit_record_last(const u32 *shape) {
+    try {
+        stwo_b200::dsl::ProofShape s{shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6]};
+        return stwo_b200::dsl::record_last_layer(s).release();
+    } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record_last: %s\n", e.what()); return nullptr; }
+}
 void hs_circuit_free(void *h) { delete (RecordedCircuit *)h; }
 // info: n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance
 void hs_circuit_info(void *h, u32 *info) {
@@ -95,7 +101,7 @@ void hs_circuit_get(void *h, u32 what, u32 *out) {
     RecordedCircuit *r = (RecordedCircuit *)h;
     const auto &c = *r->cs.p;
     const std::vector<u32> *src[] = {&c.a_wire, &c.b_wire, &c.c_wire, &c.poseidon_wire, &c.enforce_c_m31, &c.op, nullptr, &c.flow_wire,
-                                     &c.flow_swap_addr, &r->gather, &r->level_start};
+                                     &c.flow_swap_addr, &r->gather, &r->level_start, &c.op2, &c.op3, &c.op4};
     if (what == 6) { for (size_t k = 0; k < c.op_follows_c.size(); k++) out[k] = c.op_follows_c[k]; return; }
     memcpy(out, src[what]->data(), src[what]->size() * 4);
 }
@@ -106,17 +112,27 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
     RecordedCircuit *r = (RecordedCircuit *)h;
     const auto &c = *r->cs.p;
     const verify::Workspace &ws = *(const verify::Workspace *)ws_base;
-    std::vector<u32> stream(c.n_input_words);
+    std::vector<u32> stream(c.n_input_words), extra(r->n_extra_words + 1);
     for (u32 p = 0; p < n; p++) {
-        for (u32 k = 0; k < c.n_input_words; k++) stream[k] = circuit::gather_word(ws, p, r->gather[k]);
+        for (const auto &j : r->jobs) {
+            circuit::ExtraJob job{j.kind, j.tree, j.query, j.col_off, j.n_cols, j.slot};
+            circuit::extra_job(ws, p, job, extra.data());
+        }
+        for (u32 k = 0; k < c.n_input_words; k++) stream[k] = circuit::gather_word(ws, p, r->gather[k], extra.data());
         if (stream_out) memcpy(stream_out + (size_t)p * c.n_input_words, stream.data(), stream.size() * 4);
         tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
                      flow_swap + (size_t)p * c.num_poseidon_invocations(), 1};
         tape::prologue(v);
         for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data());
         bad_row[p] = -1;
-        for (u32 i = 0; i < c.num_plonk_rows(); i++)
-            if (!tape::row_ok(v, c.a_wire[i], c.b_wire[i], c.c_wire[i], c.op[i], c.enforce_c_m31[i], c.op_follows_c[i] != 0)) { bad_row[p] = i; break; }
+        for (u32 i = 0; i < c.num_plonk_rows(); i++) {
+            bool ok;
+            if (c.without()) {
+                const qm31_t vc = tape::ldv(v, c.c_wire[i]);
+                ok = tape::gate_ok_without(tape::ldv(v, c.a_wire[i]), tape::ldv(v, c.b_wire[i]), vc, c.op_follows_c[i] ? vc.v[0] : c.op[i], c.op2[i], c.op3[i], c.op4[i]);
+            } else ok = tape::row_ok(v, c.a_wire[i], c.b_wire[i], c.c_wire[i], c.op[i], c.enforce_c_m31[i], c.op_follows_c[i] != 0);
+            if (!ok) { bad_row[p] = i; break; }
+        }
     }
 }
 }

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_py as O
-from circuit_common import compare_wiring, oracle_circuit
+from circuit_common import compare_wiring, compare_wiring_without, oracle_circuit, oracle_last_circuit
 from verify_common import Detail, pack, shape_of
 
 INFO = ("n_rows", "n_rows_unpadded", "n_vars", "n_flow", "n_flow_padded", "n_input_words", "n_ins", "n_levels", "num_input",
@@ -19,6 +19,21 @@ def record(hs, shape, inputs, multipliers=1):
     idx = np.array(inputs[0], dtype=np.uint32)
     vals = np.array(inputs[1], dtype=np.uint32)
     h = hs.hs_circuit_record(O.vp(shape), O.vp(idx), O.vp(vals), idx.size, multipliers)
+    assert h, "recorder failed"
+    h = ctypes.c_void_p(h)
+    info = np.zeros(len(INFO), dtype=np.uint32)
+    hs.hs_circuit_info(h, O.vp(info))
+
+    def get(what, n):
+        out = np.zeros(n, dtype=np.uint32)
+        hs.hs_circuit_get(h, what, O.vp(out))
+        return out
+    return h, dict(zip(INFO, (int(x) for x in info))), get
+
+
+def record_last(hs, shape):
+    hs.hs_circuit_record_last.restype = ctypes.c_void_p
+    h = hs.hs_circuit_record_last(O.vp(shape))
     assert h, "recorder failed"
     h = ctypes.c_void_p(h)
     info = np.zeros(len(INFO), dtype=np.uint32)
@@ -81,4 +96,20 @@ def test_tampered_proof_fails_check_arithmetics(hostsim, orc):
     dt, variables, fh, fs, bad = evaluate(hostsim, h, info, [(buf, n), (bad_buf, n)], shape, O.inputs_for(name))
     assert (dt[0].verdict, bad[0]) == (0, -1)
     assert dt[1].verdict == 1 and bad[1] >= 0
+    hostsim.hs_circuit_free(h)
+
+
+@pytest.mark.parametrize("name", ["level13-1.bin", "level10-1.bin"])
+def test_last_layer_circuit_matches_oracle(hostsim, orc, name):
+    """examples/last-layer (Plonk-without-Poseidon system, emulated Poseidon2): wiring and variables against the oracle"""
+    cs, out = oracle_last_circuit(name)
+    buf, n = O.load_proof(name)
+    shape = shape_of(buf)
+    h, info, get = record_last(hostsim, shape)
+    compare_wiring_without(cs, info, get)
+    dt, variables, fh, fs, bad = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name))
+    assert dt[0].verdict == 0 and bad[0] == -1
+    want = np.array(cs.variables, dtype=np.uint32)
+    diff = np.nonzero((variables[0] != want).any(axis=1))[0]
+    assert diff.size == 0, "variable %d differs: %s != %s" % (diff[0], variables[0][diff[0]], want[diff[0]])
     hostsim.hs_circuit_free(h)
