@@ -214,6 +214,12 @@ typedef struct {
                                                         c_val_0 of that item (CirclePointM31Var::select, primitives/circle/src/lib.rs:80-92) */
     const uint32_t *flow_wire;                       /* n_flow x 4  (PoseidonEntry.wire of entries 1..4) */
     const uint32_t *flow_swap_addr;                  /* n_flow      (SwapOption.addr) */
+    /* kind 0: Plonk-with-Poseidon.  kind 1: Plonk-without-Poseidon (constraint_system/src/plonk_without_poseidon.rs:12-25):
+     * `op` is op1, op2..op4 select among the arithmetic / hadamard / m4 / pow5m4 / pow5 / grand-sum gates (:410-599),
+     * poseidon_wire and enforce_c_m31 are all-zero, n_flow = 0, the logup argument only carries mult_c (:600-632) and the
+     * preprocessed block is the 8 columns mult_c, a_wire, b_wire, c_wire, op1, op2, op3, op4 (:633-713). */
+    uint32_t kind;
+    const uint32_t *op2, *op3, *op4;                 /* n_rows each (kind 1) */
 } stwo_b200_cs_wiring;
 typedef struct {
     uint32_t n_batch, lanes;                         /* lanes: 1 or 32 */
@@ -283,9 +289,16 @@ int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *w, const stwo_b200_cs_v
 typedef struct stwo_b200_circuit stwo_b200_circuit;
 typedef struct {
     uint32_t n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance;
+    uint32_t kind;                                   /* stwo_b200_cs_wiring.kind */
+    uint32_t n_preprocessed_columns;                 /* 10 (kind 0) or 8 (kind 1) */
 } stwo_b200_circuit_info;
 int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,
                                           uint32_t n_inputs, uint32_t multipliers, stwo_b200_circuit **out);
+/* The last-layer circuit of examples/last-layer/src/main.rs:26-97 (components/last/*) over the Plonk-without-Poseidon
+ * system: every Fiat-Shamir output and opening is a public input (n_public_inputs of them, in the order of main.rs:102-185),
+ * the hashes are recomputed by the emulated Poseidon2 gadget (primitives/poseidon31/src/emulated.rs).  The trace pass of such
+ * a circuit writes an 8-column preprocessed block and the same 13 per-proof value columns (the last one is op1). */
+int32_t stwo_b200_circuit_record_last_layer(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out);
 void stwo_b200_circuit_free(stwo_b200_circuit *c);
 int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b200_circuit_info *out);
 #define STWO_B200_COL_A_WIRE 0
@@ -298,13 +311,16 @@ int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b200_circuit
 #define STWO_B200_COL_FLOW_WIRE 7
 #define STWO_B200_COL_FLOW_SWAP_ADDR 8
 #define STWO_B200_COL_LEVEL_START 10
+#define STWO_B200_COL_OP2 11
+#define STWO_B200_COL_OP3 12
+#define STWO_B200_COL_OP4 13
 /* host copy of one recorded column (n_words must match its length) */
 int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, uint32_t *out, size_t n_words);
 
 #define STWO_B200_TRACE_CHECK_ARITHMETICS 1u
 #define STWO_B200_TRACE_CHECK_POSEIDON 2u
 #define STWO_B200_TRACE_TIMED 4u
-/* stage kernels of the trace pass in launch order: gather, eval, check_arithmetics, check_poseidon, export */
+/* stage kernels of the trace pass in launch order: gather (+ public-input hashes), eval, check_arithmetics, check_poseidon, export */
 #define STWO_B200_N_TRACE_STAGES 5
 size_t stwo_b200_circuit_workspace_bytes(const stwo_b200_circuit *c, uint32_t n_proofs);
 /* Trace generation for a verified batch: run after stwo_b200_verify_proofs_batch_dev on the same blobs / workspace (the

@@ -90,7 +90,7 @@ class CsWiring(ctypes.Structure):
     """stwo_b200_cs_wiring"""
     _fields_ = [(n, ctypes.c_uint32) for n in ("n_vars", "n_rows", "n_flow", "num_input")] + [
         (n, ctypes.c_void_p) for n in ("a_wire", "b_wire", "c_wire", "poseidon_wire", "enforce_c_m31", "op", "op_follows_c", "flow_wire",
-                                       "flow_swap_addr")]
+                                       "flow_swap_addr")] + [("kind", ctypes.c_uint32)] + [(n, ctypes.c_void_p) for n in ("op2", "op3", "op4")]
 
 
 class CsValues(ctypes.Structure):
@@ -108,13 +108,13 @@ class CsTape(ctypes.Structure):
 class CircuitInfo(ctypes.Structure):
     """stwo_b200_circuit_info"""
     _fields_ = [(n, ctypes.c_uint32) for n in ("n_rows", "n_rows_unpadded", "n_vars", "n_flow", "n_flow_padded", "n_input_words", "n_ins",
-                                               "n_levels", "num_input", "words_per_instance")]
+                                               "n_levels", "num_input", "words_per_instance", "kind", "n_preprocessed_columns")]
 
 
 TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED = 1, 2, 4
 TRACE_STAGES = ("gather", "eval", "check_arithmetics", "check_poseidon", "export")
 COLUMNS = {"a_wire": 0, "b_wire": 1, "c_wire": 2, "poseidon_wire": 3, "enforce_c_m31": 4, "op": 5, "op_follows_c": 6, "flow_wire": 7,
-           "flow_swap_addr": 8, "level_start": 10}
+           "flow_swap_addr": 8, "level_start": 10, "op2": 11, "op3": 12, "op4": 13}
 CFETCH = {"variables": 0, "flow_hash": 1, "flow_swap": 2, "witness": 3}
 
 _vp, _u32, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_size_t, ctypes.c_uint64
@@ -153,6 +153,7 @@ SIGNATURES = {
     "stwo_b200_cs_export_trace_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_finalize": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp]),
     "stwo_b200_circuit_record_verifier": (_i32, [_PSHAPE_P, _vp, _vp, _u32, _u32, ctypes.POINTER(_vp)]),
+    "stwo_b200_circuit_record_last_layer": (_i32, [_PSHAPE_P, ctypes.POINTER(_vp)]),
     "stwo_b200_circuit_free": (None, [_vp]),
     "stwo_b200_circuit_get_info": (_i32, [_vp, _INFO_P]),
     "stwo_b200_circuit_get_column": (_i32, [_vp, _u32, _vp, _sz]),

@@ -20,15 +20,24 @@ COLUMN_NAMES = ("mult_a", "mult_b", "mult_c", "poseidon_wire", "mult_poseidon", 
                 "c_val_3")          # PlonkWithAcceleratorCircuitTrace field order (plonk_with_poseidon.rs:542-619)
 
 
-class VerifierCircuit:
-    """A recorded verifier circuit for one proof shape."""
+COLUMN_NAMES_WITHOUT = ("mult_c", "a_wire", "b_wire", "c_wire", "op1", "op2", "op3", "op4", "a_val_0", "a_val_1", "a_val_2", "a_val_3",
+                        "b_val_0", "b_val_1", "b_val_2", "b_val_3", "c_val_0", "c_val_1", "c_val_2", "c_val_3")
+# PlonkWithoutAcceleratorCircuitTrace field order (plonk_without_poseidon.rs:645-708)
 
-    def __init__(self, shape, inputs=INPUTS_RECURSIVE, multipliers=1):
-        idx = np.ascontiguousarray(inputs[0], dtype=np.uint32)
-        vals = np.ascontiguousarray(inputs[1], dtype=np.uint32)
+
+class VerifierCircuit:
+    """A recorded verifier circuit for one proof shape.  last_layer=True records the circuit of examples/last-layer
+    (components/last/*, Plonk-without-Poseidon system, emulated Poseidon2) instead of the recursive verifier."""
+
+    def __init__(self, shape, inputs=INPUTS_RECURSIVE, multipliers=1, last_layer=False):
         h = ctypes.c_void_p()
-        _lib.call("stwo_b200_circuit_record_verifier", ctypes.byref(shape), idx.ctypes.data_as(ctypes.c_void_p),
-                  vals.ctypes.data_as(ctypes.c_void_p), idx.size, multipliers, ctypes.byref(h))
+        if last_layer:
+            _lib.call("stwo_b200_circuit_record_last_layer", ctypes.byref(shape), ctypes.byref(h))
+        else:
+            idx = np.ascontiguousarray(inputs[0], dtype=np.uint32)
+            vals = np.ascontiguousarray(inputs[1], dtype=np.uint32)
+            _lib.call("stwo_b200_circuit_record_verifier", ctypes.byref(shape), idx.ctypes.data_as(ctypes.c_void_p),
+                      vals.ctypes.data_as(ctypes.c_void_p), idx.size, multipliers, ctypes.byref(h))
         self._h = h
         self.shape, self.multipliers = shape, multipliers
         info = CircuitInfo()
@@ -70,7 +79,7 @@ class VerifierCircuit:
                 self._values = torch.empty((n, 13, nr), dtype=torch.int32, device=dev)
             out["values"] = self._values
         if preprocessed:
-            out["preprocessed"] = torch.empty((10, nr), dtype=torch.int32, device=dev)
+            out["preprocessed"] = torch.empty((self.info.n_preprocessed_columns, nr), dtype=torch.int32, device=dev)
         if check:
             out["bad_row"] = torch.empty(n, dtype=torch.int64, device=dev)
             out["bad_flow"] = torch.empty(n, dtype=torch.int64, device=dev)
@@ -101,6 +110,13 @@ class VerifierCircuit:
         """22 trace columns of one proof in the reference's order from the shared preprocessed block and its 13 value columns"""
         pre = preprocessed.cpu().numpy().view(np.uint32)
         val = values_of_one.cpu().numpy().view(np.uint32)
+        if pre.shape[0] == 8:                    # Plonk-without-Poseidon: mult_c, wires, op1 (per proof), op2..op4, 12 values
+            out = np.empty((20, pre.shape[1]), dtype=np.uint32)
+            out[:4] = pre[:4]
+            out[4] = val[12]
+            out[5:8] = pre[5:8]
+            out[8:] = val[:12]
+            return out
         out = np.empty((22, pre.shape[1]), dtype=np.uint32)
         out[:9] = pre[:9]
         out[9] = val[12]

@@ -16,6 +16,8 @@ struct stwo_b200_circuit {
     stwo_b200_cs_wiring wiring{};
     stwo_b200_cs_tape tape_{};
     const u32 *gather = nullptr;
+    const circuit::ExtraJob *jobs = nullptr;      // last-layer circuit only
+    u32 n_jobs = 0, n_extra_words = 0;
 };
 
 namespace {
@@ -24,7 +26,16 @@ inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
 
 // witness streams, lane-interleaved over groups of 32 proofs; thread = (word, proof) with the proof fastest (coalesced
 // stores; the loads walk each proof's own blob / workspace rows)
-__global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, const u32 *__restrict__ gather, u32 n_words, u32 *out) {
+// public-input hashes of the last-layer circuit: thread = (job, proof), the proof fastest; extra: [proof][n_extra_words]
+__global__ void __launch_bounds__(64) k_last_extra(verify::Workspace ws, const circuit::ExtraJob *__restrict__ jobs, u32 n_jobs, u32 n_extra_words, u32 *extra) {
+    const size_t g = blockIdx.x * (size_t)64 + threadIdx.x;
+    if (g >= (size_t)n_jobs * ws.n_proofs) return;
+    const u32 p = (u32)(g % ws.n_proofs), j = (u32)(g / ws.n_proofs);
+    if (!ws.desc[p].ok) return;
+    circuit::extra_job(ws, p, jobs[j], extra + (size_t)p * n_extra_words);
+}
+__global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, const u32 *__restrict__ gather, u32 n_words, u32 *out, const u32 *extra,
+                                                       u32 n_extra_words) {
     const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
     const u32 n_groups = (ws.n_proofs + 31) / 32;
     if (g >= (size_t)n_groups * n_words * 32) return;
@@ -33,11 +44,11 @@ __global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, con
     const u32 word = (u32)(t % n_words), grp = (u32)(t / n_words), p = grp * 32 + lane;
     if (p >= ws.n_proofs) return;
     const bool ok = ws.desc[p].ok != 0;          // a blob that did not parse has no sections: its stream is all zero
-    out[g] = ok ? circuit::gather_word(ws, p, __ldg(gather + word)) : 0u;
+    out[g] = ok ? circuit::gather_word(ws, p, __ldg(gather + word), extra ? extra + (size_t)p * n_extra_words : nullptr) : 0u;
 }
 
 struct Carve {
-    u32 *witness, *vars, *flow_hash; uint8_t *flow_swap; int32_t *mult; u32 *scratch, *status;
+    u32 *witness, *vars, *flow_hash; uint8_t *flow_swap; int32_t *mult; u32 *scratch, *status, *extra;
     size_t bytes;
 };
 Carve carve(const RecordedCircuit &r, u32 n_proofs, uint8_t *base) {
@@ -53,6 +64,7 @@ Carve carve(const RecordedCircuit &r, u32 n_proofs, uint8_t *base) {
     k.mult = (int32_t *)take((size_t)4 * c.num_plonk_rows() * 4);
     k.scratch = (u32 *)take(((size_t)4 * c.n_vars + 4) * 4);
     k.status = (u32 *)take(256);
+    k.extra = (u32 *)take((size_t)n_proofs * r.n_extra_words * 4 + 4);
     k.bytes = align_up(at, 256);
     return k;
 }
@@ -64,12 +76,14 @@ int32_t upload(stwo_b200_circuit *c) {
     const size_t nr = cs.num_plonk_rows(), nf = cs.num_poseidon_invocations();
     size_t at = 0;
     auto take = [&](size_t bytes) { at = align_up(at, 256); size_t o = at; at += bytes; return o; };
-    const size_t o_w = take(6 * nr * 4), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
+    const size_t o_w = take(9 * nr * 4), o_jobs = take(r.jobs.size() * sizeof(circuit::ExtraJob) + 16), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
                  o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4);
     uint8_t *d = nullptr;
     STWO_CUDA(cudaMalloc(&d, at));
-    const std::vector<u32> *cols[6] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op};
-    for (int k = 0; k < 6; k++) STWO_CUDA(cudaMemcpy(d + o_w + k * nr * 4, cols[k]->data(), nr * 4, cudaMemcpyHostToDevice));
+    const std::vector<u32> *cols[9] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op, &cs.op2, &cs.op3, &cs.op4};
+    for (int k = 0; k < 9; k++) STWO_CUDA(cudaMemcpy(d + o_w + k * nr * 4, cols[k]->data(), nr * 4, cudaMemcpyHostToDevice));
+    static_assert(sizeof(circuit::ExtraJob) == sizeof(dsl::ExtraHashJob), "job records mirror");
+    if (!r.jobs.empty()) STWO_CUDA(cudaMemcpy(d + o_jobs, r.jobs.data(), r.jobs.size() * sizeof(circuit::ExtraJob), cudaMemcpyHostToDevice));
     STWO_CUDA(cudaMemcpy(d + o_fol, cs.op_follows_c.data(), nr, cudaMemcpyHostToDevice));
     if (nf) {
         STWO_CUDA(cudaMemcpy(d + o_fw, cs.flow_wire.data(), nf * 16, cudaMemcpyHostToDevice));
@@ -81,7 +95,8 @@ int32_t upload(stwo_b200_circuit *c) {
     if (!r.gather.empty()) STWO_CUDA(cudaMemcpy(d + o_g, r.gather.data(), r.gather.size() * 4, cudaMemcpyHostToDevice));
     const u32 *w = (const u32 *)(d + o_w);
     c->wiring = {cs.n_vars, (u32)nr, (u32)nf, cs.num_input, w, w + nr, w + 2 * nr, w + 3 * nr, w + 4 * nr, w + 5 * nr, d + o_fol,
-                 (const u32 *)(d + o_fw), (const u32 *)(d + o_fa)};
+                 (const u32 *)(d + o_fw), (const u32 *)(d + o_fa), cs.without() ? 1u : 0u, w + 6 * nr, w + 7 * nr, w + 8 * nr};
+    c->jobs = (const circuit::ExtraJob *)(d + o_jobs); c->n_jobs = (u32)r.jobs.size(); c->n_extra_words = r.n_extra_words;
     c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
                 (const u32 *)(d + o_perm)};
     c->gather = (const u32 *)(d + o_g);
@@ -117,6 +132,23 @@ extern "C" int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape
         return STWO_B200_OK;
     } catch (const std::exception &) { return STWO_B200_E_SHAPE; }
 }
+extern "C" int32_t stwo_b200_circuit_record_last_layer(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out) {
+    if (!shape || !out) return STWO_B200_E_BAD_ARG;
+    if (shape->n_queries == 0 || shape->n_queries > proof::MAX_QUERIES || shape->n_inner >= proof::MAX_INNER || shape->log_last > 12 ||
+        shape->pow_bits >= 32 || !shape->log_size_plonk || !shape->log_size_poseidon)
+        return STWO_B200_E_SHAPE;
+    verify::Shape v;
+    memcpy(&v, shape, sizeof v);
+    if (v.max_first() > 29 || v.log_plonk() > v.max_first() || v.log_pos() > v.max_first()) return STWO_B200_E_SHAPE;
+    try {
+        dsl::ProofShape s;
+        memcpy(&s, shape, sizeof s);
+        stwo_b200_circuit *c = new stwo_b200_circuit();
+        c->rec = dsl::record_last_layer(s);
+        *out = c;
+        return STWO_B200_OK;
+    } catch (const std::exception &) { return STWO_B200_E_SHAPE; }
+}
 extern "C" void stwo_b200_circuit_free(stwo_b200_circuit *c) {
     if (!c) return;
     if (c->dev) cudaFree(c->dev);
@@ -126,7 +158,7 @@ extern "C" int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b
     if (!c || !out) return STWO_B200_E_BAD_ARG;
     const auto &cs = *c->rec->cs.p;
     *out = {cs.num_plonk_rows(), cs.n_rows_unpadded, cs.n_vars, cs.num_poseidon_invocations(), cs.padded_poseidon_len(), cs.n_input_words,
-            (u32)c->rec->ins.size(), c->rec->n_levels(), cs.num_input, c->rec->words_per_instance};
+            (u32)c->rec->ins.size(), c->rec->n_levels(), cs.num_input, c->rec->words_per_instance, cs.without() ? 1u : 0u, cs.without() ? 8u : 10u};
     return STWO_B200_OK;
 }
 extern "C" int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, uint32_t *out, size_t n_words) {
@@ -140,6 +172,9 @@ extern "C" int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint
         case STWO_B200_COL_POSEIDON_WIRE: src = &cs.poseidon_wire; break;
         case STWO_B200_COL_ENFORCE_C_M31: src = &cs.enforce_c_m31; break;
         case STWO_B200_COL_OP: src = &cs.op; break;
+        case STWO_B200_COL_OP2: src = &cs.op2; break;
+        case STWO_B200_COL_OP3: src = &cs.op3; break;
+        case STWO_B200_COL_OP4: src = &cs.op4; break;
         case STWO_B200_COL_FLOW_WIRE: src = &cs.flow_wire; break;
         case STWO_B200_COL_FLOW_SWAP_ADDR: src = &cs.flow_swap_addr; break;
         case STWO_B200_COL_LEVEL_START: src = &c->rec->level_start; break;
@@ -185,7 +220,11 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
     const u32 nw = c->tape_.n_input_words;
     const size_t groups = (n_proofs + 31) / 32;
     MARK();
-    k_gather_witness<<<nblk(groups * nw * 32), kT, 0, st>>>(ws, c->gather, nw, k.witness);
+    if (c->n_jobs) {
+        k_last_extra<<<(unsigned)(((size_t)c->n_jobs * n_proofs + 63) / 64), 64, 0, st>>>(ws, c->jobs, c->n_jobs, c->n_extra_words, k.extra);
+        note_launch(1);
+    }
+    k_gather_witness<<<nblk(groups * nw * 32), kT, 0, st>>>(ws, c->gather, nw, k.witness, c->n_jobs ? k.extra : nullptr, c->n_extra_words);
     note_launch(1);
     stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap};
     MARK();
@@ -200,7 +239,9 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
     const bool need_mult = preprocessed || (flags & STWO_B200_TRACE_CHECK_POSEIDON);
     if (need_mult)
         if ((rc = stwo_b200_cs_populate_logup_dev(&c->wiring, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, k.scratch, k.status, st))) return rc;
-    if (flags & STWO_B200_TRACE_CHECK_POSEIDON)
+    if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 1)      // unimplemented!() for this system: nothing to check
+        if ((rc = cuda_status(cudaMemsetAsync(bad_flow, 0xff, (size_t)n_proofs * 8, st)))) return rc;
+    if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 0)
         if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, st))) return rc;
     MARK();
     if (preprocessed || values)

@@ -112,8 +112,14 @@ __global__ void __launch_bounds__(kT) k_cs_check_arith(stwo_b200_cs_wiring w, Ba
     if (item >= b.n_batch) return;
     const tape::View v = b.view(item, nullptr, 0);
     const bool follows = w.op_follows_c && w.op_follows_c[row];
-    if (!tape::row_ok(v, __ldg(w.a_wire + row), __ldg(w.b_wire + row), __ldg(w.c_wire + row), __ldg(w.op + row), __ldg(w.enforce_c_m31 + row), follows))
-        atomicMin(first_bad + item, (unsigned long long)row);
+    bool ok;
+    if (w.kind == 1) {
+        const qm31_t vc = tape::ldv(v, __ldg(w.c_wire + row));
+        ok = tape::gate_ok_without(tape::ldv(v, __ldg(w.a_wire + row)), tape::ldv(v, __ldg(w.b_wire + row)), vc, follows ? vc.v[0] : __ldg(w.op + row),
+                                   __ldg(w.op2 + row), __ldg(w.op3 + row), __ldg(w.op4 + row));
+    } else
+        ok = tape::row_ok(v, __ldg(w.a_wire + row), __ldg(w.b_wire + row), __ldg(w.c_wire + row), __ldg(w.op + row), __ldg(w.enforce_c_m31 + row), follows);
+    if (!ok) atomicMin(first_bad + item, (unsigned long long)row);
 }
 
 // ---- K7: populate_logup_arguments (wiring only) ------------------------------------------------------------------------------
@@ -124,8 +130,11 @@ __global__ void __launch_bounds__(kT) k_cs_count(stwo_b200_cs_wiring w, u32 *cou
         const u32 i = (u32)g;
         const u32 a = w.a_wire[i], b = w.b_wire[i], c = w.c_wire[i];
         atomicAdd(counts + a, 1u); atomicAdd(counts + b, 1u); atomicAdd(counts + c, 1u);
-        atomicMin(first_key + a, 3 * i); atomicMin(first_key + b, 3 * i + 1); atomicMin(first_key + c, 3 * i + 2);
-        atomicMin(first_prow + w.poseidon_wire[i], i);
+        if (w.kind == 1) atomicMin(first_key + c, i);             // plonk_without_poseidon.rs:617-628: first occurrence among the c wires
+        else {
+            atomicMin(first_key + a, 3 * i); atomicMin(first_key + b, 3 * i + 1); atomicMin(first_key + c, 3 * i + 2);
+            atomicMin(first_prow + w.poseidon_wire[i], i);
+        }
     }
     if (g < w.num_input) atomicAdd(counts + g + 1, 1u);
     if (g < w.n_flow) {
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__(kT) k_cs_mult(stwo_b200_cs_wiring w, const u32
                                                 int32_t *mult_poseidon, u32 *status) {
     const u32 i = blockIdx.x * kT + threadIdx.x;
     if (i >= w.n_rows) return;
+    if (w.kind == 1) { mult_c[i] = first_key[w.c_wire[i]] == i ? 1 - (int32_t)counts[w.c_wire[i]] : 1; return; }
     const u32 a = w.a_wire[i], b = w.b_wire[i], c = w.c_wire[i], pw = w.poseidon_wire[i];
     // first occurrence in the row-major scan a_0,b_0,c_0,a_1,... gets 1 - count, later ones 1.  A wire repeated inside
     // one row (a == b) is a first occurrence only in its earliest slot, which is what the minimum key encodes.
@@ -195,6 +205,11 @@ __global__ void __launch_bounds__(kT) k_cs_export_pre(stwo_b200_cs_wiring w, con
     const u32 i = blockIdx.x * kT + threadIdx.x;
     if (i >= w.n_rows) return;
     const size_t n = w.n_rows;
+    if (w.kind == 1) {
+        pre[0 * n + i] = m31_of_i32(mult_c[i]); pre[1 * n + i] = w.a_wire[i]; pre[2 * n + i] = w.b_wire[i]; pre[3 * n + i] = w.c_wire[i];
+        pre[4 * n + i] = w.op[i]; pre[5 * n + i] = w.op2[i]; pre[6 * n + i] = w.op3[i]; pre[7 * n + i] = w.op4[i];
+        return;
+    }
     pre[0 * n + i] = m31_of_i32(mult_a[i]); pre[1 * n + i] = m31_of_i32(mult_b[i]); pre[2 * n + i] = m31_of_i32(mult_c[i]);
     pre[3 * n + i] = w.poseidon_wire[i]; pre[4 * n + i] = (u32)mult_poseidon[i]; pre[5 * n + i] = w.enforce_c_m31[i];
     pre[6 * n + i] = w.a_wire[i]; pre[7 * n + i] = w.b_wire[i]; pre[8 * n + i] = w.c_wire[i]; pre[9 * n + i] = w.op[i];
@@ -214,7 +229,10 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring
     for (int k = 0; k < 4; k++) { o[k * n] = a.v[k]; o[(4 + k) * n] = bb.v[k]; o[(8 + k) * n] = c.v[k]; }
     const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : w.op[i];
     o[12 * n] = op;
-    if (first_bad && !tape::gate_ok(a, bb, c, op, w.enforce_c_m31[i])) atomicMin(first_bad + item, (unsigned long long)i);
+    if (first_bad) {
+        const bool ok = w.kind == 1 ? tape::gate_ok_without(a, bb, c, op, w.op2[i], w.op3[i], w.op4[i]) : tape::gate_ok(a, bb, c, op, w.enforce_c_m31[i]);
+        if (!ok) atomicMin(first_bad + item, (unsigned long long)i);
+    }
 }
 // lanes = 32: a CTA transposes a tile of 32 rows x 32 items through shared memory.  Load phase: a warp reads one row's
 // three variables for 32 items (3 x 512 contiguous bytes).  Store phase: a warp writes 32 consecutive rows of one
@@ -239,7 +257,11 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring
             }
             const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
             tile[(12 * 32 + lane) * 33 + r] = op;
-            if (first_bad && !tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i))) atomicMin(first_bad + item, (unsigned long long)i);
+            if (first_bad) {
+                const bool ok = w.kind == 1 ? tape::gate_ok_without(a, bb, c, op, __ldg(w.op2 + i), __ldg(w.op3 + i), __ldg(w.op4 + i))
+                                            : tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i));
+                if (!ok) atomicMin(first_bad + item, (unsigned long long)i);
+            }
         }
     }
     __syncthreads();
@@ -254,8 +276,9 @@ __global__ void k_fill64(unsigned long long *p, size_t n, unsigned long long v) 
     if (i < n) p[i] = v;
 }
 bool wiring_ok(const stwo_b200_cs_wiring *w) {
-    return w && w->n_rows >= 16 && (w->n_rows & (w->n_rows - 1)) == 0 && w->n_vars >= 4 && w->a_wire && w->b_wire && w->c_wire &&
-           w->poseidon_wire && w->enforce_c_m31 && w->op && (w->n_flow == 0 || (w->flow_wire && w->flow_swap_addr));
+    if (!w || w->n_rows < 16 || (w->n_rows & (w->n_rows - 1)) || w->n_vars < 4 || !w->a_wire || !w->b_wire || !w->c_wire || !w->op || w->kind > 1) return false;
+    if (w->kind == 1) return w->op2 && w->op3 && w->op4 && w->n_flow == 0;
+    return w->poseidon_wire && w->enforce_c_m31 && (w->n_flow == 0 || (w->flow_wire && w->flow_swap_addr));
 }
 bool values_ok(const stwo_b200_cs_values *v) { return v && v->n_batch && (v->lanes == 1 || v->lanes == 32) && v->variables; }
 Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
@@ -324,7 +347,8 @@ extern "C" int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring 
 extern "C" int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w, int32_t *mult_a, int32_t *mult_b, int32_t *mult_c,
                                                    int32_t *mult_poseidon, uint32_t *scratch, uint32_t *status_out, void *stream) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(w) || !mult_a || !mult_b || !mult_c || !mult_poseidon || !scratch || !status_out) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(w) || !mult_c || !scratch || !status_out) return STWO_B200_E_BAD_ARG;
+    if (w->kind == 0 && (!mult_a || !mult_b || !mult_poseidon)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nv = w->n_vars;
     u32 *counts = scratch, *first_key = scratch + nv, *first_prow = scratch + 2 * nv, *mpv = scratch + 3 * nv;
@@ -364,7 +388,7 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
     if (!wiring_ok(w) || !values_ok(v) || (!values && !preprocessed)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (preprocessed) {
-        if (!mult_a || !mult_b || !mult_c || !mult_poseidon) return STWO_B200_E_BAD_ARG;
+        if (!mult_c || (w->kind == 0 && (!mult_a || !mult_b || !mult_poseidon))) return STWO_B200_E_BAD_ARG;
         k_cs_export_pre<<<nblk(w->n_rows), kT, 0, st>>>(*w, mult_a, mult_b, mult_c, mult_poseidon, preprocessed);
         note_launch(1);
     }
@@ -392,7 +416,7 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
 extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const stwo_b200_cs_values *hv, uint32_t *trace,
                                          int64_t *bad_row, int64_t *bad_flow) {
     STWO_CHECK_DEVICE();
-    if (!wiring_ok(hw) || !hv || hv->n_batch != 1 || hv->lanes != 1 || !hv->variables || !trace || !bad_row || !bad_flow) return STWO_B200_E_BAD_ARG;
+    if (!wiring_ok(hw) || hw->kind != 0 || !hv || hv->n_batch != 1 || hv->lanes != 1 || !hv->variables || !trace || !bad_row || !bad_flow) return STWO_B200_E_BAD_ARG;
     const size_t nr = hw->n_rows, nv = hw->n_vars, nf = hw->n_flow;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };

@@ -42,3 +42,18 @@ def test_trace_needs_a_device(pkg):
     circ = pkg.VerifierCircuit(pkg.proof_shape(blob), inputs=pkg.INPUTS_SINGLE)
     rc = pkg._lib.load().stwo_b200_circuit_trace_batch_dev(circ._h, 1, 1, 1, 1, 1, 1 << 30, 0, None, None, None, None, None)
     assert rc == pkg._lib.E_NO_DEVICE
+
+
+@pytest.mark.parametrize("name", ["level13-1.bin", "level12-1.bin"])
+def test_recorded_last_layer_wiring_matches_oracle(pkg, orc, name):
+    """examples/last-layer: Plonk-without-Poseidon wiring (wires + four selectors) through the C ABI"""
+    from circuit_common import compare_wiring_without, oracle_last_circuit
+    cs, _ = oracle_last_circuit(name)
+    blob = open(O.PROOFS_DIR + "/" + name, "rb").read()
+    circ = pkg.VerifierCircuit(pkg.proof_shape(blob), last_layer=True)
+    info = {k: getattr(circ.info, k) for k, _ in circ.info._fields_}
+    assert (info["kind"], info["n_preprocessed_columns"]) == (1, 8)
+    names = {v: k for k, v in pkg._lib.COLUMNS.items()}
+    compare_wiring_without(cs, info, lambda what, n: circ.column(names[what]))
+    if name == "level13-1.bin":
+        assert info["n_rows"] == 1 << 17            # header of examples/last-layer/data/bitcoin_proof.bin

@@ -102,3 +102,41 @@ def test_cs_finalize_host_entry(pkg, gpu, orc):
     wh[17, 20] ^= 1
     L.call("stwo_b200_cs_finalize", ctypes.byref(w), ctypes.byref(v), vp(trace), ctypes.byref(bad_row), ctypes.byref(bad_flow))
     assert 0 <= bad_row.value <= row and bad_flow.value == 17
+
+
+@pytest.mark.parametrize("name", ["level13-1.bin", "level12-1.bin"])
+def test_last_layer_trace_matches_oracle(pkg, gpu, orc, name):
+    """BASELINE configs[1] (examples/last-layer): the 20-column trace of the last-layer circuit, batch of replicas"""
+    from circuit_common import oracle_last_circuit
+    cs, out = oracle_last_circuit(name)
+    blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+    n = 35
+    vb = pkg.VerifyBatch([blob] * n, inputs=pkg.INPUTS_RECURSIVE)
+    verdict, _ = vb.run(full=True)
+    assert not verdict.cpu().numpy().any()
+    circ = pkg.VerifierCircuit(vb.shape, last_layer=True)
+    r = circ.trace(vb, check=True, export=True)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    want = np.array(cs.variables, dtype=np.uint32)
+    for p in (0, 32, n - 1):
+        got = circ.fetch(p, "variables")
+        diff = np.nonzero((got != want).any(axis=1))[0]
+        assert diff.size == 0, "variable %d of proof %d" % (diff[0], p)
+    tr = cs.trace_columns()
+    gold = {g["src"]: g for g in json.load(open(os.path.join(O.ROOT, "tests", "golden", "trace_digests.json")))["last_layer"]}
+    for p in (1, n - 1):
+        got = pkg.VerifierCircuit.assemble_trace(r["preprocessed"], r["values"][p])
+        bad = np.argwhere(got != tr)
+        assert bad.size == 0, "column %s row %d" % (pkg.circuit.COLUMN_NAMES_WITHOUT[bad[0][0]], bad[0][1])
+        assert D.trace_digest(got) == gold[name]["trace_sha256"]
+    # a tampered proof breaks a row of this circuit too
+    buf, ln = O.load_proof(name)
+    offs = O.proof_offsets(buf, ln)
+    b = buf.copy()
+    b[offs["sampled0"] + 2] ^= 8
+    vb2 = pkg.VerifyBatch([blob, bytes(b[:ln])], inputs=pkg.INPUTS_RECURSIVE)
+    v2, _ = vb2.run(full=True)
+    r2 = circ.trace(vb2, export=False, preprocessed=False)
+    assert v2.cpu().numpy().tolist() == [0, 1]
+    br = r2["bad_row"].cpu().numpy()
+    assert br[0] == -1 and br[1] >= 0
