@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--fixture", default="small_proof.bin")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--last-layer", action="store_true", help="the circuit of examples/last-layer instead of the recursive verifier")
     args = ap.parse_args()
     import torch
     pkg = importlib.import_module("recursive-stwo_b200")
@@ -24,7 +25,7 @@ def main():
     vb = pkg.VerifyBatch([blob] * args.proofs, inputs=inputs)
     v, _ = vb.run(full=True)
     assert int(v.sum().item()) == 0
-    circ = pkg.VerifierCircuit(vb.shape, inputs=inputs)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=inputs, last_layer=args.last_layer)
     info = {k: getattr(circ.info, k) for k, _ in circ.info._fields_}
     acc = {}
     for r in range(args.reps + 1):
@@ -48,7 +49,8 @@ def main():
     print(json.dumps({"fixture": args.fixture, "proofs": n, "info": info, "trace_stage_ms": acc, "verify_plus_trace_ms": ms,
                       "proofs_per_sec_verify_plus_trace": n / (ms * 1e-3),
                       "export_gbs": export_bytes / (acc["export"] * 1e-3) / 1e9,
-                      "eval_perms_per_sec": n * info["n_flow"] / (acc["eval"] * 1e-3),
+                      "eval_perms_per_sec": n * info["n_flow"] / (acc["eval"] * 1e-3), "last_layer": args.last_layer,
+                      "eval_tape_instructions_per_sec": n * info["n_ins"] / (acc["eval"] * 1e-3),
                       "circuit_workspace_mb": circ.workspace_bytes(n) >> 20}))
 
 
