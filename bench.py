@@ -39,6 +39,9 @@ FIXTURE = "small_proof.bin"
 # warp instructions one permutation executes in the path kernels (ncu smsp__inst_executed / permutations,
 # profiles/r01*_ncu.txt) — the unit of the integer-issue roofline
 LANE_OPS_PER_PERM = 4719
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per proof of shape S from the ncu --set full captures of the
+# 4096-proof step: profiles/r01l_k_tape_eval_grid_ncu.txt (3.00 + 5.21 GB) and profiles/r01l_k_export_fused_ncu.txt (3.60 + 13.90 GB)
+TRAFFIC_PER_PROOF = {"k_tape_eval": (2.999618e9 + 5.212075e9) / 4096, "k_cs_export_vals_tiled": (3.598645e9 + 13.901859e9) / 4096}
 
 
 def peaks():
@@ -355,7 +358,8 @@ def main():
     roofline = {
         "bound": "int32-issue", "kernel": kernel_of.get(dom, "k_" + dom), "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
-        "perms_per_launch": dom_perms, "launch_ms": acc[dom], "share_of_step": acc[dom] / total_ms, "traffic": None,
+        "perms_per_launch": dom_perms, "launch_ms": acc[dom], "share_of_step": acc[dom] / total_ms,
+        "traffic": TRAFFIC_PER_PROOF.get(kernel_of.get(dom, "k_" + dom), 0) * n_local or None,
         "stage_ms": acc,
         "hbm": {"bound": "hbm", "achieved": path_bytes / (acc[dom] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": path_bytes / (acc[dom] * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": path_bytes,
@@ -367,7 +371,9 @@ def main():
     export_gbs = export_bytes / (acc["trace_export"] * 1e-3) / 1e9
     roofline_export = {"bound": "hbm", "kernel": "k_cs_export_vals_tiled", "achieved": export_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                        "frac": export_gbs / pk["hbm_gbs"], "peak_src": pk["src"], "algorithmic_bytes_per_launch": export_bytes,
-                       "launch_ms": acc["trace_export"], "share_of_step": acc["trace_export"] / total_ms, "traffic": None}
+                       "launch_ms": acc["trace_export"], "share_of_step": acc["trace_export"] / total_ms,
+                       "traffic": TRAFFIC_PER_PROOF["k_cs_export_vals_tiled"] * n_local,
+                       "note": "check_arithmetics is fused into this pass; traffic < algorithmic bytes because variables are re-read from L2"}
     secondary = {}
     if not args.no_secondary and rank == 0:
         n_states = 1 << 22

@@ -233,6 +233,10 @@ typedef struct {
 typedef struct {
     uint32_t n_ins, n_perms, n_levels, n_input_words;
     const uint32_t *ins, *level_start /* n_levels + 1 */, *perms;
+    /* emulated permutations (STWO_B200_T_EPOSEIDON): n_eperms records of 405 words = the four limb variables, then the 401
+     * variables poseidon_permute_emulated creates (primitives/poseidon31/src/emulated.rs:104-221), in creation order */
+    uint32_t n_eperms;
+    const uint32_t *eperms;
 } stwo_b200_cs_tape;
 #define STWO_B200_T_ADD 1
 #define STWO_B200_T_MUL 2
@@ -246,6 +250,12 @@ typedef struct {
 #define STWO_B200_T_COORD 10
 #define STWO_B200_T_BIT 11
 #define STWO_B200_T_POSEIDON 12
+#define STWO_B200_T_M4 13
+#define STWO_B200_T_POW5M4 14
+#define STWO_B200_T_HADAMARD 15
+#define STWO_B200_T_GRANDSUM 16
+#define STWO_B200_T_POW4 17
+#define STWO_B200_T_EPOSEIDON 18
 
 /* K6: variables[] (and the Poseidon flow) of every batch item from its witness stream (n_input_words words per item,
  * lane-interleaved like the values).  Replaces the `value` arithmetic of every DSL call: primitives/fields/src/*.rs,

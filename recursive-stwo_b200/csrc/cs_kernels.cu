@@ -36,7 +36,8 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
 // the instructions of a level; a barrier separates levels.  Instruction words are warp-uniform broadcast loads.
 constexpr int kEvalThreads = 1024;
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
-                                                            const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words) {
+                                                            const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
+                                                            const u32 *__restrict__ eperms) {
     const u32 lane = threadIdx.x % b.lanes, slot = threadIdx.x / b.lanes, n_slots = kEvalThreads / b.lanes;
     const u32 item = blockIdx.x * b.lanes + lane;
     const bool live = item < b.n_batch;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__r
             for (u32 k = lo + slot; k < hi; k += n_slots) {
                 const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
                 tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                tape::eval(v, in, perms);
+                tape::eval(v, in, perms, eperms);
             }
         __syncthreads();
     }
@@ -74,7 +75,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned n_ctas,
 template <bool UNROLLED>
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                  const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
-                                                                 unsigned *barrier) {
+                                                                 unsigned *barrier, const u32 *__restrict__ eperms) {
     const u32 lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     const u32 n_groups = (b.n_batch + 31) / 32, n_warps = gridDim.x * (kEvalThreads / 32);
     const u32 gw = warp * gridDim.x + blockIdx.x;            // consecutive work items land on different SMs
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
             if (item < b.n_batch) {
                 const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
                 tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms);
+                tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
             }
         }
         grid_barrier(barrier, gridDim.x, phase);
@@ -290,7 +291,7 @@ Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
 }  // namespace
 
 static_assert(sizeof(tape::Perm) == 48 && sizeof(tape::Ins) == 16, "tape records mirror the C ABI");
-static_assert(tape::T_POSEIDON == STWO_B200_T_POSEIDON && tape::T_ADD == STWO_B200_T_ADD && tape::T_BIT == STWO_B200_T_BIT, "opcodes mirror the C ABI");
+static_assert(tape::T_EPOSEIDON == STWO_B200_T_EPOSEIDON && tape::T_M4 == STWO_B200_T_M4 && tape::T_POSEIDON == STWO_B200_T_POSEIDON && tape::T_ADD == STWO_B200_T_ADD && tape::T_BIT == STWO_B200_T_BIT, "opcodes mirror the C ABI");
 
 extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
                                               void *stream) {
@@ -304,6 +305,8 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     const tape::Perm *perms = reinterpret_cast<const tape::Perm *>(t->perms);
     const u32 *level_start = t->level_start;
     u32 n_levels = t->n_levels, n_input_words = t->n_input_words;
+    const u32 *eperms = t->eperms;
+    if (t->n_eperms && !eperms) return STWO_B200_E_BAD_ARG;
     // grid-wide levels while the batch has fewer lane groups than a few waves of SMs; CTA-local levels beyond that
     static int n_sm = 0, coop = 0, grid_mode = -1, unrolled = 0;
     if (!n_sm) {
@@ -323,11 +326,11 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
         if (!barriers) STWO_CUDA(cudaMalloc(&barriers, 64 * sizeof(unsigned)));
         unsigned *bar = barriers + (next++ % 64);
         STWO_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-        void *args[] = {(void *)&ins, (void *)&level_start, (void *)&n_levels, (void *)&perms, (void *)&b, (void *)&witness, (void *)&n_input_words, (void *)&bar};
+        void *args[] = {(void *)&ins, (void *)&level_start, (void *)&n_levels, (void *)&perms, (void *)&b, (void *)&witness, (void *)&n_input_words, (void *)&bar, (void *)&eperms};
         const void *fn = unrolled ? (const void *)k_tape_eval_grid<true> : (const void *)k_tape_eval_grid<false>;
         STWO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)n_sm), dim3(kEvalThreads), args, 0, st));
     } else {
-        k_tape_eval<<<n_groups, kEvalThreads, 0, st>>>(ins, level_start, n_levels, perms, b, witness, n_input_words);
+        k_tape_eval<<<n_groups, kEvalThreads, 0, st>>>(ins, level_start, n_levels, perms, b, witness, n_input_words, eperms);
     }
     note_launch(1);
     return cuda_status(cudaGetLastError());

@@ -54,6 +54,9 @@ public:
     // value definitions
     std::vector<tape::Ins> tape_;                   // recording order
     std::vector<tape::Perm> perms;                  // one per Poseidon flow entry
+    std::vector<u32> eperms;                        // one tape::EPOSEIDON_REC record per emulated permutation
+    bool macro_on = false;                          // inside an emulated permutation: variables are defined by its record
+    std::vector<u32> macro_vars;
     u32 n_vars = 0, n_input_words = 0, num_input = 3;
     bool is_program_started = false, padded = false;
     u32 n_rows_unpadded = 0, n_flow_unpadded = 0;
@@ -87,8 +90,25 @@ public:
     u32 do_grandsum_gate(u32 a, u32 b) { return special_gate(tape::T_GRANDSUM, a, b, 0, 1, 1); } // :224-245
     u32 fresh(u32 op_, u32 a, u32 b) {
         const u32 c = n_vars++;
-        if (op_ != tape::T_NONE) tape_.push_back({op_, c, a, b});
+        if (macro_on) macro_vars.push_back(c);
+        else if (op_ != tape::T_NONE) tape_.push_back({op_, c, a, b});
         return c;
+    }
+    // Brackets the body of poseidon_permute_emulated: the rows are recorded as usual, the 401 variable definitions collapse
+    // into one T_EPOSEIDON instruction.  Constants allocated on first use inside the body keep their own definitions.
+    struct MacroPause {
+        ConstraintSystem &cs; bool was;
+        explicit MacroPause(ConstraintSystem &c) : cs(c), was(c.macro_on) { cs.macro_on = false; }
+        ~MacroPause() { cs.macro_on = was; }
+    };
+    void begin_macro() { macro_on = true; macro_vars.clear(); }
+    void end_macro(const u32 in[4]) {
+        macro_on = false;
+        if (macro_vars.size() != tape::EPOSEIDON_VARS) throw std::logic_error("emulated permutation did not create 401 variables");
+        const u32 rec = (u32)(eperms.size() / tape::EPOSEIDON_REC);
+        eperms.insert(eperms.end(), in, in + 4);
+        eperms.insert(eperms.end(), macro_vars.begin(), macro_vars.end());
+        tape_.push_back({tape::T_EPOSEIDON, rec, 0, 0});
     }
     void insert_gate(u32 a, u32 b, u32 c, u32 op_) {                 // :101-115
         is_program_started = true;
@@ -113,6 +133,7 @@ public:
         return c;
     }
     u32 new_m31_constant(u32 value) {                                // :221-230
+        MacroPause pause(*this);
         is_program_started = true;
         const u32 c = fresh(tape::T_MULC, 1, value % M31_P);
         row(1, 0, c, value);
@@ -143,6 +164,7 @@ public:
         return c;
     }
     u32 new_qm31_constant(const QM31Const &v) {                      // :256-277
+        MacroPause pause(*this);
         is_program_started = true;
         const u32 c = n_vars++;                                      // value = a + b of the tie row, defined below
         const u32 fr = new_m31_constant(v.v[0]), fi = new_m31_constant(v.v[1]);

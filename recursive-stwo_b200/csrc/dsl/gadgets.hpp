@@ -202,6 +202,8 @@ struct Poseidon2HalfVar {
             const QM31Var nr0 = re[0] - db0, nr1 = re[1] - db1;
             state[0] = nl0; state[1] = nl1; state[2] = nr0; state[3] = nr1;
         } else { state[0] = le[0]; state[1] = le[1]; state[2] = re[0]; state[3] = re[1]; }
+        const u32 limbs[4] = {state[0].variable, state[1].variable, state[2].variable, state[3].variable};
+        cs->begin_macro();
         apply_16x16_mds_matrix(state);
         full_rounds(cs, state, p2k::RC_FIRST);
         for (u32 r = 0; r < 14; r++) {
@@ -224,6 +226,7 @@ struct Poseidon2HalfVar {
             }
         }
         full_rounds(cs, state, p2k::RC_LAST);
+        cs->end_macro(limbs);
         Poseidon2HalfVar out_left, out_right;
         out_left.cs = out_right.cs = cs;
         out_left.left_variable = state[0].variable; out_left.right_variable = state[1].variable;

@@ -38,6 +38,9 @@ struct RecordedCircuit {
                 l = std::max(l, lv(p.swap_var));
                 break;
             }
+            case tape::T_EPOSEIDON:
+                for (u32 q = 0; q < 4; q++) l = std::max(l, lv(c.eperms[(size_t)in.dst * tape::EPOSEIDON_REC + q]));
+                break;
             default: break;
             }
             l += 1;
@@ -45,6 +48,8 @@ struct RecordedCircuit {
             max_level = std::max(max_level, l);
             if (in.op == tape::T_POSEIDON) {
                 for (u32 o : c.perms[in.dst].out) if (o != tape::NO_VAR) var_level[o] = l;
+            } else if (in.op == tape::T_EPOSEIDON) {
+                for (u32 q = 0; q < tape::EPOSEIDON_VARS; q++) var_level[c.eperms[(size_t)in.dst * tape::EPOSEIDON_REC + 4 + q]] = l;
             } else var_level[in.dst] = l;
         }
         // levels are 1 .. max_level; level l occupies ins[level_start[l-1] .. level_start[l])

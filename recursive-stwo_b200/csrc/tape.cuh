@@ -30,7 +30,13 @@ enum : u32 {
     T_HADAMARD,                                 // dst = a (.) b              (do_hadamard, do_pow5_gate)
     T_GRANDSUM,                                 // dst = (s, s, s, s), s = sum of the 8 coordinates of a and b
     T_POW4,                                     // dst = a^4 coordinate-wise  (the witness of pow5m4 / pow5, emulated.rs:37-78)
+    T_EPOSEIDON,                                // one whole emulated permutation: record dst defines its 401 variables
 };
+// A whole poseidon_permute_emulated call (primitives/poseidon31/src/emulated.rs:104-221, after the swap) as ONE instruction:
+// the 401 variables it creates form a dependency chain ~170 levels deep, which one warp walks in registers instead of the
+// grid synchronising 170 times.  Record: the four limb variables, then the 401 created variables in creation order
+// (11 initial MDS + 8 x 19 full rounds + 14 x 17 partial rounds).
+constexpr u32 EPOSEIDON_VARS = 401, EPOSEIDON_REC = 4 + EPOSEIDON_VARS;
 constexpr u32 NO_VAR = 0xffffffffu;
 
 struct Ins { u32 op, dst, a, b; };
@@ -133,8 +139,54 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(st[4 * k], st[4 * k + 1], st[4 * k + 2], st[4 * k + 3]));
 }
 
+HD void eval_eposeidon(const View &v, const u32 *rec) {
+    const u32 *out = rec + 4;
+    u32 k = 0;
+    qm31_t s[4];
+    for (int i = 0; i < 4; i++) s[i] = ldv(v, rec[i]);
+    auto emit = [&](qm31_t x) { stv(v, out[k++], x); return x; };
+    auto sum_mix = [&]() {                       // t = s0 + s1 + s2 + s3 (three rows), s_i += t
+        qm31_t t = emit(qm31::add(s[0], s[1]));
+        t = emit(qm31::add(t, s[2]));
+        t = emit(qm31::add(t, s[3]));
+        for (int i = 0; i < 4; i++) s[i] = emit(qm31::add(s[i], t));
+    };
+    auto full_rounds = [&](const u32 *rc) {      // emulated.rs:121-150 / :190-219
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < 4; i++) {
+                const u32 *c = rc + 16 * r + 4 * i;
+                s[i] = emit(qm31::add(s[i], qm31::mk(c[0], c[1], c[2], c[3])));
+            }
+            for (int i = 0; i < 4; i++) {
+                const qm31_t b = emit(q_pow4(s[i]));
+                s[i] = emit(q_m4(q_had(s[i], b)));
+            }
+            sum_mix();
+        }
+    };
+    for (int i = 0; i < 4; i++) s[i] = emit(q_m4(s[i]));                 // apply_16x16_mds_matrix (:24-35)
+    sum_mix();
+    full_rounds(poseidon2::K.rc_first);
+    for (int r = 0; r < 14; r++) {                                      // :151-189
+        const qm31_t first_only = emit(qm31::mk(s[0].v[0], 0, 0, 0));   // hadamard with the variable 1
+        const qm31_t without_first = emit(qm31::mk(0, s[0].v[1], s[0].v[2], s[0].v[3]));
+        const qm31_t a = emit(qm31::add(first_only, qm31::from_m31(poseidon2::K.rc_part[r])));
+        const qm31_t b = emit(q_pow4(a));
+        const qm31_t g = emit(q_had(a, b));
+        s[0] = emit(qm31::add(g, without_first));
+        const qm31_t sum_1 = emit(q_grandsum(s[0], s[1])), sum_2 = emit(q_grandsum(s[2], s[3]));
+        const qm31_t sum = emit(qm31::add(sum_1, sum_2));
+        for (int i = 0; i < 4; i++) {
+            const u32 *d = poseidon2::K.diag + 4 * i;
+            const qm31_t hv = emit(q_had(s[i], qm31::mk(d[0], d[1], d[2], d[3])));
+            s[i] = emit(qm31::add(sum, hv));
+        }
+    }
+    full_rounds(poseidon2::K.rc_last);
+}
+
 template <bool UNROLLED = false>
-HD void eval(const View &v, const Ins &in, const Perm *perms) {
+HD void eval(const View &v, const Ins &in, const Perm *perms, const u32 *eperms = nullptr) {
     switch (in.op) {
     case T_ADD: stv(v, in.dst, qm31::add(ldv(v, in.a), ldv(v, in.b))); break;
     case T_MUL: stv(v, in.dst, qm31::mul(ldv(v, in.a), ldv(v, in.b))); break;
@@ -153,6 +205,7 @@ HD void eval(const View &v, const Ins &in, const Perm *perms) {
     case T_HADAMARD: stv(v, in.dst, q_had(ldv(v, in.a), ldv(v, in.b))); break;
     case T_GRANDSUM: stv(v, in.dst, q_grandsum(ldv(v, in.a), ldv(v, in.b))); break;
     case T_POW4: stv(v, in.dst, q_pow4(ldv(v, in.a))); break;
+    case T_EPOSEIDON: eval_eposeidon(v, eperms + (size_t)in.dst * EPOSEIDON_REC); break;
     default: break;
     }
 }
@@ -160,7 +213,11 @@ HD void eval(const View &v, const Ins &in, const Perm *perms) {
 // ---- the O(n_rows) loops of the constraint system, per batch item ------------------------------------------------------
 // check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): one row
 HD bool gate_ok(qm31_t va, qm31_t vb, qm31_t vc, u32 op, u32 enforce_c_m31) {
-    const qm31_t want = qm31::add(qm31::mul_m31(qm31::add(va, vb), op), qm31::mul_m31(qm31::mul(va, vb), m31::subc(1, op)));
+    // op is a row constant, i.e. uniform across a warp of batch items: the two pure gates skip half of the general formula
+    qm31_t want;
+    if (op == 1) want = qm31::add(va, vb);
+    else if (op == 0) want = qm31::mul(va, vb);
+    else want = qm31::add(qm31::mul_m31(qm31::add(va, vb), op), qm31::mul_m31(qm31::mul(va, vb), m31::subc(1, op)));
     bool ok = qm31::eq(want, vc);
     if (enforce_c_m31 && (vc.v[1] | vc.v[2] | vc.v[3])) ok = false;
     return ok;

@@ -123,7 +123,7 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
         tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
                      flow_swap + (size_t)p * c.num_poseidon_invocations(), 1};
         tape::prologue(v);
-        for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data());
+        for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data(), c.eperms.data());
         bad_row[p] = -1;
         for (u32 i = 0; i < c.num_plonk_rows(); i++) {
             bool ok;
