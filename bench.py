@@ -392,6 +392,32 @@ def main():
                      "merkle_sweep_perms_per_sec": merkle_sweep(pkg, dev),
                      "merkle_sweep_config": "2 trees x 2^20 leaves x 8 cols, 128 queries (BASELINE configs[2])"}
 
+    if not args.no_secondary and rank == 0:
+        # BASELINE configs[1] (examples/last-layer): the last-layer circuit's trace for 256 replicas of the Poseidon31 twin of
+        # hybrid_hash.bin (Plonk-without-Poseidon system, emulated Poseidon2, 2^17 rows x 20 columns), verification included
+        lblob = open(os.path.join(ROOT, "tests", "golden", "proofs", "level13-1.bin"), "rb").read()
+        lvb = pkg.VerifyBatch([lblob] * 256, inputs=pkg.INPUTS_RECURSIVE)
+        lcirc = pkg.VerifierCircuit(lvb.shape, last_layer=True)
+
+        def last_step(pre=False):
+            lv, _ = lvb.run(full=True)
+            return lv, lcirc.trace(lvb, check=True, export=True, preprocessed=pre)
+        for _ in range(3):
+            lv, lr = last_step(pre=True)
+        assert int(lv.sum().item()) == 0 and int((lr["bad_row"] != -1).sum().item()) == 0
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(5):
+            last_step()
+        k1.record()
+        torch.cuda.synchronize()
+        lms = k0.elapsed_time(k1) / 5
+        lcirc.trace(lvb, check=True, export=True, preprocessed=False, timed=True)
+        secondary["last_layer"] = {"config": "BASELINE configs[1]: 256 replicas of level13-1.bin, verify + last-layer circuit trace",
+                                   "rows": lcirc.info.n_rows, "columns": 20, "tape_levels": lcirc.info.n_levels,
+                                   "ms_per_batch": lms, "proofs_per_sec": 256 / (lms * 1e-3), "trace_stage_ms": lcirc.stage_ms()}
+        del lvb, lcirc
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,

@@ -8,6 +8,7 @@
 #pragma once
 #include "fri.cuh"
 #include "merkle.cuh"
+#include "decommit_coop.cuh"
 
 namespace verify {
 
@@ -147,6 +148,58 @@ HD void stage_single_tree(const Workspace &ws, u32 p, u32 t) {
                                     ws.scratch_single(p, t), idx, &perms);
     VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
     if (!ok) fail_shared(&dt, proof::ST_MERKLE);
+}
+
+// cooperative form: a group of lanes per (proof, tree); tab = group-shared scratch of decommit::single_tab_words(nq) words.
+// The node tables use this tree's slice of single_scratch contiguously (16 * nq words).
+template <class Co>
+HD void stage_single_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 t, u32 *tab) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries;
+    decommit::SingleShape sh;
+    if (t < 3) {
+        sh.hA = d.log_plonk; sh.nA = proof::plonk_cols(t); sh.hB = d.log_pos; sh.nB = proof::n_cols(t) - proof::plonk_cols(t);
+        sh.depth = sh.hA > sh.hB ? sh.hA : sh.hB;
+    } else { sh.hA = d.max_first; sh.nA = 8; sh.hB = 0; sh.nB = 0; sh.depth = d.max_first; }
+    u32 *q = tab + decommit::single_tab_words(nq);                     // query positions, group-shared
+    for (u32 i = co.lane(); i < nq; i += co.size()) q[i] = fri::position(d, dt.fs.raw_queries[i], sh.depth);
+    co.sync();
+    u32 perms = 0;
+    u32 *nodes = ws.single_scratch + ((size_t)p * 4 + t) * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq;
+    const bool ok = decommit::single_tree_coop(co, sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
+                                               w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
+                                               nodes, tab, &perms);
+    if (co.lane() == 0) {
+        VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
+        if (!ok) fail_shared(&dt, proof::ST_MERKLE);
+    }
+}
+template <class Co>
+HD void stage_pair_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 f, u32 *tab) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries, depth = ws.shape.fri_depth(f);
+    u32 *q = tab + decommit::pair_tab_words(nq);
+    for (u32 i = co.lane(); i < nq; i += co.size()) q[i] = fri::position(d, dt.fs.raw_queries[i], depth);
+    co.sync();
+    const u32 *hw = w + (f ? d.in_hash_witness[f - 1] : d.fl_hash_witness);
+    const u32 n_hw = f ? d.in_n_hash_witness[f - 1] : d.fl_n_hash_witness;
+    const u32 *root = w + (f ? d.in_commitment[f - 1] : d.fl_commitment);
+    u32 *hint = ws.hint_of(p, f, 0);
+    u32 *self_vals = hint, *sib_vals = hint + nq * decommit::MAX_DATA_LAYERS * 4, *sib_hashes = sib_vals + nq * decommit::MAX_DATA_LAYERS * 4;
+    u32 *nodes = ws.pair_scratch + ((size_t)p * ws.shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq;
+    u32 perms = 0;
+    const bool ok = decommit::pair_tree_coop(co, depth, ws.shape.fri_data_mask(f), q, nq, ws.vals_of(p, f), *ws.nvals_of(p, f), hw, n_hw, root,
+                                             self_vals, sib_vals, sib_hashes, nodes, tab, &perms);
+    if (co.lane() == 0) {
+        VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
+        if (!ok) fail_shared(&dt, f ? proof::ST_FRI_INNER : proof::ST_FRI_FIRST);
+    }
 }
 
 // full mode: SinglePathMerkleProofVar::verify for one (proof, tree, query)

@@ -7,6 +7,7 @@
 #include <map>
 #include <array>
 #include <string.h>
+#include <stdlib.h>
 
 using namespace stwo_b200;
 using verify::Workspace;
@@ -43,6 +44,37 @@ __global__ void __launch_bounds__(kT) k_pair_tree(const Workspace ws, u32 p0, u3
     u32 idx = blockIdx.x * kT + threadIdx.x;
     if (idx < pn * ws.shape.n_fri_trees()) verify::stage_pair_tree(ws, p0 + idx % pn, idx / pn);
 }
+// Cooperative tree rebuilds (decommit_coop.cuh): G lanes of a warp per (proof, tree).  G trades latency (long chains per
+// lane when small) against lane utilisation (idle lanes near the root when large): 16 for small batches, 4 for large ones.
+template <int G>
+struct CoopGroup {
+    u32 l; unsigned mask;
+    __device__ __forceinline__ u32 lane() const { return l; }
+    __device__ __forceinline__ u32 size() const { return G; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+constexpr int kCoopThreads = 64;          // upper bound; the launch shrinks the block when the group tables would not fit
+template <int G>
+__global__ void __launch_bounds__(kCoopThreads) k_single_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+    extern __shared__ u32 smem[];
+    const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= pn * 4) return;                                       // whole groups leave together
+    CoopGroup<G> co;
+    co.l = threadIdx.x % G;
+    co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
+    verify::stage_single_tree_coop(co, ws, p0 + grp % pn, grp / pn, smem + (threadIdx.x / G) * tab_words);
+}
+template <int G>
+__global__ void __launch_bounds__(kCoopThreads) k_pair_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+    extern __shared__ u32 smem[];
+    const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= pn * ws.shape.n_fri_trees()) return;
+    CoopGroup<G> co;
+    co.l = threadIdx.x % G;
+    co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
+    verify::stage_pair_tree_coop(co, ws, p0 + grp % pn, grp / pn, smem + (threadIdx.x / G) * tab_words);
+}
+
 __global__ void __launch_bounds__(kT) k_single_path(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
     const u32 per_t = pn * ws.shape.n_queries;
@@ -82,6 +114,49 @@ bool pool_init() {
         if (cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
     }
     return true;
+}
+
+// group width of the tree-rebuild kernels: 0 = one thread per tree (decommit.cuh); STWO_B200_TREE_G overrides the choice
+int tree_group_width(u32 n_proofs) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("STWO_B200_TREE_G");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return forced;
+    return n_proofs <= 1024 ? 16 : 8;
+}
+// shared memory of a block = (threads / G) group tables; large query counts need the opt-in limit
+constexpr size_t kCoopSmemMax = 160 * 1024;
+template <class K>
+bool coop_launch(K kernel, int G, size_t groups, u32 tab_words, const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    int threads = kCoopThreads;
+    while (threads > 32 && (size_t)(threads / G) * tab_words * 4 > kCoopSmemMax) threads /= 2;
+    const size_t smem = (size_t)(threads / G) * tab_words * 4;
+    if (smem > kCoopSmemMax) return false;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmemMax) != cudaSuccess) return false;
+    kernel<<<(unsigned)((groups * G + threads - 1) / threads), threads, smem, st>>>(ws, p0, n, tab_words);
+    return true;
+}
+void launch_single_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    const int G = tree_group_width(ws.n_proofs);
+    const u32 nq = ws.shape.n_queries, tab = decommit::single_tab_words(nq) + nq;
+    const size_t groups = (size_t)n * 4;
+    bool done = false;
+    if (G == 16) done = coop_launch(k_single_tree_coop<16>, 16, groups, tab, ws, p0, n, st);
+    else if (G == 8) done = coop_launch(k_single_tree_coop<8>, 8, groups, tab, ws, p0, n, st);
+    else if (G == 4) done = coop_launch(k_single_tree_coop<4>, 4, groups, tab, ws, p0, n, st);
+    if (!done) k_single_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+}
+void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    const int G = tree_group_width(ws.n_proofs);
+    const u32 nq = ws.shape.n_queries, tab = decommit::pair_tab_words(nq) + nq;
+    const size_t groups = (size_t)n * ws.shape.n_fri_trees();
+    bool done = false;
+    if (G == 16) done = coop_launch(k_pair_tree_coop<16>, 16, groups, tab, ws, p0, n, st);
+    else if (G == 8) done = coop_launch(k_pair_tree_coop<8>, 8, groups, tab, ws, p0, n, st);
+    else if (G == 4) done = coop_launch(k_pair_tree_coop<4>, 4, groups, tab, ws, p0, n, st);
+    if (!done) k_pair_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 
 cudaEvent_t g_ev[STWO_B200_N_STAGE_KERNELS + 1] = {nullptr};
@@ -166,11 +241,11 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         int e = 0;
 #define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
         MARK(); k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws, 0, n);
-        MARK(); k_single_tree<<<nblk((size_t)n * 4), kT, 0, st>>>(ws, 0, n);
+        MARK(); launch_single_tree(ws, 0, n, st);
         MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
         MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
         MARK(); k_folds<<<nblk(n), kT, 0, st>>>(ws, 0, n);
-        MARK(); k_pair_tree<<<nblk((size_t)n * nf), kT, 0, st>>>(ws, 0, n);
+        MARK(); launch_pair_tree(ws, 0, n, st);
         MARK();
         if (full) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
         MARK();
@@ -191,7 +266,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         cudaStream_t a = g_pool[2 * sl], b = g_pool[2 * sl + 1];
         STWO_CUDA(cudaStreamWaitEvent(a, g_fork, 0));
         k_fiat_shamir<<<nblk(n), kT, 0, a>>>(ws, p0, n);
-        k_single_tree<<<nblk((size_t)n * 4), kT, 0, a>>>(ws, p0, n);
+        launch_single_tree(ws, p0, n, a);
         if (full) {
             STWO_CUDA(cudaEventRecord(g_tree_done[sl], a));
             STWO_CUDA(cudaStreamWaitEvent(b, g_tree_done[sl], 0));
@@ -201,7 +276,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, a>>>(ws, p0, n);
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
         k_folds<<<nblk(n), kT, 0, a>>>(ws, p0, n);
-        k_pair_tree<<<nblk((size_t)n * nf), kT, 0, a>>>(ws, p0, n);
+        launch_pair_tree(ws, p0, n, a);
         if (full) {
             k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
             STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));

@@ -34,6 +34,7 @@ void hs_path_root(const stwo_b200_path_shape *shape, u32 index, const u32 *cols,
 // ---- full verifier on the host: same stage functions the CUDA kernels dispatch, grids emulated by loops -----------------
 #include "../../recursive-stwo_b200/csrc/verify.cuh"
 #include <stdlib.h>
+#include <vector>
 #include <string.h>
 extern "C" {
 size_t hs_detail_size() { return sizeof(verify::Detail); }
@@ -49,11 +50,19 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     verify::carve(ws, base);
     const u32 nq = ws.shape.n_queries, nf = ws.shape.n_fri_trees();
     for (u32 p = 0; p < n; p++) verify::stage_fiat_shamir(ws, p);
-    for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) verify::stage_single_tree(ws, p, t);
+    const bool coop = (full & 2) != 0;          // bit 1: the cooperative tree rebuilds (group of one lane on the host)
+    full &= 1;
+    std::vector<u32> tab(decommit::pair_tab_words(nq) + decommit::single_tab_words(nq) + 2 * nq + 64);
+    decommit::CoopOne one;
+    for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) {
+        if (coop) verify::stage_single_tree_coop(one, ws, p, t, tab.data()); else verify::stage_single_tree(ws, p, t);
+    }
     for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) verify::stage_group(ws, p, g);
     for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) for (u32 i = 0; i < nq; i++) verify::stage_answer(ws, p, g, i);
     for (u32 p = 0; p < n; p++) verify::stage_folds(ws, p);
-    for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) verify::stage_pair_tree(ws, p, f);
+    for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) {
+        if (coop) verify::stage_pair_tree_coop(one, ws, p, f, tab.data()); else verify::stage_pair_tree(ws, p, f);
+    }
     if (full) {
         for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) for (u32 i = 0; i < nq; i++) verify::stage_single_path(ws, p, t, i);
         for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) for (u32 i = 0; i < nq; i++) verify::stage_pair_path(ws, p, f, i);

@@ -28,11 +28,12 @@ def test_detail_struct_layout(hostsim):
     assert hostsim.hs_detail_size() == ctypes.sizeof(Detail)
 
 
+@pytest.mark.parametrize("coop", [0, 2], ids=["thread-per-tree", "cooperative"])
 @pytest.mark.parametrize("name", FIXTURES)
-def test_fixture_matches_oracle(hostsim, orc, name):
+def test_fixture_matches_oracle(hostsim, orc, name, coop):
     buf, n = O.load_proof(name)
     o = O.verify_proof(buf, n, O.inputs_for(name))
-    dt = run_hostsim(hostsim, [(buf, n)], shape_of(buf), O.inputs_for(name))
+    dt = run_hostsim(hostsim, [(buf, n)], shape_of(buf), O.inputs_for(name), full=1 | coop)
     compare_detail(dt[0], o)
     assert dt[0].verdict == 0 and dt[0].n_perms_hints == o.n_perms_hints
 
@@ -41,8 +42,9 @@ REGIONS = ["commitment0", "sampled0", "pow_nonce", "last_coeffs", "queried0", "h
            "fri_first_hash_witness", "fri_inner0_witness", "fri_inner0_hash_witness", "fri_inner_last_witness"]
 
 
+@pytest.mark.parametrize("coop", [0, 2], ids=["thread-per-tree", "cooperative"])
 @pytest.mark.parametrize("name", ["small_proof.bin", "level13-1.bin"])
-def test_tampered_batch_matches_oracle(hostsim, orc, name):
+def test_tampered_batch_matches_oracle(hostsim, orc, name, coop):
     buf, n = O.load_proof(name)
     offs = O.proof_offsets(buf, n)
     blobs = [(buf, n)]
@@ -53,7 +55,7 @@ def test_tampered_batch_matches_oracle(hostsim, orc, name):
             blobs.append((bad, n))
     blobs.append((buf, n - 4))             # truncated
     blobs.append((buf[:64].copy(), 64))    # header only
-    dts = run_hostsim(hostsim, blobs, shape_of(buf), O.inputs_for(name))
+    dts = run_hostsim(hostsim, blobs, shape_of(buf), O.inputs_for(name), full=1 | coop)
     stages = set()
     for (b, ln), dt in zip(blobs, dts):
         o = O.verify_proof(b, ln, O.inputs_for(name))
