@@ -379,6 +379,178 @@ HD void stage_folds(const Workspace &ws, u32 p) {
     if (!last_ok) fail_shared(&dt, proof::ST_FRI_LAST);
 }
 
+// Cooperative form of stage_folds: a group of lanes per proof, one query per lane for the arithmetic (domain points, M31
+// inversions, folds, last-layer polynomial), lane 0 for the short stream-order bookkeeping (which evaluation of a pair comes
+// from fri_witness).  tab: group-shared, folds_tab_words(nq) words.
+HD u32 folds_tab_words(u32 nq) { return 3 * nq + 8 * nq + 8; }
+template <class Co>
+HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    const u32 nq = d.n_queries, max_first = d.max_first, L = co.lane(), G = co.size();
+    u32 *pos = tab, *sp = pos + nq;
+    u32 *folded = sp + 2 * nq, *sibv = folded + 4 * nq;               // qm31 per query / per unique position
+    u32 *ctl = sibv + 4 * nq;                                          // [0] ns  [1] ok flags
+    if (L == 0) ctl[1] = 0;
+    // ---- first layer: per log size descending, per sorted pair subset, both evaluations
+    {
+        u32 *vals = ws.vals_of(p, 0);
+        if (L == 0) { ctl[2] = 0; ctl[3] = 0; }                        // nv, wi
+        co.sync();
+        for (u32 g = 0; g < dt.n_logs; g++) {
+            const u32 Lg = dt.log_sizes[g];
+            for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], Lg);
+            co.sync();
+            if (L == 0) {
+                for (u32 i = 0; i < nq; i++) sp[i] = pos[i];
+                const u32 ns = decommit::sort_unique(sp, nq);
+                u32 nv = ctl[2], wi = ctl[3];
+                bool ok = true;
+                for (u32 k = 0; k < ns && ok;) {
+                    const u32 start = sp[k] & ~1u;
+                    for (u32 e = start; e < start + 2; e++) {
+                        const u32 *src;
+                        if (k < ns && sp[k] == e) {
+                            u32 i = 0;
+                            while (pos[i] != e) i++;
+                            src = ws.q4(ws.answers, p, g, fri::MAX_LOGS, i);
+                            k++;
+                        } else {
+                            if (wi >= d.fl_n_fri_witness) { ok = false; break; }
+                            src = w + d.fl_fri_witness + 4 * wi++;
+                        }
+                        for (int c = 0; c < 4; c++) vals[nv++] = src[c];
+                    }
+                }
+                if (!ok) ctl[1] |= 1;
+                ctl[2] = nv; ctl[3] = wi;
+            }
+            co.sync();
+        }
+        if (L == 0) {
+            if (ctl[3] != d.fl_n_fri_witness) ctl[1] |= 1;
+            *ws.nvals_of(p, 0) = ctl[2];
+            if (ctl[1] & 1) fail_shared(&dt, proof::ST_FRI_FIRST);
+        }
+        co.sync();
+    }
+    // ---- circle folds, one query per lane
+    {
+        u32 base = 0;
+        const u32 *vals = ws.vals_of(p, 0);
+        for (u32 g = 0; g < dt.n_logs; g++) {
+            const u32 Lg = dt.log_sizes[g];
+            for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], Lg);
+            co.sync();
+            if (L == 0) {
+                for (u32 i = 0; i < nq; i++) sp[i] = pos[i] >> 1;
+                ctl[0] = decommit::sort_unique(sp, nq);
+            }
+            co.sync();
+            const u32 npairs = ctl[0];
+            for (u32 i = L; i < nq; i += G) {
+                const int pi = decommit::find(sp, npairs, pos[i] >> 1);
+                const u32 *pr = vals + base + 8 * (u32)pi;
+                const qm31_t l = fs::qload(pr), r = fs::qload(pr + 4);
+                const qm31_t self = (pos[i] & 1u) ? r : l, sib = (pos[i] & 1u) ? l : r;
+                const cpoint_t pt = circle::dbl(fri::absolute_point(Lg, pos[i]));
+                const qm31_t f = fri::fold_pair(self, sib, pos[i], fs::minv(pt.y), dt.fs.fri_alphas[max_first - Lg]);
+                fs::qstore(ws.q4(ws.circle_folds, p, g, fri::MAX_LOGS, i), f);
+            }
+            co.sync();
+            base += npairs * 8;
+        }
+    }
+    // ---- inner layers
+    for (u32 i = L; i < nq; i += G) fs::qstore(folded + 4 * i, qm31::zero());
+    co.sync();
+    u32 log_size = max_first;
+    for (u32 li = 0; li < d.n_inner; li++) {
+        for (u32 g = 0; g < dt.n_logs; g++)
+            if (dt.log_sizes[g] == log_size) {
+                const qm31_t a2 = fs::qmul(dt.fs.fri_alphas[li], dt.fs.fri_alphas[li]);
+                for (u32 i = L; i < nq; i += G)
+                    fs::qstore(folded + 4 * i, fs::qadd(fs::qmul(a2, fs::qload(folded + 4 * i)), fs::qload(ws.q4(ws.circle_folds, p, g, fri::MAX_LOGS, i))));
+            }
+        log_size -= 1;
+        for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], log_size);
+        co.sync();
+        if (L == 0) {
+            for (u32 i = 0; i < nq; i++) sp[i] = pos[i];
+            const u32 ns = decommit::sort_unique(sp, nq);
+            ctl[0] = ns;
+            u32 *vals = ws.vals_of(p, 1 + li), nv = 0, wi = 0;
+            bool ok = true;
+            for (u32 k = 0; k < ns; k++) {
+                const u32 e = sp[k];
+                u32 i = 0;
+                while (pos[i] != e) i++;
+                qm31_t sv;
+                const int sk = decommit::find(sp, ns, e ^ 1u);
+                if (sk >= 0) { u32 j = 0; while (pos[j] != (e ^ 1u)) j++; sv = fs::qload(folded + 4 * j); }
+                else if (wi < d.in_n_fri_witness[li]) sv = fs::qload(w + d.in_fri_witness[li] + 4 * wi++);
+                else { ok = false; sv = qm31::zero(); }
+                fs::qstore(sibv + 4 * k, sv);
+                if (k == 0 || (sp[k - 1] >> 1) != (e >> 1)) {
+                    const qm31_t fv = fs::qload(folded + 4 * i);
+                    const qm31_t l = (e & 1u) ? sv : fv, r = (e & 1u) ? fv : sv;
+                    fs::qstore(vals + nv, l); fs::qstore(vals + nv + 4, r); nv += 8;
+                }
+            }
+            if (wi != d.in_n_fri_witness[li]) ok = false;
+            *ws.nvals_of(p, 1 + li) = nv;
+            if (!ok) ctl[1] |= 2;
+        }
+        co.sync();
+        const u32 ns = ctl[0];
+        for (u32 i = L; i < nq; i += G) {
+            const int k = decommit::find(sp, ns, pos[i]);
+            const u32 x_inv = fs::minv(fri::absolute_point(log_size, pos[i]).x);
+            const qm31_t f = fri::fold_pair(fs::qload(folded + 4 * i), fs::qload(sibv + 4 * (u32)k), pos[i], x_inv, dt.fs.fri_alphas[li + 1]);
+            fs::qstore(ws.q4(ws.line_folds, p, li, proof::MAX_INNER, i), f);
+            // lanes read folded[] of other queries only through sibv (filled by lane 0 before the barrier): writing now is safe
+            fs::qstore(folded + 4 * i, f);
+        }
+        co.sync();
+    }
+    if (L == 0 && (ctl[1] & 2)) fail_shared(&dt, proof::ST_FRI_INNER);
+    // ---- last layer, one query per lane (each lane folds the polynomial in its own slice of fold_buf when it is large)
+    bool last_ok = true;
+    for (u32 i = L; i < nq; i += G) {
+        const cpoint_t ab = fri::absolute_point(log_size, fri::position(d, dt.fs.raw_queries[i], log_size));
+        const u32 x = m31::subc(m31::mulc(ab.x, ab.x), m31::mulc(ab.y, ab.y));
+        qm31_t ev;
+        if (d.log_last == 0) ev = fs::qload(w + d.last_coeffs);
+        else {
+            // Horner-free evaluation of the fold: value = sum_k coeff[k] * prod_{bits b of k} dbl[log_last - 1 - b'] -- done
+            // iteratively over the coefficients with a per-lane stack of partial sums (depth log_last), no shared buffer
+            u32 dbl[16];
+            dbl[0] = x;
+            for (u32 k = 1; k < d.log_last; k++) { u32 sq = m31::mulc(dbl[k - 1], dbl[k - 1]); dbl[k] = m31::subc(m31::addc(sq, sq), 1); }
+            qm31_t stack[16];
+            u32 depth_used = 0;
+            const u32 n = 1u << d.log_last;
+            for (u32 k = 0; k < n; k++) {
+                qm31_t cur = fs::qload(w + d.last_coeffs + 4 * k);
+                // merge completed pairs: after coefficient k, every trailing 1-bit of k closes a level
+                u32 kk = k, lev = d.log_last;
+                while (kk & 1u) {
+                    lev--;
+                    cur = fs::qadd(stack[--depth_used], qm31::mul_m31(cur, dbl[lev]));
+                    kk >>= 1;
+                }
+                stack[depth_used++] = cur;
+            }
+            ev = stack[0];
+        }
+        fs::qstore(ws.last_evals + ((size_t)p * nq + i) * 4, ev);
+        if (!qm31::eq(ev, fs::qload(folded + 4 * i))) last_ok = false;
+    }
+    if (!last_ok) fail_shared(&dt, proof::ST_FRI_LAST);
+}
+
 // ---- stage 5: FRI layer trees (one thread per (proof, layer)) ---------------------------------------------------------
 HD void stage_pair_tree(const Workspace &ws, u32 p, u32 f) {
     const Desc &d = ws.desc[p];

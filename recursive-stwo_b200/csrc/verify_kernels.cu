@@ -75,6 +75,17 @@ __global__ void __launch_bounds__(kCoopThreads) k_pair_tree_coop(const Workspace
     verify::stage_pair_tree_coop(co, ws, p0 + grp % pn, grp / pn, smem + (threadIdx.x / G) * tab_words);
 }
 
+template <int G>
+__global__ void __launch_bounds__(kCoopThreads) k_folds_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+    extern __shared__ u32 smem[];
+    const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= pn) return;
+    CoopGroup<G> co;
+    co.l = threadIdx.x % G;
+    co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
+    verify::stage_folds_coop(co, ws, p0 + grp, smem + (threadIdx.x / G) * tab_words);
+}
+
 __global__ void __launch_bounds__(kT) k_single_path(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
     const u32 per_t = pn * ws.shape.n_queries;
@@ -157,6 +168,16 @@ void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     else if (G == 8) done = coop_launch(k_pair_tree_coop<8>, 8, groups, tab, ws, p0, n, st);
     else if (G == 4) done = coop_launch(k_pair_tree_coop<4>, 4, groups, tab, ws, p0, n, st);
     if (!done) k_pair_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+}
+
+void launch_folds(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    // one query per lane: 16 lanes per proof (8 when the batch alone fills the GPU)
+    const int G = tree_group_width(ws.n_proofs);
+    const u32 tab = verify::folds_tab_words(ws.shape.n_queries);
+    bool done = false;
+    if (G == 16) done = coop_launch(k_folds_coop<16>, 16, n, tab, ws, p0, n, st);
+    else if (G == 8 || G == 4) done = coop_launch(k_folds_coop<8>, 8, n, tab, ws, p0, n, st);
+    if (!done) k_folds<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 
 cudaEvent_t g_ev[STWO_B200_N_STAGE_KERNELS + 1] = {nullptr};
@@ -244,7 +265,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         MARK(); launch_single_tree(ws, 0, n, st);
         MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
         MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
-        MARK(); k_folds<<<nblk(n), kT, 0, st>>>(ws, 0, n);
+        MARK(); launch_folds(ws, 0, n, st);
         MARK(); launch_pair_tree(ws, 0, n, st);
         MARK();
         if (full) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
@@ -275,7 +296,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         }
         k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, a>>>(ws, p0, n);
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
-        k_folds<<<nblk(n), kT, 0, a>>>(ws, p0, n);
+        launch_folds(ws, p0, n, a);
         launch_pair_tree(ws, p0, n, a);
         if (full) {
             k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);

@@ -52,14 +52,14 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     for (u32 p = 0; p < n; p++) verify::stage_fiat_shamir(ws, p);
     const bool coop = (full & 2) != 0;          // bit 1: the cooperative tree rebuilds (group of one lane on the host)
     full &= 1;
-    std::vector<u32> tab(decommit::pair_tab_words(nq) + decommit::single_tab_words(nq) + 2 * nq + 64);
+    std::vector<u32> tab(decommit::pair_tab_words(nq) + decommit::single_tab_words(nq) + verify::folds_tab_words(nq) + 2 * nq + 64);
     decommit::CoopOne one;
     for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) {
         if (coop) verify::stage_single_tree_coop(one, ws, p, t, tab.data()); else verify::stage_single_tree(ws, p, t);
     }
     for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) verify::stage_group(ws, p, g);
     for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) for (u32 i = 0; i < nq; i++) verify::stage_answer(ws, p, g, i);
-    for (u32 p = 0; p < n; p++) verify::stage_folds(ws, p);
+    for (u32 p = 0; p < n; p++) { if (coop) verify::stage_folds_coop(one, ws, p, tab.data()); else verify::stage_folds(ws, p); }
     for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) {
         if (coop) verify::stage_pair_tree_coop(one, ws, p, f, tab.data()); else verify::stage_pair_tree(ws, p, f);
     }
