@@ -51,13 +51,17 @@ HD u32 sample_off(const Desc &d, u32 t, u32 c, u32 m) {
 
 struct Reader {
     const u32 *w; size_t n, at; bool bad;
+    // deferred canonicity check: when `ranges` is set, words() records (offset, count) pairs there instead of walking the
+    // range, and a group of lanes checks them afterwards (verify::stage_parse_coop); a full list falls back to the walk
+    u32 *ranges = nullptr; u32 n_ranges = 0, max_ranges = 0;
     HDM u32 r32() { if (bad || at + 1 > n) { bad = true; return 0; } return w[at++]; }
     HDM u64 r64() { if (bad || at + 2 > n) { bad = true; return 0; } u64 v = (u64)w[at] | ((u64)w[at + 1] << 32); at += 2; return v; }
     // n_words canonical M31 words; returns their offset
     HDM u32 words(u64 n_words) {
         if (bad || n_words > n - at) { bad = true; return 0; }
         u32 off = (u32)at;
-        for (u64 i = 0; i < n_words; i++) if (w[at + i] >= M31_P) bad = true;
+        if (ranges && n_ranges < max_ranges) { ranges[2 * n_ranges] = off; ranges[2 * n_ranges + 1] = (u32)n_words; n_ranges++; }
+        else for (u64 i = 0; i < n_words; i++) if (w[at + i] >= M31_P) bad = true;
         at += (size_t)n_words;
         return off;
     }
@@ -71,8 +75,10 @@ struct Reader {
 };
 
 // Returns true when the blob is a well-formed proof of a supported shape.
-HD bool parse(const u32 *w, size_t n_words, Desc &d) {
+HD bool parse(const u32 *w, size_t n_words, Desc &d, u32 *ranges = nullptr, u32 max_ranges = 0, u32 *n_ranges_out = nullptr) {
     Reader r{w, n_words, 0, false};
+    r.ranges = ranges; r.max_ranges = max_ranges;
+    struct Done { Reader &r; u32 *out; HDM ~Done() { if (out) *out = r.n_ranges; } } done{r, n_ranges_out};
     d.ok = 0;
     d.log_size_plonk = r.r32();
     d.log_size_poseidon = r.r32();

@@ -106,26 +106,74 @@ HD void fail(Detail &dt, u32 stage) { dt.fail_mask |= 1u << stage; }
 #endif
 HD void fail_shared(Detail *dt, u32 stage) { VERIFY_ATOMIC_OR(&dt->fail_mask, 1u << stage); }
 
-// ---- stage 1: parse + transcript + logup + OODS (one thread per proof) ---------------------------------------------
-HD void stage_fiat_shamir(const Workspace &ws, u32 p) {
-    Desc &d = ws.desc[p];
-    Detail &dt = ws.detail[p];
+// ---- stage 1: parse + transcript + logup + OODS -------------------------------------------------------------------------
+// Three pieces so that only what gates the rest (parse, transcript) sits on the critical path: the canonicity walk over the
+// blob is shared by a group of lanes, and the OODS / logup check runs beside the tree rebuilds.
+HD void reset_detail(Detail &dt) {
     dt.fail_mask = 0; dt.verdict = proof::REJECT; dt.stage = 0; dt.n_perms_hints = 0; dt.n_perms_paths = 0; dt.n_logs = 0;
-    const u32 *w = ws.blob(p);
-    if (!proof::parse(w, ws.blob_words(p), d) || !ws.shape.matches(d)) { d.ok = 0; fail(dt, proof::ST_PARSE); return; }
-    fs::transcript(w, d, dt.fs);
-    dt.n_perms_paths = dt.fs.n_transcript_perms;
-    if (!dt.fs.pow_ok) fail(dt, proof::ST_POW);
-    if (!fs::logup_sum_ok(w, d, dt.fs, ws.input_idx, ws.input_vals, ws.n_inputs)) fail(dt, proof::ST_LOGUP);
-    if (!fs::oods_ok(w, d, dt.fs, &dt.oods_computed, &dt.oods_expected)) fail(dt, proof::ST_OODS);
+}
+// transcript + PoW + the query-collision check (thread per proof)
+HD void stage_transcript(const Workspace &ws, u32 p) {
+    Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    fs::transcript(ws.blob(p), d, dt.fs);
+    VERIFY_ATOMIC_ADD(&dt.n_perms_paths, dt.fs.n_transcript_perms);
+    if (!dt.fs.pow_ok) fail_shared(&dt, proof::ST_POW);
     dt.n_logs = fri::log_sizes(d, dt.log_sizes);
     // duplicated queries at the largest size are not supported by the reference (answer/src/lib.rs:190-195)
     for (u32 i = 0; i < d.n_queries; i++)
         for (u32 j = 0; j < i; j++)
             if (fri::position(d, dt.fs.raw_queries[i], d.max_first) == fri::position(d, dt.fs.raw_queries[j], d.max_first)) {
-                fail(dt, proof::ST_UNSUPPORTED);
+                fail_shared(&dt, proof::ST_UNSUPPORTED);
                 i = d.n_queries; break;
             }
+}
+// logup sum + OODS composition check (thread per proof; needs only the transcript)
+HD void stage_oods(const Workspace &ws, u32 p) {
+    Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    const u32 *w = ws.blob(p);
+    if (!fs::logup_sum_ok(w, d, dt.fs, ws.input_idx, ws.input_vals, ws.n_inputs)) fail_shared(&dt, proof::ST_LOGUP);
+    if (!fs::oods_ok(w, d, dt.fs, &dt.oods_computed, &dt.oods_expected)) fail_shared(&dt, proof::ST_OODS);
+}
+HD void stage_fiat_shamir(const Workspace &ws, u32 p) {
+    Desc &d = ws.desc[p];
+    Detail &dt = ws.detail[p];
+    reset_detail(dt);
+    if (!proof::parse(ws.blob(p), ws.blob_words(p), d) || !ws.shape.matches(d)) { d.ok = 0; fail(dt, proof::ST_PARSE); return; }
+    stage_transcript(ws, p);
+    stage_oods(ws, p);
+}
+// cooperative parse: lane 0 walks the structure, every lane checks a share of the field-element ranges for canonicity.
+// tab: group-shared, parse_tab_words() words.
+constexpr u32 PARSE_MAX_RANGES = 320;
+HD u32 parse_tab_words() { return 2 * PARSE_MAX_RANGES + 8; }
+template <class Co>
+HD void stage_parse_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
+    Desc &d = ws.desc[p];
+    Detail &dt = ws.detail[p];
+    u32 *ranges = tab, *ctl = tab + 2 * PARSE_MAX_RANGES;      // [0] n_ranges  [1] structure ok  [2] non-canonical word seen
+    const u32 *w = ws.blob(p);
+    if (co.lane() == 0) {
+        reset_detail(dt);
+        u32 n_ranges = 0;
+        const bool ok = proof::parse(w, ws.blob_words(p), d, ranges, PARSE_MAX_RANGES, &n_ranges) && ws.shape.matches(d);
+        ctl[0] = n_ranges; ctl[1] = ok ? 1u : 0u; ctl[2] = 0;
+    }
+    co.sync();
+    if (ctl[1]) {
+        u32 bad = 0;
+        for (u32 r = 0; r < ctl[0]; r++) {
+            const u32 off = ranges[2 * r], len = ranges[2 * r + 1];
+            for (u32 i = co.lane(); i < len; i += co.size()) bad |= (w[off + i] >= M31_P) ? 1u : 0u;
+        }
+        if (bad) ctl[2] = 1;
+    }
+    co.sync();
+    if (co.lane() == 0 && (!ctl[1] || ctl[2])) { d.ok = 0; fail(dt, proof::ST_PARSE); }
+    co.sync();
 }
 
 // ---- stage 2: commitment-tree decommitment -> per-query paths (one thread per (proof, tree)) -----------------------

@@ -76,6 +76,24 @@ __global__ void __launch_bounds__(kCoopThreads) k_pair_tree_coop(const Workspace
 }
 
 template <int G>
+__global__ void __launch_bounds__(kCoopThreads) k_parse_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+    extern __shared__ u32 smem[];
+    const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= pn) return;
+    CoopGroup<G> co;
+    co.l = threadIdx.x % G;
+    co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
+    verify::stage_parse_coop(co, ws, p0 + grp, smem + (threadIdx.x / G) * tab_words);
+}
+__global__ void __launch_bounds__(kT) k_transcript(const Workspace ws, u32 p0, u32 pn) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < pn) verify::stage_transcript(ws, p0 + idx);
+}
+__global__ void __launch_bounds__(kT) k_oods(const Workspace ws, u32 p0, u32 pn) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < pn) verify::stage_oods(ws, p0 + idx);
+}
+template <int G>
 __global__ void __launch_bounds__(kCoopThreads) k_folds_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
     extern __shared__ u32 smem[];
     const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -114,13 +132,14 @@ __global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, u32 p0, u32 
 // stream pool for sliced batches: per slice a main chain and a side stream for the commitment-tree path recomputation
 constexpr int kSlices = 4;
 cudaStream_t g_pool[2 * kSlices] = {nullptr};
-cudaEvent_t g_fork = nullptr, g_tree_done[kSlices] = {nullptr}, g_side_done[kSlices] = {nullptr}, g_join[kSlices] = {nullptr};
+cudaEvent_t g_fork = nullptr, g_fs_done[kSlices] = {nullptr}, g_tree_done[kSlices] = {nullptr}, g_side_done[kSlices] = {nullptr}, g_join[kSlices] = {nullptr};
 bool pool_init() {
     if (g_fork) return true;
     for (int i = 0; i < 2 * kSlices; i++) if (cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess) return false;
     for (int i = 0; i < kSlices; i++) {
         if (cudaEventCreateWithFlags(&g_tree_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&g_fs_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
         if (cudaEventCreateWithFlags(&g_side_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
         if (cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
     }
@@ -170,6 +189,16 @@ void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     if (!done) k_pair_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 
+// parse (a warp per proof shares the canonicity walk) + transcript: what gates every later stage
+void launch_parse_transcript(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    if (tree_group_width(ws.n_proofs) == 0) { k_fiat_shamir<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n); return; }
+    coop_launch(k_parse_coop<32>, 32, n, verify::parse_tab_words(), ws, p0, n, st);
+    k_transcript<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+}
+void launch_oods(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    if (tree_group_width(ws.n_proofs) == 0) return;                  // k_fiat_shamir already did it
+    k_oods<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+}
 void launch_folds(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     // one query per lane: 16 lanes per proof (8 when the batch alone fills the GPU)
     const int G = tree_group_width(ws.n_proofs);
@@ -261,7 +290,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
         int e = 0;
 #define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
-        MARK(); k_fiat_shamir<<<nblk(n), kT, 0, st>>>(ws, 0, n);
+        MARK(); launch_parse_transcript(ws, 0, n, st); launch_oods(ws, 0, n, st);
         MARK(); launch_single_tree(ws, 0, n, st);
         MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
         MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
@@ -275,7 +304,7 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         MARK();
 #undef MARK
         g_timed_valid = timed;
-        note_launch(full ? 9 : 7);
+        note_launch((full ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
         return cuda_status(cudaGetLastError());
     }
     // sliced: the per-proof and per-tree stages have far fewer threads than the GPU holds, so independent slices of the
@@ -286,26 +315,28 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         const u32 p0 = (u32)((uint64_t)n_proofs * sl / kSlices), p1 = (u32)((uint64_t)n_proofs * (sl + 1) / kSlices), n = p1 - p0;
         cudaStream_t a = g_pool[2 * sl], b = g_pool[2 * sl + 1];
         STWO_CUDA(cudaStreamWaitEvent(a, g_fork, 0));
-        k_fiat_shamir<<<nblk(n), kT, 0, a>>>(ws, p0, n);
+        launch_parse_transcript(ws, p0, n, a);
+        // the side stream takes what does not gate the FRI chain: the OODS / logup check, then the commitment-tree paths
+        STWO_CUDA(cudaEventRecord(g_fs_done[sl], a));
+        STWO_CUDA(cudaStreamWaitEvent(b, g_fs_done[sl], 0));
+        launch_oods(ws, p0, n, b);
         launch_single_tree(ws, p0, n, a);
         if (full) {
             STWO_CUDA(cudaEventRecord(g_tree_done[sl], a));
             STWO_CUDA(cudaStreamWaitEvent(b, g_tree_done[sl], 0));
             k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, b>>>(ws, p0, n);
-            STWO_CUDA(cudaEventRecord(g_side_done[sl], b));
         }
+        STWO_CUDA(cudaEventRecord(g_side_done[sl], b));
         k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, a>>>(ws, p0, n);
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
         launch_folds(ws, p0, n, a);
         launch_pair_tree(ws, p0, n, a);
-        if (full) {
-            k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
-            STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));
-        }
+        if (full) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
+        STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));
         k_verdict<<<nblk(n), kT, 0, a>>>(ws, p0, n, verdict, stage);
         STWO_CUDA(cudaEventRecord(g_join[sl], a));
         STWO_CUDA(cudaStreamWaitEvent(st, g_join[sl], 0));
-        note_launch(full ? 9 : 7);
+        note_launch((full ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
     }
     return cuda_status(cudaGetLastError());
 }

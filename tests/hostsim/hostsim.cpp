@@ -49,7 +49,15 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     uint8_t *base = (uint8_t *)calloc(bytes, 1);
     verify::carve(ws, base);
     const u32 nq = ws.shape.n_queries, nf = ws.shape.n_fri_trees();
-    for (u32 p = 0; p < n; p++) verify::stage_fiat_shamir(ws, p);
+    const bool coop_fs = (full & 2) != 0;
+    {
+        std::vector<u32> ptab(verify::parse_tab_words());
+        decommit::CoopOne one0;
+        for (u32 p = 0; p < n; p++) {
+            if (coop_fs) { verify::stage_parse_coop(one0, ws, p, ptab.data()); verify::stage_transcript(ws, p); verify::stage_oods(ws, p); }
+            else verify::stage_fiat_shamir(ws, p);
+        }
+    }
     const bool coop = (full & 2) != 0;          // bit 1: the cooperative tree rebuilds (group of one lane on the host)
     full &= 1;
     std::vector<u32> tab(decommit::pair_tab_words(nq) + decommit::single_tab_words(nq) + verify::folds_tab_words(nq) + 2 * nq + 64);
