@@ -112,12 +112,18 @@ HD void fail_shared(Detail *dt, u32 stage) { VERIFY_ATOMIC_OR(&dt->fail_mask, 1u
 HD void reset_detail(Detail &dt) {
     dt.fail_mask = 0; dt.verdict = proof::REJECT; dt.stage = 0; dt.n_perms_hints = 0; dt.n_perms_paths = 0; dt.n_logs = 0;
 }
+// what follows the transcript proper: PoW verdict, log sizes, the query-collision check
+HD void stage_after_transcript(const Workspace &ws, u32 p);
 // transcript + PoW + the query-collision check (thread per proof)
 HD void stage_transcript(const Workspace &ws, u32 p) {
     Desc &d = ws.desc[p];
     if (!d.ok) return;
+    fs::transcript(ws.blob(p), d, ws.detail[p].fs);
+    stage_after_transcript(ws, p);
+}
+HD void stage_after_transcript(const Workspace &ws, u32 p) {
+    Desc &d = ws.desc[p];
     Detail &dt = ws.detail[p];
-    fs::transcript(ws.blob(p), d, dt.fs);
     VERIFY_ATOMIC_ADD(&dt.n_perms_paths, dt.fs.n_transcript_perms);
     if (!dt.fs.pow_ok) fail_shared(&dt, proof::ST_POW);
     dt.n_logs = fri::log_sizes(d, dt.log_sizes);

@@ -85,6 +85,129 @@ __global__ void __launch_bounds__(kCoopThreads) k_parse_coop(const Workspace ws,
     co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
     verify::stage_parse_coop(co, ws, p0 + grp, smem + (threadIdx.x / G) * tab_words);
 }
+// ---- transcript with the Poseidon2 state spread over 16 lanes (one word per lane, warp-shuffle MDS mixing) ---------------
+// The Fiat-Shamir chain is strictly sequential (105-255 permutations) and gates every later stage, so what matters is the
+// LATENCY of one permutation: ~6.3 us with the state in one thread's registers (tools/perm_latency_microbench.cu), ~2 us
+// with one state word per lane: the S-boxes of a full round run in parallel, the external matrix is 6 shuffles, the internal
+// matrix a 4-step butterfly sum.  Same transcript order as fs::transcript (components/recursive/fiat_shamir/src/lib.rs:39-131).
+struct Lanes16 {
+    unsigned mask; u32 l;                                   // l = 0..15: which state word this lane holds
+    __device__ __forceinline__ u32 get(u32 x, u32 src) const { return __shfl_sync(mask, x, src, 16); }
+    __device__ __forceinline__ u32 get_xor(u32 x, u32 m) const { return __shfl_xor_sync(mask, x, m, 16); }
+    // circ(2 M4, M4, M4, M4) x, M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] (primitives/poseidon31/src/implementation.rs:7-58)
+    __device__ __forceinline__ u32 ext_mds(u32 x) const {
+        const u32 base = l & ~3u, row = l & 3u;
+        const u32 x0 = get(x, base), x1 = get(x, base + 1), x2 = get(x, base + 2), x3 = get(x, base + 3);
+        const u32 c0 = row == 0 ? 5u : row == 1 ? 4u : 1u, c1 = row == 0 ? 7u : row == 1 ? 6u : row == 2 ? 3u : 1u;
+        const u32 c2 = row < 2 ? 1u : row == 2 ? 5u : 4u, c3 = row == 0 ? 3u : row == 1 ? 1u : row == 2 ? 7u : 6u;
+        const u32 t = m31::red64((u64)c0 * x0 + (u64)c1 * x1 + (u64)c2 * x2 + (u64)c3 * x3);
+        u32 col = m31::addc(t, get_xor(t, 4));
+        col = m31::addc(col, get_xor(col, 8));
+        return m31::addc(t, col);
+    }
+    __device__ __forceinline__ static u32 pow5(u32 x) { const u32 x2 = m31::mulc(x, x), x4 = m31::mulc(x2, x2); return m31::mulc(x4, x); }
+    __device__ u32 permute(u32 x) const {                   // canonical in, canonical out; implementation.rs:108-149
+        x = ext_mds(x);
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, poseidon2::K.rc_first[16 * r + l])));
+#pragma unroll 1
+        for (int r = 0; r < 14; r++) {
+            if (l == 0) x = pow5(m31::addc(x, poseidon2::K.rc_part[r]));
+            u32 sum = m31::addc(x, get_xor(x, 1));
+            sum = m31::addc(sum, get_xor(sum, 2));
+            sum = m31::addc(sum, get_xor(sum, 4));
+            sum = m31::addc(sum, get_xor(sum, 8));
+            x = m31::addc(sum, m31::mulc(x, poseidon2::K.diag[l]));
+        }
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, poseidon2::K.rc_last[16 * r + l])));
+        return x;
+    }
+};
+struct Channel16 {                                          // primitives/channel/src/lib.rs:23-58 on a lane-spread state
+    Lanes16 g; u32 s, n_sent, n_perms;
+    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); n_sent = 0; n_perms++; }
+    __device__ void mix8(const u32 *w8) { absorb(g.l < 8 ? w8[g.l] : 0u); }
+    __device__ void mix4(const u32 *w4) { absorb(g.l < 4 ? w4[g.l] : 0u); }
+    __device__ void mix4v(u32 v) { absorb(g.l < 4 ? v : 0u); }              // lanes 0..3 already hold the four words
+    __device__ void mix44(const u32 *a, const u32 *b) { absorb(g.l < 4 ? a[g.l] : g.l < 8 ? b[g.l - 4] : 0u); }
+    __device__ u32 draw() {                                 // lanes 0..7 return the eight drawn words
+        const u32 t = g.permute(g.l == 0 ? n_sent : g.l < 8 ? 0u : s);
+        n_sent++; n_perms++;
+        return t;
+    }
+};
+__device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o) {
+    Channel16 ch{g, 0u, 0u, 0u};
+    const u32 l = g.l;
+    auto store_q = [&](qm31_t *dst, u32 t, u32 first_lane) { if (l >= first_lane && l < first_lane + 4) dst->v[l - first_lane] = t; };
+    ch.mix8(w + d.commitments[0]);
+    ch.mix4v(l == 0 ? d.log_size_plonk : 0u);
+    ch.mix4v(l == 0 ? d.log_size_poseidon : 0u);
+    ch.mix8(w + d.commitments[1]);
+    u32 t = ch.draw();
+    store_q(&o.z, t, 0); store_q(&o.alpha, t, 4);
+    ch.mix8(w + d.stmt1);
+    ch.mix8(w + d.commitments[2]);
+    t = ch.draw(); store_q(&o.random_coeff, t, 0);
+    ch.mix8(w + d.commitments[3]);
+    t = ch.draw(); store_q(&o.oods_t, t, 0);
+    {
+        // the OODS point from t (every lane computes it from the broadcast words; lane 0 stores)
+        const qm31_t ot = qm31::mk(g.get(t, 0), g.get(t, 1), g.get(t, 2), g.get(t, 3));
+        if (l == 0) {
+            const qm31_t t2 = fs::qmul(ot, ot);
+            const qm31_t inv = fs::qinv(qm31::add_m31(t2, 1));
+            o.oods_x = fs::qmul(fs::qsub(qm31::one(), t2), inv);
+            o.oods_y = fs::qmul(fs::qadd(ot, ot), inv);
+        }
+    }
+    const u32 *pend = nullptr;
+    for (u32 tr = 0; tr < 4; tr++)
+        for (u32 c = 0; c < proof::n_cols(tr); c++)
+            for (u32 m = 0; m < proof::n_masks(tr, c); m++) {
+                const u32 *v = w + proof::sample_off(d, tr, c, m);
+                if (pend) { ch.mix44(pend, v); pend = nullptr; } else pend = v;
+            }
+    if (pend) ch.mix4(pend);
+    t = ch.draw(); store_q(&o.after_coeff, t, 0);
+    ch.mix8(w + d.fl_commitment);
+    t = ch.draw(); store_q(&o.fri_alphas[0], t, 0);
+    for (u32 i = 0; i < d.n_inner; i++) {
+        ch.mix8(w + d.in_commitment[i]);
+        t = ch.draw(); store_q(&o.fri_alphas[i + 1], t, 0);
+    }
+    for (u32 i = 0; i < d.n_last_coeffs; i += 2) {
+        if (i + 1 < d.n_last_coeffs) ch.mix8(w + d.last_coeffs + 4 * i);
+        else ch.mix4(w + d.last_coeffs + 4 * i);
+    }
+    const u64 nonce = (u64)w[d.pow_nonce] | ((u64)w[d.pow_nonce + 1] << 32);
+    const u32 limb = l == 0 ? (u32)(nonce & ((1u << 22) - 1)) : l == 1 ? (u32)((nonce >> 22) & ((1u << 21) - 1)) : l == 2 ? (u32)((nonce >> 43) & ((1u << 21) - 1)) : 0u;
+    ch.mix4v(limb);
+    if (l >= 8) o.digest_after_nonce[l - 8] = ch.s;
+    if (l == 8) o.pow_ok = (ch.s & ((1u << d.pow_bits) - 1)) == 0;
+    u32 got = 0;
+    for (u32 k = 0; k < (d.n_queries + 3) / 4; k++) {
+        t = ch.draw();
+        if (l < 8 && got + l < d.n_queries) o.raw_queries[got + l] = t;
+        got += 8;
+    }
+    if (l == 0) o.n_transcript_perms = ch.n_perms;
+}
+__global__ void __launch_bounds__(kT) k_transcript16(const Workspace ws, u32 p0, u32 pn) {
+    const u32 grp = (blockIdx.x * kT + threadIdx.x) / 16;
+    if (grp >= pn) return;
+    const u32 p = p0 + grp;
+    const proof::Desc &d = ws.desc[p];
+    if (!d.ok) return;                                       // whole groups leave together
+    Lanes16 g;
+    g.l = threadIdx.x % 16;
+    g.mask = 0xffffu << (16 * ((threadIdx.x % 32) / 16));
+    verify::Detail &dt = ws.detail[p];
+    transcript16(g, ws.blob(p), d, dt.fs);
+    __syncwarp(g.mask);
+    if (g.l == 0) verify::stage_after_transcript(ws, p);
+}
 __global__ void __launch_bounds__(kT) k_transcript(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
     if (idx < pn) verify::stage_transcript(ws, p0 + idx);
@@ -193,7 +316,10 @@ void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
 void launch_parse_transcript(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     if (tree_group_width(ws.n_proofs) == 0) { k_fiat_shamir<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n); return; }
     coop_launch(k_parse_coop<32>, 32, n, verify::parse_tab_words(), ws, p0, n, st);
-    k_transcript<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+    static int lanes16 = -1;
+    if (lanes16 < 0) { const char *e = getenv("STWO_B200_TRANSCRIPT_LANES"); lanes16 = (e && atoi(e) == 1) ? 0 : 1; }   // "1": thread-local state
+    if (lanes16) k_transcript16<<<(unsigned)(((size_t)n * 16 + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+    else k_transcript<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 void launch_oods(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     if (tree_group_width(ws.n_proofs) == 0) return;                  // k_fiat_shamir already did it
