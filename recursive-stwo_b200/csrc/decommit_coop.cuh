@@ -13,7 +13,7 @@
 //   components/hints/src/folding.rs:93-287    SinglePairMerkleProof::from_stwo_proof (FRI layer trees)
 //
 // `Co` abstracts the group: lane(), size(), sync().  On the device it is a 16-lane half-warp (CoopHalfWarp in
-// verify_kernels.cu); on the host (tests/hostsim) a group of one, so the very same code is checked against the oracle.
+// verify_kernels.cu); on the host (tests/hostsim) a group of one, so the very same code runs in the CPU test tier.
 // `tab` is group-shared scratch (shared memory on the device), `nodes` group-private global scratch for node hashes.
 #pragma once
 #include "decommit.cuh"

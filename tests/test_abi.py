@@ -47,7 +47,7 @@ def test_product_never_touches_oracle():
     bad = []
     for d, _, files in os.walk(os.path.join(ROOT, "recursive-stwo_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 if re.search(r"oracle|liborc|orc_", txt):
                     bad.append(os.path.join(d, f))
