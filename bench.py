@@ -301,36 +301,14 @@ def main():
     value = n_total * args.steps / (ms * 1e-3)
 
     # ---- e2e: pinned host blobs -> device -> verdicts on the host, every step ---------------------------
-    # The user-level pattern for host-resident input: the shard is cut into two half-batches on two CUDA streams, so that the
-    # host->device copy of one half overlaps the kernels of the other (each half: upload -> verify -> trace).
-    n_local_all = hi - lo
-    cut = n_local_all // 2 if n_local_all >= 64 else n_local_all
-    halves = []
-    for a, b in ((0, cut), (cut, n_local_all)):
-        if b > a:
-            hvb = pkg.VerifyBatch([blob] * (b - a), inputs=pkg.INPUTS_SINGLE)
-            halves.append((hvb, pkg.VerifierCircuit(hvb.shape, inputs=pkg.INPUTS_SINGLE), torch.cuda.Stream(device=dev)))
-
     def e2e_step():
-        main = torch.cuda.current_stream()
-        parts = []
-        for hvb, hcirc, st in halves:
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                hvb.upload()
-                v, s = hvb.run(full=True)
-                r = hcirc.trace(hvb, check=True, export=True, preprocessed=False)
-                bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
-                v = torch.where(bad & (v == 0), torch.full_like(v, 1), v)
-                parts.append((v, s, r["bad_row"], r["bad_flow"]))
-        for _, _, st in halves:
-            main.wait_stream(st)
-        for part in parts:
-            for t in part:
-                t.record_stream(main)
-        v = torch.cat([p_[0] for p_ in parts]); s = torch.cat([p_[1] for p_ in parts])
+        # blobs come from pinned host memory: each slice of the batch is uploaded on the stream that verifies it
+        v, s = vb.run_from_host(full=True)
+        r = circ.trace(vb, check=True, export=True, preprocessed=False)
+        bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
+        v = torch.where(bad & (v == 0), torch.full_like(v, 1), v)
         v, s = sharding.gather_verdicts(v, s, n_total)
-        return v.cpu(), s.cpu(), torch.cat([p_[2] for p_ in parts]).cpu(), torch.cat([p_[3] for p_ in parts]).cpu()
+        return v.cpu(), s.cpu(), r["bad_row"].cpu(), r["bad_flow"].cpu()
 
     for _ in range(2):
         hv, hs, hb, hf = e2e_step()
@@ -346,12 +324,8 @@ def main():
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / float(t_e.item())
-    h2d = sum(h[0].h_words.numel() * 4 + h[0].h_off.numel() * 8 for h in halves)
+    h2d = vb.h_words.numel() * 4 + vb.h_off.numel() * 8
     d2h = 2 * n_total + 16 * (hi - lo)
-    for h in halves:
-        h[1]._values = None
-    del halves
-    torch.cuda.empty_cache()
 
     # ---- stage breakdown + roofline of the dominant kernel (CUDA events between the stage kernels) -------
     pk = peaks()
@@ -462,8 +436,7 @@ def main():
             "poseidon31_perms_per_sec": value * perms_per_proof,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t_e.item()) / e2e_steps * 1e3,
-                    "pipelining": "two half-batches on two streams: the pinned-host -> device copy of one overlaps the kernels of the other"},
+                    "ms_per_step": float(t_e.item()) / e2e_steps * 1e3},
             "roofline": roofline,
             "roofline_export": roofline_export,
             "secondary": secondary,

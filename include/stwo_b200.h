@@ -165,6 +165,14 @@ int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, const uint64_t 
                                           const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags,
                                           void *workspace, size_t workspace_bytes, uint8_t *verdict, uint8_t *stage,
                                           void *stream);
+/* Same, with the blobs still in PINNED HOST memory: host_blobs / host_blob_off mirror blobs / blob_off (which must be
+ * device buffers of the same sizes).  The library copies each slice of the batch to the device on the stream that verifies
+ * it, so the host->device transfer of one slice overlaps the kernels of the others (the copy is inside the call). */
+int32_t stwo_b200_verify_proofs_batch_pinned_dev(const uint32_t *host_blobs, const uint64_t *host_blob_off, uint32_t *blobs,
+                                                 uint64_t *blob_off, uint32_t n_proofs, const stwo_b200_proof_shape *shape,
+                                                 const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
+                                                 uint32_t flags, void *workspace, size_t workspace_bytes, uint8_t *verdict,
+                                                 uint8_t *stage, void *stream);
 /* Host entry: host blobs of any mix of shapes (grouped internally), verdicts back in the caller's arrays. */
 int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs,
                                       const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,

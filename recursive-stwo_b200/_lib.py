@@ -143,6 +143,7 @@ SIGNATURES = {
     "stwo_b200_verify_workspace_bytes": (_sz, [_PSHAPE_P, _u32]),
     "stwo_b200_proof_perms": (_u64, [_PSHAPE_P]),
     "stwo_b200_verify_proofs_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
+    "stwo_b200_verify_proofs_batch_pinned_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
     "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),

@@ -391,11 +391,31 @@ extern "C" uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape) {
     return n;
 }
 
+static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *host_blob_off, const uint32_t *blobs, const uint64_t *blob_off,
+                                 uint32_t n_proofs, const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
+                                 const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                 uint8_t *verdict, uint8_t *stage, void *stream);
 extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
                                                      const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
                                                      const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags,
                                                      void *workspace, size_t workspace_bytes, uint8_t *verdict, uint8_t *stage,
                                                      void *stream) {
+    return verify_batch_impl(nullptr, nullptr, blobs, blob_off, n_proofs, shape, input_idx, input_vals, n_inputs, flags, workspace,
+                             workspace_bytes, verdict, stage, stream);
+}
+extern "C" int32_t stwo_b200_verify_proofs_batch_pinned_dev(const uint32_t *host_blobs, const uint64_t *host_blob_off, uint32_t *blobs,
+                                                            uint64_t *blob_off, uint32_t n_proofs, const stwo_b200_proof_shape *shape,
+                                                            const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
+                                                            uint32_t flags, void *workspace, size_t workspace_bytes, uint8_t *verdict,
+                                                            uint8_t *stage, void *stream) {
+    if (!host_blobs || !host_blob_off) return STWO_B200_E_BAD_ARG;
+    return verify_batch_impl(host_blobs, host_blob_off, blobs, blob_off, n_proofs, shape, input_idx, input_vals, n_inputs, flags, workspace,
+                             workspace_bytes, verdict, stage, stream);
+}
+static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *host_blob_off, const uint32_t *blobs, const uint64_t *blob_off,
+                                 uint32_t n_proofs, const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
+                                 const uint32_t *input_vals, uint32_t n_inputs, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                 uint8_t *verdict, uint8_t *stage, void *stream) {
     STWO_CHECK_DEVICE();
     if (n_proofs == 0) return STWO_B200_OK;
     if (!shape_ok(shape)) return STWO_B200_E_SHAPE;
@@ -410,7 +430,11 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
     const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees();
     const bool timed = flags & STWO_B200_VERIFY_TIMED, full = flags & STWO_B200_VERIFY_FULL;
     g_timed_valid = false;
+    if (host_blobs)      // the offsets are needed by every slice: they go first, on the caller's stream
+        STWO_CUDA(cudaMemcpyAsync(const_cast<uint64_t *>(blob_off), host_blob_off, ((size_t)n_proofs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (timed || n_proofs < 256 || (flags & STWO_B200_VERIFY_ONE_STREAM)) {
+        if (host_blobs)
+            STWO_CUDA(cudaMemcpyAsync(const_cast<uint32_t *>(blobs), host_blobs, host_blob_off[n_proofs] * 4, cudaMemcpyHostToDevice, st));
         // one stream, stage after stage (clean per-stage timings; small batches)
         const u32 n = n_proofs;
         if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
@@ -441,6 +465,9 @@ extern "C" int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, cons
         const u32 p0 = (u32)((uint64_t)n_proofs * sl / kSlices), p1 = (u32)((uint64_t)n_proofs * (sl + 1) / kSlices), n = p1 - p0;
         cudaStream_t a = g_pool[2 * sl], b = g_pool[2 * sl + 1];
         STWO_CUDA(cudaStreamWaitEvent(a, g_fork, 0));
+        if (host_blobs && n)     // this slice's blobs, on the stream that consumes them: overlaps the other slices' kernels
+            STWO_CUDA(cudaMemcpyAsync(const_cast<uint32_t *>(blobs) + host_blob_off[p0], host_blobs + host_blob_off[p0],
+                                      (host_blob_off[p1] - host_blob_off[p0]) * 4, cudaMemcpyHostToDevice, a));
         launch_parse_transcript(ws, p0, n, a);
         // the side stream takes what does not gate the FRI chain: the OODS / logup check, then the commitment-tree paths
         STWO_CUDA(cudaEventRecord(g_fs_done[sl], a));

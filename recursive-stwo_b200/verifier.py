@@ -97,6 +97,15 @@ class VerifyBatch:
                   _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
         return self.d_verdict, self.d_stage
 
+    def run_from_host(self, full=True):
+        """verify with the blobs taken from the pinned host copy: the library uploads each slice on the stream that verifies it,
+        so the transfer overlaps the kernels of the other slices (replaces upload() + run())"""
+        flags = VERIFY_FULL if full else 0
+        _lib.call("stwo_b200_verify_proofs_batch_pinned_dev", ctypes.c_void_p(self.h_words.data_ptr()), ctypes.c_void_p(self.h_off.data_ptr()),
+                  _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape), _dptr(self.d_idx), _dptr(self.d_vals),
+                  self.n_inputs, flags, _dptr(self.d_ws), self.ws_bytes, _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
+        return self.d_verdict, self.d_stage
+
     def stage_ms(self):
         """device time of each stage kernel of the last run(timed=True) -> {kernel: ms}"""
         ms = (ctypes.c_float * len(STAGE_KERNELS))()

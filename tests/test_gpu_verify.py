@@ -103,3 +103,22 @@ def test_large_replica_batch_is_uniform(pkg, gpu, orc):
     verdict = verdict.cpu().numpy()
     assert np.array_equal(np.nonzero(verdict)[0], np.arange(5, 1024, 16))
     assert (stage.cpu().numpy()[verdict != 0] == 5).all()
+
+
+def test_pinned_host_entry_matches_device_entry(pkg, gpu, orc):
+    """stwo_b200_verify_proofs_batch_pinned_dev: per-slice upload inside the call (sliced path: >= 256 proofs, tampered mixed in)"""
+    buf, n = O.load_proof("small_proof.bin")
+    offs = O.proof_offsets(buf, n)
+    blobs = []
+    for k in range(300):
+        b = buf.copy()
+        if k % 37 == 5:
+            b[offs["queried0"] + k % 64] ^= 2
+        blobs.append(bytes(b[:n]))
+    vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_SINGLE)
+    v1, s1 = vb.run(full=True)
+    v1, s1 = v1.cpu().numpy().copy(), s1.cpu().numpy().copy()
+    vb.d_words.zero_()                                   # the device copy must come from the pinned host buffer
+    v2, s2 = vb.run_from_host(full=True)
+    assert np.array_equal(v1, v2.cpu().numpy()) and np.array_equal(s1, s2.cpu().numpy())
+    assert v1.sum() == sum(1 for k in range(300) if k % 37 == 5)
