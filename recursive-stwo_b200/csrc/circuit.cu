@@ -5,6 +5,7 @@
 #include "circuit.cuh"
 #include "dsl/recorded.hpp"
 #include <string.h>
+#include <stdlib.h>
 
 using namespace stwo_b200;
 using dsl::RecordedCircuit;
@@ -106,6 +107,11 @@ int32_t upload(stwo_b200_circuit *c) {
 }
 
 cudaEvent_t g_ev[STWO_B200_N_TRACE_STAGES + 1] = {nullptr};
+cudaStream_t g_side = nullptr;                 // runs check_poseidon_invocations beside the export
+cudaEvent_t g_side_fork = nullptr, g_side_join = nullptr;
+// CTAs per SM of the check when it runs beside the export (STWO_B200_BESIDE_CTAS=k); 0 = one after the other, the default: measured
+// on B200 at 4096 proofs the pair takes 7.0-8.7 ms beside each other (k = 2..5, run-to-run unstable) against 8.2 ms in sequence
+int g_beside_ctas = [] { const char *e = getenv("STWO_B200_BESIDE_CTAS"); return e ? atoi(e) : 0; }();
 bool g_timed_valid = false;
 }  // namespace
 
@@ -242,12 +248,30 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         if ((rc = stwo_b200_cs_populate_logup_dev(&c->wiring, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, k.scratch, k.status, st))) return rc;
     if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 1)      // unimplemented!() for this system: nothing to check
         if ((rc = cuda_status(cudaMemsetAsync(bad_flow, 0xff, (size_t)n_proofs * 8, st)))) return rc;
-    if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 0)
+    // check_poseidon_invocations is integer-issue bound (it re-executes every flow permutation), the export HBM bound, and both
+    // only read variables[] and the flow. Outside timed mode the check runs as a thin persistent layer (a few CTAs per SM, all
+    // resident from the start) on a high-priority side stream, and the export's CTAs fill the rest of every SM beside it.
+    const bool do_check_poseidon = (flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 0;
+    const bool beside = do_check_poseidon && !timed && (preprocessed || values) && g_beside_ctas > 0;
+    if (beside) {
+        if (!g_side) {
+            int lo = 0, hi = 0;
+            STWO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            STWO_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, hi));
+            STWO_CUDA(cudaEventCreateWithFlags(&g_side_fork, cudaEventDisableTiming));
+            STWO_CUDA(cudaEventCreateWithFlags(&g_side_join, cudaEventDisableTiming));
+        }
+        STWO_CUDA(cudaEventRecord(g_side_fork, st));
+        STWO_CUDA(cudaStreamWaitEvent(g_side, g_side_fork, 0));
+        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, g_side, g_beside_ctas))) return rc;
+        STWO_CUDA(cudaEventRecord(g_side_join, g_side));
+    } else if (do_check_poseidon)
         if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, st))) return rc;
     MARK();
     if (preprocessed || values)
         if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, preprocessed, values,
                                                 fuse_check ? bad_row : nullptr, st))) return rc;
+    if (beside) STWO_CUDA(cudaStreamWaitEvent(st, g_side_join, 0));
     MARK();
 #undef MARK
     g_timed_valid = timed;

@@ -13,6 +13,9 @@ int32_t stage_reserve(size_t dev_bytes);
 uint8_t *stage_dev();
 bool device_ready();
 cudaStream_t stage_stream();
+// K7 check_poseidon_invocations with an occupancy knob (cs_kernels.cu): ctas_per_sm 0 = fill the SMs, k = a thin resident layer
+int32_t cs_check_poseidon_launch(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_poseidon,
+                                 const uint32_t *scratch, int64_t *first_bad, cudaStream_t st, int ctas_per_sm);
 inline int32_t cuda_status(cudaError_t e) { return e == cudaSuccess ? STWO_B200_OK : -(int32_t)e; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace stwo_b200

@@ -164,38 +164,40 @@ __global__ void __launch_bounds__(kT) k_cs_mult(stwo_b200_cs_wiring w, const u32
 }
 
 // ---- K7: check_poseidon_invocations ----------------------------------------------------------------------------------------
-// thread = (flow entry, item), item fastest
-__global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
+// thread = (flow entry, item), item fastest. Persistent: the grid is a fixed number of CTAs per SM looping over the flow, so that it
+// can run as a thin, fully resident layer (2-3 CTAs per SM) under the HBM-bound export on another stream, or fill the SMs alone.
+__global__ void __launch_bounds__(128, 8) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
                                                            const u32 *first_prow, unsigned long long *first_bad) {
-    const size_t g = blockIdx.x * (size_t)128 + threadIdx.x;
     const u32 padded = (b.n_batch + b.lanes - 1) / b.lanes * b.lanes;
-    if (g >= (size_t)w.n_flow * padded) return;
-    const u32 lane = (u32)(g % b.lanes);
-    const size_t t = g / b.lanes;
-    const u32 e = (u32)(t % w.n_flow), grp = (u32)(t / w.n_flow), item = grp * b.lanes + lane;
-    if (item >= b.n_batch) return;
-    const tape::View v = b.view(item, nullptr, 0);
-    const u32 *h = v.flow_hash + (size_t)e * 32 * v.stride;
-    u32 hh[32];
+    const size_t total = (size_t)w.n_flow * padded;
+    for (size_t g = blockIdx.x * (size_t)128 + threadIdx.x; g < total; g += (size_t)gridDim.x * 128) {
+        const u32 lane = (u32)(g % b.lanes);
+        const size_t t = g / b.lanes;
+        const u32 e = (u32)(t % w.n_flow), grp = (u32)(t / w.n_flow), item = grp * b.lanes + lane;
+        if (item >= b.n_batch) continue;
+        const tape::View v = b.view(item, nullptr, 0);
+        const u32 *h = v.flow_hash + (size_t)e * 32 * v.stride;
+        u32 hh[32];
 #pragma unroll
-    for (int k = 0; k < 32; k++) hh[k] = h[(size_t)k * v.stride];
-    bool ok = true;
-    for (int k = 0; k < 4; k++) {
-        const u32 wire = w.flow_wire[4 * e + k];
-        if (!wire) continue;
-        const u32 row = first_prow[wire];
-        if (row >= w.n_rows || mult_poseidon[row] == 0) { ok = false; continue; }    // map.get(..).unwrap() would panic
-        const qm31_t l = tape::ldv(v, w.a_wire[row]), r = tape::ldv(v, w.b_wire[row]);
-        for (int j = 0; j < 4; j++) ok &= (l.v[j] == hh[8 * k + j]) & (r.v[j] == hh[8 * k + 4 + j]);
+        for (int k = 0; k < 32; k++) hh[k] = h[(size_t)k * v.stride];
+        bool ok = true;
+        for (int k = 0; k < 4; k++) {
+            const u32 wire = w.flow_wire[4 * e + k];
+            if (!wire) continue;
+            const u32 row = first_prow[wire];
+            if (row >= w.n_rows || mult_poseidon[row] == 0) { ok = false; continue; }    // map.get(..).unwrap() would panic
+            const qm31_t l = tape::ldv(v, w.a_wire[row]), r = tape::ldv(v, w.b_wire[row]);
+            for (int j = 0; j < 4; j++) ok &= (l.v[j] == hh[8 * k + j]) & (r.v[j] == hh[8 * k + 4 + j]);
+        }
+        u32 st[16];
+        const bool swap = v.flow_swap[(size_t)e * v.stride] != 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { st[j] = hh[(swap ? 8 : 0) + j]; st[8 + j] = hh[(swap ? 0 : 8) + j]; }
+        poseidon2::permute<false>(st);
+#pragma unroll
+        for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
+        if (!ok) atomicMin(first_bad + item, (unsigned long long)e);
     }
-    u32 st[16];
-    const bool swap = v.flow_swap[(size_t)e * v.stride] != 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) { st[j] = hh[(swap ? 8 : 0) + j]; st[8 + j] = hh[(swap ? 0 : 8) + j]; }
-    poseidon2::permute<false>(st);
-#pragma unroll
-    for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
-    if (!ok) atomicMin(first_bad + item, (unsigned long long)e);
 }
 
 // ---- K7: trace export ------------------------------------------------------------------------------------------------------------
@@ -367,22 +369,29 @@ extern "C" int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w,
     note_launch(2);
     return cuda_status(cudaGetLastError());
 }
-extern "C" int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
-                                                   const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream) {
+// ctas_per_sm: 0 = fill the SMs (the kernel alone), k = a resident layer of k CTAs per SM (beside another kernel)
+int32_t stwo_b200::cs_check_poseidon_launch(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_poseidon,
+                                            const uint32_t *scratch, int64_t *first_bad, cudaStream_t st, int ctas_per_sm) {
     STWO_CHECK_DEVICE();
     if (!wiring_ok(w) || !values_ok(v) || !first_bad || !mult_poseidon || !scratch) return STWO_B200_E_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     k_fill64<<<nblk(v->n_batch), kT, 0, st>>>((unsigned long long *)first_bad, v->n_batch, ~0ull);
     note_launch(1);
     if (w->n_flow) {
         if (!v->flow_hash || !v->flow_swap) return STWO_B200_E_BAD_ARG;
         const Batch b = batch_of(v, w->n_vars, w->n_flow);
         const size_t padded = (size_t)(v->n_batch + v->lanes - 1) / v->lanes * v->lanes;
-        k_cs_check_poseidon<<<nblk((size_t)w->n_flow * padded, 128), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
-                                                                                  (unsigned long long *)first_bad);
+        static int n_sm = 0;
+        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        const size_t want = nblk((size_t)w->n_flow * padded, 128), cap = (size_t)n_sm * (ctas_per_sm > 0 ? ctas_per_sm : 16);
+        k_cs_check_poseidon<<<(unsigned)(want < cap ? want : cap), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
+                                                                               (unsigned long long *)first_bad);
         note_launch(1);
     }
     return cuda_status(cudaGetLastError());
+}
+extern "C" int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
+                                                   const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream) {
+    return stwo_b200::cs_check_poseidon_launch(w, v, mult_poseidon, scratch, first_bad, (cudaStream_t)stream, 0);
 }
 extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                                  const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,

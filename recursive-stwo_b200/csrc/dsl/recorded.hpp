@@ -59,7 +59,13 @@ struct RecordedCircuit {
         for (u32 l = 1; l <= max_level; l++) level_start[l] = level_start[l - 1] + cnt[l];
         std::vector<u32> at(level_start.begin(), level_start.end());
         ins.resize(c.tape_.size());
-        for (size_t k = 0; k < c.tape_.size(); k++) ins[at[ins_level[k] - 1]++] = c.tape_[k];
+        // inside a level the permutations go first: the evaluator deals a level's instructions round-robin to its warps, and
+        // the heavy items (a permutation is ~50x a field gate) then spread evenly instead of following the recording pattern
+        for (int pass = 0; pass < 2; pass++)
+            for (size_t k = 0; k < c.tape_.size(); k++) {
+                const bool heavy = c.tape_[k].op == tape::T_POSEIDON || c.tape_[k].op == tape::T_EPOSEIDON;
+                if (heavy == (pass == 0)) ins[at[ins_level[k] - 1]++] = c.tape_[k];
+            }
     }
 };
 

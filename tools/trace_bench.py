@@ -44,9 +44,15 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
+    e0.record()
+    for _ in range(args.reps):
+        circ.trace(vb, check=not args.no_check, export=True, preprocessed=False)
+    e1.record()
+    torch.cuda.synchronize()
+    trace_ms = e0.elapsed_time(e1) / args.reps
     n, nr = args.proofs, info["n_rows"]
     export_bytes = n * nr * (3 * 16 + 13 * 4)
-    print(json.dumps({"fixture": args.fixture, "proofs": n, "info": info, "trace_stage_ms": acc, "verify_plus_trace_ms": ms,
+    print(json.dumps({"fixture": args.fixture, "proofs": n, "info": info, "trace_stage_ms": acc, "verify_plus_trace_ms": ms, "trace_untimed_ms": trace_ms,
                       "proofs_per_sec_verify_plus_trace": n / (ms * 1e-3),
                       "export_gbs": export_bytes / (acc["export"] * 1e-3) / 1e9,
                       "eval_perms_per_sec": n * info["n_flow"] / (acc["eval"] * 1e-3), "last_layer": args.last_layer,
