@@ -44,6 +44,15 @@ LANE_OPS_PER_PERM = 4719
 TRAFFIC_PER_PROOF = {"k_tape_eval": (2.999618e9 + 5.212075e9) / 4096, "k_cs_export_vals_tiled": (3.598645e9 + 13.901859e9) / 4096}
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    f = _JSON_OUT or sys.stdout
+    f.write(line + "\n")
+    f.flush()
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "src": "fallback"}
     try:
@@ -167,7 +176,7 @@ def run_reference(args):
     val = n * args.steps / dt
     sample = "%d replicas of %s per step on %d pthreads: native verifier + circuit value log replay, checks and export " \
              "(the GPU arm's step is %d per GPU)" % (n, FIXTURE, cores, args.proofs)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
@@ -179,8 +188,10 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-def merkle_sweep(pkg, dev, log_n=20, C=8, Q=128, T=2, reps=3):
-    """BASELINE configs[2]: commit T trees of 2^log_n leaves, decommit Q queries, verify every path -> perms/s"""
+def merkle_sweep(pkg, dev, log_n=20, C=8, Q=128, T=2, reps=3, hbm_peak=None):
+    """BASELINE configs[2]: commit T trees of 2^log_n leaves (C columns), decommit Q queries per tree, verify every path.
+    Returns the commit and the path legs timed apart: the commit streams C*4 B per leaf (HBM-bound for wide leaves), the
+    paths are permutation-bound."""
     import torch
     import oracle_py as O
     n = 1 << log_n
@@ -190,23 +201,126 @@ def merkle_sweep(pkg, dev, log_n=20, C=8, Q=128, T=2, reps=3):
     rid = torch.arange(T, dtype=torch.int32, device=dev).repeat_interleave(Q).contiguous()
     shape = pkg.PathShape.make(log_n, {log_n: C})
 
-    def step():
+    def commit():
         pkg.merkle_commit(cols, nodes)
+
+    def paths():
         pc, sib = pkg.merkle_decommit(cols, nodes, idx)
         return pkg.merkle_path_verify(shape, idx.reshape(-1), pc, sib, nodes[:, 0, :].contiguous(), rid)
 
-    for _ in range(3):
-        v = step()
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    for _ in range(2):
+        commit()
+        v = paths()
     assert bool(v.all().item())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    commit_ms, paths_ms = timed(commit, reps), timed(paths, reps * 4)
+    leaf = (C + 7) // 8 + 1
+    commit_perms, path_perms = T * (n * leaf + n - 1), T * Q * (leaf + log_n)
+    commit_bytes = T * (n * C * 4 + (2 * n - 1) * 32)          # leaves read once, every node written once
+    out = {"log_leaves": log_n, "columns": C, "queries": Q, "trees": T, "commit_ms": commit_ms, "paths_ms": paths_ms,
+           "commit_perms_per_sec": commit_perms / (commit_ms * 1e-3), "path_perms_per_sec": path_perms / (paths_ms * 1e-3),
+           "commit_gb_per_sec": commit_bytes / (commit_ms * 1e-3) / 1e9,
+           "perms_per_sec": (commit_perms + path_perms) / ((commit_ms + paths_ms) * 1e-3)}
+    if hbm_peak:
+        out["commit_frac_of_hbm_peak"] = out["commit_gb_per_sec"] / hbm_peak
+    return out
+
+
+def fixture_names():
+    """the 15 Poseidon31 fixtures in the order of BASELINE configs[3]"""
+    d = os.path.join(ROOT, "tests", "golden", "proofs")
+    lv = sorted((f for f in os.listdir(d) if f.startswith("level") and f != "level14-1.bin"),
+                key=lambda f: (int(f[5:].split("-")[0]), f))
+    return ["small_proof.bin", "recursive_proof_16_15.bin"] + lv
+
+
+def multi_proofs_leg(pkg, sharding, rank, world, dev, n_total=256, reps=3):
+    """BASELINE configs[3] (examples/multi-proofs): 256 independent proofs = the 15 fixtures cycled, through the host entry
+    stwo_b200_verify_proofs_batch (any mix of shapes; grouping by shape and every copy inside the call), sharded over the
+    ranks in contiguous blocks.  Returns proofs/s over all ranks (wall clock around the host calls, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    d = os.path.join(ROOT, "tests", "golden", "proofs")
+    names = fixture_names()
+    blobs = {f: open(os.path.join(d, f), "rb").read() for f in names}
+    order = [names[i % len(names)] for i in range(n_total)]
+    lo, hi = sharding.shard_range(n_total, rank, world)
+    mine = order[lo:hi]
+    # the single-proof fixture carries one public input, the recursion fixtures three: two calls
+    small = [blobs[f] for f in mine if f.startswith("small")]
+    rest = [blobs[f] for f in mine if not f.startswith("small")]
+
+    def step():
+        bad = 0
+        if small:
+            v, _ = pkg.verify_proofs(small, inputs=pkg.INPUTS_SINGLE)
+            bad += int(v.sum())
+        if rest:
+            v, _ = pkg.verify_proofs(rest, inputs=pkg.INPUTS_RECURSIVE)
+            bad += int(v.sum())
+        return bad
+
+    assert step() == 0, "every fixture must be accepted"
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     for _ in range(reps):
         step()
-    e1.record()
     torch.cuda.synchronize()
-    leaf = (C + 7) // 8 + 1
-    perms = T * (n * leaf + n - 1 + Q * (leaf + log_n))
-    return perms * reps / (e0.elapsed_time(e1) * 1e-3)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item()) / reps
+    return {"config": "BASELINE configs[3]: 256 proofs = 15 fixtures cycled, host blobs -> verdicts, grouped by shape inside the call",
+            "proofs": n_total, "shapes": len({tuple(pkg.proof_shape(blobs[f]).key()) for f in names}), "ms_per_batch": dt * 1e3,
+            "proofs_per_sec": n_total / dt, "bytes_per_batch": sum(len(blobs[f]) for f in order)}
+
+
+def divergence_leg(pkg, dev, n=1024, reps=5):
+    """What replicas hide: lanes of a warp hold different proofs in production.  The same shape (16, 15; 10 queries) verified and
+    traced as n replicas of level10-1.bin and as n proofs alternating level10-1.bin / level11-1.bin (different query positions
+    and decommitment layouts in neighbouring lanes)."""
+    import torch
+    d = os.path.join(ROOT, "tests", "golden", "proofs")
+    a, b = (open(os.path.join(d, f), "rb").read() for f in ("level10-1.bin", "level11-1.bin"))
+    out = {"shape": "level10-1 / level11-1 (2^16 Plonk rows, 2^15 Poseidon rows, 10 queries)", "proofs": n}
+    circ = None
+    for name, blobs in (("replicas", [a] * n), ("alternating", [a, b] * (n // 2))):
+        vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_RECURSIVE)
+        if circ is None:
+            circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_RECURSIVE)
+
+        def step():
+            v, _ = vb.run(full=True)
+            return v, circ.trace(vb, check=True, export=True, preprocessed=False)
+        for _ in range(2):
+            v, r = step()
+        assert int(v.sum().item()) == 0 and int((r["bad_row"] != -1).sum().item()) == 0 and int((r["bad_flow"] != -1).sum().item()) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            vb.run(full=True)
+        e1.record()
+        for _ in range(reps):
+            step()
+        e2 = torch.cuda.Event(enable_timing=True)
+        e2.record()
+        torch.cuda.synchronize()
+        out[name] = {"verify_ms": e0.elapsed_time(e1) / reps, "verify_plus_trace_ms": e1.elapsed_time(e2) / reps,
+                     "proofs_per_sec": n / (e1.elapsed_time(e2) / reps * 1e-3)}
+        del vb
+    out["alternating_over_replicas"] = out["alternating"]["proofs_per_sec"] / out["replicas"]["proofs_per_sec"]
+    return out
 
 
 def main():
@@ -220,6 +334,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the K1 / Merkle-sweep side measurements")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner) go to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -392,9 +511,16 @@ def main():
         k1_rate = n_states * 5 / (k0.elapsed_time(k1) * 1e-3)
         del st
         secondary = {"k1_permute_perms_per_sec": k1_rate, "k1_frac_of_int_peak": k1_rate * 4264 / 1e12 / pk["int_tlops"],
-                     "merkle_sweep_perms_per_sec": merkle_sweep(pkg, dev),
-                     "merkle_sweep_config": "2 trees x 2^20 leaves x 8 cols, 128 queries (BASELINE configs[2])"}
+                     "merkle_sweep_config": "BASELINE configs[2]: 2 trees x 2^20 leaves, leaf width C, Q queries per tree; commit and "
+                                            "decommit+path-verify timed apart (SURVEY.md 8d config 3)",
+                     "merkle_sweep": [merkle_sweep(pkg, dev, C=C, Q=Q, hbm_peak=pk["hbm_gbs"]) for C, Q in ((4, 16), (8, 128), (50, 64), (60, 16), (60, 128))]}
+        secondary["merkle_sweep_perms_per_sec"] = secondary["merkle_sweep"][1]["perms_per_sec"]
+        secondary["lane_divergence"] = divergence_leg(pkg, dev)
 
+    if not args.no_secondary:
+        mp = multi_proofs_leg(pkg, sharding, rank, world, dev)            # every rank takes its block of the 256
+        if rank == 0:
+            secondary["multi_proofs"] = mp
     if not args.no_secondary and rank == 0:
         # BASELINE configs[1] (examples/last-layer): the last-layer circuit's trace for 256 replicas of the Poseidon31 twin of
         # hybrid_hash.bin (Plonk-without-Poseidon system, emulated Poseidon2, 2^17 rows x 20 columns), verification included
@@ -447,7 +573,7 @@ def main():
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "poseidon31_perms_per_sec": prate,
                                    "sample": "%d x %d replicas of %s with the oracle port (native verifier + circuit value-log replay, checks, "
                                              "export) on %d pthreads (%.1f s)" % (reps_c, max(cores * 4, 64), FIXTURE, cores, dtc)}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

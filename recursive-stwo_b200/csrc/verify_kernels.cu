@@ -5,6 +5,7 @@
 #include "verify.cuh"
 #include <vector>
 #include <map>
+#include <algorithm>
 #include <array>
 #include <string.h>
 #include <stdlib.h>
@@ -553,39 +554,71 @@ extern "C" int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, co
         memcpy(k.data(), &s, sizeof s);
         groups[k].push_back(i);
     }
-    cudaStream_t st = stage_stream();
+    // every shape group gets its own region of the staging area and one of a few streams: the groups are small and latency
+    // bound (a transcript is a sequential chain), so they run beside each other; one synchronisation at the end
+    struct Plan { stwo_b200_proof_shape s; const std::vector<uint32_t> *ids; std::vector<uint64_t> off; size_t base, b_blobs, b_off, b_in, b_ws; size_t out_at; uint8_t *d_verdict; cudaStream_t st; };
+    std::vector<Plan> plans;
+    size_t total = 0, out_total = 0;
     for (auto &kv : groups) {
-        stwo_b200_proof_shape s;
-        memcpy(&s, kv.first.data(), sizeof s);
-        const std::vector<uint32_t> &ids = kv.second;
+        Plan pl;
+        memcpy(&pl.s, kv.first.data(), sizeof pl.s);
+        pl.ids = &kv.second;
+        const uint32_t n = (uint32_t)kv.second.size();
+        pl.off.assign(n + 1, 0);
+        for (uint32_t k = 0; k < n; k++) pl.off[k + 1] = pl.off[k] + lens[kv.second[k]] / 4;
+        pl.b_blobs = align_up(pl.off[n] * 4, 256); pl.b_off = align_up((n + 1) * 8, 256); pl.b_in = align_up((size_t)n_inputs * 20 + 4, 256);
+        pl.b_ws = align_up(stwo_b200_verify_workspace_bytes(&pl.s, n), 256);
+        pl.base = total; pl.out_at = out_total;
+        total += pl.b_blobs + pl.b_off + pl.b_in + pl.b_ws + align_up(2 * (size_t)n, 256);
+        out_total += 2 * (size_t)n;
+        plans.push_back(std::move(pl));
+    }
+    int32_t rc = stage_reserve(total);
+    if (rc) return rc;
+    constexpr int kGroupStreams = 4;
+    static cudaStream_t gs[kGroupStreams] = {nullptr};
+    if (!gs[0]) for (int i = 0; i < kGroupStreams; i++) STWO_CUDA(cudaStreamCreateWithFlags(&gs[i], cudaStreamNonBlocking));
+    // nothing of an earlier call on the staging stream may still be using the area
+    STWO_CUDA(cudaStreamSynchronize(stage_stream()));
+    std::vector<uint8_t> out(out_total);
+    // largest groups first: the long chains start early and the short ones fill in beside them
+    std::vector<size_t> order(plans.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return plans[x].b_ws > plans[y].b_ws; });
+    int next = 0;
+    for (size_t oi : order) {
+        Plan &pl = plans[oi];
+        cudaStream_t st = gs[next++ % kGroupStreams];
+        const std::vector<uint32_t> &ids = *pl.ids;
         const uint32_t n = (uint32_t)ids.size();
-        std::vector<uint64_t> off(n + 1, 0);
-        for (uint32_t k = 0; k < n; k++) off[k + 1] = off[k] + lens[ids[k]] / 4;
-        const size_t b_blobs = align_up(off[n] * 4, 256), b_off = align_up((n + 1) * 8, 256), b_in = align_up((size_t)n_inputs * 20 + 4, 256);
-        const size_t b_ws = stwo_b200_verify_workspace_bytes(&s, n), b_out = align_up(2 * (size_t)n, 256);
-        int32_t rc = stage_reserve(b_blobs + b_off + b_in + b_ws + b_out);
-        if (rc) return rc;
-        uint8_t *d = stage_dev();
-        u32 *d_blobs = (u32 *)d; d += b_blobs;
-        u64 *d_off = (u64 *)d; d += b_off;
-        u32 *d_idx = (u32 *)d, *d_vals = d_idx + n_inputs; d += b_in;
-        uint8_t *d_ws = d; d += b_ws;
+        uint8_t *d = stage_dev() + pl.base;
+        u32 *d_blobs = (u32 *)d; d += pl.b_blobs;
+        u64 *d_off = (u64 *)d; d += pl.b_off;
+        u32 *d_idx = (u32 *)d, *d_vals = d_idx + n_inputs; d += pl.b_in;
+        uint8_t *d_ws = d; d += pl.b_ws;
         uint8_t *d_verdict = d, *d_stage = d + n;
         for (uint32_t k = 0; k < n; k++)
-            STWO_CUDA(cudaMemcpyAsync(d_blobs + off[k], blobs[ids[k]], lens[ids[k]], cudaMemcpyHostToDevice, st));
-        STWO_CUDA(cudaMemcpyAsync(d_off, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+            STWO_CUDA(cudaMemcpyAsync(d_blobs + pl.off[k], blobs[ids[k]], lens[ids[k]], cudaMemcpyHostToDevice, st));
+        STWO_CUDA(cudaMemcpyAsync(d_off, pl.off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n_inputs) {
             STWO_CUDA(cudaMemcpyAsync(d_idx, input_idx, n_inputs * 4, cudaMemcpyHostToDevice, st));
             STWO_CUDA(cudaMemcpyAsync(d_vals, input_vals, n_inputs * 16, cudaMemcpyHostToDevice, st));
         }
-        rc = stwo_b200_verify_proofs_batch_dev(d_blobs, d_off, n, &s, d_idx, d_vals, n_inputs, flags, d_ws, b_ws, d_verdict, d_stage, st);
+        rc = stwo_b200_verify_proofs_batch_dev(d_blobs, d_off, n, &pl.s, d_idx, d_vals, n_inputs, flags, d_ws, pl.b_ws, d_verdict, d_stage, st);
         if (rc) return rc;
-        std::vector<uint8_t> out(2 * (size_t)n);
-        STWO_CUDA(cudaMemcpyAsync(out.data(), d_verdict, 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
-        STWO_CUDA(cudaStreamSynchronize(st));
+        pl.d_verdict = d_verdict; pl.st = st;
+    }
+    // the read-backs go last: a copy into pageable host memory blocks the host until the group has finished
+    for (size_t oi : order) {
+        Plan &pl = plans[oi];
+        STWO_CUDA(cudaMemcpyAsync(out.data() + pl.out_at, pl.d_verdict, 2 * pl.ids->size(), cudaMemcpyDeviceToHost, pl.st));
+    }
+    for (int i = 0; i < kGroupStreams; i++) STWO_CUDA(cudaStreamSynchronize(gs[i]));
+    for (const Plan &pl : plans) {
+        const uint32_t n = (uint32_t)pl.ids->size();
         for (uint32_t k = 0; k < n; k++) {
-            verdict[ids[k]] = out[k];
-            if (stage) stage[ids[k]] = out[n + k];
+            verdict[(*pl.ids)[k]] = out[pl.out_at + k];
+            if (stage) stage[(*pl.ids)[k]] = out[pl.out_at + n + k];
         }
     }
     return STWO_B200_OK;

@@ -23,6 +23,8 @@ def _as_aligned(blob):
     """bytes / uint8 array -> (uint8 array whose buffer is 4-byte aligned, length)"""
     a = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
     n = a.size
+    if n % 4 == 0 and a.ctypes.data % 4 == 0 and a.flags["C_CONTIGUOUS"]:
+        return a, n                                      # already word-aligned: no copy
     buf = np.zeros((n + 3) // 4, dtype=np.uint32).view(np.uint8)
     buf[:n] = a
     return buf, n
