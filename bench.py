@@ -40,8 +40,10 @@ FIXTURE = "small_proof.bin"
 # profiles/r01*_ncu.txt) — the unit of the integer-issue roofline
 LANE_OPS_PER_PERM = 4719
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per proof of shape S from the ncu --set full captures of the
-# 4096-proof step: profiles/r01l_k_tape_eval_grid_ncu.txt (3.00 + 5.21 GB) and profiles/r01l_k_export_fused_ncu.txt (3.60 + 13.90 GB)
-TRAFFIC_PER_PROOF = {"k_tape_eval": (2.999618e9 + 5.212075e9) / 4096, "k_cs_export_vals_tiled": (3.598645e9 + 13.901859e9) / 4096}
+# 4096-proof step: profiles/r01u_k_tape_eval_grid_ncu.txt (3.31 + 5.21 GB), profiles/r01u_k_cs_export_vals_tiled_ncu.txt
+# (3.60 + 13.90 GB) and profiles/r01u_k_cs_check_poseidon_ncu.txt (2.37 + 0.06 GB)
+TRAFFIC_PER_PROOF = {"k_tape_eval": (3.310613e9 + 5.210664e9) / 4096, "k_cs_export_vals_tiled": (3.598031e9 + 13.900619e9) / 4096,
+                     "k_cs_check_poseidon": (2.369094e9 + 0.055406e9) / 4096}
 
 
 _JSON_OUT = None
