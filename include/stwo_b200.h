@@ -270,6 +270,9 @@ typedef struct {
  * primitives/bits/src/lib.rs:48-82, primitives/poseidon31/src/lib.rs:282-407, plonk_with_poseidon.rs:141-281. */
 int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
                                    void *stream);
+/* Diagnostics: when level_clock is a device array of n_levels + 1 uint64, the grid-wide form of K6 stores the GPU's
+ * globaltimer (ns) after the prologue and after every level; NULL (the default) turns it off. */
+int32_t stwo_b200_cs_eval_level_clock(uint64_t *level_clock);
 /* check_arithmetics (constraint_system/src/plonk_with_poseidon.rs:337-380): first_bad[b] = index of the first row whose
  * gate c = op(a+b) + (1-op)ab (or whose enforce_c_m31) fails for batch item b, or -1. */
 int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,

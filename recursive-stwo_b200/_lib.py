@@ -148,6 +148,7 @@ SIGNATURES = {
     "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
     "stwo_b200_cs_eval_tape_dev": (_i32, [_TAPE_P, _u32, _vp, _VAL_P, _vp]),
+    "stwo_b200_cs_eval_level_clock": (_i32, [_vp]),
     "stwo_b200_cs_check_arithmetics_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp]),
     "stwo_b200_cs_populate_logup_dev": (_i32, [_WIR_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_check_poseidon_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp]),

@@ -72,6 +72,19 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned n_ctas,
     }
     __syncthreads();
 }
+__device__ unsigned long long *g_level_clock = nullptr;      // diagnostics (stwo_b200_cs_eval_level_clock)
+__device__ __forceinline__ void stamp_level(u32 l) {
+    if (g_level_clock && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_level_clock[l] = t;
+    }
+}
+// Measured and dropped (tools/level_clock.py, 4096 proofs): dealing a level's permutations to fewer warps so that the rounds come
+// out even -- no gain (the permutation levels run at 3.4 G perms/s whatever the rounding); keeping the operand loads of two gates
+// in flight per warp -- no gain (a 1000-gate level moves 193 MB in 39 us: the gate levels are bound by L2/HBM bandwidth at 16 B per
+// variable, not by latency); walking the items backwards in the odd warps so that gates and permutations overlap -- no gain;
+// taking gates in chunks from a per-level atomic counter -- same-address atomics serialise at ~2 ns.
 template <bool UNROLLED>
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                  const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
@@ -83,6 +96,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
     for (u32 g = gw; g < n_groups; g += n_warps)
         if (g * 32 + lane < b.n_batch) tape::prologue(b.view(g * 32 + lane, input, n_input_words));
     grid_barrier(barrier, gridDim.x, phase);
+    stamp_level(0);
     for (u32 l = 0; l < n_levels; l++) {
         const u32 lo = __ldg(level_start + l), hi = __ldg(level_start + l + 1);
         const u32 n_items = (hi - lo) * n_groups;
@@ -97,6 +111,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
             }
         }
         grid_barrier(barrier, gridDim.x, phase);
+        stamp_level(l + 1);
     }
 }
 
@@ -336,6 +351,11 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     }
     note_launch(1);
     return cuda_status(cudaGetLastError());
+}
+extern "C" int32_t stwo_b200_cs_eval_level_clock(uint64_t *level_clock) {
+    STWO_CHECK_DEVICE();
+    unsigned long long *p = (unsigned long long *)level_clock;
+    return cuda_status(cudaMemcpyToSymbol(g_level_clock, &p, sizeof p));
 }
 extern "C" int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,
                                                       void *stream) {
