@@ -13,8 +13,9 @@ pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers).  One "step" = one ba
       tape (3 481 in-circuit Poseidon2 permutations per proof), check_arithmetics, check_poseidon_invocations,
       export of the 2^16-row x 13 per-proof trace columns (examples/single-proof/src/main.rs:33-90).
 Metric: verified proofs/s over all GPUs (a proof counts when its verdict is accept AND its circuit checks pass);
-`poseidon31_perms_per_sec` rides along.  `value`: blobs already in HBM.  `e2e`: pinned host blobs -> device ->
-verdicts + check results back on the host, every step (traces stay in HBM for the prover that consumes them).
+`poseidon31_perms_per_sec` rides along.  `value`: blobs already in HBM.  `e2e`: a stream of batches through
+VerifyStream: every step uploads one batch of blobs from pinned host memory (double-buffered: the copy runs beside the previous
+batch's kernels) and reads verdicts + check results back to the host (traces stay in HBM for the prover that consumes them).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -422,15 +423,23 @@ def main():
     value = n_total * args.steps / (ms * 1e-3)
 
     # ---- e2e: pinned host blobs -> device -> verdicts on the host, every step ---------------------------
+    # A stream of batches through the public API (VerifyStream): every step uploads one batch of blobs from pinned host memory
+    # (on the copy stream, beside the previous step's kernels), verifies and traces the batch uploaded the step before, and reads
+    # verdicts + check results back to the host.
+    vs = pkg.VerifyStream([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
+
     def e2e_step():
-        # blobs come from pinned host memory: each slice of the batch is uploaded on the stream that verifies it
-        v, s = vb.run_from_host(full=True)
-        r = circ.trace(vb, check=True, export=True, preprocessed=False)
+        vs.feed()                                   # upload of the next batch
+        bt = vs.take()
+        v, s = bt.run(full=True)
+        r = circ.trace(bt, check=True, export=True, preprocessed=False)
+        vs.release(bt)
         bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
         v = torch.where(bad & (v == 0), torch.full_like(v, 1), v)
         v, s = sharding.gather_verdicts(v, s, n_total)
         return v.cpu(), s.cpu(), r["bad_row"].cpu(), r["bad_flow"].cpu()
 
+    vs.feed()
     for _ in range(2):
         hv, hs, hb, hf = e2e_step()
     assert int(hv.sum()) == 0 and int((hb != -1).sum()) == 0

@@ -11,11 +11,11 @@ from .hashing import (init, poseidon2_permute, poseidon2_permute_host, hash_node
                       merkle_commit_host, merkle_decommit, merkle_path_verify, merkle_path_verify_host,
                       launch_count, path_perms)
 
-from .verifier import verify_proofs, VerifyBatch, proof_shape, proof_perms, INPUTS_SINGLE, INPUTS_RECURSIVE
+from .verifier import verify_proofs, VerifyBatch, VerifyStream, proof_shape, proof_perms, INPUTS_SINGLE, INPUTS_RECURSIVE
 from ._lib import ProofShape, VerifyDetail, STAGES
 from .circuit import VerifierCircuit
 
-__all__ = ["VerifierCircuit", "verify_proofs", "VerifyBatch", "proof_shape", "proof_perms", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
+__all__ = ["VerifierCircuit", "verify_proofs", "VerifyBatch", "VerifyStream", "proof_shape", "proof_perms", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
            "VerifyDetail", "STAGES","init", "poseidon2_permute", "poseidon2_permute_host", "hash_node_batch", "merkle_commit",
            "merkle_commit_host", "merkle_decommit", "merkle_path_verify", "merkle_path_verify_host", "launch_count",
            "path_perms", "PathShape", "StwoB200Error"]

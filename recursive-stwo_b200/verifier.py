@@ -132,3 +132,59 @@ class VerifyBatch:
         _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what],
                   out.ctypes.data_as(ctypes.c_void_p), out.nbytes, _stream())
         return out
+
+
+class VerifyStream:
+    """A stream of same-shape batches: two device slots, the next batch uploads (pinned host -> device, its own stream) while
+    the current one is verified and traced, so a steady flow of batches runs at the device-resident rate.
+
+        vs = VerifyStream(first_blobs, inputs); circ = VerifierCircuit(vs.shape, inputs)
+        vs.feed(blobs_0)                               # upload of batch 0 starts
+        for k in ...:
+            vs.feed(blobs_k+1)                         # upload of the next batch, beside the work below (None: reuse the host copy)
+            batch = vs.take()                          # the uploaded batch (a VerifyBatch), ordered after its upload
+            verdict, stage = batch.run(); trace = circ.trace(batch, ...)
+            vs.release(batch)                          # its slot may be overwritten once the work queued so far is done
+    """
+
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE):
+        import torch
+        self.slots = [VerifyBatch(blobs, inputs=inputs), VerifyBatch(blobs, inputs=inputs)]
+        self.shape, self.n = self.slots[0].shape, self.slots[0].n
+        self.copy_stream = torch.cuda.Stream()
+        self.uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.free:
+            e.record()
+        self._fed, self._taken = 0, 0
+
+    def feed(self, blobs=None):
+        """queue the upload of one batch into the next slot; blobs=None re-sends the slot's pinned host copy"""
+        import torch
+        i = self._fed % 2
+        assert self._fed - self._taken < 2, "both slots hold batches that were not taken yet"
+        slot = self.slots[i]
+        if blobs is not None:
+            words = np.concatenate([np.frombuffer(_as_aligned(b)[0].tobytes(), dtype=np.uint32) for b in blobs])
+            off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([(len(b) + 3) // 4 for b in blobs])
+            if len(blobs) != slot.n or words.size > slot.h_words.numel():
+                raise ValueError("a VerifyStream takes batches of the size and (at most) the byte length it was built with")
+            slot.h_words[: words.size].copy_(torch.from_numpy(words.view(np.int32)))
+            slot.h_off.copy_(torch.from_numpy(off.view(np.int64)))
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[i])
+            slot.upload()
+            self.uploaded[i].record(self.copy_stream)
+        self._fed += 1
+
+    def take(self):
+        import torch
+        assert self._taken < self._fed, "nothing was fed"
+        i = self._taken % 2
+        torch.cuda.current_stream().wait_event(self.uploaded[i])
+        self._taken += 1
+        return self.slots[i]
+
+    def release(self, batch):
+        self.free[self.slots.index(batch)].record()

@@ -122,3 +122,36 @@ def test_pinned_host_entry_matches_device_entry(pkg, gpu, orc):
     v2, s2 = vb.run_from_host(full=True)
     assert np.array_equal(v1, v2.cpu().numpy()) and np.array_equal(s1, s2.cpu().numpy())
     assert v1.sum() == sum(1 for k in range(300) if k % 37 == 5)
+
+
+def test_verify_stream_double_buffer(pkg, gpu, orc):
+    """VerifyStream: batches fed while the previous one is verified come out with their own verdicts, in order"""
+    import torch
+    buf, n = O.load_proof("small_proof.bin")
+    offs = O.proof_offsets(buf, n)
+    good = bytes(buf[:n])
+
+    def batch(seed):
+        out = []
+        for k in range(64):
+            b = buf.copy()
+            if (k + seed) % 7 == 0:
+                b[offs["queried0"] + (k + seed) % 64] ^= 2
+            out.append(bytes(b[:n]))
+        return out
+
+    vs = pkg.VerifyStream([good] * 64, inputs=pkg.INPUTS_SINGLE)
+    batches = [batch(s) for s in range(5)]
+    vs.feed(batches[0])
+    got = []
+    for k in range(5):
+        if k + 1 < 5:
+            vs.feed(batches[k + 1])
+        bt = vs.take()
+        v, s = bt.run(full=True)
+        got.append(v.cpu().numpy().copy())
+        vs.release(bt)
+    torch.cuda.synchronize()
+    for k in range(5):
+        want = np.array([1 if (j + k) % 7 == 0 else 0 for j in range(64)], dtype=np.uint8)
+        assert np.array_equal(got[k] != 0, want != 0), k
