@@ -436,7 +436,34 @@ HD void stage_folds(const Workspace &ws, u32 p) {
 // Cooperative form of stage_folds: a group of lanes per proof, one query per lane for the arithmetic (domain points, M31
 // inversions, folds, last-layer polynomial), lane 0 for the short stream-order bookkeeping (which evaluation of a pair comes
 // from fri_witness).  tab: group-shared, folds_tab_words(nq) words.
-HD u32 folds_tab_words(u32 nq) { return 3 * nq + 8 * nq + 8; }
+HD u32 folds_tab_words(u32 nq) { return 3 * nq + 8 * nq + 8 + 4 * nq; }
+// Sorted distinct values of pos[i] >> shift, by all lanes of the group: sp[0..ns) ascending, rep[k] = the first query that
+// has value sp[k].  flag: nq scratch words.  Rank sort: every lane ranks its own queries against all the others.
+template <class Co>
+HD u32 coop_sort_unique(const Co &co, const u32 *pos, u32 nq, u32 shift, u32 *sp, u32 *rep, u32 *flag, u32 *count) {
+    const u32 L = co.lane(), G = co.size();
+    for (u32 i = L; i < nq; i += G) {
+        const u32 v = pos[i] >> shift;
+        u32 first = 1;
+        for (u32 j = 0; j < i; j++) if ((pos[j] >> shift) == v) { first = 0; break; }
+        flag[i] = first;
+    }
+    co.sync();
+    for (u32 i = L; i < nq; i += G) {
+        if (!flag[i]) continue;
+        const u32 v = pos[i] >> shift;
+        u32 rank = 0;
+        for (u32 j = 0; j < nq; j++) rank += (flag[j] && (pos[j] >> shift) < v) ? 1u : 0u;
+        sp[rank] = v; rep[rank] = i;
+    }
+    if (L == 0) {
+        u32 c = 0;
+        for (u32 j = 0; j < nq; j++) c += flag[j];
+        *count = c;
+    }
+    co.sync();
+    return *count;
+}
 template <class Co>
 HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
     const Desc &d = ws.desc[p];
@@ -447,6 +474,7 @@ HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
     u32 *pos = tab, *sp = pos + nq;
     u32 *folded = sp + 2 * nq, *sibv = folded + 4 * nq;               // qm31 per query / per unique position
     u32 *ctl = sibv + 4 * nq;                                          // [0] ns  [1] ok flags
+    u32 *rep = ctl + 8, *flag = rep + nq, *widx = flag + nq, *pidx = widx + nq;
     if (L == 0) ctl[1] = 0;
     // ---- first layer: per log size descending, per sorted pair subset, both evaluations
     {
@@ -457,9 +485,8 @@ HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
             const u32 Lg = dt.log_sizes[g];
             for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], Lg);
             co.sync();
+            const u32 ns = coop_sort_unique(co, pos, nq, 0, sp, rep, flag, ctl);
             if (L == 0) {
-                for (u32 i = 0; i < nq; i++) sp[i] = pos[i];
-                const u32 ns = decommit::sort_unique(sp, nq);
                 u32 nv = ctl[2], wi = ctl[3];
                 bool ok = true;
                 for (u32 k = 0; k < ns && ok;) {
@@ -467,9 +494,7 @@ HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
                     for (u32 e = start; e < start + 2; e++) {
                         const u32 *src;
                         if (k < ns && sp[k] == e) {
-                            u32 i = 0;
-                            while (pos[i] != e) i++;
-                            src = ws.q4(ws.answers, p, g, fri::MAX_LOGS, i);
+                            src = ws.q4(ws.answers, p, g, fri::MAX_LOGS, rep[k]);
                             k++;
                         } else {
                             if (wi >= d.fl_n_fri_witness) { ok = false; break; }
@@ -498,12 +523,7 @@ HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
             const u32 Lg = dt.log_sizes[g];
             for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], Lg);
             co.sync();
-            if (L == 0) {
-                for (u32 i = 0; i < nq; i++) sp[i] = pos[i] >> 1;
-                ctl[0] = decommit::sort_unique(sp, nq);
-            }
-            co.sync();
-            const u32 npairs = ctl[0];
+            const u32 npairs = coop_sort_unique(co, pos, nq, 1, sp, rep, flag, ctl);
             for (u32 i = L; i < nq; i += G) {
                 const int pi = decommit::find(sp, npairs, pos[i] >> 1);
                 const u32 *pr = vals + base + 8 * (u32)pi;
@@ -531,40 +551,49 @@ HD void stage_folds_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
         log_size -= 1;
         for (u32 i = L; i < nq; i += G) pos[i] = fri::position(d, dt.fs.raw_queries[i], log_size);
         co.sync();
-        if (L == 0) {
-            for (u32 i = 0; i < nq; i++) sp[i] = pos[i];
-            const u32 ns = decommit::sort_unique(sp, nq);
-            ctl[0] = ns;
-            u32 *vals = ws.vals_of(p, 1 + li), nv = 0, wi = 0;
-            bool ok = true;
-            for (u32 k = 0; k < ns; k++) {
-                const u32 e = sp[k];
-                u32 i = 0;
-                while (pos[i] != e) i++;
-                qm31_t sv;
-                const int sk = decommit::find(sp, ns, e ^ 1u);
-                if (sk >= 0) { u32 j = 0; while (pos[j] != (e ^ 1u)) j++; sv = fs::qload(folded + 4 * j); }
-                else if (wi < d.in_n_fri_witness[li]) sv = fs::qload(w + d.in_fri_witness[li] + 4 * wi++);
-                else { ok = false; sv = qm31::zero(); }
-                fs::qstore(sibv + 4 * k, sv);
-                if (k == 0 || (sp[k - 1] >> 1) != (e >> 1)) {
-                    const qm31_t fv = fs::qload(folded + 4 * i);
-                    const qm31_t l = (e & 1u) ? sv : fv, r = (e & 1u) ? fv : sv;
-                    fs::qstore(vals + nv, l); fs::qstore(vals + nv + 4, r); nv += 8;
-                }
-            }
-            if (wi != d.in_n_fri_witness[li]) ok = false;
-            *ws.nvals_of(p, 1 + li) = nv;
-            if (!ok) ctl[1] |= 2;
+        const u32 ns = coop_sort_unique(co, pos, nq, 0, sp, rep, flag, ctl);
+        // per distinct position k: does its sibling come from the witness (widx), does it open a new pair (pidx)?
+        for (u32 k = L; k < ns; k += G) {
+            widx[k] = decommit::find(sp, ns, sp[k] ^ 1u) < 0 ? 1u : 0u;
+            pidx[k] = (k == 0 || (sp[k - 1] >> 1) != (sp[k] >> 1)) ? 1u : 0u;
         }
         co.sync();
-        const u32 ns = ctl[0];
+        if (L == 0) {                                  // exclusive prefix sums; bit 31 keeps the flag
+            u32 wi = 0, np = 0;
+            for (u32 k = 0; k < ns; k++) {
+                const u32 fw = widx[k], fp = pidx[k];
+                widx[k] = wi | (fw << 31); pidx[k] = np | (fp << 31);
+                wi += fw; np += fp;
+            }
+            if (wi != d.in_n_fri_witness[li]) ctl[1] |= 2;
+            *ws.nvals_of(p, 1 + li) = 8 * np;
+        }
+        co.sync();
+        {
+            u32 *vals = ws.vals_of(p, 1 + li);
+            for (u32 k = L; k < ns; k += G) {
+                const u32 e = sp[k];
+                qm31_t sv;
+                if (widx[k] >> 31) {
+                    const u32 wi = widx[k] & 0x7fffffffu;
+                    sv = wi < d.in_n_fri_witness[li] ? fs::qload(w + d.in_fri_witness[li] + 4 * wi) : qm31::zero();
+                } else sv = fs::qload(folded + 4 * rep[(u32)decommit::find(sp, ns, e ^ 1u)]);
+                fs::qstore(sibv + 4 * k, sv);
+                if (pidx[k] >> 31) {
+                    const qm31_t fv = fs::qload(folded + 4 * rep[k]);
+                    const qm31_t l = (e & 1u) ? sv : fv, r = (e & 1u) ? fv : sv;
+                    u32 *out = vals + 8 * (pidx[k] & 0x7fffffffu);
+                    fs::qstore(out, l); fs::qstore(out + 4, r);
+                }
+            }
+        }
+        co.sync();
         for (u32 i = L; i < nq; i += G) {
             const int k = decommit::find(sp, ns, pos[i]);
             const u32 x_inv = fs::minv(fri::absolute_point(log_size, pos[i]).x);
             const qm31_t f = fri::fold_pair(fs::qload(folded + 4 * i), fs::qload(sibv + 4 * (u32)k), pos[i], x_inv, dt.fs.fri_alphas[li + 1]);
             fs::qstore(ws.q4(ws.line_folds, p, li, proof::MAX_INNER, i), f);
-            // lanes read folded[] of other queries only through sibv (filled by lane 0 before the barrier): writing now is safe
+            // lanes read folded[] of other queries only through sibv (filled before the barrier): writing now is safe
             fs::qstore(folded + 4 * i, f);
         }
         co.sync();
