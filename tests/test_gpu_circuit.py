@@ -43,6 +43,23 @@ def test_trace_matches_oracle_and_golden(pkg, gpu, orc, name):
         assert D.trace_digest(got) == GOLD[name]["trace_sha256"]
 
 
+@pytest.mark.parametrize("pair", [("level10-1.bin", "level11-1.bin"), ("level2-1.bin", "level5-1.bin")])
+def test_different_proofs_in_neighbouring_lanes(pkg, gpu, orc, pair):
+    """one batch, one shape, two different proofs alternating lane by lane (the second pair also differs in byte length):
+    every proof's trace equals the golden digest of its own fixture"""
+    blobs = [open(os.path.join(O.PROOFS_DIR, f), "rb").read() for f in pair]
+    n = 70
+    vb = pkg.VerifyBatch([blobs[k % 2] for k in range(n)], inputs=pkg.INPUTS_RECURSIVE)
+    verdict, _ = vb.run(full=True)
+    assert not verdict.cpu().numpy().any()
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_RECURSIVE)
+    r = circ.trace(vb, check=True, export=True)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    for p in (0, 1, 31, 32, 63, 64, n - 1):
+        got = pkg.VerifierCircuit.assemble_trace(r["preprocessed"], r["values"][p])
+        assert D.trace_digest(got) == GOLD[pair[p % 2]]["trace_sha256"], p
+
+
 def test_multipliers(pkg, gpu, orc):
     """examples/multi-proofs: the same proof verified twice inside one constraint system"""
     name = "small_proof.bin"
