@@ -289,6 +289,35 @@ def multi_proofs_leg(pkg, sharding, rank, world, dev, n_total=256, reps=3):
             "proofs_per_sec": n_total / dt, "bytes_per_batch": sum(len(blobs[f]) for f in order)}
 
 
+def trace_gather_leg(sharding, values, rank, world, dev, n_each=256, reps=3):
+    """north_star's second collective: the trace columns of n_each proofs per rank gathered on rank 0 over NCCL (NVLink / NVSwitch).
+    values: this rank's [n_local, 13, n_rows] trace columns.  Device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    n_each = min(n_each, values.shape[0])
+    local = values[:n_each]
+    out = sharding.gather_trace_columns(local, n_each * world, dst=0)             # warm-up (NCCL channel setup)
+    ok = True
+    if rank == 0:
+        ok = bool(torch.equal(out[:n_each], local)) and out.shape[0] == n_each * world
+    del out
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = sharding.gather_trace_columns(local, n_each * world, dst=0)
+        del out
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    recv = (world - 1) * local.numel() * 4
+    return {"config": "trace columns of %d proofs per rank gathered on rank 0 (NCCL gather)" % n_each, "ok": ok, "ms": ms,
+            "bytes_received_by_rank0": recv, "gb_per_sec_into_rank0": recv / (ms * 1e-3) / 1e9}
+
+
 def divergence_leg(pkg, dev, n=1024, reps=5):
     """What replicas hide: lanes of a warp hold different proofs in production.  The same shape (16, 15; 10 queries) verified and
     traced as n replicas of level10-1.bin and as n proofs alternating level10-1.bin / level11-1.bin (different query positions
@@ -532,6 +561,12 @@ def main():
         mp = multi_proofs_leg(pkg, sharding, rank, world, dev)            # every rank takes its block of the 256
         if rank == 0:
             secondary["multi_proofs"] = mp
+        if world > 1:
+            _, _, rr = local_step()
+            tg = trace_gather_leg(sharding, rr["values"], rank, world, dev)
+            del rr
+            if rank == 0:
+                secondary["trace_gather"] = tg
     if not args.no_secondary and rank == 0:
         # BASELINE configs[1] (examples/last-layer): the last-layer circuit's trace for 256 replicas of the Poseidon31 twin of
         # hybrid_hash.bin (Plonk-without-Poseidon system, emulated Poseidon2, 2^17 rows x 20 columns), verification included

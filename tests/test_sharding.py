@@ -58,3 +58,41 @@ def test_gather_under_gloo(world, n_total):
     want_s = np.where(ids % 5 == 0, ids % 9, 0).astype(np.uint8).tolist()
     for rank, v, s in got:
         assert v == want_v and s == want_s, rank
+
+
+def _trace_worker(rank, world, port, n_total, dst, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = importlib.import_module("recursive-stwo_b200.sharding")
+    lo, hi = sh.shard_range(n_total, rank, world)
+    # stand-in trace columns: cell (p, c, r) = p * 1000 + c * 10 + r
+    p = torch.arange(lo, hi, dtype=torch.int32).reshape(-1, 1, 1)
+    local = p * 1000 + torch.arange(3, dtype=torch.int32).reshape(1, -1, 1) * 10 + torch.arange(4, dtype=torch.int32).reshape(1, 1, -1)
+    out = sh.gather_trace_columns(local, n_total, dst=dst)
+    q.put((rank, None if out is None else out.numpy().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total,dst", [(2, 7, 0), (3, 10, None), (2, 8, 1)])
+def test_gather_trace_columns_under_gloo(world, n_total, dst):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_trace_worker, args=(r, world, port, n_total, dst, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pp = np.arange(n_total).reshape(-1, 1, 1)
+    want = (pp * 1000 + np.arange(3).reshape(1, -1, 1) * 10 + np.arange(4).reshape(1, 1, -1)).tolist()
+    for rank, out in got:
+        if dst is None or rank == dst:
+            assert out == want, rank
+        else:
+            assert out is None
