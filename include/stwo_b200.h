@@ -234,10 +234,16 @@ typedef struct {
     uint32_t *variables;                             /* n_vars QM31 per item */
     uint32_t *flow_hash;                             /* n_flow x 32 words per item (PoseidonEntry.hash of entries 1..4) */
     uint8_t *flow_swap;                              /* n_flow bytes per item (SwapOption.swap) */
+    /* Optional (NULL / 0 = none), read by stwo_b200_cs_eval_tape_dev only: output states of permutations that were executed
+     * before -- item b's record k is the 16 words at perm_hints[b * perm_hint_stride + 16 k] (item-major, NOT lane-interleaved).
+     * A tape permutation whose record names a slot (word 11 of its 12 words = k + 1) takes its output from there instead
+     * of permuting; stwo_b200_cs_check_poseidon_dev re-executes every flow entry regardless. */
+    const uint32_t *perm_hints;
+    uint32_t perm_hint_stride;
 } stwo_b200_cs_values;
 /* The value definitions of a recorded circuit, sorted by dependency level (instructions of a level are independent).
  * ins: n_ins x {op, dst, a, b} (STWO_B200_T_*); perms: n_perms x 12 words {l_kind, l_a, l_b, r_kind, r_a, r_b, swap_var,
- * out[4], 0}: half kind 0 = the two QM31 variables (a, b), kind 1 = eight witness-stream words at slot a. */
+ * out[4], hint}: half kind 0 = the two QM31 variables (a, b), kind 1 = eight witness-stream words at slot a. */
 typedef struct {
     uint32_t n_ins, n_perms, n_levels, n_input_words;
     const uint32_t *ins, *level_start /* n_levels + 1 */, *perms;
@@ -341,6 +347,10 @@ int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, 
 #define STWO_B200_TRACE_CHECK_ARITHMETICS 1u
 #define STWO_B200_TRACE_CHECK_POSEIDON 2u
 #define STWO_B200_TRACE_TIMED 4u
+/* the batch was verified with STWO_B200_VERIFY_FULL on this workspace: the circuit's Poseidon permutations (transcript and
+ * per-query authentication paths) are the ones the native verifier just executed and recorded there; K6 takes their output
+ * states as hints instead of permuting again (check_poseidon_invocations still re-executes all of them) */
+#define STWO_B200_TRACE_NATIVE_HINTS 8u
 /* stage kernels of the trace pass in launch order: gather (+ public-input hashes), eval, check_arithmetics, check_poseidon, export */
 #define STWO_B200_N_TRACE_STAGES 5
 size_t stwo_b200_circuit_workspace_bytes(const stwo_b200_circuit *c, uint32_t n_proofs);

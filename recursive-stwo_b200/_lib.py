@@ -96,7 +96,7 @@ class CsWiring(ctypes.Structure):
 class CsValues(ctypes.Structure):
     """stwo_b200_cs_values"""
     _fields_ = [("n_batch", ctypes.c_uint32), ("lanes", ctypes.c_uint32), ("variables", ctypes.c_void_p), ("flow_hash", ctypes.c_void_p),
-                ("flow_swap", ctypes.c_void_p)]
+                ("flow_swap", ctypes.c_void_p), ("perm_hints", ctypes.c_void_p), ("perm_hint_stride", ctypes.c_uint32)]
 
 
 class CsTape(ctypes.Structure):
@@ -111,7 +111,7 @@ class CircuitInfo(ctypes.Structure):
                                                "n_levels", "num_input", "words_per_instance", "kind", "n_preprocessed_columns")]
 
 
-TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED = 1, 2, 4
+TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED, TRACE_NATIVE_HINTS = 1, 2, 4, 8
 TRACE_STAGES = ("gather", "eval", "check_arithmetics", "check_poseidon", "export")
 COLUMNS = {"a_wire": 0, "b_wire": 1, "c_wire": 2, "poseidon_wire": 3, "enforce_c_m31": 4, "op": 5, "op_follows_c": 6, "flow_wire": 7,
            "flow_swap_addr": 8, "level_start": 10, "op2": 11, "op3": 12, "op4": 13}

@@ -27,12 +27,17 @@ HD void st8(const Strided &s, u32 k, const u32 in[8]) { for (u32 i = 0; i < 8; i
 
 // hash_node on register-resident children (L == nullptr: leaf); cols is contiguous memory (the proof blob).
 // primitives/merkle/src/lib.rs:9-181
-HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr) {
+// sink (optional, advanced): receives the 16-word output state of every permutation, in execution order
+HD void tap(u32 **sink, const u32 *st) {
+    if (sink && *sink) { for (int i = 0; i < 16; i++) (*sink)[i] = st[i]; *sink += 16; }
+}
+HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr, u32 **sink = nullptr) {
     u32 st[16];
     u32 tree[8];
     if (L) {
         for (int i = 0; i < 8; i++) { st[i] = L[i]; st[8 + i] = R[i]; }
         permute_mem(st);
+        tap(sink, st);
         if (tree_out) for (int i = 0; i < 8; i++) tree_out[i] = st[i];
         if (nc == 0) { for (int i = 0; i < 8; i++) out[i] = st[i]; return; }
         for (int i = 0; i < 8; i++) tree[i] = st[i];
@@ -42,9 +47,11 @@ HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out
     for (u32 c = 0; c < n_chunks; c++) {
         for (u32 i = 0; i < 8; i++) st[i] = 8 * c + i < nc ? cols[8 * c + i] : 0u;
         permute_mem(st);
+        tap(sink, st);
     }
     for (int i = 0; i < 8; i++) st[i] = L ? tree[i] : 0u;
     permute_mem(st);
+    tap(sink, st);
     for (int i = 0; i < 8; i++) out[i] = st[i];
 }
 HD u32 node_perms(bool leaf, u32 nc) { return leaf ? (nc ? (nc + 7) / 8 : 1) + 1 : 1 + (nc ? (nc + 7) / 8 + 1 : 0); }
@@ -253,11 +260,12 @@ HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *val
 // SinglePairMerkleProof::verify for one query (components/hints/src/folding.rs:33-91): recompute the root from the
 // per-query hints.  Returns the root in out[8].
 HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals, const u32 *sib_vals, const u32 *sib_hashes,
-                       u32 *out, u32 *perms) {
+                       u32 *out, u32 *perms, u32 *sink = nullptr) {
     u32 self_h[8], sib_h[8];
     u32 d_idx = 0, np = 4;
-    hash_node2(nullptr, nullptr, self_vals, 4, self_h);
-    hash_node2(nullptr, nullptr, sib_vals, 4, sib_h);
+    u32 **sk = sink ? &sink : nullptr;
+    hash_node2(nullptr, nullptr, self_vals, 4, self_h, nullptr, sk);
+    hash_node2(nullptr, nullptr, sib_vals, 4, sib_h, nullptr, sk);
     d_idx = 1;
     for (u32 i = 0; i < depth; i++) {
         const u32 h = depth - i - 1;
@@ -265,11 +273,11 @@ HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals,
         const u32 *L = ((qpos >> i) & 1u) ? sib_h : self_h, *R = ((qpos >> i) & 1u) ? self_h : sib_h;
         u32 nxt[8];
         if (!data) {
-            hash_node2(L, R, nullptr, 0, nxt);
+            hash_node2(L, R, nullptr, 0, nxt, nullptr, sk);
             np += 1;
             if (i != depth - 1) cp8(sib_h, sib_hashes + 8 * i);
         } else {
-            hash_node2(L, R, self_vals + 4 * d_idx, 4, nxt);
+            hash_node2(L, R, self_vals + 4 * d_idx, 4, nxt, nullptr, sk);
             np += 3;
             if (h >= 1) {
                 // sibling = rate(perm(sibling tree hash || capacity(sibling evaluation)))
@@ -277,8 +285,10 @@ HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals,
                 for (int k = 0; k < 4; k++) st[k] = sib_vals[4 * d_idx + k];
                 for (int k = 4; k < 16; k++) st[k] = 0;
                 permute_mem(st);
+                tap(sk, st);
                 for (int k = 0; k < 8; k++) st[k] = sib_hashes[8 * i + k];
                 permute_mem(st);
+                tap(sk, st);
                 cp8(sib_h, st);
                 np += 2;
             }
@@ -288,6 +298,15 @@ HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals,
     }
     cp8(out, self_h);
     if (perms) *perms += np;
+}
+// permutations pair_path_root executes (a function of the tree's shape only)
+HD u32 pair_path_perms(u32 depth, u32 data_mask) {
+    u32 np = 4;
+    for (u32 i = 0; i < depth; i++) {
+        const u32 h = depth - i - 1;
+        np += ((data_mask >> h) & 1u) ? (h >= 1 ? 5u : 3u) : 1u;
+    }
+    return np;
 }
 
 }  // namespace decommit

@@ -8,6 +8,7 @@
 // per batch item, levelised so that independent definitions run on different warps.
 #pragma once
 #include <cstdint>
+#include <deque>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -182,12 +183,19 @@ public:
 
     // The permutation must precede, on the tape, the rows that consume its outputs (their assembling gates are recorded
     // before the flow entry): the caller reserves the tape slot first and hands it back here.
+    // Native-verifier hints (verify.cuh HintLayout): a gadget that knows which permutation of the native pass it is about to
+    // repeat queues that permutation's slot; the next recorded permutation takes it.
+    std::deque<u32> hint_queue;
+    u32 transcript_slot = 0;
+    bool native_hints = false;
+    void push_hint(u32 slot) { if (native_hints && !without()) hint_queue.push_back(slot); }
     size_t reserve_tape_slot() { tape_.push_back({tape::T_NONE, 0, 0, 0}); return tape_.size() - 1; }
     void invoke_poseidon_accelerator(PoseidonEntry e1, PoseidonEntry e2, PoseidonEntry e3, PoseidonEntry e4, SwapOption s,
                                      const tape::Perm &p, size_t tape_slot) {
         flow_wire.push_back(e1.wire); flow_wire.push_back(e2.wire); flow_wire.push_back(e3.wire); flow_wire.push_back(e4.wire);
         flow_swap_addr.push_back(s.has_swap ? s.addr : 0);
         perms.push_back(p);
+        if (!hint_queue.empty()) { perms.back().hint = hint_queue.front() + 1; hint_queue.pop_front(); }
         tape_[tape_slot] = {tape::T_POSEIDON, (u32)perms.size() - 1, 0, 0};
     }
     u32 num_plonk_rows() const { return (u32)a_wire.size(); }

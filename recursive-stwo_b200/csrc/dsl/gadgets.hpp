@@ -306,21 +306,26 @@ struct Poseidon31MerkleHasherVar {
 struct ChannelVar {
     u32 n_sent = 0;
     Poseidon2HalfVar digest;
-    explicit ChannelVar(const ConstraintSystemRef &cs) : digest(Poseidon2HalfVar::zero(cs)) {}
+    explicit ChannelVar(const ConstraintSystemRef &cs) : digest(Poseidon2HalfVar::zero(cs)) { cs->transcript_slot = 0; }
     const ConstraintSystemRef &cs() const { return digest.cs; }
-    void mix_root(const HashVar &root) { digest = Poseidon2HalfVar::permute_get_capacity(root, digest); n_sent = 0; }
+    // every channel operation is one permutation, the k-th of the native transcript (fiat_shamir.cuh)
+    void hint() const { cs()->push_hint(cs()->transcript_slot++); }
+    void mix_root(const HashVar &root) { hint(); digest = Poseidon2HalfVar::permute_get_capacity(root, digest); n_sent = 0; }
     std::array<QM31Var, 2> draw_felts() {
         const M31Var n = M31Var::new_constant(cs(), n_sent);
         n_sent += 1;
         const Poseidon2HalfVar left = Poseidon2HalfVar::from_qm31(QM31Var::from(n), QM31Var::zero(cs()));
+        hint();
         return Poseidon2HalfVar::permute_get_rate(left, digest).to_qm31();
     }
     void mix_one_felt(const QM31Var &felt) {
         const Poseidon2HalfVar left = Poseidon2HalfVar::from_qm31(felt, QM31Var::zero(cs()));
+        hint();
         digest = Poseidon2HalfVar::permute_get_capacity(left, digest);
         n_sent = 0;
     }
     void mix_two_felts(const QM31Var &a, const QM31Var &b) {
+        hint();
         digest = Poseidon2HalfVar::permute_get_capacity(Poseidon2HalfVar::from_qm31(a, b), digest);
         n_sent = 0;
     }

@@ -16,6 +16,7 @@
 #include <functional>
 
 #include "gadgets.hpp"
+#include "../verify.cuh"
 
 namespace stwo_b200 {
 namespace dsl {
@@ -27,7 +28,9 @@ struct ShapeFacts {                       // the value-independent part of FiatS
     ProofShape s;
     u32 max_first, log_plonk, log_pos, composition_log_degree_bound;
     std::vector<u32> all_log_sizes;       // ascending
+    verify::HintLayout hints;             // where the native verifier records the permutations this circuit repeats
     explicit ShapeFacts(const ProofShape &p) : s(p) {
+        hints = verify::hint_layout(verify::Shape{p.log_size_plonk, p.log_size_poseidon, p.pow_bits, p.log_blowup, p.log_last, p.n_queries, p.n_inner});
         max_first = p.log_last + p.log_blowup + 1 + p.n_inner;
         log_plonk = p.log_size_plonk + p.log_blowup; log_pos = p.log_size_poseidon + p.log_blowup;
         composition_log_degree_bound = max_first - p.log_blowup + 1;
@@ -489,7 +492,26 @@ struct SinglePathMerkleProofVar {
         }
         return v;
     }
-    void verify(const HashVar &root, const BitsVar &query) const {                        // :315-354
+    // hint_base: slot of this (tree, query) path in the native verifier's permutation record (verify.cuh HintLayout), whose
+    // order is merkle::path_root's: leaf sponge, leaf final, then per level node [, column sponge, combine].  The circuit
+    // hashes a level's columns BEFORE the node, so the slots are queued in the circuit's order.
+    void verify(const HashVar &root, const BitsVar &query, u32 hint_base = tape::NO_VAR) const {     // :315-354
+        if (hint_base != tape::NO_VAR) {
+            const ConstraintSystemRef &cs = root.cs;
+            u32 at = hint_base;
+            const u32 leaf_chunks = ((u32)columns.at(depth).size() + 7) / 8;
+            for (u32 k = 0; k <= leaf_chunks; k++) cs->push_hint(at++);
+            for (u32 i = 0; i < depth; i++) {
+                auto it = columns.find(depth - i - 1);
+                if (it != columns.end()) {
+                    const u32 chunks = ((u32)it->second.size() + 7) / 8;
+                    for (u32 k = 0; k < chunks; k++) cs->push_hint(at + 1 + k);
+                    cs->push_hint(at);
+                    cs->push_hint(at + 1 + chunks);
+                    at += chunks + 2;
+                } else cs->push_hint(at++);
+            }
+        }
         HashVar cur_hash = Poseidon31MerkleHasherVar::hash_m31_columns_get_rate(columns.at(depth));
         for (u32 i = 0; i < depth; i++) {
             const u32 h = depth - i - 1;
@@ -526,8 +548,22 @@ struct SinglePairMerkleProofVar {
             }
         return v;
     }
-    void verify(const HashVar &root, const BitsVar &query) const {                        // :400-464
+    // hint_base: as above; native order (decommit::pair_path_root): self leaf (2), sibling leaf (2), then per level either
+    // node, or node, self sponge, self combine, sibling sponge, sibling combine
+    void verify(const HashVar &root, const BitsVar &query, u32 hint_base = tape::NO_VAR) const {     // :400-464
         const ConstraintSystemRef &cs = root.cs;
+        if (hint_base != tape::NO_VAR) {
+            u32 at = hint_base;
+            for (u32 k = 0; k < 4; k++) cs->push_hint(at++);
+            for (u32 i = 0; i < depth; i++) {
+                if (!self_columns.count(depth - i - 1)) cs->push_hint(at++);
+                else {
+                    const u32 order[5] = {1, 3, 0, 2, 4};
+                    for (u32 k = 0; k < 5; k++) cs->push_hint(at + order[k]);
+                    at += 5;
+                }
+            }
+        }
         HashVar self_hash = Poseidon31MerkleHasherVar::hash_qm31_columns_get_rate({self_columns.at(depth), QM31Var::zero(cs)});
         HashVar sibling_hash = Poseidon31MerkleHasherVar::hash_qm31_columns_get_rate({siblings_columns.at(depth), QM31Var::zero(cs)});
         for (u32 i = 0; i < depth; i++) {
@@ -575,7 +611,7 @@ struct AnswerResults {
             std::vector<std::vector<Columns>> cols(4);
             for (u32 t = 0; t < 4; t++)
                 for (u32 i = 0; i < nq; i++) {
-                    dec_proofs[t][i].verify(proof.commitments[t], qp[f.tree_depth(t)][i].bits);
+                    dec_proofs[t][i].verify(proof.commitments[t], qp[f.tree_depth(t)][i].bits, f.hints.single_slot(t, i));
                     cols[t].push_back(dec_proofs[t][i].columns);
                 }
             return cols;
@@ -705,7 +741,7 @@ struct FoldingResults {
         std::vector<SinglePairMerkleProofVar> proofs;
         for (u32 i = 0; i < nq; i++) {
             proofs.push_back(SinglePairMerkleProofVar::new_(w, f, 0, i));
-            proofs.back().verify(proof.first_layer_commitment, qp[f.max_first][i].bits);
+            proofs.back().verify(proof.first_layer_commitment, qp[f.max_first][i].bits, f.hints.pair_slot(0, i));
         }
         for (auto it = f.all_log_sizes.rbegin(); it != f.all_log_sizes.rend(); ++it)
             for (u32 i = 0; i < nq; i++) proofs[i].self_columns.at(*it).equalverify(ans.fri_answers.at(*it)[i]);
@@ -749,7 +785,7 @@ struct FoldingResults {
                 const QM31Var new_right_val = diff * x_inv;
                 const QM31Var ra = new_right_val * fs.fri_alphas[i + 1];
                 new_folded.push_back(new_left_val + ra);
-                merkle_proof.verify(proof.inner_layer_commitments[i], query.bits);
+                merkle_proof.verify(proof.inner_layer_commitments[i], query.bits, f.hints.pair_slot(1 + i, k));
             }
             folded = new_folded;
         }
@@ -774,6 +810,7 @@ inline VerifierCircuit record_verifier_circuit(const ProofShape &shape, const st
     const ShapeFacts f(shape);
     WitnessStream w{ConstraintSystemRef::new_plonk_with_poseidon_ref(), {}};
     const ConstraintSystemRef &cs = w.cs;
+    cs->native_hints = true;
     VerifierCircuit out;
     for (u32 m = 0; m < multipliers; m++) {
         PlonkWithPoseidonProofVar proof = PlonkWithPoseidonProofVar::new_witness(w, f);
@@ -784,6 +821,7 @@ inline VerifierCircuit record_verifier_circuit(const ProofShape &shape, const st
         const CirclePointQM31Var oods_witness = CirclePointQM31Var::new_witness(cs, w.take(tape::S_OODS, 0, 0, 0, 8));
         const AnswerResults ans = AnswerResults::compute(w, oods_witness, f, fs, proof);
         FoldingResults::compute(w, proof, f, fs, ans);
+        if (!cs->hint_queue.empty()) throw std::logic_error("native-hint slots left over: the circuit recorded fewer permutations than it announced");
         if (m == 0) out.words_per_instance = cs->n_input_words;
     }
     cs->pad();

@@ -50,10 +50,13 @@ struct Channel {
     u32 st[16];        // st[8..16] = digest between operations
     u32 n_sent;
     u32 n_perms;
-    HDM void init() { for (int i = 0; i < 16; i++) st[i] = 0; n_sent = 0; n_perms = 0; }
+    u32 *sink;         // optional: the 16-word output state of permutation k goes to sink[16 k ..]
+    HDM void init(u32 *sink_ = nullptr) { for (int i = 0; i < 16; i++) st[i] = 0; n_sent = 0; n_perms = 0; sink = sink_; }
+    HDM void emit(const u32 *t) { if (sink) for (int i = 0; i < 16; i++) sink[16 * (size_t)n_perms + i] = t[i]; }
     HDM void mix8(const u32 *w8) {            // mix_root / mix_two_felts: digest <- capacity(perm(w8 || digest))
         for (int i = 0; i < 8; i++) st[i] = w8[i];
         permute_mem(st);
+        emit(st);
         n_sent = 0; n_perms++;
     }
     HDM void mix4(const u32 *w4) {            // mix_one_felt
@@ -70,6 +73,7 @@ struct Channel {
         for (int i = 1; i < 8; i++) t[i] = 0;
         for (int i = 8; i < 16; i++) t[i] = st[i];
         permute_mem(t);
+        emit(t);
         for (int i = 0; i < 8; i++) out[i] = t[i];
         n_perms++;
     }
@@ -84,9 +88,9 @@ struct Out {                                   // Fiat-Shamir results of one pro
     u32 pow_ok;
 };
 
-HD void transcript(const u32 *w, const proof::Desc &d, Out &o) {
+HD void transcript(const u32 *w, const proof::Desc &d, Out &o, u32 *sink = nullptr) {
     Channel ch;
-    ch.init();
+    ch.init(sink);
     ch.mix8(w + d.commitments[0]);
     u32 f[4] = {d.log_size_plonk, 0, 0, 0};
     ch.mix4(f);

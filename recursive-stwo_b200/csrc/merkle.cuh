@@ -61,7 +61,8 @@ HD void hash_node(const u32 *children, LoadCol load_col, u32 n_cols, u32 out[8])
 // Walk one authentication path; returns the recomputed root in out[8].
 //   cols: this path's column values (leaf layer first, then injected layers, descending log size)
 //   sib : depth x 8 sibling words, leaf level first
-HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols, const u32 *sib, u32 out[8]) {
+// sink (optional): receives the 16-word output state of every permutation, in execution order
+HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols, const u32 *sib, u32 out[8], u32 *sink = nullptr) {
     enum { PH_SPONGE = 0, PH_FINAL_LEAF = 1, PH_NODE = 2, PH_COMBINE = 3 };
     u32 st[16];
     u32 saved[8];
@@ -99,6 +100,11 @@ HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols,
             for (int i = 0; i < 8; i++) st[i] = saved[i];
         }
         poseidon2::permute<false>(st);
+        if (sink) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) sink[i] = st[i];
+            sink += 16;
+        }
         // transitions
         if (ph == PH_SPONGE) {
             if (rem == 0) ph = leaf ? PH_FINAL_LEAF : PH_COMBINE;

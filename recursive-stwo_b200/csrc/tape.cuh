@@ -48,7 +48,8 @@ struct Perm {
     u32 r_kind, r_a, r_b;
     u32 swap_var;                               // NO_VAR: never swapped
     u32 out[4];                                 // variables receiving state[4k .. 4k+4); NO_VAR when the half is ignored
-    u32 reserved;
+    u32 hint;                                   // 0: none; k + 1: the output state is word 16 k .. 16 k + 16 of the item's permutation
+                                                // hints (the native verifier already executed this permutation: verify.cuh HintLayout)
 };
 
 struct alignas(16) Q4 { u32 x, y, z, w; };
@@ -77,6 +78,7 @@ struct View {
     u32 *flow_hash;                             // + (entry * 32 + word) * stride     may be null
     uint8_t *flow_swap;                         // + entry * stride                   may be null
     u32 stride;
+    const u32 *hint;                            // the item's permutation hints, 16 consecutive words per slot; may be null
 };
 
 HD qm31_t ldv(const View &v, u32 i) {
@@ -129,7 +131,10 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];          // PoseidonEntry 1, 2: the halves as given
     }
-    poseidon2::permute<UNROLLED>(st);
+    if (v.hint && p.hint) {                     // executed once already by the native verifier: take its output state
+        const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
+        for (int k = 0; k < 16; k++) st[k] = h[k];
+    } else poseidon2::permute<UNROLLED>(st);
     if (v.flow_hash) {
         u32 *fh = v.flow_hash + ((size_t)entry * 32 + 16) * v.stride;
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = st[k];          // PoseidonEntry 3, 4: the full output

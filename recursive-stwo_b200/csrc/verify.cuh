@@ -34,6 +34,45 @@ struct Shape {            // mirror of stwo_b200_proof_shape (include/stwo_b200.
     }
 };
 
+// Where the native verifier leaves the output state of the permutations that the verifier CIRCUIT executes as well (the
+// transcript and every per-query authentication path: together exactly the circuit's Poseidon flow).  K6 may take them as hints
+// instead of permuting again (tape::Perm::hint); check_poseidon_invocations still re-executes every flow entry.
+// Slot order inside a path = execution order of merkle::path_root / decommit::pair_path_root.
+constexpr u32 HINT_TRANSCRIPT_SLOTS = 512;
+struct HintLayout {
+    u32 single_base[4], single_n[4];
+    u32 pair_base[proof::MAX_INNER + 1], pair_n[proof::MAX_INNER + 1];
+    u32 total;
+    HDM u32 single_slot(u32 t, u32 i) const { return single_base[t] + i * single_n[t]; }
+    HDM u32 pair_slot(u32 f, u32 i) const { return pair_base[f] + i * pair_n[f]; }
+};
+HD void single_path_shape(const Shape &s, u32 t, stwo_b200_path_shape &shp) {
+    const u32 depth = s.tree_depth(t);
+    shp.depth = depth;
+    for (u32 h = 0; h <= depth; h++) shp.n_cols[h] = 0;
+    if (t < 3) { shp.n_cols[s.log_plonk()] += proof::plonk_cols(t); shp.n_cols[s.log_pos()] += proof::n_cols(t) - proof::plonk_cols(t); }
+    else shp.n_cols[s.max_first()] = 8;
+}
+HD HintLayout hint_layout(const Shape &s) {
+    HintLayout h;
+    u32 at = HINT_TRANSCRIPT_SLOTS;
+    for (u32 t = 0; t < 4; t++) {
+        stwo_b200_path_shape shp;
+        single_path_shape(s, t, shp);
+        h.single_n[t] = merkle::path_perms(shp);
+        h.single_base[t] = at;
+        at += h.single_n[t] * s.n_queries;
+    }
+    for (u32 f = 0; f <= proof::MAX_INNER; f++) { h.pair_base[f] = at; h.pair_n[f] = 0; }
+    for (u32 f = 0; f < s.n_fri_trees(); f++) {
+        h.pair_n[f] = decommit::pair_path_perms(s.fri_depth(f), s.fri_data_mask(f));
+        h.pair_base[f] = at;
+        at += h.pair_n[f] * s.n_queries;
+    }
+    h.total = at;
+    return h;
+}
+
 constexpr u32 MAX_DEPTH = 30;
 constexpr u32 PATH_COLS_STRIDE = 64;                           // >= widest tree (60 columns)
 constexpr u32 PAIR_HINT_WORDS = 2 * decommit::MAX_DATA_LAYERS * 4 + (MAX_DEPTH - 1) * 8;   // self, sib, sibling hashes
@@ -73,6 +112,7 @@ struct Workspace {
     u32 *pair_hints;                     // [p][f][i][PAIR_HINT_WORDS]
     u32 *pair_scratch;                   // [p][f][88 * nq]
     u32 *fold_buf;                       // [p][max(1, 2^(log_last-1))][4]  last-layer polynomial fold buffer
+    u32 *perm_out;                       // [p][HintLayout::total][16]  output state of every transcript / per-query path permutation
 
     HDM const u32 *blob(u32 p) const { return blobs + blob_off[p]; }
     HDM size_t blob_words(u32 p) const { return (size_t)(blob_off[p + 1] - blob_off[p]); }
@@ -94,6 +134,8 @@ struct Workspace {
     HDM decommit::Strided scratch_pair(u32 p, u32 f) const { decommit::Strided s; s.p = pair_scratch + ((size_t)p * shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq(); s.stride = 1; return s; }
 #endif
     HDM u32 *q4(u32 *base, u32 p, u32 a, u32 na, u32 i) const { return base + (((size_t)p * na + a) * nq() + i) * 4; }
+    u32 hint_total, pair_hint_base;      // HintLayout::total / pair_base[0] of `shape` (set by carve)
+    HDM u32 *perm_out_of(u32 p, u32 slot) const { return perm_out ? perm_out + ((size_t)p * hint_total + slot) * 16 : nullptr; }
 };
 
 HD void fail(Detail &dt, u32 stage) { dt.fail_mask |= 1u << stage; }
@@ -118,7 +160,7 @@ HD void stage_after_transcript(const Workspace &ws, u32 p);
 HD void stage_transcript(const Workspace &ws, u32 p) {
     Desc &d = ws.desc[p];
     if (!d.ok) return;
-    fs::transcript(ws.blob(p), d, ws.detail[p].fs);
+    fs::transcript(ws.blob(p), d, ws.detail[p].fs, ws.perm_out_of(p, 0));
     stage_after_transcript(ws, p);
 }
 HD void stage_after_transcript(const Workspace &ws, u32 p) {
@@ -263,12 +305,16 @@ HD void stage_single_path(const Workspace &ws, u32 p, u32 t, u32 i) {
     Detail &dt = ws.detail[p];
     stwo_b200_path_shape shp;
     const u32 depth = ws.shape.tree_depth(t);
-    shp.depth = depth;
-    for (u32 h = 0; h <= depth; h++) shp.n_cols[h] = 0;
-    if (t < 3) { shp.n_cols[d.log_plonk] += proof::plonk_cols(t); shp.n_cols[d.log_pos] += proof::n_cols(t) - proof::plonk_cols(t); }
-    else shp.n_cols[d.max_first] = 8;
+    single_path_shape(ws.shape, t, shp);
     u32 root[8];
-    merkle::path_root(shp, fri::position(d, dt.fs.raw_queries[i], depth), ws.cols_of(p, t, i), ws.sib_of(p, t, i), root);
+    u32 *sink = nullptr;
+    if (ws.perm_out) {
+        // slot base of (tree t, query i): the same prefix sums as hint_layout(), without building the whole table per thread
+        u32 at = HINT_TRANSCRIPT_SLOTS;
+        for (u32 tt = 0; tt < t; tt++) { stwo_b200_path_shape o; single_path_shape(ws.shape, tt, o); at += merkle::path_perms(o) * ws.nq(); }
+        sink = ws.perm_out_of(p, at + i * merkle::path_perms(shp));
+    }
+    merkle::path_root(shp, fri::position(d, dt.fs.raw_queries[i], depth), ws.cols_of(p, t, i), ws.sib_of(p, t, i), root, sink);
     decommit::cp8(ws.root_of(p, t, i), root);
     VERIFY_ATOMIC_ADD(&dt.n_perms_paths, merkle::path_perms(shp));
     if (!decommit::eq8(root, ws.blob(p) + d.commitments[t])) fail_shared(&dt, proof::ST_MERKLE);
@@ -674,7 +720,13 @@ HD void stage_pair_path(const Workspace &ws, u32 p, u32 f, u32 i) {
     const u32 depth = ws.shape.fri_depth(f);
     const u32 q = fri::position(d, dt.fs.raw_queries[i], depth);
     u32 root[8], perms = 0;
-    decommit::pair_path_root(depth, ws.shape.fri_data_mask(f), q, hint_self(ws, p, f, i), hint_sib(ws, p, f, i), hint_hashes(ws, p, f, i), root, &perms);
+    u32 *sink = nullptr;
+    if (ws.perm_out) {
+        u32 at = ws.pair_hint_base;
+        for (u32 ff = 0; ff < f; ff++) at += decommit::pair_path_perms(ws.shape.fri_depth(ff), ws.shape.fri_data_mask(ff)) * ws.nq();
+        sink = ws.perm_out_of(p, at + i * decommit::pair_path_perms(depth, ws.shape.fri_data_mask(f)));
+    }
+    decommit::pair_path_root(depth, ws.shape.fri_data_mask(f), q, hint_self(ws, p, f, i), hint_sib(ws, p, f, i), hint_hashes(ws, p, f, i), root, &perms, sink);
     decommit::cp8(ws.root_of(p, 4 + f, i), root);
     VERIFY_ATOMIC_ADD(&dt.n_perms_paths, perms);
     const u32 *want = ws.blob(p) + (f ? d.in_commitment[f - 1] : d.fl_commitment);
@@ -727,6 +779,9 @@ inline size_t carve(Workspace &ws, uint8_t *base) {
     ws.pair_hints = c.take<u32>(n * nf * nq * PAIR_HINT_WORDS);
     ws.pair_scratch = c.take<u32>(n * nf * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq);
     ws.fold_buf = c.take<u32>(n * (ws.shape.log_last ? ((size_t)1 << (ws.shape.log_last - 1)) : 1) * 4);
+    const HintLayout hl = hint_layout(ws.shape);
+    ws.hint_total = hl.total; ws.pair_hint_base = hl.pair_base[0];
+    ws.perm_out = c.take<u32>(n * (size_t)hl.total * 16);
     return (c.at + 255) & ~(size_t)255;
 }
 

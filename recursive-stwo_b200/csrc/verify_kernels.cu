@@ -127,19 +127,21 @@ struct Lanes16 {
 };
 struct Channel16 {                                          // primitives/channel/src/lib.rs:23-58 on a lane-spread state
     Lanes16 g; u32 s, n_sent, n_perms;
-    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); n_sent = 0; n_perms++; }
+    u32 *sink;                                              // optional: output state of permutation k at sink[16 k ..], a word per lane
+    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); if (sink) sink[16 * (size_t)n_perms + g.l] = s; n_sent = 0; n_perms++; }
     __device__ void mix8(const u32 *w8) { absorb(g.l < 8 ? w8[g.l] : 0u); }
     __device__ void mix4(const u32 *w4) { absorb(g.l < 4 ? w4[g.l] : 0u); }
     __device__ void mix4v(u32 v) { absorb(g.l < 4 ? v : 0u); }              // lanes 0..3 already hold the four words
     __device__ void mix44(const u32 *a, const u32 *b) { absorb(g.l < 4 ? a[g.l] : g.l < 8 ? b[g.l - 4] : 0u); }
     __device__ u32 draw() {                                 // lanes 0..7 return the eight drawn words
         const u32 t = g.permute(g.l == 0 ? n_sent : g.l < 8 ? 0u : s);
+        if (sink) sink[16 * (size_t)n_perms + g.l] = t;
         n_sent++; n_perms++;
         return t;
     }
 };
-__device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o) {
-    Channel16 ch{g, 0u, 0u, 0u};
+__device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o, u32 *sink) {
+    Channel16 ch{g, 0u, 0u, 0u, sink};
     const u32 l = g.l;
     auto store_q = [&](qm31_t *dst, u32 t, u32 first_lane) { if (l >= first_lane && l < first_lane + 4) dst->v[l - first_lane] = t; };
     ch.mix8(w + d.commitments[0]);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kT) k_transcript16(const Workspace ws, u32 p0,
     g.l = threadIdx.x % 16;
     g.mask = 0xffffu << (16 * ((threadIdx.x % 32) / 16));
     verify::Detail &dt = ws.detail[p];
-    transcript16(g, ws.blob(p), d, dt.fs);
+    transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0));
     __syncwarp(g.mask);
     if (g.l == 0) verify::stage_after_transcript(ws, p);
 }

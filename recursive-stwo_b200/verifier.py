@@ -94,6 +94,7 @@ class VerifyBatch:
 
     def run(self, full=True, timed=False):
         flags = (VERIFY_FULL if full else 0) | (VERIFY_TIMED if timed else 0)
+        self.last_full = bool(full)          # full mode records the path permutations the circuit reuses (TRACE_NATIVE_HINTS)
         _lib.call("stwo_b200_verify_proofs_batch_dev", _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape),
                   _dptr(self.d_idx), _dptr(self.d_vals), self.n_inputs, flags, _dptr(self.d_ws), self.ws_bytes,
                   _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
@@ -103,6 +104,7 @@ class VerifyBatch:
         """verify with the blobs taken from the pinned host copy: the library uploads each slice on the stream that verifies it,
         so the transfer overlaps the kernels of the other slices (replaces upload() + run())"""
         flags = VERIFY_FULL if full else 0
+        self.last_full = bool(full)
         _lib.call("stwo_b200_verify_proofs_batch_pinned_dev", ctypes.c_void_p(self.h_words.data_ptr()), ctypes.c_void_p(self.h_off.data_ptr()),
                   _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape), _dptr(self.d_idx), _dptr(self.d_vals),
                   self.n_inputs, flags, _dptr(self.d_ws), self.ws_bytes, _dptr(self.d_verdict), _dptr(self.d_stage), _stream())

@@ -124,8 +124,8 @@ void hs_circuit_get(void *h, u32 what, u32 *out) {
 }
 // evaluates the tape for every proof of a verified batch (ws_base from hs_verify_batch) in level order, lanes = 1.
 // vars: n x n_vars x 4, flow_hash: n x n_flow x 32, flow_swap: n x n_flow, stream (optional): n x n_input_words.
-// bad_row[p] = first row failing check_arithmetics or -1.
-void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, uint8_t *flow_swap, u32 *stream_out, int64_t *bad_row) {
+// bad_row[p] = first row failing check_arithmetics or -1.  use_hints: permutation outputs from the native pass (Perm::hint).
+void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, uint8_t *flow_swap, u32 *stream_out, int64_t *bad_row, int use_hints) {
     RecordedCircuit *r = (RecordedCircuit *)h;
     const auto &c = *r->cs.p;
     const verify::Workspace &ws = *(const verify::Workspace *)ws_base;
@@ -138,7 +138,8 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
         for (u32 k = 0; k < c.n_input_words; k++) stream[k] = circuit::gather_word(ws, p, r->gather[k], extra.data());
         if (stream_out) memcpy(stream_out + (size_t)p * c.n_input_words, stream.data(), stream.size() * 4);
         tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
-                     flow_swap + (size_t)p * c.num_poseidon_invocations(), 1};
+                     flow_swap + (size_t)p * c.num_poseidon_invocations(), 1,
+                     use_hints && !c.without() ? ws.perm_out_of(p, 0) : nullptr};
         tape::prologue(v);
         for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data(), c.eperms.data());
         bad_row[p] = -1;
@@ -152,6 +153,13 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
         }
     }
 }
+}
+// permutations of the recorded circuit that name a slot of the native verifier's record
+extern "C" u32 hs_circuit_hint_count(void *h) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    u32 n = 0;
+    for (const auto &p : r->cs.p->perms) n += p.hint != 0;
+    return n;
 }
 extern "C" void hs_circuit_level_perms(void *h, u32 *perms_per_level) {
     RecordedCircuit *r = (RecordedCircuit *)h;

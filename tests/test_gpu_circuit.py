@@ -60,6 +60,25 @@ def test_different_proofs_in_neighbouring_lanes(pkg, gpu, orc, pair):
         assert D.trace_digest(got) == GOLD[pair[p % 2]]["trace_sha256"], p
 
 
+def test_native_hints_and_recomputation_agree(pkg, gpu, orc):
+    """K6 with the circuit's permutations taken from the native verifier's record (the default after run(full=True)) and with
+    every permutation executed again: identical variables, flow and trace; without full mode the hints are not used"""
+    blob = open(os.path.join(O.PROOFS_DIR, "small_proof.bin"), "rb").read()
+    vb = pkg.VerifyBatch([blob] * 37, inputs=pkg.INPUTS_SINGLE)
+    vb.run(full=True)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)
+    got = {}
+    for mode in (True, False):
+        r = circ.trace(vb, check=True, export=True, native_hints=mode)
+        assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+        got[mode] = (circ.fetch(36, "variables").copy(), circ.fetch(36, "flow_hash").copy(), r["values"].cpu().numpy().copy())
+    for a, b in zip(got[True], got[False]):
+        assert np.array_equal(a, b)
+    vb.run(full=False)                                  # no per-query paths: nothing to reuse
+    r = circ.trace(vb, check=True, export=True)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and np.array_equal(r["values"].cpu().numpy(), got[True][2])
+
+
 def test_multipliers(pkg, gpu, orc):
     """examples/multi-proofs: the same proof verified twice inside one constraint system"""
     name = "small_proof.bin"

@@ -46,7 +46,7 @@ def record_last(hs, shape):
     return h, dict(zip(INFO, (int(x) for x in info))), get
 
 
-def evaluate(hs, h, info, blobs, shape, inputs):
+def evaluate(hs, h, info, blobs, shape, inputs, use_hints=0):
     hs.hs_verify_batch.restype = ctypes.c_void_p
     words, off = pack(blobs)
     idx = np.array(inputs[0], dtype=np.uint32)
@@ -59,7 +59,7 @@ def evaluate(hs, h, info, blobs, shape, inputs):
     fh = np.zeros((n, info["n_flow"], 32), dtype=np.uint32)
     fs = np.zeros((n, info["n_flow"]), dtype=np.uint8)
     bad = np.zeros(n, dtype=np.int64)
-    hs.hs_circuit_eval(h, O.vp(ws), n, O.vp(variables), O.vp(fh), O.vp(fs), None, O.vp(bad))
+    hs.hs_circuit_eval(h, O.vp(ws), n, O.vp(variables), O.vp(fh), O.vp(fs), None, O.vp(bad), use_hints)
     hs.hs_free(ctypes.c_void_p(base))
     return dt, variables, fh, fs, bad
 
@@ -79,6 +79,11 @@ def test_recorded_circuit_matches_oracle(hostsim, orc, name, mult):
     want = np.array(cs.variables, dtype=np.uint32)
     diff = np.nonzero((variables[0] != want).any(axis=1))[0]
     assert diff.size == 0, "variable %d differs: %s != %s" % (diff[0], variables[0][diff[0]], want[diff[0]])
+    # the same with every circuit permutation taken from the native verifier's record (tape::Perm::hint): identical
+    # variables and flow prove the slot map -- transcript order, path order, the circuit's columns-before-node order
+    assert hostsim.hs_circuit_hint_count(h) == info["n_flow"]          # every permutation of the circuit is one the native pass executes
+    dt2, variables2, fh2, fs2, bad2 = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name), use_hints=1)
+    assert bad2[0] == -1 and np.array_equal(variables2, variables) and np.array_equal(fh2, fh) and np.array_equal(fs2, fs)
     wire, addr, wh, wsw = cs.flow_arrays()
     assert np.array_equal(fh[0], wh) and np.array_equal(fs[0], wsw)
     hostsim.hs_circuit_free(h)
