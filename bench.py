@@ -10,8 +10,10 @@ pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers).  One "step" = one ba
   (1) native verification: transcript + PoW, logup sum, OODS, batched Merkle decommitment re-shaped into
       per-query paths, DEEP answers, circle/line folds, last layer, every per-query authentication path;
   (2) the verifier circuit's trace: witness streams gathered from (1), variables[] evaluated along the recorded
-      tape (3 481 in-circuit Poseidon2 permutations per proof), check_arithmetics, check_poseidon_invocations,
-      export of the 2^16-row x 13 per-proof trace columns (examples/single-proof/src/main.rs:33-90).
+      tape (its 3 481 Poseidon2 permutations per proof are exactly the transcript + per-query path permutations (1) just
+      executed: their output states are taken from (1)'s record instead of permuting again), check_arithmetics,
+      check_poseidon_invocations (re-executes all 3 481 flow entries), export of the 2^16-row x 13 per-proof trace
+      columns (examples/single-proof/src/main.rs:33-90).
 Metric: verified proofs/s over all GPUs (a proof counts when its verdict is accept AND its circuit checks pass);
 `poseidon31_perms_per_sec` rides along.  `value`: blobs already in HBM.  `e2e`: a stream of batches through
 VerifyStream: every step uploads one batch of blobs from pinned host memory (double-buffered: the copy runs beside the previous
@@ -41,9 +43,9 @@ FIXTURE = "small_proof.bin"
 # profiles/r01*_ncu.txt) — the unit of the integer-issue roofline
 LANE_OPS_PER_PERM = 4719
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per proof of shape S from the ncu --set full captures of the
-# 4096-proof step: profiles/r01u_k_tape_eval_grid_ncu.txt (3.31 + 5.21 GB), profiles/r01u_k_cs_export_vals_tiled_ncu.txt
+# 4096-proof step: profiles/r01y_k_tape_eval_grid_ncu.txt (5.14 + 5.22 GB), profiles/r01y_k_cs_export_vals_tiled_ncu.txt
 # (3.60 + 13.90 GB) and profiles/r01u_k_cs_check_poseidon_ncu.txt (2.37 + 0.06 GB)
-TRAFFIC_PER_PROOF = {"k_tape_eval": (3.310613e9 + 5.210664e9) / 4096, "k_cs_export_vals_tiled": (3.598031e9 + 13.900619e9) / 4096,
+TRAFFIC_PER_PROOF = {"k_tape_eval_grid": (5.136187e9 + 5.222587e9) / 4096, "k_cs_export_vals_tiled": (3.598031e9 + 13.900619e9) / 4096,
                      "k_cs_check_poseidon": (2.369094e9 + 0.055406e9) / 4096}
 
 
@@ -427,7 +429,9 @@ def main():
     tr = pkg.VerifierCircuit.assemble_trace(r0["preprocessed"], r0["values"][(hi - lo) // 2])
     assert hashlib.sha256(np.ascontiguousarray(tr, dtype="<u4").tobytes()).hexdigest() == gold["trace_sha256"], "trace differs from the golden"
     dt0 = vb.fetch(0, "detail")
-    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths + 2 * ci.n_flow      # + tape evaluation + check_poseidon_invocations
+    # tree rebuilds + transcript and per-query paths + check_poseidon_invocations; the tape evaluation executes none: it takes the
+    # outputs of the circuit's permutations from the native pass's record (STWO_B200_TRACE_NATIVE_HINTS)
+    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths + ci.n_flow
     assert dt0.n_perms_paths == 3481, "permutation count of the per-query paths differs from the reference's (SURVEY App. C)"
 
     # ---- timed region: device-resident ----------------------------------------------------------------
@@ -501,32 +505,9 @@ def main():
     dom = max(acc, key=acc.get)
     n_local = hi - lo
     sh = vb.shape
-    # permutations each stage kernel executes per proof (counted by the kernels themselves)
-    single_paths = sum(pkg.path_perms(pkg.PathShape.make(d, lay)) for d, lay in _tree_shapes(sh)) * sh.n_queries
-    pair_paths = pkg.proof_perms(sh) - single_paths
-    perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths,
-                "trace_eval": ci.n_flow, "trace_check_poseidon": ci.n_flow}
-    kernel_of = {"trace_eval": "k_tape_eval", "trace_check_poseidon": "k_cs_check_poseidon", "trace_export": "k_cs_export_vals_tiled",
-                 "trace_check_arithmetics": "k_cs_check_arith", "trace_gather": "k_gather_witness"}
-    hints_total = dt0.n_perms_hints
-    if dom in ("single_tree", "pair_tree"):
-        # the two hint kernels split n_perms_hints; attribute by the per-query path permutations of their trees
-        share = single_paths / float(single_paths + pair_paths)
-        perms_of["single_tree"], perms_of["pair_tree"] = hints_total * share, hints_total * (1 - share)
-    dom_perms = perms_of.get(dom, 0) * n_local
-    dom_rate = dom_perms / (acc[dom] * 1e-3) if acc[dom] > 0 else 0.0
-    achieved = dom_rate * LANE_OPS_PER_PERM / 1e12
-    path_bytes = n_local * sh.n_queries * (4 * (64 * 4 + 30 * 32))      # what the path kernels stream per proof (cols + siblings)
-    roofline = {
-        "bound": "int32-issue", "kernel": kernel_of.get(dom, "k_" + dom), "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
-        "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
-        "perms_per_launch": dom_perms, "launch_ms": acc[dom], "share_of_step": acc[dom] / total_ms,
-        "traffic": TRAFFIC_PER_PROOF.get(kernel_of.get(dom, "k_" + dom), 0) * n_local or None,
-        "stage_ms": acc,
-        "hbm": {"bound": "hbm", "achieved": path_bytes / (acc[dom] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": path_bytes / (acc[dom] * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": path_bytes,
-                "peak_src": pk["src"], "note": "hashing is integer-bound; HBM figure shown for completeness"},
-    }
+    kernel_of = {"trace_eval": "k_tape_eval_grid", "trace_check_poseidon": "k_cs_check_poseidon", "trace_export": "k_cs_export_vals_tiled",
+                 "trace_check_arithmetics": "k_cs_check_arith", "trace_gather": "k_gather_witness", "fiat_shamir": "k_transcript16",
+                 "single_tree": "k_single_tree_coop", "pair_tree": "k_pair_tree_coop", "folds": "k_folds_coop"}
 
     # the HBM-bound kernel of the path: trace export, 3 x 16-byte variable reads + 13 x 4-byte column writes per (row, proof)
     export_bytes = n_local * ci.n_rows * (3 * 16 + 13 * 4)
@@ -536,6 +517,40 @@ def main():
                        "launch_ms": acc["trace_export"], "share_of_step": acc["trace_export"] / total_ms,
                        "traffic": TRAFFIC_PER_PROOF["k_cs_export_vals_tiled"] * n_local,
                        "note": "check_arithmetics is fused into this pass; traffic < algorithmic bytes because variables are re-read from L2"}
+
+    # the busiest permutation kernel against the integer roofline (permutations each stage executes per proof: SURVEY App. C,
+    # counted by the kernels themselves)
+    single_paths = sum(pkg.path_perms(pkg.PathShape.make(d, lay)) for d, lay in _tree_shapes(sh)) * sh.n_queries
+    pair_paths = pkg.proof_perms(sh) - single_paths
+    share = single_paths / float(single_paths + pair_paths)
+    perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths,
+                "trace_check_poseidon": ci.n_flow, "single_tree": dt0.n_perms_hints * share, "pair_tree": dt0.n_perms_hints * (1 - share)}
+    hdom = max(perms_of, key=lambda k: acc.get(k, 0.0))
+    h_perms = perms_of[hdom] * n_local
+    h_rate = h_perms / (acc[hdom] * 1e-3)
+    achieved = h_rate * LANE_OPS_PER_PERM / 1e12
+    roofline_hashing = {
+        "bound": "int32-issue", "kernel": kernel_of.get(hdom, "k_" + hdom), "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
+        "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
+        "perms_per_launch": h_perms, "perms_per_sec": h_rate, "launch_ms": acc[hdom], "share_of_step": acc[hdom] / total_ms,
+        "traffic": TRAFFIC_PER_PROOF.get(kernel_of.get(hdom, ""), 0) * n_local or None,
+        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r01u_k_cs_check_poseidon_ncu.txt); the "
+                "multiplier pipe bounds a permutation at ~6.1 G perms/s per GPU"}
+    # `roofline` = the kernel with the largest share of the step
+    if dom == "trace_export":
+        roofline = dict(roofline_export)
+    elif dom in perms_of:
+        roofline = dict(roofline_hashing)
+    else:
+        # K6 with native hints moves variables only: count what one launch reads and writes per proof (operands + results of every
+        # tape instruction, 16 B each, + 64 B hint + 192 B flow record per permutation)
+        eval_bytes = n_local * ((ci.n_ins - ci.n_flow) * 48 + ci.n_flow * (64 + 64 + 192 + 64))
+        gbs = eval_bytes / (acc[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kernel_of.get(dom, "k_" + dom), "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm_gbs"], "peak_src": pk["src"], "algorithmic_bytes_per_launch": eval_bytes, "launch_ms": acc[dom],
+                    "share_of_step": acc[dom] / total_ms, "traffic": None}
+    roofline["stage_ms"] = acc
+
     secondary = {}
     if not args.no_secondary and rank == 0:
         n_states = 1 << 22
@@ -611,6 +626,7 @@ def main():
                     "ms_per_step": float(t_e.item()) / e2e_steps * 1e3},
             "roofline": roofline,
             "roofline_export": roofline_export,
+            "roofline_hashing": roofline_hashing,
             "secondary": secondary,
         }
         if not args.no_cpu_baseline and world == 1:
