@@ -87,6 +87,7 @@ __device__ __forceinline__ void stamp_level(u32 l) {
 // in flight per warp -- no gain (a 1000-gate level moves 193 MB in 39 us: the gate levels are bound by L2/HBM bandwidth at 16 B per
 // variable, not by latency); walking the items backwards in the odd warps so that gates and permutations overlap -- no gain;
 // taking gates in chunks from a per-level atomic counter -- same-address atomics serialise at ~2 ns.
+constexpr u32 kNarrowItems = 128;     // (instructions x lane groups per CTA) up to which a level runs CTA-locally
 template <bool UNROLLED>
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                  const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
@@ -99,20 +100,41 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
         if (g * 32 + lane < b.n_batch) tape::prologue(b.view(g * 32 + lane, input, n_input_words));
     grid_barrier(barrier, gridDim.x, phase);
     stamp_level(0);
+    // A level with only a few instructions costs a grid barrier and a chain of dependent loads, not bandwidth.  Stretches of such
+    // levels run CTA-locally: CTA c owns the lane groups c, c + gridDim.x, ... (a group's variables are then produced and consumed
+    // on one SM), its warps share the level's instructions and __syncthreads() separates the levels; the grid barrier returns
+    // where a wide level follows.
+    const u32 groups_here = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const u32 groups_max = (n_groups + gridDim.x - 1) / gridDim.x;
+    auto is_narrow = [&](u32 l) { return (__ldg(level_start + l + 1) - __ldg(level_start + l)) * groups_max <= kNarrowItems; };
     for (u32 l = 0; l < n_levels; l++) {
         const u32 lo = __ldg(level_start + l), hi = __ldg(level_start + l + 1);
-        const u32 n_items = (hi - lo) * n_groups;
-        for (u32 t = gw; t < n_items; t += n_warps) {
-            // group fastest: a warp's successive items (stride n_warps) walk through different instructions of the level, so
-            // permutations and cheap gates mix evenly; the groups of a one-instruction level land on different SMs
-            const u32 k = lo + t / n_groups, item = (t % n_groups) * 32 + lane;
-            if (item < b.n_batch) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
-                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
+        const bool narrow = is_narrow(l);
+        if (narrow) {
+            const u32 n_items = (hi - lo) * groups_here;
+            for (u32 t = warp; t < n_items; t += kEvalThreads / 32) {
+                const u32 k = lo + t / groups_here, item = (blockIdx.x + (t % groups_here) * gridDim.x) * 32 + lane;
+                if (item < b.n_batch) {
+                    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
+                    tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                    tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
+                }
+            }
+        } else {
+            const u32 n_items = (hi - lo) * n_groups;
+            for (u32 t = gw; t < n_items; t += n_warps) {
+                // group fastest: a warp's successive items (stride n_warps) walk through different instructions of the level, so
+                // permutations and cheap gates mix evenly; the groups of a one-instruction level land on different SMs
+                const u32 k = lo + t / n_groups, item = (t % n_groups) * 32 + lane;
+                if (item < b.n_batch) {
+                    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
+                    tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                    tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
+                }
             }
         }
-        grid_barrier(barrier, gridDim.x, phase);
+        if (narrow && l + 1 < n_levels && is_narrow(l + 1)) __syncthreads();
+        else grid_barrier(barrier, gridDim.x, phase);
         stamp_level(l + 1);
     }
 }
@@ -259,24 +281,29 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_plain(stwo_b200_cs_wiring
 // (item, column) = one 128-byte line.
 constexpr int kTileRows = 32;
 // first_bad != nullptr fuses check_arithmetics into the pass (the three variables of the row are in registers anyway).
+// ITEMS = batch items per tile (32; 16 as an experiment: half the shared memory per CTA and 6 CTAs per SM instead of 4, a warp
+// reads two rows at a time, 256 B per row -- slower, 5.15 vs 4.66 ms: the shorter runs per row cost more than the occupancy buys).
+template <int ITEMS>
 __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring w, Batch b, u32 *vals, unsigned long long *first_bad) {
-    extern __shared__ u32 tile[];                        // [kCols][32 items][33]
+    extern __shared__ u32 tile[];                        // [kCols][ITEMS items][33]
+    constexpr u32 ROWS_PER_WARP = 32 / ITEMS;
     const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32, n_warps = kT / 32;
+    const u32 il = lane % ITEMS, rsub = lane / ITEMS;
     const u32 row0 = blockIdx.x * kTileRows, grp = blockIdx.y;
-    const u32 item = grp * 32 + lane;
+    const u32 item = grp * ITEMS + il;
     if (item < b.n_batch) {
         const tape::View v = b.view(item, nullptr, 0);
-        for (u32 r = warp; r < kTileRows; r += n_warps) {
+        for (u32 r = warp * ROWS_PER_WARP + rsub; r < kTileRows; r += n_warps * ROWS_PER_WARP) {
             const u32 i = row0 + r;
             const qm31_t a = tape::ldv(v, __ldg(w.a_wire + i)), bb = tape::ldv(v, __ldg(w.b_wire + i)), c = tape::ldv(v, __ldg(w.c_wire + i));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                tile[((0 + k) * 32 + lane) * 33 + r] = a.v[k];
-                tile[((4 + k) * 32 + lane) * 33 + r] = bb.v[k];
-                tile[((8 + k) * 32 + lane) * 33 + r] = c.v[k];
+                tile[((0 + k) * ITEMS + il) * 33 + r] = a.v[k];
+                tile[((4 + k) * ITEMS + il) * 33 + r] = bb.v[k];
+                tile[((8 + k) * ITEMS + il) * 33 + r] = c.v[k];
             }
             const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
-            tile[(12 * 32 + lane) * 33 + r] = op;
+            tile[(12 * ITEMS + il) * 33 + r] = op;
             if (first_bad) {
                 const bool ok = w.kind == 1 ? tape::gate_ok_without(a, bb, c, op, __ldg(w.op2 + i), __ldg(w.op3 + i), __ldg(w.op4 + i))
                                             : tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i));
@@ -286,9 +313,9 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring
     }
     __syncthreads();
     const size_t n = w.n_rows;
-    for (u32 pair = warp; pair < 32 * kCols; pair += n_warps) {
+    for (u32 pair = warp; pair < ITEMS * kCols; pair += n_warps) {
         const u32 it = pair / kCols, col = pair % kCols;
-        if (grp * 32 + it < b.n_batch) vals[((size_t)(grp * 32 + it) * kCols + col) * n + row0 + lane] = tile[(col * 32 + it) * 33 + lane];
+        if (grp * ITEMS + it < b.n_batch) vals[((size_t)(grp * ITEMS + it) * kCols + col) * n + row0 + lane] = tile[(col * ITEMS + it) * 33 + lane];
     }
 }
 __global__ void k_fill64(unsigned long long *p, size_t n, unsigned long long v) {
@@ -434,14 +461,17 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
         if (fb) { k_fill64<<<nblk(v->n_batch), kT, 0, st>>>(fb, v->n_batch, ~0ull); note_launch(1); }
         if (v->lanes == 1) k_cs_export_vals_plain<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, b, values, fb);
         else {
-            const size_t smem = (size_t)kCols * 32 * 33 * 4;
-            static bool attr_set = false;
-            if (!attr_set) {
-                STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+            static int items = 0;
+            if (!items) {
+                const char *e = getenv("STWO_B200_EXPORT_ITEMS");          // 16 / 32 (profiling); measured at 4096 proofs: 32 -> 4.66 ms, 16 -> 5.15 ms
+                items = e && atoi(e) == 16 ? 16 : 32;
+                STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 32 * 33 * 4));
+                STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 16 * 33 * 4));
             }
-            dim3 grid(w->n_rows / kTileRows, (v->n_batch + 31) / 32);
-            k_cs_export_vals_tiled<<<grid, kT, smem, st>>>(*w, b, values, fb);
+            const size_t smem = (size_t)kCols * items * 33 * 4;
+            dim3 grid(w->n_rows / kTileRows, (v->n_batch + items - 1) / items);
+            if (items == 32) k_cs_export_vals_tiled<32><<<grid, kT, smem, st>>>(*w, b, values, fb);
+            else k_cs_export_vals_tiled<16><<<grid, kT, smem, st>>>(*w, b, values, fb);
         }
         note_launch(1);
     }
