@@ -47,7 +47,10 @@ class VerifierCircuit:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            _lib.load().stwo_b200_circuit_free(self._h)
+            try:
+                _lib.load().stwo_b200_circuit_free(self._h)
+            except Exception:                        # interpreter shutdown: the module globals are already gone
+                pass
             self._h = None
 
     def column(self, name):
