@@ -566,9 +566,10 @@ def main():
         k1_rate = n_states * 5 / (k0.elapsed_time(k1) * 1e-3)
         del st
         secondary = {"k1_permute_perms_per_sec": k1_rate, "k1_frac_of_int_peak": k1_rate * 4264 / 1e12 / pk["int_tlops"],
-                     "merkle_sweep_config": "BASELINE configs[2]: 2 trees x 2^20 leaves, leaf width C, Q queries per tree; commit and "
+                     "merkle_sweep_config": "BASELINE configs[2]: T trees x 2^20 leaves, leaf width C, Q queries per tree; commit and "
                                             "decommit+path-verify timed apart (SURVEY.md 8d config 3)",
-                     "merkle_sweep": [merkle_sweep(pkg, dev, C=C, Q=Q, hbm_peak=pk["hbm_gbs"]) for C, Q in ((4, 16), (8, 128), (50, 64), (60, 16), (60, 128))]}
+                     "merkle_sweep": [merkle_sweep(pkg, dev, C=C, Q=Q, T=T, hbm_peak=pk["hbm_gbs"])
+                                      for C, Q, T in ((4, 16, 2), (8, 128, 2), (50, 64, 2), (60, 16, 2), (60, 128, 2), (8, 32, 1), (4, 32, 64))]}
         secondary["merkle_sweep_perms_per_sec"] = secondary["merkle_sweep"][1]["perms_per_sec"]
         secondary["lane_divergence"] = divergence_leg(pkg, dev)
 
