@@ -79,6 +79,28 @@ def test_native_hints_and_recomputation_agree(pkg, gpu, orc):
     assert (r["bad_row"].cpu().numpy() == -1).all() and np.array_equal(r["values"].cpu().numpy(), got[True][2])
 
 
+@pytest.mark.parametrize("name,n", [("small_proof.bin", 300), ("level2-1.bin", 9)])
+def test_repeated_runs_are_bit_identical(pkg, gpu, orc, name, n):
+    """the cooperative stages, the stream pool and the grid-wide tape evaluation leave no room for a race: three runs of the same
+    batch (sliced path for 300 proofs) give the same workspace-derived values, variables and trace, bit for bit"""
+    import hashlib
+    blob = open(os.path.join(O.PROOFS_DIR, name), "rb").read()
+    vb = pkg.VerifyBatch([blob] * n, inputs=_inputs(pkg, name))
+    circ = pkg.VerifierCircuit(vb.shape, inputs=_inputs(pkg, name))
+    seen = set()
+    for _ in range(3):
+        v, s = vb.run(full=True)
+        r = circ.trace(vb, check=True, export=True, preprocessed=False)
+        assert not v.cpu().numpy().any() and (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+        h = hashlib.sha256()
+        h.update(r["values"].cpu().numpy().tobytes())
+        h.update(circ.fetch(n - 1, "variables").tobytes())
+        for what in ("answers", "line_folds", "path_roots", "pair_hints"):
+            h.update(vb.fetch(n // 2, what).tobytes())
+        seen.add(h.hexdigest())
+    assert len(seen) == 1
+
+
 def test_multipliers(pkg, gpu, orc):
     """examples/multi-proofs: the same proof verified twice inside one constraint system"""
     name = "small_proof.bin"
