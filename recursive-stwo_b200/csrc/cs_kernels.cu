@@ -293,21 +293,35 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring
     const u32 item = grp * ITEMS + il;
     if (item < b.n_batch) {
         const tape::View v = b.view(item, nullptr, 0);
-        for (u32 r = warp * ROWS_PER_WARP + rsub; r < kTileRows; r += n_warps * ROWS_PER_WARP) {
-            const u32 i = row0 + r;
-            const qm31_t a = tape::ldv(v, __ldg(w.a_wire + i)), bb = tape::ldv(v, __ldg(w.b_wire + i)), c = tape::ldv(v, __ldg(w.c_wire + i));
+        // two rows per trip: the six wire loads, then the six 16-byte variable gathers, are in flight together (the pass is bound
+        // by the latency of these dependent loads, and the tile's shared memory, not registers, limits the CTAs per SM)
+        constexpr u32 STEP = (kT / 32) * ROWS_PER_WARP;
+        static_assert(kTileRows % (2 * STEP) == 0, "rows of a tile come in pairs per warp");
+        for (u32 r = warp * ROWS_PER_WARP + rsub; r < kTileRows; r += 2 * STEP) {
+            const u32 rr[2] = {r, r + STEP};
+            u32 wa[2], wb[2], wc[2];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                tile[((0 + k) * ITEMS + il) * 33 + r] = a.v[k];
-                tile[((4 + k) * ITEMS + il) * 33 + r] = bb.v[k];
-                tile[((8 + k) * ITEMS + il) * 33 + r] = c.v[k];
-            }
-            const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
-            tile[(12 * ITEMS + il) * 33 + r] = op;
-            if (first_bad) {
-                const bool ok = w.kind == 1 ? tape::gate_ok_without(a, bb, c, op, __ldg(w.op2 + i), __ldg(w.op3 + i), __ldg(w.op4 + i))
-                                            : tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i));
-                if (!ok) atomicMin(first_bad + item, (unsigned long long)i);
+            for (int j = 0; j < 2; j++) { wa[j] = __ldg(w.a_wire + row0 + rr[j]); wb[j] = __ldg(w.b_wire + row0 + rr[j]); wc[j] = __ldg(w.c_wire + row0 + rr[j]); }
+            qm31_t va[2], vb[2], vc[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) { va[j] = tape::ldv(v, wa[j]); vb[j] = tape::ldv(v, wb[j]); vc[j] = tape::ldv(v, wc[j]); }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const u32 i = row0 + rr[j], r_ = rr[j];
+                const qm31_t a = va[j], bb = vb[j], c = vc[j];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    tile[((0 + k) * ITEMS + il) * 33 + r_] = a.v[k];
+                    tile[((4 + k) * ITEMS + il) * 33 + r_] = bb.v[k];
+                    tile[((8 + k) * ITEMS + il) * 33 + r_] = c.v[k];
+                }
+                const u32 op = (w.op_follows_c && w.op_follows_c[i]) ? c.v[0] : __ldg(w.op + i);
+                tile[(12 * ITEMS + il) * 33 + r_] = op;
+                if (first_bad) {
+                    const bool ok = w.kind == 1 ? tape::gate_ok_without(a, bb, c, op, __ldg(w.op2 + i), __ldg(w.op3 + i), __ldg(w.op4 + i))
+                                                : tape::gate_ok(a, bb, c, op, __ldg(w.enforce_c_m31 + i));
+                    if (!ok) atomicMin(first_bad + item, (unsigned long long)i);
+                }
             }
         }
     }
