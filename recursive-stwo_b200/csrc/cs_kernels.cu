@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kT) k_cs_mult(stwo_b200_cs_wiring w, const u32
 // ---- K7: check_poseidon_invocations ----------------------------------------------------------------------------------------
 // thread = (flow entry, item), item fastest. Persistent: the grid is a fixed number of CTAs per SM looping over the flow, so that it
 // can run as a thin, fully resident layer (2-3 CTAs per SM) under the HBM-bound export on another stream, or fill the SMs alone.
-__global__ void __launch_bounds__(128, 8) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
+__global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
                                                            const u32 *first_prow, unsigned long long *first_bad) {
     const u32 padded = (b.n_batch + b.lanes - 1) / b.lanes * b.lanes;
     const size_t total = (size_t)w.n_flow * padded;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128, 8) k_cs_check_poseidon(stwo_b200_cs_wirin
         u32 st[16];
         const bool swap = v.flow_swap[(size_t)e * v.stride] != 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { st[j] = hh[(swap ? 8 : 0) + j]; st[8 + j] = hh[(swap ? 0 : 8) + j]; }
+        for (int j = 0; j < 8; j++) { st[j] = swap ? hh[8 + j] : hh[j]; st[8 + j] = swap ? hh[j] : hh[8 + j]; }    // selects: hh stays in registers
         poseidon2::permute<false>(st);
 #pragma unroll
         for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
