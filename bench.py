@@ -44,7 +44,7 @@ FIXTURE = "small_proof.bin"
 LANE_OPS_PER_PERM = 4719
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per proof of shape S from the ncu --set full captures of the
 # 4096-proof step: profiles/r01y_k_tape_eval_grid_ncu.txt (5.14 + 5.22 GB), profiles/r01y_k_cs_export_vals_tiled_ncu.txt
-# (3.60 + 13.90 GB) and profiles/r01u_k_cs_check_poseidon_ncu.txt (2.37 + 0.06 GB)
+# (3.60 + 13.90 GB) and profiles/r01y_k_cs_check_poseidon_ncu.txt (2.37 + 0.06 GB)
 TRAFFIC_PER_PROOF = {"k_tape_eval_grid": (5.136187e9 + 5.222587e9) / 4096, "k_cs_export_vals_tiled": (3.598031e9 + 13.900619e9) / 4096,
                      "k_cs_check_poseidon": (2.369094e9 + 0.055406e9) / 4096}
 
@@ -534,7 +534,7 @@ def main():
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
         "perms_per_launch": h_perms, "perms_per_sec": h_rate, "launch_ms": acc[hdom], "share_of_step": acc[hdom] / total_ms,
         "traffic": TRAFFIC_PER_PROOF.get(kernel_of.get(hdom, ""), 0) * n_local or None,
-        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r01u_k_cs_check_poseidon_ncu.txt); the "
+        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r01y_k_cs_check_poseidon_ncu.txt); the "
                 "multiplier pipe bounds a permutation at ~6.1 G perms/s per GPU"}
     # `roofline` = the kernel with the largest share of the step
     if dom == "trace_export":
