@@ -320,6 +320,31 @@ def trace_gather_leg(sharding, values, rank, world, dev, n_each=256, reps=3):
             "bytes_received_by_rank0": recv, "gb_per_sec_into_rank0": recv / (ms * 1e-3) / 1e9}
 
 
+def shape_leg(pkg, dev, fixture, n, reps=5):
+    """the headline step (verify + circuit trace) on replicas of another fixture: SURVEY.md 8a's shape R (recursive_proof_16_15.bin:
+    2^16 / 2^15 rows, 16 queries, 8 inner layers, 5 289 path permutations)"""
+    import torch
+    blob = open(os.path.join(ROOT, "tests", "golden", "proofs", fixture), "rb").read()
+    vb = pkg.VerifyBatch([blob] * n, inputs=pkg.INPUTS_RECURSIVE)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_RECURSIVE)
+
+    def step():
+        v, _ = vb.run(full=True)
+        return v, circ.trace(vb, check=True, export=True, preprocessed=False)
+    for _ in range(2):
+        v, r = step()
+    assert int(v.sum().item()) == 0 and int((r["bad_row"] != -1).sum().item()) == 0 and int((r["bad_flow"] != -1).sum().item()) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"fixture": fixture, "proofs": n, "rows": circ.info.n_rows, "poseidon_flow": circ.info.n_flow, "tape_levels": circ.info.n_levels,
+            "ms_per_batch": ms, "proofs_per_sec": n / (ms * 1e-3)}
+
+
 def divergence_leg(pkg, dev, n=1024, reps=5):
     """What replicas hide: lanes of a warp hold different proofs in production.  The same shape (16, 15; 10 queries) verified and
     traced as n replicas of level10-1.bin and as n proofs alternating level10-1.bin / level11-1.bin (different query positions
@@ -572,6 +597,7 @@ def main():
                                       for C, Q, T in ((4, 16, 2), (8, 128, 2), (50, 64, 2), (60, 16, 2), (60, 128, 2), (8, 32, 1), (4, 32, 64))]}
         secondary["merkle_sweep_perms_per_sec"] = secondary["merkle_sweep"][1]["perms_per_sec"]
         secondary["lane_divergence"] = divergence_leg(pkg, dev)
+        secondary["shape_R"] = shape_leg(pkg, dev, "recursive_proof_16_15.bin", 1024)
 
     if not args.no_secondary:
         mp = multi_proofs_leg(pkg, sharding, rank, world, dev)            # every rank takes its block of the 256
