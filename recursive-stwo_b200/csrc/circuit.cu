@@ -25,8 +25,7 @@ namespace {
 constexpr int kT = 256;
 inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
 
-// witness streams, lane-interleaved over groups of 32 proofs; thread = (word, proof) with the proof fastest (coalesced
-// stores; the loads walk each proof's own blob / workspace rows)
+// witness streams, lane-interleaved over groups of 32 proofs
 // public-input hashes of the last-layer circuit: thread = (job, proof), the proof fastest; extra: [proof][n_extra_words]
 __global__ void __launch_bounds__(64) k_last_extra(verify::Workspace ws, const circuit::ExtraJob *__restrict__ jobs, u32 n_jobs, u32 n_extra_words, u32 *extra) {
     const size_t g = blockIdx.x * (size_t)64 + threadIdx.x;
@@ -35,17 +34,27 @@ __global__ void __launch_bounds__(64) k_last_extra(verify::Workspace ws, const c
     if (!ws.desc[p].ok) return;
     circuit::extra_job(ws, p, jobs[j], extra + (size_t)p * n_extra_words);
 }
+// Tile = 32 consecutive stream words x the 32 proofs of a lane group.  A warp reads ALONG the words of one proof -- consecutive
+// stream words mostly come from consecutive source words (a hash is 8, a column run up to 60), so the loads are 32-240 B runs
+// instead of one 4-byte word out of every proof's 32-byte sector -- and the tile is written back transposed, 128-byte lines of
+// the lane-interleaved stream.
 __global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, const u32 *__restrict__ gather, u32 n_words, u32 *out, const u32 *extra,
                                                        u32 n_extra_words) {
-    const size_t g = blockIdx.x * (size_t)kT + threadIdx.x;
-    const u32 n_groups = (ws.n_proofs + 31) / 32;
-    if (g >= (size_t)n_groups * n_words * 32) return;
-    const u32 lane = (u32)(g % 32);
-    const size_t t = g / 32;
-    const u32 word = (u32)(t % n_words), grp = (u32)(t / n_words), p = grp * 32 + lane;
-    if (p >= ws.n_proofs) return;
-    const bool ok = ws.desc[p].ok != 0;          // a blob that did not parse has no sections: its stream is all zero
-    out[g] = ok ? circuit::gather_word(ws, p, __ldg(gather + word), extra ? extra + (size_t)p * n_extra_words : nullptr) : 0u;
+    __shared__ u32 tile[32][33];
+    const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32, n_warps = kT / 32;
+    const u32 word0 = blockIdx.x * 32, grp = blockIdx.y;
+    const u32 word = word0 + lane;
+    const u32 src = word < n_words ? __ldg(gather + word) : 0u;
+    for (u32 pl = warp; pl < 32; pl += n_warps) {
+        const u32 p = grp * 32 + pl;
+        u32 v = 0;
+        // a blob that did not parse has no sections: its stream is all zero
+        if (p < ws.n_proofs && word < n_words && ws.desc[p].ok) v = circuit::gather_word(ws, p, src, extra ? extra + (size_t)p * n_extra_words : nullptr);
+        tile[lane][pl] = v;
+    }
+    __syncthreads();
+    for (u32 wl = warp; wl < 32; wl += n_warps)
+        if (word0 + wl < n_words && grp * 32 + lane < ws.n_proofs) out[((size_t)grp * n_words + word0 + wl) * 32 + lane] = tile[wl][lane];
 }
 
 struct Carve {
@@ -231,7 +240,7 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         k_last_extra<<<(unsigned)(((size_t)c->n_jobs * n_proofs + 63) / 64), 64, 0, st>>>(ws, c->jobs, c->n_jobs, c->n_extra_words, k.extra);
         note_launch(1);
     }
-    k_gather_witness<<<nblk(groups * nw * 32), kT, 0, st>>>(ws, c->gather, nw, k.witness, c->n_jobs ? k.extra : nullptr, c->n_extra_words);
+    k_gather_witness<<<dim3((nw + 31) / 32, (unsigned)groups), kT, 0, st>>>(ws, c->gather, nw, k.witness, c->n_jobs ? k.extra : nullptr, c->n_extra_words);
     note_launch(1);
     stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0};
     if ((flags & STWO_B200_TRACE_NATIVE_HINTS) && c->wiring.kind == 0 && ws.perm_out) { v.perm_hints = ws.perm_out; v.perm_hint_stride = ws.hint_total * 16; }
