@@ -130,6 +130,21 @@ typedef struct {
     uint32_t n_queries, n_inner;                    /* FriConfig.n_queries, number of inner FRI layers */
 } stwo_b200_proof_shape;
 
+/* The commitment-scheme parameters the CALLER fixes (stwo PcsConfig { pow_bits, fri_config: FriConfig { log_blowup_factor,
+ * log_last_layer_degree_bound, n_queries } }), the `config` argument of FiatShamirHints::new / FiatShamirResults::compute
+ * (components/hints/src/fiat_shamir.rs:69-73, components/recursive/fiat_shamir/src/lib.rs:31-38).  A proof is verified under
+ * the caller's config, never under the one its own header claims: a blob whose header differs is REJECTed at STAGE_PARSE. */
+typedef struct {
+    uint32_t pow_bits, log_blowup, log_last, n_queries;
+} stwo_b200_pcs_config;
+/* The batch shape the caller's config implies for proofs of the given component log sizes (the statement, stmt0): n_inner
+ * follows from the FRI layer relation stwo enforces (InvalidNumFriLayers): the composition columns live at log size
+ * max(log_size_plonk + 1, log_size_poseidon + 2) + log_blowup, which n_inner + 1 folds must bring down to log_last +
+ * log_blowup.  STWO_B200_E_SHAPE when no such shape exists or a bound (log sizes 1..28, blow-up 1..16, log_last <= 12,
+ * n_queries 1..128) is exceeded. */
+int32_t stwo_b200_shape_from_config(const stwo_b200_pcs_config *config, uint32_t log_size_plonk, uint32_t log_size_poseidon,
+                                    stwo_b200_proof_shape *out);
+
 #define STWO_B200_VERDICT_ACCEPT 0
 #define STWO_B200_VERDICT_REJECT 1
 #define STWO_B200_VERDICT_UNSUPPORTED 2
@@ -153,7 +168,9 @@ typedef struct {
 /* device time of each stage kernel of the last STWO_B200_VERIFY_TIMED batch on this thread (synchronises) */
 int32_t stwo_b200_verify_stage_ms(float *ms /* [STWO_B200_N_STAGE_KERNELS] */);
 
-/* host-side header read (no device needed): shape of one blob; STWO_B200_E_SHAPE when it does not parse */
+/* host-side header read (no device needed): the shape one blob CLAIMS; STWO_B200_E_SHAPE when it does not parse or breaks the
+ * FRI layer relation.  Untrusted: use it to read the statement's log sizes and to group blobs, and take the PcsConfig part of
+ * the shape you verify under from your own configuration (stwo_b200_shape_from_config). */
 int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stwo_b200_proof_shape *out);
 /* bytes of device workspace a batch of n_proofs of this shape needs (0: unsupported shape) */
 size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint32_t n_proofs);
@@ -161,7 +178,7 @@ size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint
 uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape);
 
 /* Device entry: blobs = all proofs back to back as u32 words, blob_off = n_proofs+1 WORD offsets, every proof of the
- * same shape.  input_idx / input_vals: the (index, QM31 value) public inputs of the logup sum
+ * same shape -- the CALLER's shape (stwo_b200_shape_from_config); a blob whose header says otherwise is rejected at STAGE_PARSE.  input_idx / input_vals: the (index, QM31 value) public inputs of the logup sum
  * (components/recursive/fiat_shamir/src/lib.rs:133-141).  verdict/stage: n_proofs bytes each (stage may be NULL). */
 int32_t stwo_b200_verify_proofs_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
                                           const stwo_b200_proof_shape *shape, const uint32_t *input_idx,
@@ -176,8 +193,11 @@ int32_t stwo_b200_verify_proofs_batch_pinned_dev(const uint32_t *host_blobs, con
                                                  const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
                                                  uint32_t flags, void *workspace, size_t workspace_bytes, uint8_t *verdict,
                                                  uint8_t *stage, void *stream);
-/* Host entry: host blobs of any mix of shapes (grouped internally), verdicts back in the caller's arrays. */
+/* Host entry: host blobs of any mix of shapes (grouped internally), verdicts back in the caller's arrays.  configs: the
+ * PcsConfigs the caller accepts (n_configs >= 1; e.g. the six of examples/multi-proofs/src/main.rs:173-196); a blob whose
+ * header names any other config is rejected at STAGE_PARSE without being looked at further. */
 int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs,
+                                      const stwo_b200_pcs_config *configs, uint32_t n_configs,
                                       const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
                                       uint32_t flags, uint8_t *verdict, uint8_t *stage);
 

@@ -128,6 +128,10 @@ typedef struct {
 int orc_verify_proof(const uint8_t *blob, size_t len,
                      const uint32_t *input_idx, const uint32_t *input_vals /* n x4 */,
                      uint32_t n_inputs, orc_verify_out *out);
+/* the same under the caller's PcsConfig cfg = {pow_bits, log_blowup, log_last, n_queries}: a proof claiming another config is
+ * rejected at the parse stage */
+int orc_verify_proof_cfg(const uint8_t *blob, size_t len, const uint32_t *cfg, const uint32_t *input_idx, const uint32_t *input_vals,
+                         uint32_t n_inputs, orc_verify_out *o);
 
 /* per-query decommitment hints = the witnesses DecommitmentVar / SinglePairMerkleProofVar allocate
  * (components/recursive/data_structures/src/lib.rs:287-312,372-398) */

@@ -539,7 +539,18 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
     const uint32_t nq = p->n_queries, blow = p->log_blowup;
     if (p->n_last_coeffs != (1ull << p->log_last) || p->n_inner + 1 > ORC_MAX_INNER) FAIL(ORC_STAGE_PARSE, 1);
     const uint32_t max_first = p->log_last + blow + 1 + p->n_inner;
-    if (max_first > 29 || p->log_size_plonk + blow > max_first || p->log_size_poseidon + blow > max_first) FAIL(ORC_STAGE_PARSE, 1);
+    /* untrusted header words: bounded before they are added, shifted by or looped over */
+    if (p->log_size_plonk == 0 || p->log_size_plonk > 28 || p->log_size_poseidon == 0 || p->log_size_poseidon > 28 || blow == 0 || blow > 16 ||
+        p->log_last > 12 || p->pow_bits >= 32)
+        FAIL(ORC_STAGE_PARSE, 1);
+    /* FRI layer count vs column bounds: the composition columns are committed at composition_log_degree_bound - 1 + blowup
+     * (components/hints/src/fiat_shamir.rs:130-135), bound = max(log_size_plonk + 2, log_size_poseidon + 3) (constraint degrees
+     * 3 and 6 of the two components), and FriVerifier::commit (fiat_shamir.rs:177-183; stwo core/fri.rs, dependency absent from
+     * the tree) fails with InvalidNumFriLayers unless the inner layers fold that down to log_last + blowup. */
+    {
+        const uint32_t a = p->log_size_plonk + 1, b = p->log_size_poseidon + 2;
+        if (max_first > 29 || max_first != (a > b ? a : b) + blow) FAIL(ORC_STAGE_PARSE, 1);
+    }
     o->max_first_log = max_first; o->n_inner = p->n_inner; o->n_queries = nq;
 
     /* 1. transcript + PoW */
@@ -870,6 +881,22 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
 
 /* same run, additionally exporting the per-query decommitment hints the verifier circuit takes as witnesses
  * (components/hints/src/decommit.rs:10-16 SinglePathMerkleProof, folding.rs:21-28 SinglePairMerkleProof) */
+/* The verifier as the reference calls it: under the CALLER's PcsConfig (FiatShamirHints::new(&proof, config, ..),
+ * components/hints/src/fiat_shamir.rs:69-73).  cfg = {pow_bits, log_blowup, log_last, n_queries}.  stwo reads the FRI / PoW
+ * parameters from `config` and the proof carries its own copy; a proof whose copy differs cannot verify (wrong query count,
+ * wrong last-layer size, ...) -- restated here as a rejection at the parse stage. */
+int orc_verify_proof_cfg(const uint8_t *blob, size_t len, const uint32_t *cfg, const uint32_t *input_idx, const uint32_t *input_vals,
+                         uint32_t n_inputs, orc_verify_out *o) {
+    static _Thread_local orc_proof P;
+    if (orc_proof_parse(blob, len, &P) == 0 &&
+        (P.pow_bits != cfg[0] || P.log_blowup != cfg[1] || P.log_last != cfg[2] || P.n_queries != cfg[3])) {
+        memset(o, 0, sizeof *o);
+        o->verdict = 1; o->stage = ORC_STAGE_PARSE;
+        return 0;
+    }
+    return orc_verify_proof(blob, len, input_idx, input_vals, n_inputs, o);
+}
+
 int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
                            uint32_t n_inputs, orc_verify_out *o, orc_hints *h) {
     memset(h, 0, sizeof *h);

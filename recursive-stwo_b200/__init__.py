@@ -11,11 +11,13 @@ from .hashing import (init, poseidon2_permute, poseidon2_permute_host, hash_node
                       merkle_commit_host, merkle_decommit, merkle_path_verify, merkle_path_verify_host,
                       launch_count, path_perms)
 
-from .verifier import verify_proofs, VerifyBatch, VerifyStream, proof_shape, proof_perms, INPUTS_SINGLE, INPUTS_RECURSIVE
-from ._lib import ProofShape, VerifyDetail, STAGES
+from .verifier import (verify_proofs, VerifyBatch, VerifyStream, proof_shape, proof_perms, shape_for, shape_from_config,
+                       INPUTS_SINGLE, INPUTS_RECURSIVE, REFERENCE_CONFIGS, CONFIG_SINGLE, CONFIG_STANDARD, CONFIG_FAST_PROVER,
+                       CONFIG_FAST_PROVER2, CONFIG_FAST_VERIFIER, CONFIG_FAST_VERIFIER2, CONFIG_FAST_VERIFIER3)
+from ._lib import ProofShape, PcsConfig, VerifyDetail, STAGES
 from .circuit import VerifierCircuit
 
-__all__ = ["VerifierCircuit", "verify_proofs", "VerifyBatch", "VerifyStream", "proof_shape", "proof_perms", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
+__all__ = ["VerifierCircuit", "verify_proofs", "VerifyBatch", "VerifyStream", "proof_shape", "proof_perms", "shape_for", "shape_from_config", "PcsConfig", "REFERENCE_CONFIGS", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
            "VerifyDetail", "STAGES","init", "poseidon2_permute", "poseidon2_permute_host", "hash_node_batch", "merkle_commit",
            "merkle_commit_host", "merkle_decommit", "merkle_path_verify", "merkle_path_verify_host", "launch_count",
            "path_perms", "PathShape", "StwoB200Error"]

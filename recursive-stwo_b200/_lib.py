@@ -62,6 +62,17 @@ class ProofShape(ctypes.Structure):
         return self.log_last + self.log_blowup + 1 + self.n_inner
 
 
+class PcsConfig(ctypes.Structure):
+    """stwo_b200_pcs_config: the commitment-scheme parameters the CALLER fixes (stwo PcsConfig / FriConfig)"""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("pow_bits", "log_blowup", "log_last", "n_queries")]
+
+    def key(self):
+        return (self.pow_bits, self.log_blowup, self.log_last, self.n_queries)
+
+    def __repr__(self):
+        return "PcsConfig(pow_bits=%d, log_blowup=%d, log_last=%d, n_queries=%d)" % self.key()
+
+
 _Q = ctypes.c_uint32 * 4
 
 
@@ -121,6 +132,7 @@ _vp, _u32, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, c
 _WIR_P, _VAL_P, _TAPE_P, _INFO_P = ctypes.POINTER(CsWiring), ctypes.POINTER(CsValues), ctypes.POINTER(CsTape), ctypes.POINTER(CircuitInfo)
 _SHAPE_P = ctypes.POINTER(PathShape)
 _PSHAPE_P = ctypes.POINTER(ProofShape)
+_CFG_P = ctypes.POINTER(PcsConfig)
 
 # name -> (restype, argtypes); the test-suite checks this list against include/stwo_b200.h
 SIGNATURES = {
@@ -140,11 +152,12 @@ SIGNATURES = {
     "stwo_b200_merkle_path_verify": (_i32, [_SHAPE_P, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_path_perms": (_u32, [_SHAPE_P]),
     "stwo_b200_proof_shape_of": (_i32, [_vp, _sz, _PSHAPE_P]),
+    "stwo_b200_shape_from_config": (_i32, [_CFG_P, _u32, _u32, _PSHAPE_P]),
     "stwo_b200_verify_workspace_bytes": (_sz, [_PSHAPE_P, _u32]),
     "stwo_b200_proof_perms": (_u64, [_PSHAPE_P]),
     "stwo_b200_verify_proofs_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_verify_proofs_batch_pinned_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
-    "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
     "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
     "stwo_b200_cs_eval_tape_dev": (_i32, [_TAPE_P, _u32, _vp, _VAL_P, _vp]),

@@ -129,12 +129,8 @@ static_assert(sizeof(dsl::ProofShape) == sizeof(stwo_b200_proof_shape), "shape m
 extern "C" int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,
                                                      uint32_t n_inputs, uint32_t multipliers, stwo_b200_circuit **out) {
     if (!shape || !out || multipliers == 0 || (n_inputs && (!input_idx || !input_vals))) return STWO_B200_E_BAD_ARG;
-    if (shape->n_queries == 0 || shape->n_queries > proof::MAX_QUERIES || shape->n_inner >= proof::MAX_INNER || shape->log_last > 12 ||
-        shape->pow_bits >= 32 || !shape->log_size_plonk || !shape->log_size_poseidon)
-        return STWO_B200_E_SHAPE;
-    verify::Shape v;
-    memcpy(&v, shape, sizeof v);
-    if (v.max_first() > 29 || v.log_plonk() > v.max_first() || v.log_pos() > v.max_first() || v.max_first() <= shape->log_last + shape->log_blowup)
+    if (!proof::shape_consistent(shape->log_size_plonk, shape->log_size_poseidon, shape->pow_bits, shape->log_blowup, shape->log_last,
+                                 shape->n_queries, shape->n_inner))
         return STWO_B200_E_SHAPE;
     try {
         dsl::ProofShape s;
@@ -150,12 +146,9 @@ extern "C" int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape
 }
 extern "C" int32_t stwo_b200_circuit_record_last_layer(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out) {
     if (!shape || !out) return STWO_B200_E_BAD_ARG;
-    if (shape->n_queries == 0 || shape->n_queries > proof::MAX_QUERIES || shape->n_inner >= proof::MAX_INNER || shape->log_last > 12 ||
-        shape->pow_bits >= 32 || !shape->log_size_plonk || !shape->log_size_poseidon)
+    if (!proof::shape_consistent(shape->log_size_plonk, shape->log_size_poseidon, shape->pow_bits, shape->log_blowup, shape->log_last,
+                                 shape->n_queries, shape->n_inner))
         return STWO_B200_E_SHAPE;
-    verify::Shape v;
-    memcpy(&v, shape, sizeof v);
-    if (v.max_first() > 29 || v.log_plonk() > v.max_first() || v.log_pos() > v.max_first()) return STWO_B200_E_SHAPE;
     try {
         dsl::ProofShape s;
         memcpy(&s, shape, sizeof s);

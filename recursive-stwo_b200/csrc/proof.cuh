@@ -11,6 +11,28 @@ namespace proof {
 
 constexpr u32 MAX_QUERIES = 128;
 constexpr u32 MAX_INNER = 32;
+constexpr u32 MAX_LOG_SIZE = 28;        // component log sizes (stmt0) are untrusted header words: bounded BEFORE any sum is formed
+constexpr u32 MAX_LOG_BLOWUP = 16;
+constexpr u32 MAX_LOG_LAST = 12;
+constexpr u32 MAX_FIRST = 29;           // largest committed column log size
+
+// The FRI layer count is not free: the composition columns are committed at log size composition_log_degree_bound - 1 +
+// blowup, where the bound is the largest constraint degree bound of the two components (Plonk: degree 3 -> log_size + 2,
+// Poseidon: is_full * (x + rc)^5 -> log_size + 3; components/hints/src/fiat_shamir.rs:130-135), and stwo's
+// FriVerifier::commit (called at fiat_shamir.rs:177-183) rejects a proof whose inner-layer count does not bring that
+// size down to log_last + blowup (FriVerificationError::InvalidNumFriLayers).  All 16 fixtures satisfy the relation.
+HD u32 expected_max_first(u32 log_size_plonk, u32 log_size_poseidon, u32 log_blowup) {
+    const u32 a = log_size_plonk + 1, b = log_size_poseidon + 2;
+    return (a > b ? a : b) + log_blowup;
+}
+// every bound and relation a (header, PcsConfig) pair must satisfy; no sum can wrap once the three bounds hold
+HD bool shape_consistent(u32 log_size_plonk, u32 log_size_poseidon, u32 pow_bits, u32 log_blowup, u32 log_last, u64 n_queries, u64 n_inner) {
+    if (log_size_plonk == 0 || log_size_plonk > MAX_LOG_SIZE || log_size_poseidon == 0 || log_size_poseidon > MAX_LOG_SIZE) return false;
+    if (log_blowup == 0 || log_blowup > MAX_LOG_BLOWUP || log_last > MAX_LOG_LAST || pow_bits >= 32) return false;
+    if (n_queries == 0 || n_queries > MAX_QUERIES || n_inner >= MAX_INNER) return false;
+    const u32 max_first = log_last + log_blowup + 1 + (u32)n_inner;
+    return max_first <= MAX_FIRST && max_first == expected_max_first(log_size_plonk, log_size_poseidon, log_blowup);
+}
 // columns per commitment tree (preprocessed, trace, interaction, composition) and how many of the leading ones belong
 // to the Plonk component (the rest to the Poseidon component)
 HD u32 n_cols(u32 t) { return t == 0 ? 50u : t == 1 ? 60u : t == 2 ? 16u : 8u; }
@@ -87,7 +109,11 @@ HD bool parse(const u32 *w, size_t n_words, Desc &d, u32 *ranges = nullptr, u32 
     d.log_blowup = r.r32();
     d.log_last = r.r32();
     u64 nq = r.r64();
-    if (r.bad || nq == 0 || nq > MAX_QUERIES || d.pow_bits >= 32 || d.log_last > 12) return false;
+    // header words are attacker-controlled: bound each one before it is shifted by, looped over or added to anything
+    if (r.bad || nq == 0 || nq > MAX_QUERIES || d.pow_bits >= 32 || d.log_last > MAX_LOG_LAST) return false;
+    if (d.log_size_plonk == 0 || d.log_size_plonk > MAX_LOG_SIZE || d.log_size_poseidon == 0 || d.log_size_poseidon > MAX_LOG_SIZE ||
+        d.log_blowup == 0 || d.log_blowup > MAX_LOG_BLOWUP)
+        return false;
     d.n_queries = (u32)nq;
     if (r.r64() != 4) return false;
     for (int t = 0; t < 4; t++) d.commitments[t] = r.words(8);
@@ -139,8 +165,7 @@ HD bool parse(const u32 *w, size_t n_words, Desc &d, u32 *ranges = nullptr, u32 
     d.max_first = d.log_last + d.log_blowup + 1 + d.n_inner;
     d.log_plonk = d.log_size_plonk + d.log_blowup;
     d.log_pos = d.log_size_poseidon + d.log_blowup;
-    if (d.max_first > 29 || d.log_plonk > d.max_first || d.log_pos > d.max_first || d.log_size_plonk == 0 || d.log_size_poseidon == 0)
-        return false;
+    if (!shape_consistent(d.log_size_plonk, d.log_size_poseidon, d.pow_bits, d.log_blowup, d.log_last, d.n_queries, d.n_inner)) return false;
     d.ok = 1;
     return true;
 }

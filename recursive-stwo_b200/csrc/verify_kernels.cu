@@ -343,11 +343,7 @@ bool g_timed_valid = false;
 inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
 
 bool shape_ok(const stwo_b200_proof_shape *s) {
-    if (!s || s->n_queries == 0 || s->n_queries > proof::MAX_QUERIES || s->n_inner >= proof::MAX_INNER || s->log_last > 12 || s->pow_bits >= 32)
-        return false;
-    verify::Shape v;
-    memcpy(&v, s, sizeof v);
-    return v.max_first() <= 29 && v.log_plonk() <= v.max_first() && v.log_pos() <= v.max_first() && s->log_size_plonk && s->log_size_poseidon;
+    return s && proof::shape_consistent(s->log_size_plonk, s->log_size_poseidon, s->pow_bits, s->log_blowup, s->log_last, s->n_queries, s->n_inner);
 }
 }  // namespace
 
@@ -361,6 +357,19 @@ extern "C" int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stw
     out->log_size_plonk = d.log_size_plonk; out->log_size_poseidon = d.log_size_poseidon; out->pow_bits = d.pow_bits;
     out->log_blowup = d.log_blowup; out->log_last = d.log_last; out->n_queries = d.n_queries; out->n_inner = d.n_inner;
     return STWO_B200_OK;
+}
+
+extern "C" int32_t stwo_b200_shape_from_config(const stwo_b200_pcs_config *config, uint32_t log_size_plonk, uint32_t log_size_poseidon,
+                                               stwo_b200_proof_shape *out) {
+    if (!config || !out) return STWO_B200_E_BAD_ARG;
+    if (log_size_plonk == 0 || log_size_plonk > proof::MAX_LOG_SIZE || log_size_poseidon == 0 || log_size_poseidon > proof::MAX_LOG_SIZE ||
+        config->log_blowup == 0 || config->log_blowup > proof::MAX_LOG_BLOWUP || config->log_last > proof::MAX_LOG_LAST)
+        return STWO_B200_E_SHAPE;
+    const uint32_t max_first = proof::expected_max_first(log_size_plonk, log_size_poseidon, config->log_blowup);
+    if (max_first < config->log_last + config->log_blowup + 1) return STWO_B200_E_SHAPE;
+    *out = {log_size_plonk, log_size_poseidon, config->pow_bits, config->log_blowup, config->log_last, config->n_queries,
+            max_first - (config->log_last + config->log_blowup + 1)};
+    return shape_ok(out) ? STWO_B200_OK : STWO_B200_E_SHAPE;
 }
 
 extern "C" size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint32_t n_proofs) {
@@ -538,16 +547,24 @@ extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200
 
 // Host-pointer batch entry: blobs may have different shapes; they are grouped by shape and verified one group at a time.
 extern "C" int32_t stwo_b200_verify_proofs_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs,
+                                                 const stwo_b200_pcs_config *configs, uint32_t n_configs,
                                                  const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
                                                  uint32_t flags, uint8_t *verdict, uint8_t *stage) {
     STWO_CHECK_DEVICE();
     if (n_proofs == 0) return STWO_B200_OK;
-    if (!blobs || !lens || !verdict) return STWO_B200_E_BAD_ARG;
+    // the PcsConfig is the CALLER's (FiatShamirHints::new(&proof, config, ..), components/hints/src/fiat_shamir.rs:69-73): a blob
+    // is never verified under parameters it chose itself
+    if (!blobs || !lens || !verdict || !configs || n_configs == 0) return STWO_B200_E_BAD_ARG;
     std::map<std::array<uint32_t, 7>, std::vector<uint32_t>> groups;
     for (uint32_t i = 0; i < n_proofs; i++) {
         stwo_b200_proof_shape s;
         // header-only shape read; malformed blobs are rejected here exactly as the device parse would
-        if (!blobs[i] || stwo_b200_proof_shape_of(blobs[i], lens[i], &s) != STWO_B200_OK) {
+        bool allowed = false;
+        if (blobs[i] && stwo_b200_proof_shape_of(blobs[i], lens[i], &s) == STWO_B200_OK)
+            for (uint32_t c = 0; c < n_configs && !allowed; c++)
+                allowed = configs[c].pow_bits == s.pow_bits && configs[c].log_blowup == s.log_blowup && configs[c].log_last == s.log_last &&
+                          configs[c].n_queries == s.n_queries;
+        if (!allowed) {                 // malformed, or a PcsConfig the caller did not ask for
             verdict[i] = proof::REJECT;
             if (stage) stage[i] = proof::ST_PARSE;
             continue;

@@ -12,11 +12,28 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import ProofShape, VerifyDetail, VERIFY_FULL, VERIFY_TIMED, STAGE_KERNELS, FETCH, STAGES
+from ._lib import ProofShape, PcsConfig, VerifyDetail, VERIFY_FULL, VERIFY_TIMED, STAGE_KERNELS, FETCH, STAGES
 from .hashing import _need_init, _stream, _dptr
 
 INPUTS_SINGLE = ([1], [[1, 0, 0, 0]])                                            # examples/single-proof/src/main.rs:28-33
 INPUTS_RECURSIVE = ([1, 2, 3], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])      # (1,1), (2,i), (3,j)
+
+# The PcsConfigs the reference's own drivers verify under (pow_bits, log_blowup, log_last, n_queries).  A verifier never takes
+# these from the proof: FiatShamirHints::new(&proof, config, ..) gets `config` from its caller
+# (components/hints/src/fiat_shamir.rs:69-73).  This allow-list is the default of verify_proofs / VerifyBatch; pass your own.
+CONFIG_SINGLE = PcsConfig(20, 5, 2, 16)                   # examples/single-proof/src/main.rs:28-31
+CONFIG_STANDARD = PcsConfig(20, 5, 8, 16)                 # examples/multi-proofs/src/main.rs:173-196
+CONFIG_FAST_PROVER = PcsConfig(20, 1, 8, 80)
+CONFIG_FAST_PROVER2 = PcsConfig(20, 3, 8, 27)
+CONFIG_FAST_VERIFIER = PcsConfig(23, 7, 8, 11)
+CONFIG_FAST_VERIFIER2 = PcsConfig(20, 8, 8, 10)
+CONFIG_FAST_VERIFIER3 = PcsConfig(28, 9, 7, 8)            # also examples/last-layer/src/main.rs:36-39
+REFERENCE_CONFIGS = (CONFIG_SINGLE, CONFIG_STANDARD, CONFIG_FAST_PROVER, CONFIG_FAST_PROVER2, CONFIG_FAST_VERIFIER,
+                     CONFIG_FAST_VERIFIER2, CONFIG_FAST_VERIFIER3)
+
+
+def _config_list(config):
+    return [config] if isinstance(config, PcsConfig) else list(config)
 
 
 def _as_aligned(blob):
@@ -30,8 +47,28 @@ def _as_aligned(blob):
     return buf, n
 
 
+def shape_from_config(config, log_size_plonk, log_size_poseidon):
+    """The batch shape a caller's PcsConfig implies for proofs of the given component log sizes (stwo_b200_shape_from_config)."""
+    s = ProofShape()
+    rc = _lib.load().stwo_b200_shape_from_config(ctypes.byref(config), log_size_plonk, log_size_poseidon, ctypes.byref(s))
+    if rc != _lib.OK:
+        raise ValueError("no proof shape for %r with log sizes (%d, %d)" % (config, log_size_plonk, log_size_poseidon))
+    return s
+
+
+def shape_for(blob, config=REFERENCE_CONFIGS):
+    """Shape to verify `blob`'s batch under: the statement's log sizes from the blob, the PcsConfig from the CALLER's allow-list
+    (the one the header names must be in it; ValueError otherwise)."""
+    claimed = proof_shape(blob)
+    for c in _config_list(config):
+        if c.key() == (claimed.pow_bits, claimed.log_blowup, claimed.log_last, claimed.n_queries):
+            return shape_from_config(c, claimed.log_size_plonk, claimed.log_size_poseidon)
+    raise ValueError("the proof claims a PcsConfig outside the caller's allow-list: pow_bits=%d log_blowup=%d log_last=%d n_queries=%d"
+                     % (claimed.pow_bits, claimed.log_blowup, claimed.log_last, claimed.n_queries))
+
+
 def proof_shape(blob):
-    """Shape of one proof blob (host-side header walk, no device needed); raises ValueError if it does not parse."""
+    """The shape one proof blob CLAIMS (host-side header walk, no device needed, untrusted); ValueError if it does not parse."""
     buf, n = _as_aligned(blob)
     s = ProofShape()
     rc = _lib.load().stwo_b200_proof_shape_of(buf.ctypes.data_as(ctypes.c_void_p), n, ctypes.byref(s))
@@ -44,8 +81,9 @@ def proof_perms(shape):
     return int(_lib.load().stwo_b200_proof_perms(ctypes.byref(shape)))
 
 
-def verify_proofs(blobs, inputs=INPUTS_RECURSIVE, full=True):
-    """Verify host blobs (any mix of shapes) -> (verdict uint8[n], stage uint8[n]).  Copies are inside the call."""
+def verify_proofs(blobs, inputs=INPUTS_RECURSIVE, full=True, config=REFERENCE_CONFIGS):
+    """Verify host blobs (any mix of shapes) -> (verdict uint8[n], stage uint8[n]).  Copies are inside the call.
+    config: the PcsConfig (or allow-list of them) to verify under; a blob claiming another one is rejected at stage parse."""
     _need_init()
     n = len(blobs)
     keep = [_as_aligned(b) for b in blobs]
@@ -55,7 +93,9 @@ def verify_proofs(blobs, inputs=INPUTS_RECURSIVE, full=True):
     vals = np.ascontiguousarray(inputs[1], dtype=np.uint32)
     verdict = np.full(n, 255, dtype=np.uint8)
     stage = np.full(n, 255, dtype=np.uint8)
-    _lib.call("stwo_b200_verify_proofs_batch", ptrs, lens, n, idx.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p),
+    cfgs = _config_list(config)
+    c_cfgs = (PcsConfig * len(cfgs))(*[PcsConfig(*c.key()) for c in cfgs])
+    _lib.call("stwo_b200_verify_proofs_batch", ptrs, lens, n, c_cfgs, len(cfgs), idx.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p),
               idx.size, VERIFY_FULL if full else 0, verdict.ctypes.data_as(ctypes.c_void_p), stage.ctypes.data_as(ctypes.c_void_p))
     return verdict, stage
 
@@ -63,12 +103,14 @@ def verify_proofs(blobs, inputs=INPUTS_RECURSIVE, full=True):
 class VerifyBatch:
     """A same-shape batch resident in HBM: blobs, offsets, workspace, verdicts."""
 
-    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, shape=None, device=None):
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, shape=None, device=None, config=REFERENCE_CONFIGS):
+        """shape: the shape to verify under (shape_from_config); None: the statement's log sizes of blobs[0] + the PcsConfig of
+        the caller's `config` allow-list that its header names (ValueError when it names none of them)."""
         import torch
         _need_init()
         self.n = len(blobs)
         keep = [_as_aligned(b) for b in blobs]
-        self.shape = shape if shape is not None else proof_shape(blobs[0])
+        self.shape = shape if shape is not None else shape_for(blobs[0], config)
         words = [np.frombuffer(k[0][: (k[1] + 3) // 4 * 4].tobytes(), dtype=np.uint32) for k in keep]
         off = np.zeros(self.n + 1, dtype=np.uint64)
         off[1:] = np.cumsum([w.size for w in words])
@@ -149,9 +191,9 @@ class VerifyStream:
             vs.release(batch)                          # its slot may be overwritten once the work queued so far is done
     """
 
-    def __init__(self, blobs, inputs=INPUTS_RECURSIVE):
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, config=REFERENCE_CONFIGS):
         import torch
-        self.slots = [VerifyBatch(blobs, inputs=inputs), VerifyBatch(blobs, inputs=inputs)]
+        self.slots = [VerifyBatch(blobs, inputs=inputs, config=config), VerifyBatch(blobs, inputs=inputs, config=config)]
         self.shape, self.n = self.slots[0].shape, self.slots[0].n
         self.copy_stream = torch.cuda.Stream()
         self.uploaded = [torch.cuda.Event(), torch.cuda.Event()]
@@ -167,6 +209,10 @@ class VerifyStream:
         assert self._fed - self._taken < 2, "both slots hold batches that were not taken yet"
         slot = self.slots[i]
         if blobs is not None:
+            # the slot's pinned buffers may still be the source of its previous (asynchronous) upload: that copy must have left the
+            # host before they are overwritten (take() only orders the device side)
+            if self._fed >= 2:
+                self.uploaded[i].synchronize()
             words = np.concatenate([np.frombuffer(_as_aligned(b)[0].tobytes(), dtype=np.uint32) for b in blobs])
             off = np.zeros(len(blobs) + 1, dtype=np.uint64)
             off[1:] = np.cumsum([(len(b) + 3) // 4 for b in blobs])

@@ -81,6 +81,29 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     return base;
 }
 void hs_free(void *p) { free(p); }
+// stage_after_transcript + stage_verdict on forged query draws: the one way to reach the case the reference panics on (duplicated
+// queries at the largest domain, components/recursive/answer/src/lib.rs:190-195) without grinding a proof.  shape7 as above;
+// returns verdict | stage << 8.
+u32 hs_after_transcript_verdict(const u32 *shape7, const u32 *raw_queries, u32 pow_ok) {
+    verify::Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape7, 7 * 4);
+    ws.n_proofs = 1;
+    static proof::Desc d;
+    static verify::Detail dt;
+    memset(&d, 0, sizeof d); memset(&dt, 0, sizeof dt);
+    d.ok = 1;
+    d.log_size_plonk = ws.shape.log_size_plonk; d.log_size_poseidon = ws.shape.log_size_poseidon; d.pow_bits = ws.shape.pow_bits;
+    d.log_blowup = ws.shape.log_blowup; d.log_last = ws.shape.log_last; d.n_queries = ws.shape.n_queries; d.n_inner = ws.shape.n_inner;
+    d.max_first = ws.shape.max_first(); d.log_plonk = ws.shape.log_plonk(); d.log_pos = ws.shape.log_pos();
+    ws.desc = &d; ws.detail = &dt;
+    verify::reset_detail(dt);
+    for (u32 i = 0; i < d.n_queries; i++) dt.fs.raw_queries[i] = raw_queries[i];
+    dt.fs.pow_ok = pow_ok;
+    verify::stage_after_transcript(ws, 0);
+    verify::stage_verdict(ws, 0);
+    return dt.verdict | (dt.stage << 8);
+}
 }
 
 // ---- circuit recorder + tape evaluator on the host -------------------------------------------------------------------------

@@ -126,10 +126,15 @@ def load_proof(name):
     return buf, raw.size
 
 
-def verify_proof(buf, length, inputs):
+def verify_proof(buf, length, inputs, config=None):
+    """config: (pow_bits, log_blowup, log_last, n_queries) the caller verifies under; None = whatever the proof's header says"""
     idx = np.array(inputs[0], dtype=np.uint32)
     vals = np.array(inputs[1], dtype=np.uint32)
     out = VerifyOut()
+    if config is not None:
+        cfg = np.array(config, dtype=np.uint32)
+        load_oracle().orc_verify_proof_cfg(vp(buf), ctypes.c_size_t(length), vp(cfg), vp(idx), vp(vals), ctypes.c_uint32(idx.size), ctypes.byref(out))
+        return out
     load_oracle().orc_verify_proof(vp(buf), ctypes.c_size_t(length), vp(idx), vp(vals), ctypes.c_uint32(idx.size), ctypes.byref(out))
     return out
 

@@ -149,9 +149,65 @@ def test_verify_stream_double_buffer(pkg, gpu, orc):
             vs.feed(batches[k + 1])
         bt = vs.take()
         v, s = bt.run(full=True)
-        got.append(v.cpu().numpy().copy())
+        got.append(v.clone())                    # device-side copy, queued: the host must NOT wait here (the CPU runs ahead of the GPU)
         vs.release(bt)
     torch.cuda.synchronize()
     for k in range(5):
         want = np.array([1 if (j + k) % 7 == 0 else 0 for j in range(64)], dtype=np.uint8)
-        assert np.array_equal(got[k] != 0, want != 0), k
+        assert np.array_equal(got[k].cpu().numpy() != 0, want != 0), k
+
+
+def test_weak_config_forgery_is_rejected(pkg, gpu, orc):
+    """The PcsConfig is the caller's (components/hints/src/fiat_shamir.rs:69-73).  small_proof.bin with pow_bits rewritten to 0 is a
+    proof that would be ACCEPTED under its own header (the oracle without a caller config accepts it): every entry point rejects it."""
+    import ctypes
+    buf, n = O.load_proof("small_proof.bin")
+    good = bytes(buf[:n])
+    f = buf.copy()
+    f.view(np.uint32)[10] = 0                            # pow_bits
+    forged = bytes(f[:n])
+    assert O.verify_proof(f, n, O.INPUTS_SMALL).verdict == 0
+    assert O.STAGES[O.verify_proof(f, n, O.INPUTS_SMALL, config=pkg.CONFIG_SINGLE.key()).stage] == "parse"
+    # host entry, default allow-list (the reference's seven configs) and a one-config list that does not include the proof's
+    v, s = pkg.verify_proofs([good, forged, good], inputs=pkg.INPUTS_SINGLE)
+    assert v.tolist() == [0, 1, 0] and pkg.STAGES[int(s[1])] == "parse"
+    v, s = pkg.verify_proofs([good, forged], inputs=pkg.INPUTS_SINGLE, config=pkg.CONFIG_STANDARD)
+    assert v.tolist() == [1, 1] and [pkg.STAGES[int(x)] for x in s] == ["parse", "parse"]
+    v, s = pkg.verify_proofs([good, forged], inputs=pkg.INPUTS_SINGLE, config=pkg.CONFIG_SINGLE)
+    assert v.tolist() == [0, 1]
+    with pytest.raises(pkg.StwoB200Error):               # no config at all is a caller error
+        pkg.verify_proofs([good], inputs=pkg.INPUTS_SINGLE, config=[])
+    # device entry: the shape is the caller's; a forged blob inside the batch fails Shape::matches
+    with pytest.raises(ValueError):
+        pkg.VerifyBatch([forged], inputs=pkg.INPUTS_SINGLE)
+    vb = pkg.VerifyBatch([good, forged, good], inputs=pkg.INPUTS_SINGLE)
+    assert vb.shape.key() == pkg.shape_from_config(pkg.CONFIG_SINGLE, 4, 8).key()
+    v, s = vb.run(full=True)
+    assert v.cpu().numpy().tolist() == [0, 1, 0] and pkg.STAGES[int(s.cpu().numpy()[1])] == "parse"
+    # more queries / another blow-up claimed in the header: same
+    for word, val in ((13, 1), (11, 1), (12, 1)):
+        g = buf.copy()
+        g.view(np.uint32)[word] = val
+        v, s = pkg.verify_proofs([bytes(g[:n])], inputs=pkg.INPUTS_SINGLE)
+        assert (v[0], pkg.STAGES[int(s[0])]) == (1, "parse")
+
+
+def test_garbage_header_words(pkg, gpu, orc):
+    """0xFFFFFFFF header fields must neither wrap into a plausible shape nor stall the batch (a wrapped log_size_plonk would send
+    the OODS stage into a 2^32-step loop): parse rejects, the neighbours are verified, and the call returns promptly"""
+    import time
+    buf, n = O.load_proof("small_proof.bin")
+    blobs = [bytes(buf[:n])]
+    for word in (0, 1, 11):
+        for val in (0xFFFFFFFF, 0xFFFFFFFB, 0x80000004, 29, 0):
+            g = buf.copy()
+            g.view(np.uint32)[word] = val
+            blobs.append(bytes(g[:n]))
+    vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_SINGLE)
+    t0 = time.time()
+    v, s = vb.run(full=True)
+    v, s = v.cpu().numpy(), s.cpu().numpy()
+    assert time.time() - t0 < 5.0
+    assert v.tolist() == [0] + [1] * (len(blobs) - 1) and (s[1:] == 1).all()
+    v2, s2 = pkg.verify_proofs(blobs, inputs=pkg.INPUTS_SINGLE)
+    assert np.array_equal(v2, v) and np.array_equal(s2, s)

@@ -71,3 +71,94 @@ def test_wrong_inputs_and_wrong_shape(hostsim, orc):
     other, _ = O.load_proof("recursive_proof_16_15.bin")
     dt = run_hostsim(hostsim, [(buf, n)], shape_of(other), O.INPUTS_SMALL)       # batch shape != proof shape
     assert (dt[0].verdict, O.STAGES[dt[0].stage]) == (1, "parse")
+
+
+# ---- the caller's PcsConfig, adversarial headers, the reference's panic case ------------------------------------------------
+def _cfg(shape):
+    return tuple(int(x) for x in shape[2:6])            # (pow_bits, log_blowup, log_last, n_queries)
+
+
+def test_weak_config_header_is_rejected(hostsim, orc):
+    """A proof is verified under the CALLER's PcsConfig (components/hints/src/fiat_shamir.rs:69-73), never under the one its
+    header claims: small_proof.bin with pow_bits rewritten to 0 (its PoW check would then pass trivially), with fewer queries or
+    with another blow-up is rejected at the parse stage by the product (batch shape = caller's) and by the oracle alike."""
+    buf, n = O.load_proof("small_proof.bin")
+    shape = shape_of(buf)
+    w = buf.view(np.uint32)
+    blobs = [(buf, n)]
+    for word, val in ((10, 0), (10, 19), (13, 1), (13, 15), (11, 1), (11, 4), (12, 1)):     # pow_bits, n_queries, log_blowup, log_last
+        bad = buf.copy()
+        bad.view(np.uint32)[word] = val
+        blobs.append((bad, n))
+    dts = run_hostsim(hostsim, blobs, shape, O.INPUTS_SMALL)
+    assert (dts[0].verdict, dts[0].stage) == (0, 0)
+    for (b, ln), dt in list(zip(blobs, dts))[1:]:
+        o = O.verify_proof(b, ln, O.INPUTS_SMALL, config=_cfg(shape))
+        assert (o.verdict, O.STAGES[o.stage]) == (1, "parse")
+        assert (dt.verdict, O.STAGES[dt.stage]) == (1, "parse")
+    # the oracle run WITHOUT a caller config shows why: with pow_bits = 0 in its header the forged blob is accepted
+    assert O.verify_proof(blobs[1][0], n, O.INPUTS_SMALL).verdict == 0
+
+
+@pytest.mark.parametrize("word", [0, 1, 11], ids=["log_size_plonk", "log_size_poseidon", "log_blowup"])
+@pytest.mark.parametrize("val", [0xFFFFFFFF, 0xFFFFFFFB, 29, 0x80000010, 0])
+def test_garbage_header_words_do_not_wrap(hostsim, orc, word, val):
+    """0xFFFFFFFF-style header fields: the u32 sums log_size + log_blowup must not wrap into a plausible shape (a wrapped
+    log_size_plonk would send the OODS stage into a 2^32-step loop); rejected at parse by the product and the oracle"""
+    buf, n = O.load_proof("small_proof.bin")
+    shape = shape_of(buf)
+    bad = buf.copy()
+    bad.view(np.uint32)[word] = val
+    dt = run_hostsim(hostsim, [(bad, n)], shape, O.INPUTS_SMALL)
+    assert (dt[0].verdict, O.STAGES[dt[0].stage]) == (1, "parse")
+    # ... and the shape the forged header claims is refused by the library before any workspace is sized for it
+    import importlib
+    import ctypes as C
+    L = importlib.import_module("recursive-stwo_b200")._lib
+    claimed = shape.copy()
+    claimed[{0: 0, 1: 1, 11: 3}[word]] = val
+    assert L.load().stwo_b200_verify_workspace_bytes(C.cast(O.vp(claimed), C.POINTER(L.ProofShape)), 4) == 0
+    out = L.ProofShape()
+    assert L.load().stwo_b200_proof_shape_of(O.vp(bad), n, C.byref(out)) == L.E_SHAPE
+    o = O.verify_proof(bad, n, O.INPUTS_SMALL)
+    assert (o.verdict, O.STAGES[o.stage]) == (1, "parse")
+
+
+def test_fri_layer_count_is_tied_to_the_log_sizes(hostsim, orc):
+    """stwo's InvalidNumFriLayers: every fixture satisfies max_first == max(log_size_plonk + 1, log_size_poseidon + 2) + blowup;
+    a header whose log sizes were moved (so the claimed composition degree bound no longer matches the FRI layers) is rejected"""
+    for name in FIXTURES:
+        buf, n = O.load_proof(name)
+        s = shape_of(buf)
+        assert s[4] + s[3] + 1 + s[6] == max(s[0] + 1, s[1] + 2) + s[3], name
+    buf, n = O.load_proof("recursive_proof_16_15.bin")
+    shape = shape_of(buf)
+    for word, val in ((0, 17), (1, 16), (1, 14), (0, 15)):
+        bad = buf.copy()
+        bad.view(np.uint32)[word] = val
+        claimed = shape.copy()
+        claimed[word] = val
+        o = O.verify_proof(bad, n, O.INPUTS_RECURSIVE)
+        dt = run_hostsim(hostsim, [(bad, n)], claimed, O.INPUTS_RECURSIVE)
+        if max(int(claimed[0]) + 1, int(claimed[1]) + 2) == 17:      # (0, 15): the Poseidon component still sets the bound -> reaches the PoW check
+            assert O.STAGES[o.stage] != "parse" and o.verdict == 1 and dt[0].stage == o.stage
+        else:
+            assert (o.verdict, O.STAGES[o.stage]) == (1, "parse") and (dt[0].verdict, O.STAGES[dt[0].stage]) == (1, "parse")
+
+
+def test_duplicate_queries_are_unsupported(hostsim, orc):
+    """VERDICT_UNSUPPORTED: the reference panics on duplicated queries at the largest domain
+    (components/recursive/answer/src/lib.rs:190-195); forged query draws reach stage_after_transcript directly"""
+    buf, n = O.load_proof("small_proof.bin")
+    shape = shape_of(buf)
+    hostsim.hs_after_transcript_verdict.restype = ctypes.c_uint32
+    o = O.verify_proof(buf, n, O.INPUTS_SMALL)
+    raw = np.array(list(o.raw_queries)[:16], dtype=np.uint32)
+    assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(raw), 1) == 0                   # accept so far
+    dup = raw.copy()
+    dup[11] = dup[3] ^ (1 << 20)            # same position at log size 15 (max_first), different raw draw
+    assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(dup), 1) == 2 | (9 << 8)        # UNSUPPORTED / stage unsupported
+    near = raw.copy()
+    near[11] = near[3] ^ 1                  # neighbours (same pair) are fine
+    assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(near), 1) == 0
+    assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(dup), 0) == 1 | (2 << 8)        # a failed PoW is reported first
