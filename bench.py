@@ -454,10 +454,11 @@ def main():
     tr = pkg.VerifierCircuit.assemble_trace(r0["preprocessed"], r0["values"][(hi - lo) // 2])
     assert hashlib.sha256(np.ascontiguousarray(tr, dtype="<u4").tobytes()).hexdigest() == gold["trace_sha256"], "trace differs from the golden"
     dt0 = vb.fetch(0, "detail")
-    # tree rebuilds + transcript and per-query paths + check_poseidon_invocations; the tape evaluation executes none: it takes the
-    # outputs of the circuit's permutations from the native pass's record (STWO_B200_TRACE_NATIVE_HINTS)
-    perms_per_proof = dt0.n_perms_hints + dt0.n_perms_paths + ci.n_flow
-    assert dt0.n_perms_paths == 3481, "permutation count of the per-query paths differs from the reference's (SURVEY App. C)"
+    # permutations EXECUTED per proof: transcript + tree rebuilds (every node of the partial trees once) + check_poseidon_invocations.
+    # The per-query paths are not hashed again: each node's states are handed to the queries whose path runs through it, and the
+    # tape evaluation takes the circuit's permutations from that record (STWO_B200_TRACE_NATIVE_HINTS).
+    perms_per_proof = dt0.n_perms_hints + dt0.fs.n_transcript_perms + ci.n_flow
+    assert dt0.n_perms_paths == 3481, "permutation count the record covers differs from the reference's circuit (SURVEY App. C)"
 
     # ---- timed region: device-resident ----------------------------------------------------------------
     sampler = ClockSampler(local)

@@ -160,7 +160,12 @@ int32_t stwo_b200_shape_from_config(const stwo_b200_pcs_config *config, uint32_t
 #define STWO_B200_STAGE_UNSUPPORTED 9
 
 /* flags */
-#define STWO_B200_VERIFY_FULL 1u   /* also recompute every per-query authentication path (what the verifier circuit does) */
+#define STWO_B200_VERIFY_FULL 1u   /* also produce what the verifier circuit consumes beyond the verdict: the per-query roots and the
+                                      permutation record (output state of every transcript / authentication-path permutation) */
+#define STWO_B200_VERIFY_PATH_KERNELS 8u /* with FULL: produce that record by hashing every per-query path again from its hints
+                                      (SinglePathMerkleProof::verify, components/hints/src/decommit.rs:22-42), one thread per
+                                      path, instead of taking it from the tree rebuilds, which hash every node once
+                                      (from_stwo_proof, decommit.rs:44-183).  Same record; kept as the checker of the default. */
 #define STWO_B200_VERIFY_ONE_STREAM 4u /* do not slice the batch over the library's stream pool */
 #define STWO_B200_VERIFY_TIMED 2u  /* record CUDA events between the stage kernels (read with stwo_b200_verify_stage_ms) */
 /* stage kernels in launch order: fiat_shamir, single_tree, group, answer, folds, pair_tree, single_path, pair_path, verdict */
@@ -174,6 +179,8 @@ int32_t stwo_b200_verify_stage_ms(float *ms /* [STWO_B200_N_STAGE_KERNELS] */);
 int32_t stwo_b200_proof_shape_of(const uint8_t *blob, size_t len, stwo_b200_proof_shape *out);
 /* bytes of device workspace a batch of n_proofs of this shape needs (0: unsupported shape) */
 size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *shape, uint32_t n_proofs);
+/* slots of the permutation record of one proof of this shape (512 transcript slots, then every per-query path) */
+uint32_t stwo_b200_proof_record_slots(const stwo_b200_proof_shape *shape);
 /* Poseidon2 permutations of the per-query paths of one proof of this shape (transcript excluded) */
 uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape);
 
@@ -227,6 +234,9 @@ typedef struct {
 #define STWO_B200_FETCH_PATH_COLS 7       /* [4][n_queries][64]  per-query column values of the commitment trees */
 #define STWO_B200_FETCH_PATH_SIBLINGS 8   /* [4][n_queries][30][8] */
 #define STWO_B200_FETCH_PAIR_HINTS 9      /* [1 + n_inner][n_queries * 256] packed FRI pair hints */
+#define STWO_B200_FETCH_PERM_RECORD 10    /* [stwo_b200_proof_record_slots][16] the permutation record (STWO_B200_VERIFY_FULL); slots the
+                                             shape does not use (transcript slots beyond n_transcript_perms) are not written */
+#define STWO_B200_FETCH_RECORD_TREES 11   /* u32: trees of this proof whose part of the record is complete (4 + 1 + n_inner = all) */
 int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
                                uint32_t what, void *out, size_t out_bytes, void *stream);
 
@@ -263,6 +273,11 @@ typedef struct {
      * of permuting; stwo_b200_cs_check_poseidon_dev re-executes every flow entry regardless. */
     const uint32_t *perm_hints;
     uint32_t perm_hint_stride;
+    /* Optional gate on the hints, per item: item b's hints are used only when perm_hint_ready[b] == perm_hint_need (NULL: always).
+     * The batched verifier counts there the trees whose part of the record is complete for the run that just finished, so a
+     * proof that was rejected half-way, or a workspace last used without STWO_B200_VERIFY_FULL, is evaluated by permuting. */
+    const uint32_t *perm_hint_ready;
+    uint32_t perm_hint_need;
 } stwo_b200_cs_values;
 /* The value definitions of a recorded circuit, sorted by dependency level (instructions of a level are independent).
  * ins: n_ins x {op, dst, a, b} (STWO_B200_T_*); perms: n_perms x 12 words {l_kind, l_a, l_b, r_kind, r_a, r_b, swap_var,

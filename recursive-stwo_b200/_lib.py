@@ -91,9 +91,10 @@ class VerifyDetail(ctypes.Structure):
 
 VERIFY_FULL = 1
 VERIFY_TIMED = 2
+VERIFY_PATH_KERNELS = 8
 STAGE_KERNELS = ("fiat_shamir", "single_tree", "group", "answer", "folds", "pair_tree", "single_path", "pair_path", "verdict")
 FETCH = {"detail": 0, "domain_points": 1, "answers": 2, "circle_folds": 3, "line_folds": 4, "last_evals": 5, "path_roots": 6,
-         "path_cols": 7, "path_siblings": 8, "pair_hints": 9}
+         "path_cols": 7, "path_siblings": 8, "pair_hints": 9, "perm_record": 10, "record_trees": 11}
 STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
           9: "unsupported"}
 
@@ -107,7 +108,8 @@ class CsWiring(ctypes.Structure):
 class CsValues(ctypes.Structure):
     """stwo_b200_cs_values"""
     _fields_ = [("n_batch", ctypes.c_uint32), ("lanes", ctypes.c_uint32), ("variables", ctypes.c_void_p), ("flow_hash", ctypes.c_void_p),
-                ("flow_swap", ctypes.c_void_p), ("perm_hints", ctypes.c_void_p), ("perm_hint_stride", ctypes.c_uint32)]
+                ("flow_swap", ctypes.c_void_p), ("perm_hints", ctypes.c_void_p), ("perm_hint_stride", ctypes.c_uint32),
+                ("perm_hint_ready", ctypes.c_void_p), ("perm_hint_need", ctypes.c_uint32)]
 
 
 class CsTape(ctypes.Structure):
@@ -155,6 +157,7 @@ SIGNATURES = {
     "stwo_b200_shape_from_config": (_i32, [_CFG_P, _u32, _u32, _PSHAPE_P]),
     "stwo_b200_verify_workspace_bytes": (_sz, [_PSHAPE_P, _u32]),
     "stwo_b200_proof_perms": (_u64, [_PSHAPE_P]),
+    "stwo_b200_proof_record_slots": (_u32, [_PSHAPE_P]),
     "stwo_b200_verify_proofs_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_verify_proofs_batch_pinned_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _PSHAPE_P, _vp, _vp, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),

@@ -235,8 +235,12 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
     }
     k_gather_witness<<<dim3((nw + 31) / 32, (unsigned)groups), kT, 0, st>>>(ws, c->gather, nw, k.witness, c->n_jobs ? k.extra : nullptr, c->n_extra_words);
     note_launch(1);
-    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0};
-    if ((flags & STWO_B200_TRACE_NATIVE_HINTS) && c->wiring.kind == 0 && ws.perm_out) { v.perm_hints = ws.perm_out; v.perm_hint_stride = ws.hint_total * 16; }
+    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0};
+    // per proof: only a record that the verification of THIS workspace just completed is used (verify::Workspace::hint_trees)
+    if ((flags & STWO_B200_TRACE_NATIVE_HINTS) && c->wiring.kind == 0 && ws.perm_out) {
+        v.perm_hints = ws.perm_out; v.perm_hint_stride = ws.hint_total * 16;
+        v.perm_hint_ready = ws.hint_trees; v.perm_hint_need = ws.shape.n_trees();
+    }
     MARK();
     if ((rc = stwo_b200_cs_eval_tape_dev(&c->tape_, c->wiring.n_vars, k.witness, &v, st))) return rc;
     MARK();

@@ -19,6 +19,7 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
     tape::Q4 *vars; u32 *flow_hash; uint8_t *flow_swap;
     u32 n_batch, lanes, n_vars, n_flow;
     const u32 *hints; u32 hint_stride;
+    const u32 *hint_ready; u32 hint_need;
     __device__ __forceinline__ tape::View view(u32 item, const u32 *input, u32 n_input_words) const {
         const size_t g = item / lanes, l = item % lanes;
         tape::View v;
@@ -27,7 +28,7 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
         v.flow_hash = flow_hash ? flow_hash + g * n_flow * 32 * lanes + l : nullptr;
         v.flow_swap = flow_swap ? flow_swap + g * n_flow * lanes + l : nullptr;
         v.stride = lanes;
-        v.hint = hints ? hints + (size_t)item * hint_stride : nullptr;
+        v.hint = hints && (!hint_ready || hint_ready[item] == hint_need) ? hints + (size_t)item * hint_stride : nullptr;
         return v;
     }
 };
@@ -347,6 +348,7 @@ Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
     b.vars = reinterpret_cast<tape::Q4 *>(v->variables); b.flow_hash = v->flow_hash; b.flow_swap = v->flow_swap;
     b.n_batch = v->n_batch; b.lanes = v->lanes; b.n_vars = n_vars; b.n_flow = n_flow;
     b.hints = v->perm_hints; b.hint_stride = v->perm_hint_stride;
+    b.hint_ready = v->perm_hint_ready; b.hint_need = v->perm_hint_need;
     return b;
 }
 }  // namespace
@@ -522,7 +524,7 @@ extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const st
     w.a_wire = dw; w.b_wire = dw + nr; w.c_wire = dw + 2 * nr; w.poseidon_wire = dw + 3 * nr; w.enforce_c_m31 = dw + 4 * nr; w.op = dw + 5 * nr;
     w.op_follows_c = hw->op_follows_c ? d + o_follow : nullptr;
     w.flow_wire = (u32 *)(d + o_fw); w.flow_swap_addr = (u32 *)(d + o_fa);
-    stwo_b200_cs_values v = {1, 1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs, nullptr, 0};
+    stwo_b200_cs_values v = {1, 1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs, nullptr, 0, nullptr, 0};
     int32_t *m = (int32_t *)(d + o_mult);
     int64_t *bad = (int64_t *)(d + o_bad);
     u32 *scr = (u32 *)(d + o_scr), *stat = (u32 *)(d + o_stat), *pre = (u32 *)(d + o_pre), *vals = (u32 *)(d + o_vals);

@@ -54,6 +54,34 @@ HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out
     tap(sink, st);
     for (int i = 0; i < 8; i++) out[i] = st[i];
 }
+// The same node with a callback after every permutation: tap(j, st) sees the 16-word output state of the node's j-th permutation
+// (execution order: [hash of the children,] sponge chunks, finalisation).  The cooperative tree rebuilds use it to hand each
+// state to the queries whose authentication path runs through this node (decommit_coop.cuh).
+template <class Tap>
+HD void hash_node2_tap(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out, Tap tap) {
+    u32 st[16];
+    u32 tree[8];
+    u32 j = 0;
+    if (L) {
+        for (int i = 0; i < 8; i++) { st[i] = L[i]; st[8 + i] = R[i]; }
+        permute_mem(st);
+        tap(j++, st);
+        if (tree_out) for (int i = 0; i < 8; i++) tree_out[i] = st[i];
+        if (nc == 0) { for (int i = 0; i < 8; i++) out[i] = st[i]; return; }
+        for (int i = 0; i < 8; i++) tree[i] = st[i];
+    }
+    for (int i = 8; i < 16; i++) st[i] = 0;
+    u32 n_chunks = nc ? (nc + 7) / 8 : 1;
+    for (u32 c = 0; c < n_chunks; c++) {
+        for (u32 i = 0; i < 8; i++) st[i] = 8 * c + i < nc ? cols[8 * c + i] : 0u;
+        permute_mem(st);
+        tap(j++, st);
+    }
+    for (int i = 0; i < 8; i++) st[i] = L ? tree[i] : 0u;
+    permute_mem(st);
+    tap(j++, st);
+    for (int i = 0; i < 8; i++) out[i] = st[i];
+}
 HD u32 node_perms(bool leaf, u32 nc) { return leaf ? (nc ? (nc + 7) / 8 : 1) + 1 : 1 + (nc ? (nc + 7) / 8 + 1 : 0); }
 
 HD bool eq8(const u32 *a, const u32 *b) {

@@ -33,12 +33,36 @@ HD void load_hash(const u32 *nodes_tab, const u32 *hw, u32 src, u32 out[8]) {
     for (int i = 0; i < 8; i++) out[i] = p[i];
 }
 
+// Where the rebuild leaves, per query, the output state of every permutation of that query's authentication path -- the very
+// permutations SinglePathMerkleProofVar::verify / SinglePairMerkleProofVar::verify execute in the verifier circuit
+// (components/recursive/data_structures/src/lib.rs:315-354,400-464).  A node of the partial tree is hashed ONCE here
+// (like from_stwo_proof, components/hints/src/decommit.rs:44-183, folding.rs:93-287) and its states are handed to every query
+// whose path runs through it, in the slot order of merkle::path_root / pair_path_root (verify.cuh HintLayout).
+struct PermRec {
+    u32 *base;            // slot 0 of query 0 of this tree; nullptr: no record
+    u32 per_query;        // slots per query
+    u32 *roots;           // nq x 8: the recomputed root per query (= the rebuilt root); may be null
+    HDM u32 *slot(u32 query, u32 k) const { return base + ((size_t)query * per_query + k) * 16; }
+};
+HD void st16(u32 *dst, const u32 *st) {
+#if defined(__CUDA_ARCH__)
+    uint4 *d = reinterpret_cast<uint4 *>(dst);          // slots are 64-byte aligned
+    d[0] = make_uint4(st[0], st[1], st[2], st[3]); d[1] = make_uint4(st[4], st[5], st[6], st[7]);
+    d[2] = make_uint4(st[8], st[9], st[10], st[11]); d[3] = make_uint4(st[12], st[13], st[14], st[15]);
+#else
+    for (int i = 0; i < 16; i++) dst[i] = st[i];
+#endif
+}
+
 // number of tab words single_tree_coop needs
 HD u32 single_tab_words(u32 nq) { return 7 * nq + 8; }
+// after single_tree_coop returned: did it walk every level (is the PermRec complete)?
+HD bool single_rec_complete(const u32 *tab, u32 nq) { return tab[7 * nq + 5] != 0; }
 
 template <class Co>
 HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 nq, const u32 *values, u32 n_values, const u32 *hw, u32 n_hw,
-                         const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, u32 *nodes, u32 *tab, u32 *perms) {
+                         const u32 *root, u32 *path_cols, u32 cpp, u32 *path_sib, u32 sib_stride, u32 *nodes, u32 *tab, u32 *perms,
+                         const PermRec rec = PermRec{nullptr, 0, nullptr}) {
     u32 *cpos = tab, *ppos = cpos + nq, *lsrc = ppos + nq, *rsrc = lsrc + nq, *sibsrc = rsrc + nq, *par = sibsrc + nq, *qnode = par + nq;
     u32 *ctl = qnode + nq;                         // [0] m  [1] wi  [2] vi  [3] fail  [4] perms
     u32 *chash = nodes, *phash = nodes + 8 * (size_t)nq;
@@ -68,7 +92,9 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
     if (!ctl[3]) {
         for (u32 k = L; k < m; k += G) {
             u32 h8[8];
-            hash_node2(nullptr, nullptr, values + (size_t)k * nc, nc, h8);
+            hash_node2_tap(nullptr, nullptr, values + (size_t)k * nc, nc, h8, nullptr, [&](u32 j, const u32 *st) {
+                if (rec.base) for (u32 i = 0; i < nq; i++) if (qnode[i] == k) st16(rec.slot(i, j), st);
+            });
             for (int i = 0; i < 8; i++) chash[8 * k + i] = h8[i];
         }
         for (u32 i = L; i < nq; i += G) {
@@ -79,6 +105,7 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
     }
     co.sync();
     u32 colpos = nc;
+    u32 slot_off = node_perms(true, nc);               // path slots used so far (merkle::path_root order)
     for (u32 h = depth; h-- > 0;) {
         nc = sh.ncols(h);
         // ---- plan: a child starts a parent unless it is the odd partner of the previous child
@@ -116,7 +143,9 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
                 u32 l8[8], r8[8], h8[8];
                 if (ps & 1u) { load_hash(chash, hw, s, l8); load_hash(chash, hw, k, r8); }
                 else { load_hash(chash, hw, k, l8); load_hash(chash, hw, s, r8); }
-                hash_node2(l8, r8, values + vi0 + (size_t)j * nc, nc, h8);
+                hash_node2_tap(l8, r8, values + vi0 + (size_t)j * nc, nc, h8, nullptr, [&](u32 jj, const u32 *st) {
+                    if (rec.base) for (u32 i = 0; i < nq; i++) if (par[qnode[i]] == j) st16(rec.slot(i, slot_off + jj), st);
+                });
                 for (int i = 0; i < 8; i++) phash[8 * j + i] = h8[i];
                 ppos[j] = ps >> 1;
             }
@@ -140,24 +169,29 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
         }
         co.sync();
         colpos += nc;
+        slot_off += node_perms(false, nc);
         u32 *tp = cpos; cpos = ppos; ppos = tp;
         u32 *th = chash; chash = phash; phash = th;
         m = mp;
     }
     bool ok = !ctl[3] && ctl[2] == n_values && ctl[1] == n_hw && m == 1 && eq8(chash, root);
     if (perms && L == 0) *perms += ctl[4];
+    if (rec.roots && !ctl[3] && m == 1) for (u32 i = L; i < nq; i += G) cp8(rec.roots + 8 * (size_t)i, chash);
+    if (L == 0) ctl[5] = ctl[3] ? 0u : 1u;             // the record is complete (every level was walked)
     co.sync();
     return ok;
 }
 
 // ---- FRI layer trees ---------------------------------------------------------------------------------------------------
 HD u32 pair_tab_words(u32 nq) { return 2 * nq + 5 * 2 * nq + 8; }
+HD bool pair_rec_complete(const u32 *tab, u32 nq) { return tab[2 * nq + 5 * 2 * nq + 7] != 0; }
 
 // Same contract as pair_tree (decommit.cuh).  nodes: 5 tables of 8 * 2nq words (child hash, node hash, node tree hash,
 // node left child, node right child).
 template <class Co>
 HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *vals, u32 n_vals, const u32 *hw, u32 n_hw,
-                       const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, u32 *nodes, u32 *tab, u32 *perms) {
+                       const u32 *root, u32 *self_vals, u32 *sib_vals, u32 *sib_hashes, u32 *nodes, u32 *tab, u32 *perms,
+                       const PermRec rec = PermRec{nullptr, 0, nullptr}) {
     const u32 cap = 2 * nq, L = co.lane(), G = co.size();
     u32 *qs = tab, *qtmp = qs + nq;                                    // sorted unique query positions of the layer
     u32 *cpos = qtmp + nq, *npos = cpos + cap, *lsrc = npos + cap, *rsrc = lsrc + cap, *flag = rsrc + cap;
@@ -170,6 +204,7 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
     }
     co.sync();
     u32 d_idx = 0;
+    u32 slot_off = 4;                                  // path slots before the level being hashed (pair_path_root order: 2 + 2 leaf perms first)
     for (u32 h = depth + 1; h-- > 0;) {
         const bool data = (data_mask >> h) & 1u;
         // ---- plan (lane 0: the node list is short and sorted; this is integer work only)
@@ -220,13 +255,29 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
             for (u32 a = L; a < m; a += G) {
                 const u32 *val = data ? vals + vi0 + 4 * (size_t)a : nullptr;
                 u32 h8[8], t8[8], l8[8], r8[8];
+                const u32 pos = npos[a], sh_q = depth - h;
                 if (h == depth) {
-                    hash_node2(nullptr, nullptr, val, 4, h8);
+                    // a leaf is the self opening of the queries at its position (slots 0, 1) and the sibling opening of the
+                    // queries at the other member of its pair (slots 2, 3)
+                    hash_node2_tap(nullptr, nullptr, val, 4, h8, nullptr, [&](u32 j, const u32 *st) {
+                        if (rec.base) for (u32 i = 0; i < nq; i++) {
+                            if (q[i] == pos) st16(rec.slot(i, j), st);
+                            else if ((q[i] ^ 1u) == pos) st16(rec.slot(i, 2 + j), st);
+                        }
+                    });
                     for (int i = 0; i < 8; i++) nhash[8 * a + i] = h8[i];
                 } else {
                     load_hash(chash, hw, lsrc[a], l8);
                     load_hash(chash, hw, rsrc[a], r8);
-                    hash_node2(l8, r8, val, data ? 4 : 0, h8, t8);
+                    // self node of a query: all its permutations; sibling node at a data layer: the two that fold the sibling's
+                    // own evaluation into its tree hash (the tree hash itself is a hint of the path)
+                    hash_node2_tap(l8, r8, val, data ? 4 : 0, h8, t8, [&](u32 j, const u32 *st) {
+                        if (rec.base) for (u32 i = 0; i < nq; i++) {
+                            const u32 qh = q[i] >> sh_q;
+                            if (qh == pos) st16(rec.slot(i, slot_off + j), st);
+                            else if (data && h >= 1 && j >= 1 && (qh ^ 1u) == pos) st16(rec.slot(i, slot_off + 2 + j), st);
+                        }
+                    });
                     for (int i = 0; i < 8; i++) { nhash[8 * a + i] = h8[i]; ntree[8 * a + i] = t8[i]; nL[8 * a + i] = l8[i]; nR[8 * a + i] = r8[i]; }
                 }
             }
@@ -268,10 +319,13 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
         }
         co.sync();
         if (data) d_idx++;
+        if (h < depth) slot_off += data ? (h >= 1 ? 5u : 3u) : 1u;
         u32 *t = chash; chash = nhash; nhash = t;                      // this layer becomes the child table
     }
     const bool ok = !ctl[3] && ctl[2] == n_vals && ctl[1] == n_hw && ctl[6] == 1 && eq8(chash, root);
     if (perms && L == 0) *perms += ctl[4];
+    if (rec.roots && !ctl[3] && ctl[6] == 1) for (u32 i = L; i < nq; i += G) cp8(rec.roots + 8 * (size_t)i, chash);
+    if (L == 0) ctl[7] = ctl[3] ? 0u : 1u;             // the record is complete (every level was walked)
     co.sync();
     return ok;
 }

@@ -113,6 +113,9 @@ struct Workspace {
     u32 *pair_scratch;                   // [p][f][88 * nq]
     u32 *fold_buf;                       // [p][max(1, 2^(log_last-1))][4]  last-layer polynomial fold buffer
     u32 *perm_out;                       // [p][HintLayout::total][16]  output state of every transcript / per-query path permutation
+    u32 *hint_trees;                     // [p]  trees (of n_trees()) whose part of perm_out is complete for THIS run; the circuit's tape
+                                         //      evaluation takes a proof's permutations from perm_out only when all of them are
+    u32 mode;                            // MODE_* (set by the host per run)
 
     HDM const u32 *blob(u32 p) const { return blobs + blob_off[p]; }
     HDM size_t blob_words(u32 p) const { return (size_t)(blob_off[p + 1] - blob_off[p]); }
@@ -137,6 +140,11 @@ struct Workspace {
     u32 hint_total, pair_hint_base;      // HintLayout::total / pair_base[0] of `shape` (set by carve)
     HDM u32 *perm_out_of(u32 p, u32 slot) const { return perm_out ? perm_out + ((size_t)p * hint_total + slot) * 16 : nullptr; }
 };
+
+// MODE_FULL: record the circuit's permutations (perm_out) and the per-query roots.  MODE_PATH_KERNELS: the record is produced by
+// the thread-per-path kernels (stage_single_path / stage_pair_path: every path hashed again from its hints, as
+// SinglePathMerkleProof::verify does) instead of by the cooperative tree rebuilds, which hash every node once.
+enum : u32 { MODE_FULL = 1u, MODE_PATH_KERNELS = 2u };
 
 HD void fail(Detail &dt, u32 stage) { dt.fail_mask |= 1u << stage; }
 #if defined(__CUDA_ARCH__)
@@ -190,6 +198,7 @@ HD void stage_fiat_shamir(const Workspace &ws, u32 p) {
     Desc &d = ws.desc[p];
     Detail &dt = ws.detail[p];
     reset_detail(dt);
+    if (ws.hint_trees) ws.hint_trees[p] = 0;
     if (!proof::parse(ws.blob(p), ws.blob_words(p), d) || !ws.shape.matches(d)) { d.ok = 0; fail(dt, proof::ST_PARSE); return; }
     stage_transcript(ws, p);
     stage_oods(ws, p);
@@ -206,6 +215,7 @@ HD void stage_parse_coop(const Co &co, const Workspace &ws, u32 p, u32 *tab) {
     const u32 *w = ws.blob(p);
     if (co.lane() == 0) {
         reset_detail(dt);
+        if (ws.hint_trees) ws.hint_trees[p] = 0;
         u32 n_ranges = 0;
         const bool ok = proof::parse(w, ws.blob_words(p), d, ranges, PARSE_MAX_RANGES, &n_ranges) && ws.shape.matches(d);
         ctl[0] = n_ranges; ctl[1] = ok ? 1u : 0u; ctl[2] = 0;
@@ -265,12 +275,25 @@ HD void stage_single_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 t, 
     co.sync();
     u32 perms = 0;
     u32 *nodes = ws.single_scratch + ((size_t)p * 4 + t) * decommit::SINGLE_SCRATCH_WORDS_PER_QUERY * nq;
+    // full mode: the rebuild hands every node's permutation states to the queries whose path runs through the node
+    decommit::PermRec rec{nullptr, 0, nullptr};
+    const bool record = (ws.mode & MODE_FULL) && !(ws.mode & MODE_PATH_KERNELS) && ws.perm_out;
+    if (record) {
+        stwo_b200_path_shape shp;
+        u32 at = HINT_TRANSCRIPT_SLOTS;
+        for (u32 tt = 0; tt <= t; tt++) { single_path_shape(ws.shape, tt, shp); if (tt < t) at += merkle::path_perms(shp) * nq; }
+        rec.base = ws.perm_out_of(p, at); rec.per_query = merkle::path_perms(shp); rec.roots = ws.root_of(p, t, 0);
+    }
     const bool ok = decommit::single_tree_coop(co, sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
                                                w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
-                                               nodes, tab, &perms);
+                                               nodes, tab, &perms, rec);
     if (co.lane() == 0) {
         VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
         if (!ok) fail_shared(&dt, proof::ST_MERKLE);
+        if (record && decommit::single_rec_complete(tab, nq)) {
+            VERIFY_ATOMIC_ADD(&dt.n_perms_paths, rec.per_query * nq);  // the circuit's path permutations this record covers
+            VERIFY_ATOMIC_ADD(&ws.hint_trees[p], 1u);
+        }
     }
 }
 template <class Co>
@@ -290,11 +313,22 @@ HD void stage_pair_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 f, u3
     u32 *self_vals = hint, *sib_vals = hint + nq * decommit::MAX_DATA_LAYERS * 4, *sib_hashes = sib_vals + nq * decommit::MAX_DATA_LAYERS * 4;
     u32 *nodes = ws.pair_scratch + ((size_t)p * ws.shape.n_fri_trees() + f) * decommit::PAIR_SCRATCH_WORDS_PER_QUERY * nq;
     u32 perms = 0;
+    decommit::PermRec rec{nullptr, 0, nullptr};
+    const bool record = (ws.mode & MODE_FULL) && !(ws.mode & MODE_PATH_KERNELS) && ws.perm_out;
+    if (record) {
+        u32 at = ws.pair_hint_base;
+        for (u32 ff = 0; ff < f; ff++) at += decommit::pair_path_perms(ws.shape.fri_depth(ff), ws.shape.fri_data_mask(ff)) * nq;
+        rec.base = ws.perm_out_of(p, at); rec.per_query = decommit::pair_path_perms(depth, ws.shape.fri_data_mask(f)); rec.roots = ws.root_of(p, 4 + f, 0);
+    }
     const bool ok = decommit::pair_tree_coop(co, depth, ws.shape.fri_data_mask(f), q, nq, ws.vals_of(p, f), *ws.nvals_of(p, f), hw, n_hw, root,
-                                             self_vals, sib_vals, sib_hashes, nodes, tab, &perms);
+                                             self_vals, sib_vals, sib_hashes, nodes, tab, &perms, rec);
     if (co.lane() == 0) {
         VERIFY_ATOMIC_ADD(&dt.n_perms_hints, perms);
         if (!ok) fail_shared(&dt, f ? proof::ST_FRI_INNER : proof::ST_FRI_FIRST);
+        if (record && decommit::pair_rec_complete(tab, nq)) {
+            VERIFY_ATOMIC_ADD(&dt.n_perms_paths, rec.per_query * nq);
+            VERIFY_ATOMIC_ADD(&ws.hint_trees[p], 1u);
+        }
     }
 }
 
@@ -736,6 +770,8 @@ HD void stage_pair_path(const Workspace &ws, u32 p, u32 f, u32 i) {
 // ---- stage 6: verdict (one thread per proof) ------------------------------------------------------------------------
 HD void stage_verdict(const Workspace &ws, u32 p) {
     Detail &dt = ws.detail[p];
+    // the thread-per-path kernels write every slot of a parsed proof's record (they ran before this stage)
+    if ((ws.mode & MODE_FULL) && (ws.mode & MODE_PATH_KERNELS) && ws.hint_trees && ws.desc[p].ok) ws.hint_trees[p] = ws.shape.n_trees();
     const u32 order[9] = {proof::ST_PARSE, proof::ST_POW, proof::ST_LOGUP, proof::ST_OODS, proof::ST_UNSUPPORTED, proof::ST_MERKLE,
                           proof::ST_FRI_FIRST, proof::ST_FRI_INNER, proof::ST_FRI_LAST};
     dt.verdict = proof::ACCEPT; dt.stage = proof::ST_OK;
@@ -782,6 +818,7 @@ inline size_t carve(Workspace &ws, uint8_t *base) {
     const HintLayout hl = hint_layout(ws.shape);
     ws.hint_total = hl.total; ws.pair_hint_base = hl.pair_base[0];
     ws.perm_out = c.take<u32>(n * (size_t)hl.total * 16);
+    ws.hint_trees = c.take<u32>(n);
     return (c.at + 255) & ~(size_t)255;
 }
 

@@ -381,6 +381,13 @@ extern "C" size_t stwo_b200_verify_workspace_bytes(const stwo_b200_proof_shape *
     return verify::carve(ws, nullptr);
 }
 
+extern "C" uint32_t stwo_b200_proof_record_slots(const stwo_b200_proof_shape *shape) {
+    if (!shape_ok(shape)) return 0;
+    verify::Shape v;
+    memcpy(&v, shape, sizeof v);
+    return verify::hint_layout(v).total;
+}
+
 extern "C" uint64_t stwo_b200_proof_perms(const stwo_b200_proof_shape *shape) {
     // permutations of the per-query (circuit) path of one proof, excluding the transcript: trees 0-3 + FRI layers
     if (!shape_ok(shape)) return 0;
@@ -441,6 +448,11 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees();
     const bool timed = flags & STWO_B200_VERIFY_TIMED, full = flags & STWO_B200_VERIFY_FULL;
+    // Full mode: the cooperative tree rebuilds hash every node once and hand its permutation states to the queries whose path
+    // runs through it.  The thread-per-path kernels (every path hashed again from its hints) remain as the checker of that
+    // record (STWO_B200_VERIFY_PATH_KERNELS) and for the thread-per-tree rebuilds (STWO_B200_TREE_G=0), which keep no record.
+    const bool path_kernels = full && ((flags & STWO_B200_VERIFY_PATH_KERNELS) || tree_group_width(n_proofs) == 0);
+    ws.mode = (full ? verify::MODE_FULL : 0u) | (path_kernels ? verify::MODE_PATH_KERNELS : 0u);
     g_timed_valid = false;
     if (host_blobs)      // the offsets are needed by every slice: they go first, on the caller's stream
         STWO_CUDA(cudaMemcpyAsync(const_cast<uint64_t *>(blob_off), host_blob_off, ((size_t)n_proofs + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -459,14 +471,14 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         MARK(); launch_folds(ws, 0, n, st);
         MARK(); launch_pair_tree(ws, 0, n, st);
         MARK();
-        if (full) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
+        if (path_kernels) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
         MARK();
-        if (full) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, st>>>(ws, 0, n);
+        if (path_kernels) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, st>>>(ws, 0, n);
         MARK(); k_verdict<<<nblk(n), kT, 0, st>>>(ws, 0, n, verdict, stage);
         MARK();
 #undef MARK
         g_timed_valid = timed;
-        note_launch((full ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
+        note_launch((path_kernels ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
         return cuda_status(cudaGetLastError());
     }
     // sliced: the per-proof and per-tree stages have far fewer threads than the GPU holds, so independent slices of the
@@ -486,7 +498,7 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         STWO_CUDA(cudaStreamWaitEvent(b, g_fs_done[sl], 0));
         launch_oods(ws, p0, n, b);
         launch_single_tree(ws, p0, n, a);
-        if (full) {
+        if (path_kernels) {
             STWO_CUDA(cudaEventRecord(g_tree_done[sl], a));
             STWO_CUDA(cudaStreamWaitEvent(b, g_tree_done[sl], 0));
             k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, b>>>(ws, p0, n);
@@ -496,12 +508,12 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
         launch_folds(ws, p0, n, a);
         launch_pair_tree(ws, p0, n, a);
-        if (full) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
+        if (path_kernels) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
         STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));
         k_verdict<<<nblk(n), kT, 0, a>>>(ws, p0, n, verdict, stage);
         STWO_CUDA(cudaEventRecord(g_join[sl], a));
         STWO_CUDA(cudaStreamWaitEvent(st, g_join[sl], 0));
-        note_launch((full ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
+        note_launch((path_kernels ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
     }
     return cuda_status(cudaGetLastError());
 }
@@ -537,6 +549,8 @@ extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200
         case STWO_B200_FETCH_PATH_COLS: src = ws.path_cols + (size_t)p * 4 * nq * verify::PATH_COLS_STRIDE; bytes = 4 * nq * verify::PATH_COLS_STRIDE * 4; break;
         case STWO_B200_FETCH_PATH_SIBLINGS: src = ws.path_sib + (size_t)p * 4 * nq * verify::MAX_DEPTH * 8; bytes = 4 * nq * verify::MAX_DEPTH * 32; break;
         case STWO_B200_FETCH_PAIR_HINTS: src = ws.pair_hints + (size_t)p * nf * nq * verify::PAIR_HINT_WORDS; bytes = nf * nq * verify::PAIR_HINT_WORDS * 4; break;
+        case STWO_B200_FETCH_PERM_RECORD: src = ws.perm_out_of(p, 0); bytes = (size_t)ws.hint_total * 64; break;
+        case STWO_B200_FETCH_RECORD_TREES: src = ws.hint_trees + p; bytes = 4; break;
         default: return STWO_B200_E_BAD_ARG;
     }
     if (out_bytes < bytes) return STWO_B200_E_BAD_ARG;

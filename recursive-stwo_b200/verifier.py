@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import ProofShape, PcsConfig, VerifyDetail, VERIFY_FULL, VERIFY_TIMED, STAGE_KERNELS, FETCH, STAGES
+from ._lib import ProofShape, PcsConfig, VerifyDetail, VERIFY_FULL, VERIFY_TIMED, VERIFY_PATH_KERNELS, STAGE_KERNELS, FETCH, STAGES
 from .hashing import _need_init, _stream, _dptr
 
 INPUTS_SINGLE = ([1], [[1, 0, 0, 0]])                                            # examples/single-proof/src/main.rs:28-33
@@ -134,8 +134,10 @@ class VerifyBatch:
         self.d_words.copy_(self.h_words, non_blocking=True)
         self.d_off.copy_(self.h_off, non_blocking=True)
 
-    def run(self, full=True, timed=False):
-        flags = (VERIFY_FULL if full else 0) | (VERIFY_TIMED if timed else 0)
+    def run(self, full=True, timed=False, path_kernels=False):
+        """path_kernels: produce the permutation record with the thread-per-path kernels (the checker of the default, which takes
+        it from the tree rebuilds)"""
+        flags = (VERIFY_FULL if full else 0) | (VERIFY_TIMED if timed else 0) | (VERIFY_PATH_KERNELS if path_kernels else 0)
         self.last_full = bool(full)          # full mode records the path permutations the circuit reuses (TRACE_NATIVE_HINTS)
         _lib.call("stwo_b200_verify_proofs_batch_dev", _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape),
                   _dptr(self.d_idx), _dptr(self.d_vals), self.n_inputs, flags, _dptr(self.d_ws), self.ws_bytes,
@@ -171,7 +173,8 @@ class VerifyBatch:
             return out
         shapes = {"domain_points": (3, nq, 2), "answers": (3, nq, 4), "circle_folds": (3, nq, 4), "line_folds": (32, nq, 4),
                   "last_evals": (nq, 4), "path_roots": (4 + nf, nq, 8), "path_cols": (4, nq, 64), "path_siblings": (4, nq, 30, 8),
-                  "pair_hints": (nf, nq * 256)}
+                  "pair_hints": (nf, nq * 256), "record_trees": (1,),
+                  "perm_record": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16)}
         out = np.zeros(shapes[what], dtype=np.uint32)
         _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what],
                   out.ctypes.data_as(ctypes.c_void_p), out.nbytes, _stream())

@@ -50,6 +50,7 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     verify::carve(ws, base);
     const u32 nq = ws.shape.n_queries, nf = ws.shape.n_fri_trees();
     const bool coop_fs = (full & 2) != 0;
+    ws.mode = ((full & 1) ? verify::MODE_FULL : 0u) | (((full & 1) && (!(full & 2) || (full & 4))) ? verify::MODE_PATH_KERNELS : 0u);
     {
         std::vector<u32> ptab(verify::parse_tab_words());
         decommit::CoopOne one0;
@@ -59,6 +60,7 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
         }
     }
     const bool coop = (full & 2) != 0;          // bit 1: the cooperative tree rebuilds (group of one lane on the host)
+    const bool path_kernels = (full & 1) && (!coop || (full & 4));      // bit 2: the per-query path stages produce the record even with coop
     full &= 1;
     std::vector<u32> tab(decommit::pair_tab_words(nq) + decommit::single_tab_words(nq) + verify::folds_tab_words(nq) + 2 * nq + 64);
     decommit::CoopOne one;
@@ -71,7 +73,7 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) {
         if (coop) verify::stage_pair_tree_coop(one, ws, p, f, tab.data()); else verify::stage_pair_tree(ws, p, f);
     }
-    if (full) {
+    if (path_kernels) {
         for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) for (u32 i = 0; i < nq; i++) verify::stage_single_path(ws, p, t, i);
         for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) for (u32 i = 0; i < nq; i++) verify::stage_pair_path(ws, p, f, i);
     }
@@ -81,6 +83,13 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     return base;
 }
 void hs_free(void *p) { free(p); }
+// the permutation record of proof p (ws from hs_verify_batch's ws_out): hint_total x 16 words; returns hint_total
+u32 hs_perm_record(const verify::Workspace *ws, u32 p, u32 *out, u32 *trees_complete) {
+    if (out) memcpy(out, ws->perm_out_of(p, 0), (size_t)ws->hint_total * 64);
+    if (trees_complete) *trees_complete = ws->hint_trees[p];
+    return ws->hint_total;
+}
+size_t hs_workspace_struct_size() { return sizeof(verify::Workspace); }
 // stage_after_transcript + stage_verdict on forged query draws: the one way to reach the case the reference panics on (duplicated
 // queries at the largest domain, components/recursive/answer/src/lib.rs:190-195) without grinding a proof.  shape7 as above;
 // returns verdict | stage << 8.
@@ -162,7 +171,7 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
         if (stream_out) memcpy(stream_out + (size_t)p * c.n_input_words, stream.data(), stream.size() * 4);
         tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
                      flow_swap + (size_t)p * c.num_poseidon_invocations(), 1,
-                     use_hints && !c.without() ? ws.perm_out_of(p, 0) : nullptr};
+                     use_hints && !c.without() && ws.hint_trees[p] == ws.shape.n_trees() ? ws.perm_out_of(p, 0) : nullptr};
         tape::prologue(v);
         for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data(), c.eperms.data());
         bad_row[p] = -1;

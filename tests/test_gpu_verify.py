@@ -211,3 +211,28 @@ def test_garbage_header_words(pkg, gpu, orc):
     assert v.tolist() == [0] + [1] * (len(blobs) - 1) and (s[1:] == 1).all()
     v2, s2 = pkg.verify_proofs(blobs, inputs=pkg.INPUTS_SINGLE)
     assert np.array_equal(v2, v) and np.array_equal(s2, s)
+
+
+@pytest.mark.parametrize("name,n", [("small_proof.bin", 300), ("recursive_proof_16_15.bin", 40), ("level1-5.bin", 5), ("level13-1.bin", 33)])
+def test_tree_rebuild_record_equals_path_kernels(pkg, gpu, orc, name, n):
+    """Full mode takes the circuit's permutation record from the cooperative tree rebuilds (every node hashed once).  The
+    thread-per-path kernels (STWO_B200_VERIFY_PATH_KERNELS: every path hashed again from its hints) are the checker: same
+    record word for word, same per-query roots, same counters -- on the sliced (300 proofs) and the one-stream launch path."""
+    buf, ln = O.load_proof(name)
+    inputs = O.inputs_for(name)
+    o = O.verify_proof(buf, ln, inputs)
+    vb = pkg.VerifyBatch([bytes(buf[:ln])] * n, inputs=inputs)
+    got = {}
+    for pk in (False, True):
+        v, _ = vb.run(full=True, path_kernels=pk)
+        assert not v.cpu().numpy().any()
+        got[pk] = [(vb.fetch(p, "perm_record").copy(), vb.fetch(p, "path_roots").copy(), vb.fetch(p, "detail").n_perms_paths,
+                    int(vb.fetch(p, "record_trees")[0])) for p in (0, n // 2, n - 1)]
+    used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, got[True][0][0].shape[0])]
+    for a, b in zip(got[False], got[True]):
+        assert np.array_equal(a[0][used], b[0][used]) and np.array_equal(a[1], b[1])
+        assert a[2] == b[2] == o.n_perms_paths and a[3] == b[3] == 5 + o.n_inner
+        assert a[0][512:].any(axis=1).all()
+    # a verdict-only run leaves no usable record: the marker is reset, the tape evaluation then permutes itself
+    vb.run(full=False)
+    assert int(vb.fetch(0, "record_trees")[0]) == 0

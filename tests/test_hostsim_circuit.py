@@ -46,7 +46,7 @@ def record_last(hs, shape):
     return h, dict(zip(INFO, (int(x) for x in info))), get
 
 
-def evaluate(hs, h, info, blobs, shape, inputs, use_hints=0):
+def evaluate(hs, h, info, blobs, shape, inputs, use_hints=0, full=1):
     hs.hs_verify_batch.restype = ctypes.c_void_p
     words, off = pack(blobs)
     idx = np.array(inputs[0], dtype=np.uint32)
@@ -54,7 +54,7 @@ def evaluate(hs, h, info, blobs, shape, inputs, use_hints=0):
     n = len(blobs)
     dt = (Detail * n)()
     ws = np.zeros(4096, dtype=np.uint8)
-    base = hs.hs_verify_batch(O.vp(words), O.vp(off), n, O.vp(shape), O.vp(idx), O.vp(vals), idx.size, 1, dt, O.vp(ws))
+    base = hs.hs_verify_batch(O.vp(words), O.vp(off), n, O.vp(shape), O.vp(idx), O.vp(vals), idx.size, full, dt, O.vp(ws))
     variables = np.zeros((n, info["n_vars"], 4), dtype=np.uint32)
     fh = np.zeros((n, info["n_flow"], 32), dtype=np.uint32)
     fs = np.zeros((n, info["n_flow"]), dtype=np.uint8)
@@ -84,6 +84,11 @@ def test_recorded_circuit_matches_oracle(hostsim, orc, name, mult):
     assert hostsim.hs_circuit_hint_count(h) == info["n_flow"]          # every permutation of the circuit is one the native pass executes
     dt2, variables2, fh2, fs2, bad2 = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name), use_hints=1)
     assert bad2[0] == -1 and np.array_equal(variables2, variables) and np.array_equal(fh2, fh) and np.array_equal(fs2, fs)
+    # ... and with the record produced by the cooperative tree rebuilds (every node hashed once, its states handed to the queries
+    # whose path runs through it) instead of the per-query path stages: the product's default
+    dt3, variables3, fh3, fs3, bad3 = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name), use_hints=1, full=3)
+    assert dt3[0].n_perms_paths == out.n_perms_paths
+    assert bad3[0] == -1 and np.array_equal(variables3, variables) and np.array_equal(fh3, fh) and np.array_equal(fs3, fs)
     wire, addr, wh, wsw = cs.flow_arrays()
     assert np.array_equal(fh[0], wh) and np.array_equal(fs[0], wsw)
     hostsim.hs_circuit_free(h)

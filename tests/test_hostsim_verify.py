@@ -162,3 +162,35 @@ def test_duplicate_queries_are_unsupported(hostsim, orc):
     near[11] = near[3] ^ 1                  # neighbours (same pair) are fine
     assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(near), 1) == 0
     assert hostsim.hs_after_transcript_verdict(O.vp(shape), O.vp(dup), 0) == 1 | (2 << 8)        # a failed PoW is reported first
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_tree_rebuild_record_equals_path_kernels(hostsim, orc, name):
+    """The permutation record (output state of every transcript / per-query path permutation, what the circuit's tape evaluation
+    consumes) taken from the cooperative tree rebuilds -- every node of the partial tree hashed ONCE -- is word for word the
+    record the per-query path stages produce by hashing each path again from its hints, for every fixture; the per-query
+    roots equal the oracle's."""
+    buf, n = O.load_proof(name)
+    shape = shape_of(buf)
+    inputs = O.inputs_for(name)
+    o = O.verify_proof(buf, n, inputs)
+    hostsim.hs_verify_batch.restype = ctypes.c_void_p
+    hostsim.hs_perm_record.restype = ctypes.c_uint32
+    words, off = pack([(buf, n)])
+    idx, vals = np.array(inputs[0], dtype=np.uint32), np.array(inputs[1], dtype=np.uint32)
+    recs = {}
+    for mode in (3, 7, 1):               # coop trees produce the record | coop trees + path stages | thread-per-tree + path stages
+        dt = (Detail * 1)()
+        ws = np.zeros(4096, dtype=np.uint8)
+        base = hostsim.hs_verify_batch(O.vp(words), O.vp(off), 1, O.vp(shape), O.vp(idx), O.vp(vals), idx.size, mode, dt, O.vp(ws))
+        total = hostsim.hs_perm_record(O.vp(ws), 0, None, None)
+        rec = np.zeros((total, 16), dtype=np.uint32)
+        trees = ctypes.c_uint32(0)
+        hostsim.hs_perm_record(O.vp(ws), 0, O.vp(rec), ctypes.byref(trees))
+        hostsim.hs_free(ctypes.c_void_p(base))
+        assert dt[0].verdict == 0 and dt[0].n_perms_paths == o.n_perms_paths and dt[0].n_perms_hints == o.n_perms_hints
+        assert trees.value == 5 + o.n_inner
+        recs[mode] = rec
+    used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, recs[3].shape[0])]        # transcript slots beyond the chain are unused
+    assert np.array_equal(recs[3][used], recs[7][used]) and np.array_equal(recs[7][used], recs[1][used])
+    assert recs[3][512:].any(axis=1).all()                                                   # every path slot was written
