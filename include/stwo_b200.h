@@ -261,7 +261,17 @@ typedef struct {
      * preprocessed block is the 8 columns mult_c, a_wire, b_wire, c_wire, op1, op2, op3, op4 (:633-713). */
     uint32_t kind;
     const uint32_t *op2, *op3, *op4;                 /* n_rows each (kind 1) */
+    /* Optional (NULL / 0: none), read by stwo_b200_cs_export_trace_dev with lanes = 32 only: per 64-row tile the distinct variables
+     * its wires name, each wire's slot in that list and the row constants, packed by stwo_b200_cs_export_tiles_build
+     * (stwo_b200_cs_export_tiles_words(n_rows) words, 16-byte aligned); export_cap = the largest list.  With it the export gathers
+     * a variable once per tile instead of once per use, writes 256-byte runs, and needs none of the other columns. */
+    const uint32_t *export_tiles;
+    uint32_t export_cap;
 } stwo_b200_cs_wiring;
+/* Host helpers (no device): size of, and the packing of, export_tiles from a wiring whose pointers are HOST pointers
+ * (n_rows a multiple of 64; STWO_B200_E_BAD_ARG otherwise, or when a kind-1 selector column holds a value other than 0 / 1). */
+size_t stwo_b200_cs_export_tiles_words(uint32_t n_rows);
+int32_t stwo_b200_cs_export_tiles_build(const stwo_b200_cs_wiring *host_wiring, uint32_t *tiles, uint32_t *cap);
 typedef struct {
     uint32_t n_batch, lanes;                         /* lanes: 1 or 32 */
     uint32_t *variables;                             /* n_vars QM31 per item */

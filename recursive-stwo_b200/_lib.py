@@ -102,7 +102,8 @@ class CsWiring(ctypes.Structure):
     """stwo_b200_cs_wiring"""
     _fields_ = [(n, ctypes.c_uint32) for n in ("n_vars", "n_rows", "n_flow", "num_input")] + [
         (n, ctypes.c_void_p) for n in ("a_wire", "b_wire", "c_wire", "poseidon_wire", "enforce_c_m31", "op", "op_follows_c", "flow_wire",
-                                       "flow_swap_addr")] + [("kind", ctypes.c_uint32)] + [(n, ctypes.c_void_p) for n in ("op2", "op3", "op4")]
+                                       "flow_swap_addr")] + [("kind", ctypes.c_uint32)] + [(n, ctypes.c_void_p) for n in ("op2", "op3", "op4")] + [
+        ("export_tiles", ctypes.c_void_p), ("export_cap", ctypes.c_uint32)]
 
 
 class CsValues(ctypes.Structure):
@@ -170,6 +171,8 @@ SIGNATURES = {
     "stwo_b200_cs_check_poseidon_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_export_trace_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_finalize": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp]),
+    "stwo_b200_cs_export_tiles_words": (_sz, [_u32]),
+    "stwo_b200_cs_export_tiles_build": (_i32, [_WIR_P, _vp, _vp]),
     "stwo_b200_circuit_record_verifier": (_i32, [_PSHAPE_P, _vp, _vp, _u32, _u32, ctypes.POINTER(_vp)]),
     "stwo_b200_circuit_record_last_layer": (_i32, [_PSHAPE_P, ctypes.POINTER(_vp)]),
     "stwo_b200_circuit_free": (None, [_vp]),

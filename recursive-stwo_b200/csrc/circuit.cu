@@ -87,7 +87,8 @@ int32_t upload(stwo_b200_circuit *c) {
     size_t at = 0;
     auto take = [&](size_t bytes) { at = align_up(at, 256); size_t o = at; at += bytes; return o; };
     const size_t o_w = take(9 * nr * 4), o_jobs = take(r.jobs.size() * sizeof(circuit::ExtraJob) + 16), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
-                 o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4);
+                 o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4),
+                 o_xt = take(stwo_b200_cs_export_tiles_words((u32)nr) * 4 + 16);
     uint8_t *d = nullptr;
     STWO_CUDA(cudaMalloc(&d, at));
     const std::vector<u32> *cols[9] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op, &cs.op2, &cs.op3, &cs.op4};
@@ -105,8 +106,21 @@ int32_t upload(stwo_b200_circuit *c) {
     if (!cs.eperms.empty()) STWO_CUDA(cudaMemcpy(d + o_ep, cs.eperms.data(), cs.eperms.size() * 4, cudaMemcpyHostToDevice));
     if (!r.gather.empty()) STWO_CUDA(cudaMemcpy(d + o_g, r.gather.data(), r.gather.size() * 4, cudaMemcpyHostToDevice));
     const u32 *w = (const u32 *)(d + o_w);
+    // per 32-row tile of the export pass: the distinct variables its wires name
+    std::vector<u32> xt(stwo_b200_cs_export_tiles_words((u32)nr));
+    u32 xcap = 0;
+    {
+        stwo_b200_cs_wiring hw{};
+        hw.n_rows = (u32)nr; hw.kind = cs.without() ? 1u : 0u;
+        hw.a_wire = cs.a_wire.data(); hw.b_wire = cs.b_wire.data(); hw.c_wire = cs.c_wire.data(); hw.op = cs.op.data();
+        hw.enforce_c_m31 = cs.enforce_c_m31.data(); hw.op2 = cs.op2.data(); hw.op3 = cs.op3.data(); hw.op4 = cs.op4.data();
+        hw.op_follows_c = cs.op_follows_c.data();
+        if (xt.empty() || stwo_b200_cs_export_tiles_build(&hw, xt.data(), &xcap) != STWO_B200_OK) { xt.clear(); xcap = 0; }    // the tiled export remains
+        else STWO_CUDA(cudaMemcpy(d + o_xt, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
+    }
     c->wiring = {cs.n_vars, (u32)nr, (u32)nf, cs.num_input, w, w + nr, w + 2 * nr, w + 3 * nr, w + 4 * nr, w + 5 * nr, d + o_fol,
-                 (const u32 *)(d + o_fw), (const u32 *)(d + o_fa), cs.without() ? 1u : 0u, w + 6 * nr, w + 7 * nr, w + 8 * nr};
+                 (const u32 *)(d + o_fw), (const u32 *)(d + o_fa), cs.without() ? 1u : 0u, w + 6 * nr, w + 7 * nr, w + 8 * nr,
+                 xt.empty() ? nullptr : (const u32 *)(d + o_xt), xcap};
     c->jobs = (const circuit::ExtraJob *)(d + o_jobs); c->n_jobs = (u32)r.jobs.size(); c->n_extra_words = r.n_extra_words;
     c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
                 (const u32 *)(d + o_perm), (u32)(cs.eperms.size() / tape::EPOSEIDON_REC), (const u32 *)(d + o_ep)};

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "tape.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 using namespace stwo_b200;
 
@@ -333,6 +334,133 @@ __global__ void __launch_bounds__(kT) k_cs_export_vals_tiled(stwo_b200_cs_wiring
         if (grp * ITEMS + it < b.n_batch) vals[((size_t)(grp * ITEMS + it) * kCols + col) * n + row0 + lane] = tile[(col * ITEMS + it) * 33 + lane];
     }
 }
+// lanes = 32, streaming form.  A persistent CTA walks tiles of 64 rows x 16 items with two staging buffers.
+//
+// Why 64 rows: the pass writes 13.9 GB (4096 proofs) as one run per (item, column, tile).  Measured on this B200
+// (tools/scatter_write_probe.cu, stores only): 128-byte runs reach 4.2-4.4 TB/s, 256-byte runs 5.9 TB/s (cudaMemset: 7.4) -- with
+// 32-row tiles the stores alone take 3.3 ms, whatever the kernel around them does.  A lane owns two consecutive rows and every
+// store instruction writes 256 contiguous bytes of one (item, column).
+// Why a variable list per tile: the HOST lists, per 32 rows, the DISTINCT variables the 96 wires name (stwo_b200_cs_export_tiles_build:
+// 1.16 per row for the verifier circuit of shape S -- padding rows, the constants 0/1/i/j and gate chains repeat wires), so a
+// variable crosses L2 -> SM once per half tile, not once per use (5 GB instead of 12.9 GB per 4096 proofs).
+//   issue(t+1): the warps gather the two half tiles' variables with 16-byte asynchronous copies (LDGSTS; a half-warp moves the 256
+//               contiguous bytes a variable occupies across the tile's 16 items) straight into shared memory -- no registers are
+//               held, the whole tile is in flight while
+//   consume(t): check_arithmetics, fused: a warp takes a row, 16 items x the two CM31 halves of the gate (tape::gate_ok_half), so the
+//               gate kind is uniform across the warp; then the column stores: a warp takes 2 items, lane = row pair reads its
+//               rows' QM31 by their slot in the staging buffer (LDS.128) and writes 13 x 8 bytes.
+// Everything a tile needs from the wiring (variable lists, slots, row constants) is fetched three tiles ahead by asynchronous
+// copies as well: nothing a later trip depends on is held in a register across trips.  Tiles are dealt row-tile fastest: the
+// CTAs of the grid sweep one lane group's variables[] together.
+constexpr int kXRows = 64, kXItems = 16, kXPitch = kXItems + 1, kXThreads = 512, kXWarps = kXThreads / 32;
+// per 64-row tile (stwo_b200_cs_export_tiles_build), 384 words: two 32-row variable lists of 128 words ([0] count, [1..96] variables),
+// then 64 row records of 2 words: {slot_a | slot_b << 8 | slot_c << 16 | flags << 24, op}
+constexpr int kXListWords = 128, kXTileWords = 2 * kXListWords + 2 * kXRows, kXMetaStages = 4;
+enum : u32 { XF_C1 = 1u << 24, XF_OP3 = 1u << 25, XF_OP4 = 1u << 26, XF_FOLLOWS = 1u << 27, XF_SKIP = 1u << 28 };   // C1: enforce_c_m31 / op2
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__global__ void __launch_bounds__(kXThreads, 2) k_cs_export_vals_stream(stwo_b200_cs_wiring w, Batch b, u32 *vals, unsigned long long *first_bad,
+                                                                         u32 n_row_tiles, u32 n_tiles) {
+    extern __shared__ uint4 xsmem[];
+    u32 *xmeta = reinterpret_cast<u32 *>(xsmem);                                 // [kXMetaStages][kXTileWords]
+    uint4 *xstage = xsmem + kXMetaStages * kXTileWords / 4;                      // [2 buffers][2 halves][cap][kXPitch]
+    const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32, cap = w.export_cap;
+    const u32 il16 = lane & 15u, part = lane >> 4;
+    const size_t n2 = w.n_rows / 2;
+    const u32 step = gridDim.x;
+    const size_t buf_stride = (size_t)2 * cap * kXPitch;
+    auto fetch_meta = [&](u32 rt, u32 stage) {           // rt: 64-row tile; 96 x 16 bytes
+        if (warp < 3) cp_async16(xmeta + stage * kXTileWords + 128 * warp + 4 * lane, w.export_tiles + (size_t)rt * kXTileWords + 128 * warp + 4 * lane);
+    };
+    // tile = (lane group, half of its items, 64-row tile), the row tile fastest
+    auto issue = [&](u32 gh, u32 stage, u32 buf) {
+        const u32 *m0 = xmeta + stage * kXTileWords, *m1 = m0 + kXListWords;
+        const u32 count0 = m0[0], total = count0 + m1[0];
+        const u32 item = gh * kXItems + il16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.vars) + (size_t)(gh >> 1) * b.n_vars * 32 + (gh & 1u) * kXItems + il16;
+        uint4 *dst = xstage + buf * buf_stride + il16;
+        if (item < b.n_batch)
+            for (u32 e = 2 * warp + part; e < total; e += 2 * kXWarps) {
+                const bool second = e >= count0;
+                const u32 k = second ? e - count0 : e, var = (second ? m1 : m0)[1 + k];
+                cp_async16(dst + ((second ? cap : 0u) + k) * kXPitch, src + (size_t)var * 32);
+            }
+    };
+    auto advance = [&](u32 &gh, u32 &rt) { rt += step; while (rt >= n_row_tiles) { rt -= n_row_tiles; gh++; } };
+    if (blockIdx.x >= n_tiles) return;
+    u32 gh = blockIdx.x / n_row_tiles, rt = blockIdx.x % n_row_tiles;            // current tile
+    const u32 n_mine = (n_tiles - blockIdx.x + step - 1) / step;
+    u32 mg = gh, mrt = rt;                                                        // tile whose meta is fetched next
+    for (u32 k = 0; k < 3; k++) {
+        if (k < n_mine) fetch_meta(mrt, k);
+        cp_async_commit();
+        advance(mg, mrt);
+    }
+    asm volatile("cp.async.wait_group 2;" ::: "memory");                         // meta 0
+    __syncthreads();
+    issue(gh, 0, 0);
+    cp_async_commit();
+    u32 ng = gh, nrt = rt;                                                        // tile t + 1
+    advance(ng, nrt);
+    for (u32 t = 0; t < n_mine; t++) {
+        const u32 buf = t & 1u;
+        // groups committed so far, oldest first: .. meta(t+1) data(t-1) meta(t+2) data(t); this trip adds meta(t+3), data(t+1)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");                     // meta(t+1) landed (copied by other threads: barrier)
+        __syncthreads();                                                          // ... and every warp is done with tile t-1: its staging
+                                                                                  // buffer and its meta stage (= that of t+3) are free
+        if (t + 3 < n_mine) fetch_meta(mrt, (t + 3) % kXMetaStages);
+        cp_async_commit();
+        advance(mg, mrt);
+        if (t + 1 < n_mine) issue(ng, (t + 1) % kXMetaStages, buf ^ 1u);
+        cp_async_commit();
+        asm volatile("cp.async.wait_group 2;" ::: "memory");                     // data(t) landed; meta(t+3), data(t+1) may be in flight
+        __syncthreads();
+        const uint2 *rec = reinterpret_cast<const uint2 *>(xmeta + (t % kXMetaStages) * kXTileWords + 2 * kXListWords);
+        const uint4 *st = xstage + buf * buf_stride;
+        if (first_bad) {
+            const u32 item = gh * kXItems + il16;
+            if (item < b.n_batch) {
+#pragma unroll 2
+                for (u32 j = 0; j < kXRows / kXWarps; j++) {
+                    const u32 r = warp + kXWarps * j;
+                    const uint2 rr = rec[r];                                      // warp-uniform
+                    if (rr.x & XF_SKIP) continue;                                 // same wires and constants as an earlier row of this tile
+                    const uint4 *sh = st + (r >> 5) * cap * kXPitch + il16;
+                    const uint4 a = sh[(rr.x & 255u) * kXPitch], bb = sh[((rr.x >> 8) & 255u) * kXPitch], c = sh[((rr.x >> 16) & 255u) * kXPitch];
+                    const qm31_t qa = qm31::mk(a.x, a.y, a.z, a.w), qb = qm31::mk(bb.x, bb.y, bb.z, bb.w), qc = qm31::mk(c.x, c.y, c.z, c.w);
+                    const u32 op = (rr.x & XF_FOLLOWS) ? c.x : rr.y;
+                    bool ok;
+                    if (w.kind == 1) ok = part || tape::gate_ok_without(qa, qb, qc, op, (rr.x >> 24) & 1u, (rr.x >> 25) & 1u, (rr.x >> 26) & 1u);
+                    else ok = tape::gate_ok_half(qa, qb, qc, op, rr.x & XF_C1, part);
+                    if (!ok) atomicMin(first_bad + item, (unsigned long long)(rt * kXRows + r));
+                }
+            }
+        }
+        {
+            // lane = rows 2 lane, 2 lane + 1 of the tile (lanes 0..15: first half tile)
+            const uint4 r2 = reinterpret_cast<const uint4 *>(rec)[lane];         // the two row records
+            const uint4 *sh = st + part * cap * kXPitch;
+            const uint4 *sa0 = sh + (r2.x & 255u) * kXPitch, *sb0 = sh + ((r2.x >> 8) & 255u) * kXPitch, *sc0 = sh + ((r2.x >> 16) & 255u) * kXPitch;
+            const uint4 *sa1 = sh + (r2.z & 255u) * kXPitch, *sb1 = sh + ((r2.z >> 8) & 255u) * kXPitch, *sc1 = sh + ((r2.z >> 16) & 255u) * kXPitch;
+#pragma unroll
+            for (u32 j = 0; j < kXItems / kXWarps; j++) {
+                const u32 il = warp * (kXItems / kXWarps) + j, item = gh * kXItems + il;
+                if (item >= b.n_batch) continue;
+                const uint4 a0 = sa0[il], a1 = sa1[il], b0 = sb0[il], b1 = sb1[il], c0 = sc0[il], c1 = sc1[il];
+                uint2 *o = reinterpret_cast<uint2 *>(vals + (size_t)item * kCols * 2 * n2 + (size_t)rt * kXRows) + lane;
+                o[0] = make_uint2(a0.x, a1.x); o[n2] = make_uint2(a0.y, a1.y); o[2 * n2] = make_uint2(a0.z, a1.z); o[3 * n2] = make_uint2(a0.w, a1.w);
+                o[4 * n2] = make_uint2(b0.x, b1.x); o[5 * n2] = make_uint2(b0.y, b1.y); o[6 * n2] = make_uint2(b0.z, b1.z); o[7 * n2] = make_uint2(b0.w, b1.w);
+                o[8 * n2] = make_uint2(c0.x, c1.x); o[9 * n2] = make_uint2(c0.y, c1.y); o[10 * n2] = make_uint2(c0.z, c1.z); o[11 * n2] = make_uint2(c0.w, c1.w);
+                o[12 * n2] = make_uint2((r2.x & XF_FOLLOWS) ? c0.x : r2.y, (r2.z & XF_FOLLOWS) ? c1.x : r2.w);
+            }
+        }
+        gh = ng; rt = nrt;
+        advance(ng, nrt);
+        // no trailing barrier: the next trip's first barrier orders this trip's reads before anything is overwritten
+    }
+}
 __global__ void k_fill64(unsigned long long *p, size_t n, unsigned long long v) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -477,21 +605,87 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
         if (fb) { k_fill64<<<nblk(v->n_batch), kT, 0, st>>>(fb, v->n_batch, ~0ull); note_launch(1); }
         if (v->lanes == 1) k_cs_export_vals_plain<<<nblk((size_t)w->n_rows * v->n_batch), kT, 0, st>>>(*w, b, values, fb);
         else {
-            static int items = 0;
+            static int items = 0, n_sm = 0, ctas_per_sm = 2;
             if (!items) {
-                const char *e = getenv("STWO_B200_EXPORT_ITEMS");          // 16 / 32 (profiling); measured at 4096 proofs: 32 -> 4.66 ms, 16 -> 5.15 ms
-                items = e && atoi(e) == 16 ? 16 : 32;
+                const char *e = getenv("STWO_B200_EXPORT_ITEMS");          // 16 / 32: the tiled form (profiling); default: the streaming form
+                items = e && atoi(e) == 16 ? 16 : e && atoi(e) == 32 ? 32 : -1;
+                e = getenv("STWO_B200_EXPORT_CTAS");
+                if (e && atoi(e) > 0) ctas_per_sm = atoi(e);
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
                 STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 32 * 33 * 4));
                 STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_tiled<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 16 * 33 * 4));
+                STWO_CUDA(cudaFuncSetAttribute(k_cs_export_vals_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 96 * kXPitch * 16 + kXMetaStages * kXTileWords * 4));
             }
-            const size_t smem = (size_t)kCols * items * 33 * 4;
-            dim3 grid(w->n_rows / kTileRows, (v->n_batch + items - 1) / items);
-            if (items == 32) k_cs_export_vals_tiled<32><<<grid, kT, smem, st>>>(*w, b, values, fb);
-            else k_cs_export_vals_tiled<16><<<grid, kT, smem, st>>>(*w, b, values, fb);
+            auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+            if (items < 0 && w->export_tiles && w->export_cap >= 1 && w->export_cap <= 96 && al16(w->export_tiles) && al16(v->variables) && al16(values) &&
+                w->n_rows >= (u32)kXRows) {
+                const size_t kXSmem = (size_t)2 * 2 * w->export_cap * kXPitch * sizeof(uint4) + kXMetaStages * kXTileWords * 4;
+                const u32 n_row_tiles = w->n_rows / kXRows, n_item_groups = (v->n_batch + kXItems - 1) / kXItems;
+                const size_t n_tiles = (size_t)n_row_tiles * n_item_groups;
+                if (n_tiles > 0xffffffffull) return STWO_B200_E_BAD_ARG;
+                const size_t cap = (size_t)n_sm * ctas_per_sm;
+                k_cs_export_vals_stream<<<(unsigned)(n_tiles < cap ? n_tiles : cap), kXThreads, kXSmem, st>>>(*w, b, values, fb, n_row_tiles, (u32)n_tiles);
+            } else {
+                if (items < 0) items = 32;
+                const size_t smem = (size_t)kCols * items * 33 * 4;
+                dim3 grid(w->n_rows / kTileRows, (v->n_batch + items - 1) / items);
+                if (items == 32) k_cs_export_vals_tiled<32><<<grid, kT, smem, st>>>(*w, b, values, fb);
+                else k_cs_export_vals_tiled<16><<<grid, kT, smem, st>>>(*w, b, values, fb);
+            }
         }
         note_launch(1);
     }
     return cuda_status(cudaGetLastError());
+}
+
+extern "C" size_t stwo_b200_cs_export_tiles_words(uint32_t n_rows) { return n_rows < (u32)kXRows ? 0 : (size_t)(n_rows / kXRows) * kXTileWords; }
+extern "C" int32_t stwo_b200_cs_export_tiles_build(const stwo_b200_cs_wiring *hw, uint32_t *tiles, uint32_t *cap_out) {
+    if (!hw || !tiles || !cap_out || !hw->a_wire || !hw->b_wire || !hw->c_wire || !hw->op || hw->n_rows < (u32)kXRows || (hw->n_rows % kXRows) || hw->kind > 1)
+        return STWO_B200_E_BAD_ARG;
+    if (hw->kind == 1 ? (!hw->op2 || !hw->op3 || !hw->op4) : !hw->enforce_c_m31) return STWO_B200_E_BAD_ARG;
+    u32 cap = 1;
+    const u32 *cols[3] = {hw->a_wire, hw->b_wire, hw->c_wire};
+    for (u32 rt = 0; rt < hw->n_rows / kXRows; rt++) {
+        u32 *m = tiles + (size_t)rt * kXTileWords;
+        memset(m, 0, kXTileWords * 4);
+        u32 *rec = m + 2 * kXListWords;
+        for (u32 half = 0; half < 2; half++) {
+            u32 *list = m + half * kXListWords;
+            u32 count = 0;
+            for (u32 r = 0; r < 32; r++) {
+                const u32 row = rt * kXRows + half * 32 + r;
+                u32 x = 0;
+                for (u32 o = 0; o < 3; o++) {                  // first-appearance order: a gate chain gets consecutive slots
+                    const u32 v = cols[o][row];
+                    u32 k = 0;
+                    while (k < count && list[1 + k] != v) k++;
+                    if (k == count) list[1 + count++] = v;
+                    x |= k << (8 * o);
+                }
+                if (hw->kind == 1) {
+                    if (hw->op2[row] > 1 || hw->op3[row] > 1 || hw->op4[row] > 1) return STWO_B200_E_BAD_ARG;      // not a selector: no packed form
+                    x |= (hw->op2[row] ? XF_C1 : 0u) | (hw->op3[row] ? XF_OP3 : 0u) | (hw->op4[row] ? XF_OP4 : 0u);
+                } else if (hw->enforce_c_m31[row]) x |= XF_C1;
+                if (hw->op_follows_c && hw->op_follows_c[row]) x |= XF_FOLLOWS;
+                rec[2 * (half * 32 + r)] = x;
+                rec[2 * (half * 32 + r) + 1] = hw->op[row];
+            }
+            list[0] = count;
+            if (count > cap) cap = count;
+        }
+        // a row that repeats the wires and constants of an earlier row of the tile (the padding rows above all) checks nothing new
+        for (u32 r = 1; r < (u32)kXRows; r++) {
+            const u32 row = rt * kXRows + r;
+            for (u32 q = (r & 32u); q < r; q++) {              // same half: the slots of the two halves are not comparable
+                if (((rec[2 * q] ^ rec[2 * r]) & ~XF_SKIP) == 0 && rec[2 * q + 1] == rec[2 * r + 1] && cols[0][rt * kXRows + q] == cols[0][row] &&
+                    cols[1][rt * kXRows + q] == cols[1][row] && cols[2][rt * kXRows + q] == cols[2][row]) { rec[2 * r] |= XF_SKIP; break; }
+            }
+        }
+    }
+    *cap_out = cap;
+    return STWO_B200_OK;
 }
 
 extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const stwo_b200_cs_values *hv, uint32_t *trace,

@@ -227,6 +227,30 @@ HD bool gate_ok(qm31_t va, qm31_t vb, qm31_t vc, u32 op, u32 enforce_c_m31) {
     if (enforce_c_m31 && (vc.v[1] | vc.v[2] | vc.v[3])) ok = false;
     return ok;
 }
+// The same check split over TWO lanes: lane `part` (0 / 1) verifies the CM31 half (coordinates 2 part, 2 part + 1) of c.  Both parts run
+// the same instruction stream (operands are selected, not branched on), so a warp = 16 items x 2 parts stays convergent on one row, and
+// each lane pays for two of the four CM31 products of the QM31 multiplication.  ok(part 0) && ok(part 1) == gate_ok.
+HD bool gate_ok_half(qm31_t va, qm31_t vb, qm31_t vc, u32 op, u32 enforce_c_m31, u32 part) {
+    const cm31_t a_lo = qm31::lo(va), a_hi = qm31::hi(va), b_lo = qm31::lo(vb), b_hi = qm31::hi(vb);
+    const cm31_t got = part ? qm31::hi(vc) : qm31::lo(vc);
+    cm31_t want;
+    if (op == 1) want = part ? cm31::add(a_hi, b_hi) : cm31::add(a_lo, b_lo);
+    else {
+        // lo = a_lo b_lo + (2 + i) a_hi b_hi ; hi = a_lo b_hi + a_hi b_lo
+        const cm31_t y1 = part ? b_hi : b_lo, y2 = part ? b_lo : b_hi;
+        const cm31_t p1 = cm31::mul(a_lo, y1), p2 = cm31::mul(a_hi, y2);
+        const cm31_t tw = cm31::mk(m31::subc(m31::addc(p2.a, p2.a), p2.b), m31::addc(m31::addc(p2.b, p2.b), p2.a));
+        const cm31_t prod = cm31::add(p1, part ? p2 : tw);
+        if (op == 0) want = prod;
+        else {
+            const cm31_t sum = part ? cm31::add(a_hi, b_hi) : cm31::add(a_lo, b_lo);
+            want = cm31::add(cm31::mul_m31(sum, op), cm31::mul_m31(prod, m31::subc(1, op)));
+        }
+    }
+    bool ok = want.a == got.a && want.b == got.b;
+    if (enforce_c_m31 && (part ? (vc.v[2] | vc.v[3]) : vc.v[1])) ok = false;
+    return ok;
+}
 // check_arithmetics of the Plonk-without-Poseidon system (plonk_without_poseidon.rs:410-599): the selectors pick one of six gates
 HD bool gate_ok_without(qm31_t a, qm31_t b, qm31_t c, u32 op1, u32 op2, u32 op3, u32 op4) {
     if (op2 > 1 || op3 > 1 || op4 > 1) return false;

@@ -186,6 +186,13 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
     }
 }
 }
+// check_arithmetics of one row: the whole gate and its two-lane split (tape::gate_ok_half, what the export kernel runs)
+extern "C" int hs_gate_ok(const u32 *a, const u32 *b, const u32 *c, u32 op, u32 enforce) {
+    return tape::gate_ok(qm31::mk(a[0], a[1], a[2], a[3]), qm31::mk(b[0], b[1], b[2], b[3]), qm31::mk(c[0], c[1], c[2], c[3]), op, enforce);
+}
+extern "C" int hs_gate_ok_half(const u32 *a, const u32 *b, const u32 *c, u32 op, u32 enforce, u32 part) {
+    return tape::gate_ok_half(qm31::mk(a[0], a[1], a[2], a[3]), qm31::mk(b[0], b[1], b[2], b[3]), qm31::mk(c[0], c[1], c[2], c[3]), op, enforce, part);
+}
 // permutations of the recorded circuit that name a slot of the native verifier's record
 extern "C" u32 hs_circuit_hint_count(void *h) {
     RecordedCircuit *r = (RecordedCircuit *)h;

@@ -95,3 +95,37 @@ def test_hash_node_and_paths(hostsim, orc, rng):
             hostsim.hs_path_root(ctypes.byref(shape), ctypes.c_uint32(idx), O.vp(cols), O.vp(sib), O.vp(out))
             assert (out == O.path_root_mixed(depth, layers, idx, cols, sib)).all()
         assert pkg.path_perms(shape) == sum((n + 7) // 8 + 1 for n in layers.values()) + depth
+
+
+def test_gate_check_split_over_two_lanes(hostsim, rng):
+    """tape::gate_ok_half (the export kernel's fused check_arithmetics: one lane per CM31 half of the gate) == tape::gate_ok, on
+    satisfied rows of every gate kind and on rows with one corrupted coordinate (constraint_system/src/plonk_with_poseidon.rs:337-380)"""
+    import oracle_py as O
+    P = O.P
+
+    def qmul(x, y):
+        out = np.zeros(4, dtype=np.uint32)
+        hostsim.hs_qm31_mul(O.vp(x), O.vp(y), O.vp(out))
+        return out
+    n_bad = 0
+    for k in range(600):
+        a = rng.integers(0, P, 4, dtype=np.uint32)
+        b = rng.integers(0, P, 4, dtype=np.uint32) if k % 5 else np.zeros(4, dtype=np.uint32)
+        op = [0, 1, int(rng.integers(2, P))][k % 3]
+        s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+        prod = qmul(a, b)
+        c = ((s.astype(np.uint64) * op + prod.astype(np.uint64) * ((1 - op) % P)) % P).astype(np.uint32)
+        enforce = 1 if (k % 7 == 0 and not c[1:].any()) else 0
+        for corrupt in (None, k % 4):
+            cc = c.copy()
+            if corrupt is not None:
+                cc[corrupt] = (int(cc[corrupt]) + 1 + k) % P
+            whole = hostsim.hs_gate_ok(O.vp(a), O.vp(b), O.vp(cc), op, enforce)
+            halves = hostsim.hs_gate_ok_half(O.vp(a), O.vp(b), O.vp(cc), op, enforce, 0) and hostsim.hs_gate_ok_half(O.vp(a), O.vp(b), O.vp(cc), op, enforce, 1)
+            assert bool(whole) == bool(halves) == (corrupt is None), (k, corrupt)
+            n_bad += corrupt is not None
+        # enforce_c_m31 with a non-M31 c: both forms reject
+        assert not hostsim.hs_gate_ok(O.vp(a), O.vp(b), O.vp(c), op, 1) or not c[1:].any()
+        h = hostsim.hs_gate_ok_half(O.vp(a), O.vp(b), O.vp(c), op, 1, 0) and hostsim.hs_gate_ok_half(O.vp(a), O.vp(b), O.vp(c), op, 1, 1)
+        assert bool(h) == bool(hostsim.hs_gate_ok(O.vp(a), O.vp(b), O.vp(c), op, 1))
+    assert n_bad == 600
