@@ -32,6 +32,8 @@ extern "C" {
 #define STWO_B200_E_NO_DEVICE (-1000)
 #define STWO_B200_E_BAD_ARG (-1001)
 #define STWO_B200_E_SHAPE (-1002)
+#define STWO_B200_E_NO_NCCL (-1003)   /* libnccl.so.2 could not be loaded (multi-GPU entry points only) */
+#define STWO_B200_E_NCCL (-1004)      /* an NCCL call failed */
 #define STWO_B200_MAX_DEPTH 32
 
 /* library / device lifecycle.  init selects the device for the calling thread and creates the
@@ -168,6 +170,10 @@ int32_t stwo_b200_shape_from_config(const stwo_b200_pcs_config *config, uint32_t
                                       (from_stwo_proof, decommit.rs:44-183).  Same record; kept as the checker of the default. */
 #define STWO_B200_VERIFY_ONE_STREAM 4u /* do not slice the batch over the library's stream pool */
 #define STWO_B200_VERIFY_TIMED 2u  /* record CUDA events between the stage kernels (read with stwo_b200_verify_stage_ms) */
+/* stop after a stage (the stage-level entry points below use these; the batch then runs on one stream) */
+#define STWO_B200_VERIFY_UPTO_TRANSCRIPT 0x100u  /* parse, transcript, PoW, query draws, logup sum, OODS */
+#define STWO_B200_VERIFY_UPTO_ANSWERS 0x200u     /* + commitment-tree decommitments, DEEP quotient answers */
+#define STWO_B200_VERIFY_UPTO_FOLDS 0x400u       /* + circle / line folds, last-layer evaluation */
 /* stage kernels in launch order: fiat_shamir, single_tree, group, answer, folds, pair_tree, single_path, pair_path, verdict */
 #define STWO_B200_N_STAGE_KERNELS 9
 /* device time of each stage kernel of the last STWO_B200_VERIFY_TIMED batch on this thread (synchronises) */
@@ -239,6 +245,55 @@ typedef struct {
 #define STWO_B200_FETCH_RECORD_TREES 11   /* u32: trees of this proof whose part of the record is complete (4 + 1 + n_inner = all) */
 int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
                                uint32_t what, void *out, size_t out_bytes, void *stream);
+
+/* every proof of the batch at once (what = DETAIL .. LAST_EVALS): the per-proof arrays above, n_proofs of them back to back */
+int32_t stwo_b200_verify_fetch_batch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t what,
+                                     void *out, size_t out_bytes, void *stream);
+
+/* ---- stage-level entry points: replace ONE hint stage of the reference for a batch (host blobs in, host arrays out) ----------
+ * All proofs must share the shape config + the statement log sizes of the first parsable blob imply; others are rejected at
+ * STAGE_PARSE.  verdict / stage (n_proofs bytes each, may be NULL) report what failed UP TO the stage that was run.
+ *
+ * FiatShamirHints::new (components/hints/src/fiat_shamir.rs:69-307) + FiatShamirResults::compute's values
+ * (components/recursive/fiat_shamir/src/lib.rs:31-176): transcript replay, PoW, query draws, logup sum, OODS check. */
+int32_t stwo_b200_channel_replay_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs, const stwo_b200_pcs_config *config,
+                                       const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs,
+                                       stwo_b200_verify_detail *out /* n_proofs */, uint8_t *verdict, uint8_t *stage);
+/* AnswerHints::compute (components/hints/src/answer.rs:40-48) / AnswerResults::compute values
+ * (components/recursive/answer/src/lib.rs:34-382): answers n_proofs x 3 x n_queries x 4 words (log-size groups descending),
+ * domain_points (optional) n_proofs x 3 x n_queries x 2. */
+int32_t stwo_b200_fri_answers_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs, const stwo_b200_pcs_config *config,
+                                    const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs, uint32_t *answers,
+                                    uint32_t *domain_points, uint8_t *verdict, uint8_t *stage);
+/* FirstLayerHints / InnerLayersHints::compute (components/hints/src/folding.rs:326-363,481-595) / FoldingResults::compute values
+ * (components/recursive/folding/src/lib.rs:12-205): circle_folds n x 3 x n_queries x 4, line_folds n x 32 x n_queries x 4
+ * (rows >= n_inner unused), last_evals n x n_queries x 4; any of the three may be NULL. */
+int32_t stwo_b200_fri_fold_batch(const uint8_t *const *blobs, const size_t *lens, uint32_t n_proofs, const stwo_b200_pcs_config *config,
+                                 const uint32_t *input_idx, const uint32_t *input_vals, uint32_t n_inputs, uint32_t *circle_folds,
+                                 uint32_t *line_folds, uint32_t *last_evals, uint8_t *verdict, uint8_t *stage);
+/* Poseidon31MerkleHasher::hash_column_get_capacity (call site components/hints/src/folding.rs:77; restated at
+ * primitives/merkle/src/lib.rs:141-181) for n independent column vectors: cols n x n_cols words, out n x 8 words. */
+int32_t stwo_b200_hash_column_capacity_batch(const uint32_t *cols, uint32_t n_cols, size_t n, uint32_t *out);
+int32_t stwo_b200_hash_column_capacity_batch_dev(const uint32_t *cols, uint32_t n_cols, size_t n, uint32_t *out, void *stream);
+
+/* ---- multi-GPU: one process per GPU, proofs sharded in contiguous blocks, NCCL only for the two gathers -------
+ * The block [lo, hi) of `rank`: the first n % world ranks hold one proof more. */
+int32_t stwo_b200_shard_range(uint64_t n, uint32_t rank, uint32_t world, uint64_t *lo, uint64_t *hi);
+/* NCCL communicator over the ranks' devices: rank 0 calls comm_unique_id and hands the 128 bytes to the others (any side
+ * channel), every rank then calls comm_init after stwo_b200_init.  libnccl.so.2 is loaded on first use. */
+int32_t stwo_b200_comm_unique_id(uint8_t id[128]);
+int32_t stwo_b200_comm_init(const uint8_t id[128], uint32_t rank, uint32_t world, void **comm);
+int32_t stwo_b200_comm_destroy(void *comm);
+/* all-gather of the ranks' (verdict, stage) bytes into proof order on every rank; DEVICE pointers; scratch: DEVICE, at least
+ * stwo_b200_gather_verdicts_scratch_bytes.  world == 1: a copy, comm may be NULL. */
+size_t stwo_b200_gather_verdicts_scratch_bytes(uint32_t world, uint64_t n_total);
+int32_t stwo_b200_gather_verdicts(void *comm, uint32_t rank, uint32_t world, uint64_t n_total, const uint8_t *verdict_local,
+                                  const uint8_t *stage_local, uint8_t *verdict_all, uint8_t *stage_all, void *scratch, size_t scratch_bytes,
+                                  void *stream);
+/* gather of per-proof arrays (trace columns: words_per_proof = 13 * n_rows) of every rank's block onto rank dst in proof order;
+ * values_all (rank dst only): n_total x words_per_proof words. */
+int32_t stwo_b200_gather_trace_columns(void *comm, uint32_t rank, uint32_t world, uint32_t dst, uint64_t n_total, size_t words_per_proof,
+                                       const uint32_t *values_local, uint32_t *values_all, void *stream);
 
 /* ---- K6 / K7: the constraint system on the device ----------------------------------------------------------------------
  * The flat image of PlonkWithPoseidonConstraintSystem (constraint_system/src/plonk_with_poseidon.rs:18-41) after pad().
@@ -320,7 +375,7 @@ typedef struct {
 #define STWO_B200_T_EPOSEIDON 18
 
 /* K6: variables[] (and the Poseidon flow) of every batch item from its witness stream (n_input_words words per item,
- * lane-interleaved like the values).  Replaces the `value` arithmetic of every DSL call: primitives/fields/src/*.rs,
+ * lane-interleaved like the values).  Replaces the `value` arithmetic of every DSL call: primitives/fields/src/{m31,cm31,qm31}.rs,
  * primitives/bits/src/lib.rs:48-82, primitives/poseidon31/src/lib.rs:282-407, plonk_with_poseidon.rs:141-281. */
 int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
                                    void *stream);
@@ -348,6 +403,14 @@ int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo
 int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                       const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
                                       uint32_t *preprocessed, uint32_t *values, int64_t *first_bad, void *stream);
+/* PoseidonFlow export for a batch with lanes = 32: the flow the tape evaluation recorded as plain per-item arrays,
+ * padded to stwo_b200_cs_flow_padded_len(n_flow) = max(32, ceil(n_flow / 16) * 16) entries like pad() (plonk_with_poseidon.rs:296-321).
+ * pad_constants: HOST, 24 words = CONSTANT_1, CONSTANT_2, CONSTANT_3 (plonk_with_poseidon.rs:13-15; their values live in the stwo
+ * dependency, not in the reference tree -- the caller supplies them); pad_scratch: DEVICE, 32 words.
+ * flow_hash_out: n_batch x n_pad x 32 words (PoseidonEntry.hash of entries 1..4), flow_swap_out: n_batch x n_pad bytes. */
+uint32_t stwo_b200_cs_flow_padded_len(uint32_t n_flow);
+int32_t stwo_b200_cs_export_flow_dev(const stwo_b200_cs_values *v, uint32_t n_flow, const uint32_t *pad_constants, uint32_t *pad_scratch,
+                                     uint32_t *flow_hash_out, uint8_t *flow_swap_out, void *stream);
 /* Host entry for ONE constraint system whose values were produced on the host (what the finalisation block of every
  * example does: cs.check_arithmetics(); cs.populate_logup_arguments(); cs.check_poseidon_invocations();
  * cs.generate_plonk_with_poseidon_circuit()  -- examples/single-proof/src/main.rs:85-90).  Pointers in w / v are HOST
@@ -369,7 +432,7 @@ typedef struct {
 } stwo_b200_circuit_info;
 int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,
                                           uint32_t n_inputs, uint32_t multipliers, stwo_b200_circuit **out);
-/* The last-layer circuit of examples/last-layer/src/main.rs:26-97 (components/last/*) over the Plonk-without-Poseidon
+/* The last-layer circuit of examples/last-layer/src/main.rs:26-97 (the components/last crates) over the Plonk-without-Poseidon
  * system: every Fiat-Shamir output and opening is a public input (n_public_inputs of them, in the order of main.rs:102-185),
  * the hashes are recomputed by the emulated Poseidon2 gadget (primitives/poseidon31/src/emulated.rs).  The trace pass of such
  * a circuit writes an 8-column preprocessed block and the same 13 per-proof value columns (the last one is op1). */
@@ -410,6 +473,9 @@ int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const uint32_t *
                                           uint32_t flags, uint32_t *preprocessed, uint32_t *values, int64_t *bad_row, int64_t *bad_flow,
                                           void *stream);
 int32_t stwo_b200_circuit_stage_ms(float *ms /* [STWO_B200_N_TRACE_STAGES] */);
+/* PoseidonFlow of the batch stwo_b200_circuit_trace_batch_dev just traced (same circuit workspace): see stwo_b200_cs_export_flow_dev */
+int32_t stwo_b200_circuit_export_flow_dev(stwo_b200_circuit *c, uint32_t n_proofs, void *circuit_workspace, size_t circuit_workspace_bytes,
+                                          const uint32_t *pad_constants, uint32_t *flow_hash_out, uint8_t *flow_swap_out, void *stream);
 #define STWO_B200_CFETCH_VARIABLES 0      /* n_vars x 4 words of proof p */
 #define STWO_B200_CFETCH_FLOW_HASH 1      /* n_flow x 32 words */
 #define STWO_B200_CFETCH_FLOW_SWAP 2      /* n_flow bytes */

@@ -15,6 +15,8 @@ OK = 0
 E_NO_DEVICE = -1000
 E_BAD_ARG = -1001
 E_SHAPE = -1002
+E_NO_NCCL = -1003
+E_NCCL = -1004
 
 
 class PathShape(ctypes.Structure):
@@ -43,7 +45,7 @@ class StwoB200Error(RuntimeError):
         self.status = status
         if status <= -1000:
             what = {E_NO_DEVICE: "no sm_100 CUDA device / library not initialised", E_BAD_ARG: "bad argument",
-                    E_SHAPE: "unsupported shape"}.get(status, "error")
+                    E_SHAPE: "unsupported shape", E_NO_NCCL: "libnccl.so.2 not loadable", E_NCCL: "NCCL call failed"}.get(status, "error")
         else:
             what = "cudaError %d" % (-status)
         super().__init__("%s failed: %s (status %d)" % (fn, what, status))
@@ -164,6 +166,22 @@ SIGNATURES = {
     "stwo_b200_verify_proofs_batch": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp]),
     "stwo_b200_verify_stage_ms": (_i32, [_vp]),
     "stwo_b200_verify_fetch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _u32, _vp, _sz, _vp]),
+    "stwo_b200_verify_fetch_batch": (_i32, [_vp, _PSHAPE_P, _u32, _u32, _vp, _sz, _vp]),
+    "stwo_b200_channel_replay_batch": (_i32, [_vp, _vp, _u32, _CFG_P, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "stwo_b200_fri_answers_batch": (_i32, [_vp, _vp, _u32, _CFG_P, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "stwo_b200_fri_fold_batch": (_i32, [_vp, _vp, _u32, _CFG_P, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_hash_column_capacity_batch": (_i32, [_vp, _u32, _sz, _vp]),
+    "stwo_b200_hash_column_capacity_batch_dev": (_i32, [_vp, _u32, _sz, _vp, _vp]),
+    "stwo_b200_shard_range": (_i32, [_u64, _u32, _u32, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "stwo_b200_comm_unique_id": (_i32, [_vp]),
+    "stwo_b200_comm_init": (_i32, [_vp, _u32, _u32, ctypes.POINTER(_vp)]),
+    "stwo_b200_comm_destroy": (_i32, [_vp]),
+    "stwo_b200_gather_verdicts_scratch_bytes": (_sz, [_u32, _u64]),
+    "stwo_b200_gather_verdicts": (_i32, [_vp, _u32, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "stwo_b200_gather_trace_columns": (_i32, [_vp, _u32, _u32, _u32, _u64, _sz, _vp, _vp, _vp]),
+    "stwo_b200_cs_flow_padded_len": (_u32, [_u32]),
+    "stwo_b200_cs_export_flow_dev": (_i32, [_VAL_P, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "stwo_b200_circuit_export_flow_dev": (_i32, [_vp, _u32, _vp, _sz, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_eval_tape_dev": (_i32, [_TAPE_P, _u32, _vp, _VAL_P, _vp]),
     "stwo_b200_cs_eval_level_clock": (_i32, [_vp]),
     "stwo_b200_cs_check_arithmetics_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp]),

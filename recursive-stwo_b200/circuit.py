@@ -94,6 +94,26 @@ class VerifierCircuit:
                   self._ws.numel(), flags, p(out["preprocessed"]), p(out["values"]), p(out["bad_row"]), p(out["bad_flow"]), _stream())
         return out
 
+    def export_flow(self, pad_constants):
+        """The prover-facing PoseidonFlow of the batch the last trace() call traced, padded like pad() with the
+        caller's CONSTANT_1 / CONSTANT_2 / CONSTANT_3 (pad_constants: [3, 8] M31 words; plonk_with_poseidon.rs:13-15,296-321).
+        -> dict(hash=[n, n_flow_padded, 32] int32, swap=[n, n_flow_padded] uint8 on the device,
+                wire=[n_flow_padded, 4], swap_addr=[n_flow_padded] numpy: the wiring part, zero for the padding)"""
+        import torch
+        from .hashing import _dptr, _stream
+        n, n_pad = self._n, self.info.n_flow_padded
+        dev = self._ws.device
+        h = torch.empty((n, n_pad, 32), dtype=torch.int32, device=dev)
+        sw = torch.empty((n, n_pad), dtype=torch.uint8, device=dev)
+        pc = np.ascontiguousarray(pad_constants, dtype=np.uint32).reshape(24)
+        _lib.call("stwo_b200_circuit_export_flow_dev", self._h, n, _dptr(self._ws), self._ws.numel(), pc.ctypes.data_as(ctypes.c_void_p), _dptr(h),
+                  _dptr(sw), _stream())
+        wire = np.zeros((n_pad, 4), dtype=np.uint32)
+        addr = np.zeros(n_pad, dtype=np.uint32)
+        wire[: self.info.n_flow] = self.column("flow_wire").reshape(-1, 4)
+        addr[: self.info.n_flow] = self.column("flow_swap_addr")
+        return dict(hash=h, swap=sw, wire=wire, swap_addr=addr)
+
     def stage_ms(self):
         ms = (ctypes.c_float * len(TRACE_STAGES))()
         _lib.call("stwo_b200_circuit_stage_ms", ms)

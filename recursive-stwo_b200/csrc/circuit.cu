@@ -328,3 +328,20 @@ extern "C" int32_t stwo_b200_circuit_fetch(const stwo_b200_circuit *c, const voi
     STWO_CUDA(cudaMemcpy2DAsync(out, elem, src + (grp * n * 32 + lane) * elem, 32 * elem, elem, n, cudaMemcpyDeviceToHost, st));
     return cuda_status(cudaStreamSynchronize(st));
 }
+
+// The prover-facing PoseidonFlow of a traced batch: what generate_plonk_with_poseidon_circuit hands to stwo's
+// prove_plonk_with_poseidon besides the trace (plonk_with_poseidon.rs:117-128,521-628), padded like pad() (:296-321) with the
+// caller's CONSTANT_1/2/3 (their values live in the absent stwo dependency: `permute(C1 || C1) = C2 || C3`, :496-517).
+// flow_hash_out: n_proofs x n_flow_padded x 32 words, flow_swap_out: n_proofs x n_flow_padded bytes.  The entries' wires and swap
+// addresses are wiring: stwo_b200_circuit_get_column(FLOW_WIRE / FLOW_SWAP_ADDR), zero for the padding.
+extern "C" int32_t stwo_b200_circuit_export_flow_dev(stwo_b200_circuit *c, uint32_t n_proofs, void *circuit_workspace, size_t circuit_workspace_bytes,
+                                                     const uint32_t *pad_constants, uint32_t *flow_hash_out, uint8_t *flow_swap_out, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!c || !n_proofs || !circuit_workspace || !pad_constants || !flow_hash_out || !flow_swap_out) return STWO_B200_E_BAD_ARG;
+    const RecordedCircuit &r = *c->rec;
+    if (r.cs.p->without()) return STWO_B200_E_BAD_ARG;              // the Plonk-without-Poseidon system has no flow
+    const Carve k = carve(r, n_proofs, (uint8_t *)circuit_workspace);
+    if (k.bytes > circuit_workspace_bytes) return STWO_B200_E_BAD_ARG;
+    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0};
+    return stwo_b200_cs_export_flow_dev(&v, r.cs.p->num_poseidon_invocations(), pad_constants, k.status + 8, flow_hash_out, flow_swap_out, stream);
+}

@@ -461,6 +461,36 @@ __global__ void __launch_bounds__(kXThreads, 2) k_cs_export_vals_stream(stwo_b20
         // no trailing barrier: the next trip's first barrier orders this trip's reads before anything is overwritten
     }
 }
+// ---- K7: PoseidonFlow export ---------------------------------------------------------------------------------------------------
+// The flow the tape evaluation recorded (lane-interleaved: [group][entry][32 words][32 lanes]) as plain per-item arrays
+// hash[item][entry][32], swap[item][entry], padded to n_pad entries the way pad() does (plonk_with_poseidon.rs:296-321): entries
+// (wire 0, C1), (0, C1), (0, C2), (0, C3), swap = false.  A warp transposes one (group, entry) tile through shared memory: reads
+// are 128-byte rows across the lanes, writes the 128 contiguous bytes of one item's entry.
+__global__ void __launch_bounds__(256) k_cs_export_flow(Batch b, u32 n_pad, const u32 *__restrict__ pad_hash /* 32 words */, u32 *hash_out, uint8_t *swap_out) {
+    __shared__ u32 tile[8][32][33];
+    const u32 warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const u32 n_groups = (b.n_batch + 31) / 32;
+    const size_t n_tiles = (size_t)n_groups * n_pad;
+    for (size_t t = blockIdx.x * (size_t)8 + warp; t < n_tiles; t += (size_t)gridDim.x * 8) {
+        const u32 grp = (u32)(t / n_pad), e = (u32)(t % n_pad);
+        const u32 item = grp * 32 + lane;
+        if (e < b.n_flow) {
+            const u32 *src = b.flow_hash + ((size_t)grp * b.n_flow + e) * 32 * 32;
+#pragma unroll 8
+            for (u32 w = 0; w < 32; w++) tile[warp][w][lane] = src[w * 32 + lane];
+            __syncwarp();
+            for (u32 it = 0; it < 32; it++)
+                if (grp * 32 + it < b.n_batch) hash_out[((size_t)(grp * 32 + it) * n_pad + e) * 32 + lane] = tile[warp][lane][it];
+            __syncwarp();
+            if (item < b.n_batch) swap_out[(size_t)item * n_pad + e] = b.flow_swap[((size_t)grp * b.n_flow + e) * 32 + lane];
+        } else {
+            const u32 v = __ldg(pad_hash + lane);
+            for (u32 it = 0; it < 32; it++)
+                if (grp * 32 + it < b.n_batch) hash_out[((size_t)(grp * 32 + it) * n_pad + e) * 32 + lane] = v;
+            if (item < b.n_batch) swap_out[(size_t)item * n_pad + e] = 0;
+        }
+    }
+}
 __global__ void k_fill64(unsigned long long *p, size_t n, unsigned long long v) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -637,6 +667,32 @@ extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, c
         }
         note_launch(1);
     }
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" uint32_t stwo_b200_cs_flow_padded_len(uint32_t n_flow) {
+    const uint32_t r = (n_flow + 15) / 16 * 16;          // max(N_LANES * 2, n.div_ceil(16) * 16), plonk_with_poseidon.rs:297
+    return r < 32 ? 32 : r;
+}
+extern "C" int32_t stwo_b200_cs_export_flow_dev(const stwo_b200_cs_values *v, uint32_t n_flow, const uint32_t *pad_constants, uint32_t *pad_scratch,
+                                                uint32_t *flow_hash_out, uint8_t *flow_swap_out, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!values_ok(v) || v->lanes != 32 || !pad_constants || !pad_scratch || !flow_hash_out || !flow_swap_out || (n_flow && (!v->flow_hash || !v->flow_swap)))
+        return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    // padding entry = (C1, C1, C2, C3): 32 words on the device
+    uint32_t pad[32];
+    for (int k = 0; k < 8; k++) { pad[k] = pad[8 + k] = pad_constants[k]; pad[16 + k] = pad_constants[8 + k]; pad[24 + k] = pad_constants[16 + k]; }
+    for (int k = 0; k < 32; k++) if (pad[k] >= M31_P) return STWO_B200_E_BAD_ARG;
+    STWO_CUDA(cudaMemcpyAsync(pad_scratch, pad, sizeof pad, cudaMemcpyHostToDevice, st));
+    STWO_CUDA(cudaStreamSynchronize(st));                 // `pad` is a stack buffer
+    Batch b = batch_of(v, 4, n_flow);
+    const u32 n_pad = stwo_b200_cs_flow_padded_len(n_flow);
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const size_t n_tiles = (size_t)((v->n_batch + 31) / 32) * n_pad, want = (n_tiles + 7) / 8, cap = (size_t)n_sm * 8;
+    k_cs_export_flow<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(b, n_pad, pad_scratch, flow_hash_out, flow_swap_out);
+    note_launch(1);
     return cuda_status(cudaGetLastError());
 }
 

@@ -456,7 +456,8 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
     g_timed_valid = false;
     if (host_blobs)      // the offsets are needed by every slice: they go first, on the caller's stream
         STWO_CUDA(cudaMemcpyAsync(const_cast<uint64_t *>(blob_off), host_blob_off, ((size_t)n_proofs + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (timed || n_proofs < 256 || (flags & STWO_B200_VERIFY_ONE_STREAM)) {
+    const u32 upto = flags & (STWO_B200_VERIFY_UPTO_TRANSCRIPT | STWO_B200_VERIFY_UPTO_ANSWERS | STWO_B200_VERIFY_UPTO_FOLDS);
+    if (timed || n_proofs < 256 || upto || (flags & STWO_B200_VERIFY_ONE_STREAM)) {
         if (host_blobs)
             STWO_CUDA(cudaMemcpyAsync(const_cast<uint32_t *>(blobs), host_blobs, host_blob_off[n_proofs] * 4, cudaMemcpyHostToDevice, st));
         // one stream, stage after stage (clean per-stage timings; small batches)
@@ -464,11 +465,21 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         if (timed && !g_ev[0]) for (int i = 0; i <= STWO_B200_N_STAGE_KERNELS; i++) STWO_CUDA(cudaEventCreate(&g_ev[i]));
         int e = 0;
 #define MARK() do { if (timed) cudaEventRecord(g_ev[e], st); e++; } while (0)
+        // stage-level callers (stwo_b200_channel_replay_batch / _fri_answers_batch / _fri_fold_batch) stop early; the verdict kernel
+        // then reports what failed so far
+        auto stop = [&](int launched) {
+            k_verdict<<<nblk(n), kT, 0, st>>>(ws, 0, n, verdict, stage);
+            note_launch(launched + 1);
+            return cuda_status(cudaGetLastError());
+        };
         MARK(); launch_parse_transcript(ws, 0, n, st); launch_oods(ws, 0, n, st);
+        if (upto & STWO_B200_VERIFY_UPTO_TRANSCRIPT) return stop(3);
         MARK(); launch_single_tree(ws, 0, n, st);
         MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
         MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
+        if (upto & STWO_B200_VERIFY_UPTO_ANSWERS) return stop(6);
         MARK(); launch_folds(ws, 0, n, st);
+        if (upto & STWO_B200_VERIFY_UPTO_FOLDS) return stop(7);
         MARK(); launch_pair_tree(ws, 0, n, st);
         MARK();
         if (path_kernels) k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, st>>>(ws, 0, n);
@@ -551,6 +562,34 @@ extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200
         case STWO_B200_FETCH_PAIR_HINTS: src = ws.pair_hints + (size_t)p * nf * nq * verify::PAIR_HINT_WORDS; bytes = nf * nq * verify::PAIR_HINT_WORDS * 4; break;
         case STWO_B200_FETCH_PERM_RECORD: src = ws.perm_out_of(p, 0); bytes = (size_t)ws.hint_total * 64; break;
         case STWO_B200_FETCH_RECORD_TREES: src = ws.hint_trees + p; bytes = 4; break;
+        default: return STWO_B200_E_BAD_ARG;
+    }
+    if (out_bytes < bytes) return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    STWO_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st));
+    return cuda_status(cudaStreamSynchronize(st));
+}
+
+// All proofs of a batch at once: the per-proof arrays of the workspace are contiguous, so a stage's results come back with one copy
+extern "C" int32_t stwo_b200_verify_fetch_batch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t what,
+                                                void *out, size_t out_bytes, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (!shape_ok(shape) || !n_proofs || !workspace || !out) return STWO_B200_E_BAD_ARG;
+    Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs;
+    verify::carve(ws, (uint8_t *)const_cast<void *>(workspace));
+    const size_t nq = shape->n_queries, n = n_proofs;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case STWO_B200_FETCH_DETAIL: src = ws.detail; bytes = n * sizeof(verify::Detail); break;
+        case STWO_B200_FETCH_DOMAIN_POINTS: src = ws.domain_points; bytes = n * fri::MAX_LOGS * nq * 8; break;
+        case STWO_B200_FETCH_ANSWERS: src = ws.answers; bytes = n * fri::MAX_LOGS * nq * 16; break;
+        case STWO_B200_FETCH_CIRCLE_FOLDS: src = ws.circle_folds; bytes = n * fri::MAX_LOGS * nq * 16; break;
+        case STWO_B200_FETCH_LINE_FOLDS: src = ws.line_folds; bytes = n * proof::MAX_INNER * nq * 16; break;
+        case STWO_B200_FETCH_LAST_EVALS: src = ws.last_evals; bytes = n * nq * 16; break;
         default: return STWO_B200_E_BAD_ARG;
     }
     if (out_bytes < bytes) return STWO_B200_E_BAD_ARG;

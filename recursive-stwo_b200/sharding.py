@@ -2,16 +2,76 @@
 contiguous block and the only collective is the gather of the per-proof verdict bytes (NCCL over NVLink on the GPU
 box, gloo in the CPU tests).  The reference has no equivalent (single-threaded, examples/multi-proofs/src/main.rs:67-139
 shares one constraint system); this is the layer north_star adds."""
+import ctypes
+
 import numpy as np
+
+from . import _lib
 
 
 def shard_range(n_items, rank, world):
-    """Contiguous block [lo, hi) of rank `rank` out of `world`; blocks differ by at most one item."""
-    if not 0 <= rank < world:
+    """Contiguous block [lo, hi) of rank `rank` out of `world`; blocks differ by at most one item (stwo_b200_shard_range)."""
+    lo, hi = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    if not 0 <= rank < world or _lib.load().stwo_b200_shard_range(n_items, rank, world, ctypes.byref(lo), ctypes.byref(hi)) != _lib.OK:
         raise ValueError("rank outside the world")
-    base, extra = divmod(n_items, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    return int(lo.value), int(hi.value)
+
+
+def shard_by_work(work, world):
+    """Contiguous blocks of a list of units with unequal cost (proofs of different shapes: cost ~ permutations x rows): cut points at
+    the multiples of total / world of the running cost, so no rank is pinned by the expensive units.  -> [(lo, hi)] * world"""
+    work = np.asarray(work, dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, len(work)
+    for r in range(1, world + 1):
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class Comm:
+    """NCCL communicator created through the library's own C entry points (stwo_b200_comm_*): what a non-Python host uses.  The
+    128-byte unique id travels over any side channel; here torch.distributed (already initialised by the launcher) broadcasts it."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.call("stwo_b200_comm_unique_id", idbuf.ctypes.data_as(ctypes.c_void_p))
+        t = torch.from_numpy(idbuf).to(device)
+        if world > 1:
+            dist.broadcast(t, src=0)
+        idbuf = t.cpu().numpy()
+        self._h = ctypes.c_void_p()
+        _lib.call("stwo_b200_comm_init", idbuf.ctypes.data_as(ctypes.c_void_p), rank, world, ctypes.byref(self._h))
+
+    def gather_verdicts(self, local_verdict, local_stage, n_total):
+        import torch
+        from .hashing import _dptr, _stream
+        dev = local_verdict.device
+        verdict = torch.empty(n_total, dtype=torch.uint8, device=dev)
+        stage = torch.empty(n_total, dtype=torch.uint8, device=dev)
+        nbytes = int(_lib.load().stwo_b200_gather_verdicts_scratch_bytes(self.world, n_total))
+        scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _lib.call("stwo_b200_gather_verdicts", self._h, self.rank, self.world, n_total, _dptr(local_verdict), _dptr(local_stage), _dptr(verdict),
+                  _dptr(stage), _dptr(scratch), nbytes, _stream())
+        return verdict, stage
+
+    def gather_trace_columns(self, local_values, n_total, dst=0):
+        import torch
+        from .hashing import _dptr, _stream
+        words = int(np.prod(local_values.shape[1:]))
+        out = torch.empty((n_total,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device) if self.rank == dst else None
+        _lib.call("stwo_b200_gather_trace_columns", self._h, self.rank, self.world, dst, n_total, words, _dptr(local_values.contiguous()),
+                  _dptr(out), _stream())
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.load().stwo_b200_comm_destroy(self._h)
+            self._h = None
 
 
 def gather_verdicts(local_verdict, local_stage, n_total, group=None):

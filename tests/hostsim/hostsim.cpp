@@ -186,6 +186,14 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
     }
 }
 }
+// the recorded tape in recording order (n x 4 words) and the permutation records (n x 12 words): analysis / tests
+extern "C" u32 hs_circuit_tape(void *h, u32 *ins_out, u32 *perms_out) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    const auto &c = *r->cs.p;
+    if (ins_out) memcpy(ins_out, c.tape_.data(), c.tape_.size() * 16);
+    if (perms_out) memcpy(perms_out, c.perms.data(), c.perms.size() * sizeof(tape::Perm));
+    return (u32)c.tape_.size();
+}
 // check_arithmetics of one row: the whole gate and its two-lane split (tape::gate_ok_half, what the export kernel runs)
 extern "C" int hs_gate_ok(const u32 *a, const u32 *b, const u32 *c, u32 op, u32 enforce) {
     return tape::gate_ok(qm31::mk(a[0], a[1], a[2], a[3]), qm31::mk(b[0], b[1], b[2], b[3]), qm31::mk(c[0], c[1], c[2], c[3]), op, enforce);

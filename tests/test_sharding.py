@@ -96,3 +96,26 @@ def test_gather_trace_columns_under_gloo(world, n_total, dst):
             assert out == want, rank
         else:
             assert out is None
+
+
+def test_shard_range_c_entry_and_work_sharding():
+    """stwo_b200_shard_range (the C entry a non-Python host calls; no device needed) = contiguous blocks differing by at most one; shard_by_work
+    balances unequal units (proofs of different shapes) by cost"""
+    import importlib
+    sh = importlib.import_module("recursive-stwo_b200.sharding")
+    for n in (0, 1, 7, 256, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            blocks = [sh.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(ValueError):
+        sh.shard_range(10, 4, 4)
+    work = [1] * 200 + [30] * 20 + [1] * 36          # twenty expensive units in the middle
+    blocks = sh.shard_by_work(work, 4)
+    assert blocks[0][0] == 0 and blocks[-1][1] == len(work) and all(blocks[r][1] == blocks[r + 1][0] for r in range(3))
+    cost = [sum(work[lo:hi]) for lo, hi in blocks]
+    assert max(cost) <= 1.25 * sum(work) / 4
+    by_count = [sum(work[lo:hi]) for lo, hi in (sh.shard_range(len(work), r, 4) for r in range(4))]
+    assert max(by_count) > 2 * max(cost) * 0.9
