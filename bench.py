@@ -42,11 +42,15 @@ FIXTURE = "small_proof.bin"
 # warp instructions one permutation executes in the path kernels (ncu smsp__inst_executed / permutations,
 # profiles/r01*_ncu.txt) — the unit of the integer-issue roofline
 LANE_OPS_PER_PERM = 4719
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per proof of shape S from the ncu --set full captures of the
-# 4096-proof step: profiles/r01y_k_tape_eval_grid_ncu.txt (5.14 + 5.22 GB), profiles/r01y_k_cs_export_vals_tiled_ncu.txt
-# (3.60 + 13.90 GB) and profiles/r01y_k_cs_check_poseidon_ncu.txt (2.37 + 0.06 GB)
-TRAFFIC_PER_PROOF = {"k_tape_eval_grid": (5.136187e9 + 5.222587e9) / 4096, "k_cs_export_vals_tiled": (3.598031e9 + 13.900619e9) / 4096,
-                     "k_cs_check_poseidon": (2.369094e9 + 0.055406e9) / 4096}
+
+
+def ncu_traffic(kernel, n_proofs):
+    """DRAM bytes per launch of `kernel` from a committed ncu capture at exactly this batch size (profiles/ncu_traffic.json), else None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(t[kernel][str(n_proofs)]["bytes"])
+    except Exception:
+        return None
 
 
 _JSON_OUT = None
@@ -198,10 +202,10 @@ def merkle_sweep(pkg, dev, log_n=20, C=8, Q=128, T=2, reps=3, hbm_peak=None):
     Returns the commit and the path legs timed apart: the commit streams C*4 B per leaf (HBM-bound for wide leaves), the
     paths are permutation-bound."""
     import torch
-    import oracle_py as O
+    S = importlib.import_module("recursive-stwo_b200.synth")
     n = 1 << log_n
-    cols = torch.from_numpy(np.stack([O.synth_m31(t, C * n).reshape(C, n) for t in range(T)]).view(np.int32)).to(dev)
-    idx = torch.from_numpy(np.stack([(O.splitmix64(t ^ 0xABCDEF, Q) & np.uint64(n - 1)).astype(np.uint32) for t in range(T)]).view(np.int32)).to(dev)
+    cols = torch.from_numpy(np.stack([S.synth_m31(t, C * n).reshape(C, n) for t in range(T)]).view(np.int32)).to(dev)
+    idx = torch.from_numpy(np.stack([(S.splitmix64(t ^ 0xABCDEF, Q) & np.uint64(n - 1)).astype(np.uint32) for t in range(T)]).view(np.int32)).to(dev)
     nodes = torch.empty((T, 2 * n - 1, 8), dtype=torch.int32, device=dev)
     rid = torch.arange(T, dtype=torch.int32, device=dev).repeat_interleave(Q).contiguous()
     shape = pkg.PathShape.make(log_n, {log_n: C})
@@ -248,47 +252,49 @@ def fixture_names():
 
 
 def multi_proofs_leg(pkg, sharding, rank, world, dev, n_total=256, reps=3):
-    """BASELINE configs[3] (examples/multi-proofs): 256 independent proofs = the 15 fixtures cycled, through the host entry
-    stwo_b200_verify_proofs_batch (any mix of shapes; grouping by shape and every copy inside the call), sharded over the
-    ranks in contiguous blocks.  Returns proofs/s over all ranks (wall clock around the host calls, max over ranks)."""
+    """BASELINE configs[3] (examples/multi-proofs): 256 independent proofs = the 15 fixtures cycled, VERIFIED AND TRACED (every proof's
+    verifier-circuit trace generated, checked and exported, like the headline step) through MixedBatch: grouped by shape, one recorded
+    circuit per shape, sharded over the ranks in contiguous blocks of the shape-sorted order cut by WORK (permutations per proof), not
+    by count -- the 80-query level1-5 / level4-5 proofs cost ~8x a small one.  Device time, max over ranks."""
     import torch
     import torch.distributed as dist
     d = os.path.join(ROOT, "tests", "golden", "proofs")
     names = fixture_names()
     blobs = {f: open(os.path.join(d, f), "rb").read() for f in names}
-    order = [names[i % len(names)] for i in range(n_total)]
-    lo, hi = sharding.shard_range(n_total, rank, world)
+    shape_of = {f: pkg.shape_for(blobs[f]) for f in names}
+    order = sorted((names[i % len(names)] for i in range(n_total)), key=lambda f: (tuple(shape_of[f].key()), f))
+    cost = [pkg.proof_perms(shape_of[f]) for f in order]
+    lo, hi = sharding.shard_by_work(cost, world)[rank]
     mine = order[lo:hi]
-    # the single-proof fixture carries one public input, the recursion fixtures three: two calls
-    small = [blobs[f] for f in mine if f.startswith("small")]
-    rest = [blobs[f] for f in mine if not f.startswith("small")]
+    # the single-proof fixture carries one public input, the recursion fixtures three: two resident batches
+    parts = [pkg.MixedBatch([blobs[f] for f in mine if f.startswith("small") == sm], inputs=pkg.INPUTS_SINGLE if sm else pkg.INPUTS_RECURSIVE)
+             for sm in (True, False) if any(f.startswith("small") == sm for f in mine)]
 
     def step():
-        bad = 0
-        if small:
-            v, _ = pkg.verify_proofs(small, inputs=pkg.INPUTS_SINGLE)
-            bad += int(v.sum())
-        if rest:
-            v, _ = pkg.verify_proofs(rest, inputs=pkg.INPUTS_RECURSIVE)
-            bad += int(v.sum())
-        return bad
+        return sum(int(mb.run(trace=True, export=True)[0].sum().item()) for mb in parts)
 
-    assert step() == 0, "every fixture must be accepted"
+    assert step() == 0, "every fixture must be accepted and every circuit consistent"
     step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(reps):
-        step()
+        for mb in parts:
+            mb.run(trace=True, export=True)
+    e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    t = torch.tensor([e0.elapsed_time(e1) / reps, float(sum(cost[lo:hi])), float(hi - lo)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item()) / reps
-    return {"config": "BASELINE configs[3]: 256 proofs = 15 fixtures cycled, host blobs -> verdicts, grouped by shape inside the call",
-            "proofs": n_total, "shapes": len({tuple(pkg.proof_shape(blobs[f]).key()) for f in names}), "ms_per_batch": dt * 1e3,
-            "proofs_per_sec": n_total / dt, "bytes_per_batch": sum(len(blobs[f]) for f in order)}
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax[0].item())
+    rows = sum(g.circuit.info.n_rows * len(g.ids) for mb in parts for g in mb.groups)
+    return {"config": "BASELINE configs[3]: 256 proofs = 15 fixtures cycled; verify + circuit trace (check + export) per proof; one recorded circuit per shape; "
+                      "ranks take contiguous blocks of the shape-sorted order cut by work",
+            "proofs": n_total, "shapes": len({tuple(shape_of[f].key()) for f in names}), "ms_per_batch": ms, "proofs_per_sec": n_total / (ms * 1e-3),
+            "max_rank_work_share": float(tmax[1].item()) / sum(cost), "max_rank_proofs": int(tmax[2].item()), "rank0_trace_rows": rows}
 
 
 def trace_gather_leg(sharding, values, rank, world, dev, n_each=256, reps=3):
@@ -388,7 +394,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--proofs", type=int, default=4096, help="proofs per GPU per step")
+    ap.add_argument("--proofs", type=int, default=4096, help="proofs per GPU per step (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --proofs per GPU; strong: --proofs in total, ceil(proofs / N) per GPU (BASELINE configs[4]: 4096 across 8 GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the K1 / Merkle-sweep side measurements")
@@ -418,7 +426,7 @@ def main():
     warmup = max(args.warmup, 3)
 
     blob = load_fixture()
-    n_total = args.proofs * world                       # weak scaling: --proofs per GPU
+    n_total = args.proofs * world if args.scaling == "weak" else args.proofs
     lo, hi = sharding.shard_range(n_total, rank, world)
     vb = pkg.VerifyBatch([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
     circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)       # recorded once per shape (host)
@@ -531,18 +539,22 @@ def main():
     dom = max(acc, key=acc.get)
     n_local = hi - lo
     sh = vb.shape
-    kernel_of = {"trace_eval": "k_tape_eval_grid", "trace_check_poseidon": "k_cs_check_poseidon", "trace_export": "k_cs_export_vals_tiled",
+    kernel_of = {"trace_eval": "k_tape_eval_grid", "trace_check_poseidon": "k_cs_check_poseidon", "trace_export": "k_cs_export_vals_stream",
                  "trace_check_arithmetics": "k_cs_check_arith", "trace_gather": "k_gather_witness", "fiat_shamir": "k_transcript16",
                  "single_tree": "k_single_tree_coop", "pair_tree": "k_pair_tree_coop", "folds": "k_folds_coop"}
 
-    # the HBM-bound kernel of the path: trace export, 3 x 16-byte variable reads + 13 x 4-byte column writes per (row, proof)
-    export_bytes = n_local * ci.n_rows * (3 * 16 + 13 * 4)
+    # the HBM-bound kernel of the path: trace export.  Algorithmic (compulsory) bytes per proof: variables[] read once (n_vars x 16 B) +
+    # 13 value columns written (n_rows x 13 x 4 B); the ~2.6 uses of a variable are served from L2 / shared memory, not from HBM.
+    export_bytes = n_local * (ci.n_vars * 16 + ci.n_rows * 13 * 4)
     export_gbs = export_bytes / (acc["trace_export"] * 1e-3) / 1e9
-    roofline_export = {"bound": "hbm", "kernel": "k_cs_export_vals_tiled", "achieved": export_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+    export_traffic = ncu_traffic("k_cs_export_vals_stream", n_local)
+    roofline_export = {"bound": "hbm", "kernel": "k_cs_export_vals_stream", "achieved": export_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                        "frac": export_gbs / pk["hbm_gbs"], "peak_src": pk["src"], "algorithmic_bytes_per_launch": export_bytes,
                        "launch_ms": acc["trace_export"], "share_of_step": acc["trace_export"] / total_ms,
-                       "traffic": TRAFFIC_PER_PROOF["k_cs_export_vals_tiled"] * n_local,
-                       "note": "check_arithmetics is fused into this pass; traffic < algorithmic bytes because variables are re-read from L2"}
+                       "traffic": export_traffic,
+                       "dram_frac": (export_traffic / (acc["trace_export"] * 1e-3) / 1e9 / pk["hbm_gbs"]) if export_traffic else None,
+                       "note": "check_arithmetics is fused into this pass; algorithmic bytes = variables once + 13 columns per proof; dram_frac = ncu DRAM "
+                               "bytes of a capture at this batch size / this run's launch time / peak (null without such a capture)"}
 
     # the busiest permutation kernel against the integer roofline (permutations each stage executes per proof: SURVEY App. C,
     # counted by the kernels themselves)
@@ -559,7 +571,7 @@ def main():
         "bound": "int32-issue", "kernel": kernel_of.get(hdom, "k_" + hdom), "achieved": achieved, "peak": pk["int_tlops"], "unit": "T lane-ops/s",
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
         "perms_per_launch": h_perms, "perms_per_sec": h_rate, "launch_ms": acc[hdom], "share_of_step": acc[hdom] / total_ms,
-        "traffic": TRAFFIC_PER_PROOF.get(kernel_of.get(hdom, ""), 0) * n_local or None,
+        "traffic": ncu_traffic(kernel_of.get(hdom, ""), n_local),
         "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r01y_k_cs_check_poseidon_ncu.txt); the "
                 "multiplier pipe bounds a permutation at ~6.1 G perms/s per GPU"}
     # `roofline` = the kernel with the largest share of the step
@@ -639,9 +651,9 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32 (M31)", "data": "synthetic",
-            "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": args.proofs, "mode": "full+trace",
+            "config": {"workload": "verify-batch", "fixture": FIXTURE, "proofs_per_gpu": hi - lo, "proofs_total": n_total, "mode": "full+trace",
                        "circuit": {"rows": ci.n_rows, "rows_unpadded": ci.n_rows_unpadded, "variables": ci.n_vars, "poseidon_flow": ci.n_flow,
                                    "tape_levels": ci.n_levels, "witness_words": ci.n_input_words},
                        "shape": dict(zip(("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last", "n_queries", "n_inner"), sh.key())),

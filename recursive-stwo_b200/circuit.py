@@ -147,3 +147,84 @@ class VerifierCircuit:
         out[9] = val[12]
         out[10:] = val[:12]
         return out
+
+
+_CIRCUITS = {}
+
+
+def cached_circuit(shape, inputs=INPUTS_RECURSIVE, multipliers=1, last_layer=False):
+    """VerifierCircuit per (shape, public inputs, multipliers): recording is host work that depends on the shape only
+    (examples/multi-proofs/src/main.rs:62-139 re-records for every proof; here once per shape and process)."""
+    key = (tuple(shape.key()), tuple(inputs[0]), tuple(map(tuple, inputs[1])), multipliers, last_layer)
+    if key not in _CIRCUITS:
+        _CIRCUITS[key] = VerifierCircuit(shape, inputs=inputs, multipliers=multipliers, last_layer=last_layer)
+    return _CIRCUITS[key]
+
+
+class MixedBatch:
+    """A batch of proofs of ANY mix of shapes kept resident on the device, verified and traced shape group by shape group: the
+    host-side mirror of examples/multi-proofs/src/main.rs:173-296 run as one batch (BASELINE configs[3]).  Every proof's verdict
+    comes back in the caller's order; the traces stay on the device per shape group (`groups[k].trace`).
+    config: allow-list of PcsConfigs (a blob claiming another one, or not parsing at all, is rejected at stage parse)."""
+
+    class Group:
+        pass
+
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, config=None, multipliers=1):
+        from .verifier import REFERENCE_CONFIGS, VerifyBatch, proof_shape, shape_for
+        config = REFERENCE_CONFIGS if config is None else config
+        self.n = len(blobs)
+        by_shape, self.unparsed = {}, []
+        for i, b in enumerate(blobs):
+            try:
+                by_shape.setdefault(tuple(shape_for(b, config).key()), []).append(i)
+            except ValueError:
+                self.unparsed.append(i)
+        self.groups = []
+        for key, ids in sorted(by_shape.items(), key=lambda kv: -len(kv[1])):
+            g = MixedBatch.Group()
+            g.ids = np.array(ids, dtype=np.int64)
+            g.batch = VerifyBatch([blobs[i] for i in ids], inputs=inputs, config=config)
+            g.circuit = cached_circuit(g.batch.shape, inputs=inputs, multipliers=multipliers)
+            g.trace = None
+            self.groups.append(g)
+
+    def cost(self):
+        """relative cost of each group's proofs (permutations of the flow + rows / 16), for work-balanced sharding"""
+        return {tuple(g.batch.shape.key()): g.circuit.info.n_flow + g.circuit.info.n_rows / 16.0 for g in self.groups}
+
+    def run(self, trace=True, export=True, concurrent=True):
+        """-> (verdict uint8[n], stage uint8[n]) as torch tensors on the device, in the caller's order.  With trace: a proof whose circuit
+        checks fail (check_arithmetics / check_poseidon_invocations) counts as rejected.
+        concurrent: every shape group runs on its own stream.  A group of a few dozen proofs is a chain of latency-bound kernels (the
+        transcript is 100-255 sequential permutations, the tape 300-400 dependent levels) that leaves most of the GPU idle; the groups
+        of a mixed batch fill it beside each other, and the batch takes about as long as its slowest group."""
+        import torch
+        dev = self.groups[0].batch.d_words.device if self.groups else torch.device("cuda", torch.cuda.current_device())
+        verdict = torch.ones(self.n, dtype=torch.uint8, device=dev)
+        stage = torch.ones(self.n, dtype=torch.uint8, device=dev)          # unparsed: (reject, parse)
+        main = torch.cuda.current_stream(dev)
+        if concurrent and len(self.groups) > 1:
+            if not hasattr(self, "_streams"):
+                self._streams = [torch.cuda.Stream(dev) for _ in self.groups]
+                self._idx = [torch.from_numpy(g.ids).to(dev) for g in self.groups]
+            fork = torch.cuda.Event()
+            fork.record(main)
+        for k, g in enumerate(self.groups):
+            st = self._streams[k] if concurrent and len(self.groups) > 1 else main
+            if st is not main:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                v, s = g.batch.run(full=True)
+                if trace:
+                    g.trace = g.circuit.trace(g.batch, check=True, export=export, preprocessed=False)
+                    bad = (g.trace["bad_row"] != -1) | (g.trace["bad_flow"] != -1)
+                    v = torch.where(bad & (v == 0), torch.full_like(v, 1), v)
+                idx = self._idx[k] if hasattr(self, "_idx") else torch.from_numpy(g.ids).to(dev)
+                verdict[idx] = v
+                stage[idx] = s
+            if st is not main:
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+        return verdict, stage

@@ -141,6 +141,55 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
     }
 }
 
+// Cluster variant for lanes = 32: ONE THREAD-BLOCK CLUSTER per lane group (32 items).  The cluster's warps share the instructions of a
+// level and a cluster barrier (barrier.cluster, ~0.2 us, hardware co-scheduled CTAs) separates levels -- an order of magnitude
+// cheaper than the grid barrier above (~3 us x 265 levels), and a plain launch: no cooperative grid, so the evaluations of several
+// small batches (the shape groups of a mixed batch) run beside each other on different streams.  A lane group's variables[] are
+// produced and consumed by its own cluster only, while it is resident: the operand reads of a level find in L2 what the levels
+// before it wrote (the grid-wide form sweeps every group's variables at every level).
+// Consecutive instructions of a level go to different CTAs of the cluster (different SMs).
+constexpr int kClusterThreads = 512;
+// Measured and dropped: four instructions of a level per warp at once (all operand loads issued before any is consumed): 110 registers,
+// one CTA per SM, 5.2 ms against 3.1 ms at 4096 proofs and 1.4 against 1.1 ms at 512 -- the pass is not short of loads in flight.
+__global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
+                                                                       const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
+                                                                       const u32 *__restrict__ eperms) {
+    extern __shared__ u32 s_level[];                     // level_start, n_levels + 1 words: nothing of the level loop waits on it
+    u32 rank, csize, grp;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(grp));
+    const u32 lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const u32 wi = rank + csize * warp, n_w = csize * (kClusterThreads / 32);
+    const u32 item = grp * 32 + lane;
+    const bool live = item < b.n_batch;
+    const tape::View v = b.view(live ? item : 0, input, n_input_words);
+    auto cluster_sync = [] {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    };
+    for (u32 l = threadIdx.x; l <= n_levels; l += kClusterThreads) s_level[l] = __ldg(level_start + l);
+    if (live && wi == 0) tape::prologue(v);
+    __syncthreads();
+    const uint4 *iw = reinterpret_cast<const uint4 *>(ins);
+    // a level's first instruction word is fetched BEFORE the barrier that ends the level before it: one L2 round trip less per level
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (s_level[0] + wi < s_level[1]) w = __ldg(iw + s_level[0] + wi);
+    cluster_sync();
+    for (u32 l = 0; l < n_levels; l++) {
+        const u32 lo = s_level[l], hi = s_level[l + 1];
+        for (u32 k = lo + wi; k < hi; k += n_w) {
+            if (k != lo + wi) w = __ldg(iw + k);
+            if (live) {
+                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                tape::eval<false>(v, in, perms, eperms);
+            }
+        }
+        if (l + 1 < n_levels && hi + wi < s_level[l + 2]) w = __ldg(iw + hi + wi);
+        cluster_sync();
+    }
+}
+
 // ---- K7: check_arithmetics ---------------------------------------------------------------------------------------------------
 // thread = (row, item) with the item fastest: a warp checks one row for 32 items
 __global__ void __launch_bounds__(kT) k_cs_check_arith(stwo_b200_cs_wiring w, Batch b, unsigned long long *first_bad) {
@@ -529,16 +578,36 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     const u32 *eperms = t->eperms;
     if (t->n_eperms && !eperms) return STWO_B200_E_BAD_ARG;
     // grid-wide levels while the batch has fewer lane groups than a few waves of SMs; CTA-local levels beyond that
-    static int n_sm = 0, coop = 0, grid_mode = -1, unrolled = 0;
+    static int n_sm = 0, coop = 0, grid_mode = -1, unrolled = 0, cluster = -1;
     if (!n_sm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        const char *e = getenv("STWO_B200_EVAL_MODE");        // "cta" / "grid": force one kernel (profiling)
-        if (e) grid_mode = e[0] == 'g' ? 1 : 0;
+        const char *e = getenv("STWO_B200_EVAL_MODE");        // "cta" / "grid" / "cluster": force one kernel (profiling)
+        if (e) grid_mode = e[0] == 'g' ? 1 : e[0] == 'c' && e[1] == 'l' ? 2 : 0;
+        e = getenv("STWO_B200_EVAL_CLUSTER");                 // CTAs per cluster (1, 2, 4, 8, 16)
+        if (e) cluster = atoi(e);
         e = getenv("STWO_B200_EVAL_UNROLLED");                // "1": fully unrolled permutation inside the grid kernel (profiling)
         if (e) unrolled = e[0] == '1';
+    }
+    // default for lanes = 32: one cluster per lane group (a plain launch: evaluations on different streams run beside each other, which
+    // two cooperative grids must not be asked to do).  Cluster size: many CTAs for a handful of lane groups (the levels are then
+    // spread over many SMs), two when the batch alone fills the GPU (4096 proofs: all 128 clusters resident at once).
+    if (v->lanes == 32 && (grid_mode == 2 || grid_mode < 0)) {
+        int c = cluster > 0 ? cluster : (n_groups <= 2 ? 16 : n_groups <= 24 ? 8 : n_groups <= 64 ? 4 : 2);
+        if (c > 8) STWO_CUDA(cudaFuncSetAttribute(k_tape_eval_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const size_t smem = ((size_t)n_levels + 1) * 4;
+        if (smem > 48 * 1024) STWO_CUDA(cudaFuncSetAttribute(k_tape_eval_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_groups * (unsigned)c); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        STWO_CUDA(cudaLaunchKernelEx(&cfg, k_tape_eval_cluster, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms));
+        note_launch(1);
+        return cuda_status(cudaGetLastError());
     }
     const bool use_grid = v->lanes == 32 && coop && (grid_mode == 1 || (grid_mode < 0 && n_groups <= 8u * (u32)n_sm));
     if (use_grid) {
