@@ -19,6 +19,9 @@ struct stwo_b200_circuit {
     const u32 *gather = nullptr;
     const circuit::ExtraJob *jobs = nullptr;      // last-layer circuit only
     u32 n_jobs = 0, n_extra_words = 0;
+    // populate_logup_arguments depends on the wiring only (plonk_with_poseidon.rs:382-466): computed once, at upload
+    int32_t *mult = nullptr;                      // mult_a | mult_b | mult_c | mult_poseidon, n_rows each
+    u32 *scratch = nullptr, *status = nullptr;    // counts | first_key | first_prow | mult_poseidon_vars; the assert flag
 };
 
 namespace {
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(kT) k_gather_witness(verify::Workspace ws, con
 }
 
 struct Carve {
-    u32 *witness, *vars, *flow_hash; uint8_t *flow_swap; int32_t *mult; u32 *scratch, *status, *extra;
+    u32 *witness, *vars, *flow_hash; uint8_t *flow_swap; u32 *status, *extra;
     size_t bytes;
 };
 Carve carve(const RecordedCircuit &r, u32 n_proofs, uint8_t *base) {
@@ -71,8 +74,6 @@ Carve carve(const RecordedCircuit &r, u32 n_proofs, uint8_t *base) {
     k.vars = (u32 *)take(groups * c.n_vars * 32 * 16);
     k.flow_hash = (u32 *)take(groups * c.num_poseidon_invocations() * 32 * 32 * 4);
     k.flow_swap = take(groups * c.num_poseidon_invocations() * 32);
-    k.mult = (int32_t *)take((size_t)4 * c.num_plonk_rows() * 4);
-    k.scratch = (u32 *)take(((size_t)4 * c.n_vars + 4) * 4);
     k.status = (u32 *)take(256);
     k.extra = (u32 *)take((size_t)n_proofs * r.n_extra_words * 4 + 4);
     k.bytes = align_up(at, 256);
@@ -88,7 +89,8 @@ int32_t upload(stwo_b200_circuit *c) {
     auto take = [&](size_t bytes) { at = align_up(at, 256); size_t o = at; at += bytes; return o; };
     const size_t o_w = take(9 * nr * 4), o_jobs = take(r.jobs.size() * sizeof(circuit::ExtraJob) + 16), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
                  o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4),
-                 o_xt = take(stwo_b200_cs_export_tiles_words((u32)nr) * 4 + 16);
+                 o_xt = take(stwo_b200_cs_export_tiles_words((u32)nr) * 4 + 16), o_mult = take((size_t)4 * nr * 4), o_scr = take(((size_t)4 * cs.n_vars + 4) * 4),
+                 o_stat = take(256);
     uint8_t *d = nullptr;
     STWO_CUDA(cudaMalloc(&d, at));
     const std::vector<u32> *cols[9] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op, &cs.op2, &cs.op3, &cs.op4};
@@ -125,6 +127,16 @@ int32_t upload(stwo_b200_circuit *c) {
     c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
                 (const u32 *)(d + o_perm), (u32)(cs.eperms.size() / tape::EPOSEIDON_REC), (const u32 *)(d + o_ep)};
     c->gather = (const u32 *)(d + o_g);
+    c->mult = (int32_t *)(d + o_mult); c->scratch = (u32 *)(d + o_scr); c->status = (u32 *)(d + o_stat);
+    {
+        cudaStream_t st;
+        STWO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        const int32_t rc = stwo_b200_cs_populate_logup_dev(&c->wiring, c->mult, c->mult + nr, c->mult + 2 * nr, c->mult + 3 * nr, c->scratch, c->status, st);
+        const cudaError_t e = cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        if (rc) return rc;
+        if (e != cudaSuccess) return -(int32_t)e;
+    }
     c->dev = d;
     return STWO_B200_OK;
 }
@@ -264,9 +276,7 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         if ((rc = stwo_b200_cs_check_arithmetics_dev(&c->wiring, &v, bad_row, st))) return rc;
     MARK();
     const size_t nr = c->wiring.n_rows;
-    const bool need_mult = preprocessed || (flags & STWO_B200_TRACE_CHECK_POSEIDON);
-    if (need_mult)
-        if ((rc = stwo_b200_cs_populate_logup_dev(&c->wiring, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, k.scratch, k.status, st))) return rc;
+    int32_t *const mult = c->mult;                 // populate_logup_arguments: wiring only, computed at upload
     if ((flags & STWO_B200_TRACE_CHECK_POSEIDON) && c->wiring.kind == 1)      // unimplemented!() for this system: nothing to check
         if ((rc = cuda_status(cudaMemsetAsync(bad_flow, 0xff, (size_t)n_proofs * 8, st)))) return rc;
     // check_poseidon_invocations is integer-issue bound (it re-executes every flow permutation), the export HBM bound, and both
@@ -284,13 +294,13 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         }
         STWO_CUDA(cudaEventRecord(g_side_fork, st));
         STWO_CUDA(cudaStreamWaitEvent(g_side, g_side_fork, 0));
-        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, g_side, g_beside_ctas))) return rc;
+        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, g_side, g_beside_ctas))) return rc;
         STWO_CUDA(cudaEventRecord(g_side_join, g_side));
     } else if (do_check_poseidon)
-        if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, k.mult + 3 * nr, k.scratch, bad_flow, st))) return rc;
+        if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, st))) return rc;
     MARK();
     if (preprocessed || values)
-        if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, k.mult, k.mult + nr, k.mult + 2 * nr, k.mult + 3 * nr, preprocessed, values,
+        if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, mult, mult + nr, mult + 2 * nr, mult + 3 * nr, preprocessed, values,
                                                 fuse_check ? bad_row : nullptr, st))) return rc;
     if (beside) STWO_CUDA(cudaStreamWaitEvent(st, g_side_join, 0));
     MARK();

@@ -123,6 +123,89 @@ HD bool build_group(const u32 *w, const proof::Desc &d, const fs::Out &o, u32 L,
     return true;
 }
 
+// The same with a GROUP of lanes per (proof, log size): the structure passes are cheap integer walks every lane repeats (stores are dealt
+// out), the coefficient loop -- a chain of ~140 dependent QM31 products in the sequential form, alpha_{k+1} = alpha_k * after_coeff --
+// is strided: lane j owns the samples k = j, j + G, .. and walks alpha in steps of after_coeff^G.  Co: lane(), size(), sync().
+template <class Co>
+HD bool build_group_coop(const Co &co, const u32 *w, const proof::Desc &d, const fs::Out &o, u32 L, Group &g) {
+    const u32 lane = co.lane(), G = co.size();
+    int shift_of[MAX_BATCHES]; u32 key_log[MAX_BATCHES]; u32 cnt[MAX_BATCHES], fill[MAX_BATCHES], start[MAX_BATCHES + 1];
+    u32 n_batches = 0;
+    bool ok = true;
+    for (int pass = 0; pass < 2 && ok; pass++) {
+        u32 col_index = 0;
+        for (u32 t = 0; t < 4 && ok; t++)
+            for (u32 c = 0; c < proof::n_cols(t) && ok; c++) {
+                u32 comp_log, col_log;
+                column_info(d, t, c, comp_log, col_log);
+                if (col_log != L) continue;
+                const u32 nm = proof::n_masks(t, c);
+                for (u32 m = 0; m < nm; m++) {
+                    const int shift = (nm == 2 && m == 0) ? -1 : 0;
+                    const u32 kl = shift ? comp_log : 0;
+                    u32 b = 0;
+                    while (b < n_batches && !(shift_of[b] == shift && key_log[b] == kl)) b++;
+                    if (pass == 0) {
+                        if (b == n_batches) {
+                            if (b == MAX_BATCHES) { ok = false; break; }
+                            shift_of[b] = shift; key_log[b] = kl; cnt[b] = 0;
+                            if (lane == b % G) {
+                                g.point[b].x = o.oods_x; g.point[b].y = o.oods_y;
+                                if (shift) {
+                                    cpoint_t s = circle::conj(circle::mul_gen(1u << (31 - comp_log)));
+                                    g.point[b].x = qsub(qm31::mul_m31(o.oods_x, s.x), qm31::mul_m31(o.oods_y, s.y));
+                                    g.point[b].y = qadd(qm31::mul_m31(o.oods_x, s.y), qm31::mul_m31(o.oods_y, s.x));
+                                }
+                            }
+                            n_batches++;
+                        }
+                        cnt[b]++;
+                    } else {
+                        const u32 at = start[b] + fill[b]++;
+                        if (at % G == lane) {
+                            g.col[at] = col_index;
+                            g.ca[at] = qload(w + proof::sample_off(d, t, c, m));
+                        }
+                    }
+                }
+                col_index++;
+            }
+        if (lane == 0) g.n_cols = col_index;
+        if (pass == 0 && ok) {
+            start[0] = 0;
+            for (u32 b = 0; b < n_batches; b++) { start[b + 1] = start[b] + cnt[b]; fill[b] = 0; }
+            if (start[n_batches] > MAX_GROUP_SAMPLES) ok = false;
+        }
+    }
+    if (!ok) return false;                              // every lane took the same decisions
+    if (lane == 0) { g.n_batches = n_batches; for (u32 b = 0; b <= n_batches; b++) g.start[b] = start[b]; }
+    co.sync();                                          // points and sampled values are in place
+    // alpha_k = -2u * after_coeff^k over the group's samples in batch-major order; lane j: k = j, j + G, ..
+    qm31_t step = o.after_coeff, alpha = qm31::mk(0, 0, M31_P - 2, 0);
+    {
+        qm31_t sq = o.after_coeff;                       // after_coeff^(2^i)
+        for (u32 bit = 1; bit < G; bit <<= 1) {
+            if (lane & bit) alpha = qmul(alpha, sq);
+            sq = qmul(sq, sq);
+        }
+        step = G == 1 ? o.after_coeff : sq;              // after_coeff^G (G a power of two)
+    }
+    u32 b = 0;
+    for (u32 k = lane; k < start[n_batches]; k += G) {
+        while (k >= start[b + 1]) b++;
+        const cm31_t y0 = qm31::lo(g.point[b].y), y1 = qm31::hi(g.point[b].y);
+        const qm31_t v = g.ca[k];
+        const cm31_t v0 = qm31::lo(v), v1 = qm31::hi(v);
+        const cm31_t bb = cm31::sub(cm31::mul(v0, y1), cm31::mul(v1, y0));
+        g.ca[k] = qm31::mul_cm31(alpha, v1);
+        g.cb[k] = qm31::mul_cm31(alpha, bb);
+        g.cc[k] = qm31::mul_cm31(alpha, y1);
+        alpha = qmul(alpha, step);
+    }
+    co.sync();
+    return true;
+}
+
 // accumulate_row_quotients for one query: row = queried values of all columns of this log size
 HD bool row_quotient(const Group &g, const u32 *row, cpoint_t dp, qm31_t &out) {
     qm31_t acc = qm31::zero();

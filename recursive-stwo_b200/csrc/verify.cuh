@@ -362,6 +362,15 @@ HD void stage_group(const Workspace &ws, u32 p, u32 g) {
     if (g >= dt.n_logs) return;
     if (!fri::build_group(ws.blob(p), d, dt.fs, dt.log_sizes[g], ws.groups[(size_t)p * fri::MAX_LOGS + g])) fail_shared(&dt, proof::ST_PARSE);
 }
+template <class Co>
+HD void stage_group_coop(const Co &co, const Workspace &ws, u32 p, u32 g) {
+    const Desc &d = ws.desc[p];
+    if (!d.ok) return;
+    Detail &dt = ws.detail[p];
+    if (g >= dt.n_logs) return;
+    if (!fri::build_group_coop(co, ws.blob(p), d, dt.fs, dt.log_sizes[g], ws.groups[(size_t)p * fri::MAX_LOGS + g]) && co.lane() == 0)
+        fail_shared(&dt, proof::ST_PARSE);
+}
 HD void stage_answer(const Workspace &ws, u32 p, u32 g, u32 i) {
     const Desc &d = ws.desc[p];
     if (!d.ok) return;

@@ -29,6 +29,20 @@ __global__ void __launch_bounds__(kT) k_group(const Workspace ws, u32 p0, u32 pn
     u32 idx = blockIdx.x * kT + threadIdx.x;
     if (idx < pn * fri::MAX_LOGS) verify::stage_group(ws, p0 + idx % pn, idx / pn);
 }
+// 16 lanes per (proof, log-size group): the coefficient chain of build_group is strided over the lanes
+__global__ void __launch_bounds__(kT) k_group_coop(const Workspace ws, u32 p0, u32 pn) {
+    const u32 unit = (blockIdx.x * kT + threadIdx.x) / 16;
+    if (unit >= pn * fri::MAX_LOGS) return;              // whole groups leave together
+    struct Co16 {
+        u32 l; unsigned mask;
+        __device__ __forceinline__ u32 lane() const { return l; }
+        __device__ __forceinline__ u32 size() const { return 16; }
+        __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    } co;
+    co.l = threadIdx.x % 16;
+    co.mask = 0xffffu << (16 * ((threadIdx.x % 32) / 16));
+    verify::stage_group_coop(co, ws, p0 + unit % pn, unit / pn);
+}
 __global__ void __launch_bounds__(kT) k_answer(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
     const u32 per_g = pn * ws.shape.n_queries;
@@ -165,24 +179,53 @@ __device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &
             o.oods_y = fs::qmul(fs::qadd(ot, ot), inv);
         }
     }
-    const u32 *pend = nullptr;
-    for (u32 tr = 0; tr < 4; tr++)
-        for (u32 c = 0; c < proof::n_cols(tr); c++)
-            for (u32 m = 0; m < proof::n_masks(tr, c); m++) {
-                const u32 *v = w + proof::sample_off(d, tr, c, m);
-                if (pend) { ch.mix44(pend, v); pend = nullptr; } else pend = v;
-            }
-    if (pend) ch.mix4(pend);
-    t = ch.draw(); store_q(&o.after_coeff, t, 0);
-    ch.mix8(w + d.fl_commitment);
-    t = ch.draw(); store_q(&o.fri_alphas[0], t, 0);
-    for (u32 i = 0; i < d.n_inner; i++) {
-        ch.mix8(w + d.in_commitment[i]);
-        t = ch.draw(); store_q(&o.fri_alphas[i + 1], t, 0);
+    // The chain is latency bound, so no permutation may wait for its input: the rate words of absorb k + 1 are loaded before the
+    // permutation of absorb k starts (the loads do not depend on the state).
+    // sampled values, flattened tree -> column -> mask, two per permutation: word of this lane (lanes 0..7) of pair j
+    auto pair_word = [&](u32 j) -> u32 {
+        const u32 sidx = 2 * j + (l >> 2);
+        if (l >= 8 || sidx >= proof::TOTAL_SAMPLES) return 0u;
+        u32 tr, c, m = 0;
+        if (sidx < 50) { tr = 0; c = sidx; }
+        else if (sidx < 110) { tr = 1; c = sidx - 50; }
+        else if (sidx < 134) {
+            const u32 r = sidx - 110;
+            tr = 2;
+            if (r < 4) c = r;
+            else if (r < 12) { c = 4 + (r - 4) / 2; m = (r - 4) & 1u; }
+            else if (r < 16) c = 8 + (r - 12);
+            else { c = 12 + (r - 16) / 2; m = (r - 16) & 1u; }
+        } else { tr = 3; c = sidx - 134; }
+        return w[proof::sample_off(d, tr, c, m) + (l & 3u)];
+    };
+    {
+        constexpr u32 n_pairs = (proof::TOTAL_SAMPLES + 1) / 2;
+        u32 cur = pair_word(0);
+        for (u32 j = 0; j < n_pairs; j++) {
+            const u32 nxt = j + 1 < n_pairs ? pair_word(j + 1) : 0u;
+            ch.absorb(cur);
+            cur = nxt;
+        }
     }
-    for (u32 i = 0; i < d.n_last_coeffs; i += 2) {
-        if (i + 1 < d.n_last_coeffs) ch.mix8(w + d.last_coeffs + 4 * i);
-        else ch.mix4(w + d.last_coeffs + 4 * i);
+    t = ch.draw(); store_q(&o.after_coeff, t, 0);
+    {
+        u32 cur = l < 8 ? w[d.fl_commitment + l] : 0u;
+        for (u32 i = 0; i <= d.n_inner; i++) {
+            const u32 nxt = (i < d.n_inner && l < 8) ? w[d.in_commitment[i] + l] : 0u;
+            ch.absorb(cur);
+            t = ch.draw(); store_q(&o.fri_alphas[i], t, 0);
+            cur = nxt;
+        }
+    }
+    {
+        const u32 n_mix = (d.n_last_coeffs + 1) / 2;
+        auto coeff_word = [&](u32 i) -> u32 { return (l < 8 && 8 * i + l < 4 * d.n_last_coeffs) ? w[d.last_coeffs + 8 * i + l] : 0u; };
+        u32 cur = coeff_word(0);
+        for (u32 i = 0; i < n_mix; i++) {
+            const u32 nxt = i + 1 < n_mix ? coeff_word(i + 1) : 0u;
+            ch.absorb(cur);
+            cur = nxt;
+        }
     }
     const u64 nonce = (u64)w[d.pow_nonce] | ((u64)w[d.pow_nonce + 1] << 32);
     const u32 limb = l == 0 ? (u32)(nonce & ((1u << 22) - 1)) : l == 1 ? (u32)((nonce >> 22) & ((1u << 21) - 1)) : l == 2 ? (u32)((nonce >> 43) & ((1u << 21) - 1)) : 0u;
@@ -338,6 +381,10 @@ void launch_folds(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     if (!done) k_folds<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 
+void launch_group(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    if (tree_group_width(ws.n_proofs) == 0) k_group<<<(unsigned)(((size_t)n * fri::MAX_LOGS + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+    else k_group_coop<<<(unsigned)(((size_t)n * fri::MAX_LOGS * 16 + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
+}
 cudaEvent_t g_ev[STWO_B200_N_STAGE_KERNELS + 1] = {nullptr};
 bool g_timed_valid = false;
 inline unsigned nblk(size_t n) { return (unsigned)((n + kT - 1) / kT); }
@@ -475,7 +522,7 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         MARK(); launch_parse_transcript(ws, 0, n, st); launch_oods(ws, 0, n, st);
         if (upto & STWO_B200_VERIFY_UPTO_TRANSCRIPT) return stop(3);
         MARK(); launch_single_tree(ws, 0, n, st);
-        MARK(); k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, st>>>(ws, 0, n);
+        MARK(); launch_group(ws, 0, n, st);
         MARK(); k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, st>>>(ws, 0, n);
         if (upto & STWO_B200_VERIFY_UPTO_ANSWERS) return stop(6);
         MARK(); launch_folds(ws, 0, n, st);
@@ -515,7 +562,7 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
             k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, b>>>(ws, p0, n);
         }
         STWO_CUDA(cudaEventRecord(g_side_done[sl], b));
-        k_group<<<nblk((size_t)n * fri::MAX_LOGS), kT, 0, a>>>(ws, p0, n);
+        launch_group(ws, p0, n, a);
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
         launch_folds(ws, p0, n, a);
         launch_pair_tree(ws, p0, n, a);

@@ -67,7 +67,7 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     for (u32 p = 0; p < n; p++) for (u32 t = 0; t < 4; t++) {
         if (coop) verify::stage_single_tree_coop(one, ws, p, t, tab.data()); else verify::stage_single_tree(ws, p, t);
     }
-    for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) verify::stage_group(ws, p, g);
+    for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) { if (coop) verify::stage_group_coop(one, ws, p, g); else verify::stage_group(ws, p, g); }
     for (u32 p = 0; p < n; p++) for (u32 g = 0; g < fri::MAX_LOGS; g++) for (u32 i = 0; i < nq; i++) verify::stage_answer(ws, p, g, i);
     for (u32 p = 0; p < n; p++) { if (coop) verify::stage_folds_coop(one, ws, p, tab.data()); else verify::stage_folds(ws, p); }
     for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) {
@@ -83,6 +83,26 @@ void *hs_verify_batch(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     return base;
 }
 void hs_free(void *p) { free(p); }
+// fri::build_group_coop with G lanes emulated on the host against the sequential fri::build_group, for every log-size group of proof 0
+// of a verified batch (ws from hs_verify_batch's ws_out).  A lane only reads what another lane wrote across the one barrier (the batch
+// points), and re-places its own samples at the start: running the lanes one after the other TWICE therefore reproduces the lock-step
+// result.  Returns 0 when every group is bit-identical.
+int hs_build_group_lanes(const verify::Workspace *ws, u32 G) {
+    struct LaneOf { u32 l, g; u32 lane() const { return l; } u32 size() const { return g; } void sync() const {} };
+    const proof::Desc &d = ws->desc[0];
+    const verify::Detail &dt = ws->detail[0];
+    static fri::Group a, b;
+    for (u32 k = 0; k < dt.n_logs; k++) {
+        memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+        if (!fri::build_group(ws->blob(0), d, dt.fs, dt.log_sizes[k], a)) return -1;
+        for (int round = 0; round < 2; round++)
+            for (u32 l = 0; l < G; l++) { LaneOf co{l, G}; if (!fri::build_group_coop(co, ws->blob(0), d, dt.fs, dt.log_sizes[k], b)) return -2; }
+        if (a.n_batches != b.n_batches || a.n_cols != b.n_cols || memcmp(a.start, b.start, sizeof a.start) || memcmp(a.point, b.point, a.n_batches * sizeof(fri::QPoint))) return 1 + (int)k;
+        const u32 ns = a.start[a.n_batches];
+        if (memcmp(a.col, b.col, ns * 4) || memcmp(a.ca, b.ca, ns * 16) || memcmp(a.cb, b.cb, ns * 16) || memcmp(a.cc, b.cc, ns * 16)) return 10 + (int)k;
+    }
+    return 0;
+}
 // the permutation record of proof p (ws from hs_verify_batch's ws_out): hint_total x 16 words; returns hint_total
 u32 hs_perm_record(const verify::Workspace *ws, u32 p, u32 *out, u32 *trees_complete) {
     if (out) memcpy(out, ws->perm_out_of(p, 0), (size_t)ws->hint_total * 64);

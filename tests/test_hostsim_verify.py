@@ -194,3 +194,22 @@ def test_tree_rebuild_record_equals_path_kernels(hostsim, orc, name):
     used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, recs[3].shape[0])]        # transcript slots beyond the chain are unused
     assert np.array_equal(recs[3][used], recs[7][used]) and np.array_equal(recs[7][used], recs[1][used])
     assert recs[3][512:].any(axis=1).all()                                                   # every path slot was written
+
+
+@pytest.mark.parametrize("name", ["small_proof.bin", "level1-5.bin", "level7-1.bin"])
+def test_build_group_strided_over_lanes(hostsim, orc, name):
+    """fri::build_group_coop (k_group_coop: the alpha chain of the sample-batch coefficients strided over 16 lanes in steps of
+    after_coeff^16) == the sequential fri::build_group, for 1, 2, 4, 16 and 32 emulated lanes"""
+    buf, n = O.load_proof(name)
+    shape = shape_of(buf)
+    inputs = O.inputs_for(name)
+    hostsim.hs_verify_batch.restype = ctypes.c_void_p
+    words, off = pack([(buf, n)])
+    idx, vals = np.array(inputs[0], dtype=np.uint32), np.array(inputs[1], dtype=np.uint32)
+    dt = (Detail * 1)()
+    ws = np.zeros(4096, dtype=np.uint8)
+    base = hostsim.hs_verify_batch(O.vp(words), O.vp(off), 1, O.vp(shape), O.vp(idx), O.vp(vals), idx.size, 3, dt, O.vp(ws))
+    assert dt[0].verdict == 0
+    for G in (1, 2, 4, 16, 32):
+        assert hostsim.hs_build_group_lanes(O.vp(ws), G) == 0, G
+    hostsim.hs_free(ctypes.c_void_p(base))
