@@ -15,9 +15,11 @@ pow 20, blow-up 5, last 2, 16 queries, 7 inner FRI layers).  One "step" = one ba
       check_poseidon_invocations (re-executes all 3 481 flow entries), export of the 2^16-row x 13 per-proof trace
       columns (examples/single-proof/src/main.rs:33-90).
 Metric: verified proofs/s over all GPUs (a proof counts when its verdict is accept AND its circuit checks pass);
-`poseidon31_perms_per_sec` rides along.  `value`: blobs already in HBM.  `e2e`: a stream of batches through
-VerifyStream: every step uploads one batch of blobs from pinned host memory (double-buffered: the copy runs beside the previous
-batch's kernels) and reads verdicts + check results back to the host (traces stay in HBM for the prover that consumes them).
+`poseidon31_perms_per_sec` rides along.  Both legs run a stream of batches through VerifyTracePipeline (three device slots; upload,
+verification and trace pass of neighbouring batches on their own streams).  `value`: blobs already in HBM, no upload.  `e2e`: every
+step uploads one batch of blobs from pinned host memory and copies verdicts + check results back to pinned host memory (traces stay
+in HBM for the prover that consumes them; shipping them to the host instead would cost 3.4 MB per proof over PCIe, ~70 ms per
+4096-proof batch at 200 GB/s).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -428,8 +430,11 @@ def main():
     blob = load_fixture()
     n_total = args.proofs * world if args.scaling == "weak" else args.proofs
     lo, hi = sharding.shard_range(n_total, rank, world)
-    vb = pkg.VerifyBatch([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
-    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)       # recorded once per shape (host)
+    # A stream of batches through the public API: VerifyTracePipeline = three device slots, the upload / verification / trace pass of
+    # neighbouring batches on their own streams.  Every step verifies AND traces one whole batch; the device-resident leg skips the
+    # upload, the end-to-end leg does everything.
+    pipe = pkg.VerifyTracePipeline([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE, n_slots=3)
+    vb, circ = pipe.slots[0], pipe.circuit                              # the circuit is recorded once per shape (host)
     ci = circ.info
     ws_mb = (vb.ws_bytes + circ.workspace_bytes(hi - lo)) >> 20
     blob_mb = vb.h_words.numel() * 4 >> 20
@@ -440,22 +445,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def local_step(pre=False):
-        v, s = vb.run(full=True)
-        r = circ.trace(vb, check=True, export=True, preprocessed=pre)
-        # a proof counts when the native verdict is accept and both circuit checks pass (plumbing: 3 tiny elementwise ops)
-        bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
-        return torch.where(bad & (v == 0), torch.full_like(v, 1), v), s, r
-
-    def step():
-        v, s, _ = local_step()
+    def gather(v, s):
         return sharding.gather_verdicts(v, s, n_total)
 
-    _, _, r0 = local_step(pre=True)           # the 10 preprocessed columns depend on the shape only: written once
-    for _ in range(warmup):
-        v, s = step()
+    # the 10 preprocessed columns depend on the shape only: written once, outside the steps
+    v0, _ = vb.run(full=True)
+    r0 = circ.trace(vb, check=True, export=True, preprocessed=True)
     torch.cuda.synchronize()
-    assert int(v.sum().item()) == 0 and v.numel() == n_total, "every replica of the fixture must be accepted"
+    assert int(v0.sum().item()) == 0 and int((r0["bad_row"] != -1).sum().item()) == 0 and int((r0["bad_flow"] != -1).sum().item()) == 0
     # spot parity inside the bench: the exported trace of one proof against the committed golden digest
     import hashlib
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "trace_digests.json")))["chain"][0]
@@ -468,6 +465,16 @@ def main():
     perms_per_proof = dt0.n_perms_hints + dt0.fs.n_transcript_perms + ci.n_flow
     assert dt0.n_perms_paths == 3481, "permutation count the record covers differs from the reference's circuit (SURVEY App. C)"
 
+    def check_last(h):
+        hv, hs, hb, hf = pipe.result(h)
+        assert int(hv.sum()) == 0 and hv.numel() == n_total, "every replica of the fixture must be accepted"
+        assert int((hb != -1).sum()) == 0 and int((hf != -1).sum()) == 0
+
+    for _ in range(warmup):
+        h = pipe.step(upload=False, gather=gather)
+    pipe.join()
+    check_last(h)
+
     # ---- timed region: device-resident ----------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -477,46 +484,36 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        v, s = step()
+        h = pipe.step(upload=False, gather=gather)
+    pipe.fence()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = pkg.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    check_last(h)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     value = n_total * args.steps / (ms * 1e-3)
 
-    # ---- e2e: pinned host blobs -> device -> verdicts on the host, every step ---------------------------
-    # A stream of batches through the public API (VerifyStream): every step uploads one batch of blobs from pinned host memory
-    # (on the copy stream, beside the previous step's kernels), verifies and traces the batch uploaded the step before, and reads
-    # verdicts + check results back to the host.
-    vs = pkg.VerifyStream([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE)
-
-    def e2e_step():
-        vs.feed()                                   # upload of the next batch
-        bt = vs.take()
-        v, s = bt.run(full=True)
-        r = circ.trace(bt, check=True, export=True, preprocessed=False)
-        vs.release(bt)
-        bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
-        v = torch.where(bad & (v == 0), torch.full_like(v, 1), v)
-        v, s = sharding.gather_verdicts(v, s, n_total)
-        return v.cpu(), s.cpu(), r["bad_row"].cpu(), r["bad_flow"].cpu()
-
-    vs.feed()
-    for _ in range(2):
-        hv, hs, hb, hf = e2e_step()
-    assert int(hv.sum()) == 0 and int((hb != -1).sum()) == 0
-    e2e_steps = max(2, args.steps // 2)
+    # ---- e2e: pinned host blobs -> device -> verdicts and check results on the host, every step ----------
+    # the same pipeline with its upload stage: every step copies one batch of blobs from pinned host memory (copy stream, beside the
+    # kernels of the batches before it) and ends with the device->host copy of that batch's verdicts and check results into pinned
+    # memory; the timed region ends when the last of those copies has landed.
+    for _ in range(3):
+        h = pipe.step(gather=gather)
+    pipe.join()
+    check_last(h)
+    e2e_steps = max(3, args.steps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        hv, hs, hb, hf = e2e_step()
-    torch.cuda.synchronize()
+        h = pipe.step(gather=gather)
+    pipe.join()
     dt = time.perf_counter() - t0
+    check_last(h)
     t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -617,7 +614,8 @@ def main():
         if rank == 0:
             secondary["multi_proofs"] = mp
         if world > 1:
-            _, _, rr = local_step()
+            vb.run(full=True)
+            rr = circ.trace(vb, check=True, export=True, preprocessed=False)
             tg = trace_gather_leg(sharding, rr["values"], rank, world, dev)
             del rr
             if rank == 0:
@@ -659,7 +657,8 @@ def main():
                        "shape": dict(zip(("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last", "n_queries", "n_inner"), sh.key())),
                        "perms_per_proof": perms_per_proof,
                        "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace + %d MB of trace columns per step" % (blob_mb, ws_mb, trace_mb),
-                       "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only"},
+                       "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only",
+                       "pipeline": "3 device slots; upload | verification | trace pass of neighbouring steps on their own streams"},
             "poseidon31_perms_per_sec": value * perms_per_proof,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_verify.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 run() {  # name, env...
   name=$1; shift
   env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --proofs ${PROOFS:-4096} --no-secondary --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err || tail -3 gpurun_out/bench_$name.err
@@ -12,5 +12,6 @@ PY
 }
 run default X=1
 PROOFS=512 run default_512 X=1
-python tools/multi_proofs_probe2.py 2>&1 | tail -1 | cut -c 200-500
-bash tools/gpu_launches.sh small_proof.bin 512 s512 | grep -v "functor\|Functor\|direct_copy"
+
+
+PROOFS=1024 run default_1024 X=1
