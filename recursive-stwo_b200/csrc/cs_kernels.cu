@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tap
     if (live && wi == 0) tape::prologue(v);
     __syncthreads();
     const uint4 *iw = reinterpret_cast<const uint4 *>(ins);
-    // a level's first instruction word is fetched BEFORE the barrier that ends the level before it: one L2 round trip less per level
+    // a level's first instruction word is fetched BEFORE the barrier that ends the level before it: one L2 round trip less per level.
+    // Measured and dropped: prefetch.global.L2 of the next instruction's operands two instructions ahead (3.12 vs 3.04 ms at 4096
+    // proofs: with every lane group resident the pass already keeps ~7 MB of loads in flight, its bandwidth-latency product).
     uint4 w = make_uint4(0, 0, 0, 0);
     if (s_level[0] + wi < s_level[1]) w = __ldg(iw + s_level[0] + wi);
     cluster_sync();

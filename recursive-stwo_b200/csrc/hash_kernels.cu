@@ -33,6 +33,30 @@ __global__ void __launch_bounds__(kThreads) k_poseidon2_permute(u32 *states, siz
     store8(states + 16 * i + 8, s + 8);
 }
 
+// experiment shapes of K1 (stwo_b200_poseidon2_permute_dev_variant): two states per thread (instruction-level parallelism across two
+// independent permutations), and the rolled shape under tighter register caps (more resident warps)
+__global__ void __launch_bounds__(kThreads) k_poseidon2_permute_x2(u32 *states, size_t n) {
+    size_t i = 2 * (blockIdx.x * (size_t)kThreads + threadIdx.x);
+    if (i >= n) return;
+    u32 a[16], b[16];
+    load16(states + 16 * i, a);
+    const bool two = i + 1 < n;
+    load16(states + 16 * (two ? i + 1 : i), b);
+    poseidon2::permute2(a, b);
+    store8(states + 16 * i, a); store8(states + 16 * i + 8, a + 8);
+    if (two) { store8(states + 16 * (i + 1), b); store8(states + 16 * (i + 1) + 8, b + 8); }
+}
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_poseidon2_permute_occ(u32 *states, size_t n) {
+    size_t i = blockIdx.x * (size_t)kThreads + threadIdx.x;
+    if (i >= n) return;
+    u32 s[16];
+    load16(states + 16 * i, s);
+    poseidon2::permute<false>(s);
+    store8(states + 16 * i, s);
+    store8(states + 16 * i + 8, s + 8);
+}
+
 // ---- hash_node over a layer --------------------------------------------------------------------
 // children: n x 16 or nullptr; cols column-major with stride col_stride
 __global__ void __launch_bounds__(kThreads) k_hash_node_layer(const u32 *__restrict__ children,
@@ -156,7 +180,11 @@ extern "C" int32_t stwo_b200_poseidon2_permute_dev_variant(uint32_t *states, siz
     if (n == 0) return STWO_B200_OK;
     if (!states || ((uintptr_t)states & 15)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (variant == 1) k_poseidon2_permute<true><<<blocks_for(n), kThreads, 0, st>>>(states, n);
+    if (variant == 2) k_poseidon2_permute_x2<<<blocks_for((n + 1) / 2), kThreads, 0, st>>>(states, n);
+    else if (variant == 3) k_poseidon2_permute_occ<8><<<blocks_for(n), kThreads, 0, st>>>(states, n);
+    else if (variant == 4) k_poseidon2_permute_occ<10><<<blocks_for(n), kThreads, 0, st>>>(states, n);
+    else if (variant == 5) k_poseidon2_permute_occ<5><<<blocks_for(n), kThreads, 0, st>>>(states, n);
+    else if (variant == 1) k_poseidon2_permute<true><<<blocks_for(n), kThreads, 0, st>>>(states, n);
     else k_poseidon2_permute<false><<<blocks_for(n), kThreads, 0, st>>>(states, n);
     note_launch();
     return cuda_status(cudaGetLastError());

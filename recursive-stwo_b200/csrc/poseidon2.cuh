@@ -162,4 +162,27 @@ HD void permute(u32 s[16]) {
     for (int i = 0; i < 16; i++) s[i] = m31::canon(m31::fold(s[i]));
 }
 
+// two independent states through the rolled rounds together: every loop body holds two independent dependency chains
+HD void permute2(u32 a[16], u32 b[16]) {
+    ext_mds(a, P2_TAB.first[0]); ext_mds(b, P2_TAB.first[0]);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) { a[i] = sbox(a[i]); b[i] = sbox(b[i]); }
+        ext_mds(a, P2_TAB.first[r + 1]); ext_mds(b, P2_TAB.first[r + 1]);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 14; r++) { internal_round(a, P2_TAB.rc_part[r]); internal_round(b, P2_TAB.rc_part[r]); }
+#pragma unroll
+    for (int i = 0; i < 16; i++) { a[i] = m31::fold(a[i]) + P2_TAB.rc_last0[i]; b[i] = m31::fold(b[i]) + P2_TAB.rc_last0[i]; }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) { a[i] = sbox(a[i]); b[i] = sbox(b[i]); }
+        ext_mds(a, P2_TAB.last[r]); ext_mds(b, P2_TAB.last[r]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) { a[i] = m31::canon(m31::fold(a[i])); b[i] = m31::canon(m31::fold(b[i])); }
+}
+
 }  // namespace poseidon2

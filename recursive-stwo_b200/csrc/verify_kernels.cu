@@ -69,8 +69,11 @@ struct CoopGroup {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 constexpr int kCoopThreads = 64;          // upper bound; the launch shrinks the block when the group tables would not fit
+#ifndef STWO_TREE_MIN_BLOCKS
+#define STWO_TREE_MIN_BLOCKS 1
+#endif
 template <int G>
-__global__ void __launch_bounds__(kCoopThreads) k_single_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+__global__ void __launch_bounds__(kCoopThreads, STWO_TREE_MIN_BLOCKS) k_single_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
     extern __shared__ u32 smem[];
     const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (grp >= pn * 4) return;                                       // whole groups leave together
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_single_tree_coop(const Workspa
     verify::stage_single_tree_coop(co, ws, p0 + grp % pn, grp / pn, smem + (threadIdx.x / G) * tab_words);
 }
 template <int G>
-__global__ void __launch_bounds__(kCoopThreads) k_pair_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+__global__ void __launch_bounds__(kCoopThreads, STWO_TREE_MIN_BLOCKS) k_pair_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
     extern __shared__ u32 smem[];
     const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (grp >= pn * ws.shape.n_fri_trees()) return;
