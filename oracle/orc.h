@@ -128,6 +128,8 @@ typedef struct {
 int orc_verify_proof(const uint8_t *blob, size_t len,
                      const uint32_t *input_idx, const uint32_t *input_vals /* n x4 */,
                      uint32_t n_inputs, orc_verify_out *out);
+/* FRI-only verifier of a synthetic FRI + Merkle instance (blob layout: recursive-stwo_b200/csrc/synth.cuh) */
+int orc_fri_verify_synth(const uint32_t *words, size_t n_words, orc_verify_out *out);
 /* the same under the caller's PcsConfig cfg = {pow_bits, log_blowup, log_last, n_queries}: a proof claiming another config is
  * rejected at the parse stage */
 int orc_verify_proof_cfg(const uint8_t *blob, size_t len, const uint32_t *cfg, const uint32_t *input_idx, const uint32_t *input_vals,

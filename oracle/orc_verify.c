@@ -528,6 +528,176 @@ static cpoint absolute_point(uint32_t L, uint32_t q) { return cp_half_odds_at(L,
 typedef struct { int shift; uint32_t comp_log; qpoint point; uint32_t n; uint32_t col[160]; qm31 val[160]; } sample_batch;
 
 static _Thread_local orc_hints *g_hints;      /* optional sink for the per-query hints (orc_verify_proof_hints) */
+
+/* Steps 7-9 of the verifier -- the FRI query phase: first-layer pair evaluations + decommitment + circle folds, inner layers, last layer
+ * (components/hints/src/folding.rs:296-601; components/recursive/folding/src/lib.rs:12-205; primitives/line/src/lib.rs:39-67).  Needs
+ * o->fri_alphas, o->fri_answers, o->n_logs / log_sizes and the query positions per log size.  Returns 1 after setting stage / verdict
+ * when a check fails.  Also the whole of orc_fri_verify_synth (the FRI-only instances of BASELINE configs[4] part i). */
+static int fri_stage(const orc_proof *p, orc_verify_out *o, uint32_t (*pos_at)[ORC_MAX_QUERIES], uint32_t max_first, uint32_t nq) {
+#define FAIL(stage_, verdict_) do { o->stage = (stage_); o->verdict = (verdict_); return 1; } while (0)
+    /* 7. FRI first layer: rebuild pair evaluations, decommit, circle folds
+     *    (hints/folding.rs:296-452; recursive/folding/src/lib.rs:22-90) */
+    static _Thread_local qm31 self_v[ORC_MAX_QUERIES][33], sib_v[ORC_MAX_QUERIES][33];
+    {
+        uint64_t wi = 0;
+        static _Thread_local uint32_t vals[ORC_MAX_LOGS * 2 * ORC_MAX_QUERIES * 4];
+        uint64_t nv = 0;
+        uint8_t has_data[33] = {0};
+        for (uint32_t g = 0; g < o->n_logs; g++) {
+            uint32_t L = o->log_sizes[g];
+            has_data[L] = 1;
+            /* sorted unique positions and the answer of each (first occurrence) */
+            uint32_t sp[ORC_MAX_QUERIES];
+            memcpy(sp, pos_at[L], nq * 4);
+            uint32_t ns = sort_dedup(sp, nq);
+            for (uint32_t k = 0; k < ns;) {
+                uint32_t start = (sp[k] >> 1) << 1;
+                for (uint32_t e = start; e < start + 2; e++) {
+                    qm31 v;
+                    if (k < ns && sp[k] == e) {
+                        uint32_t i = 0;
+                        while (pos_at[L][i] != e) i++;
+                        v = o->fri_answers[g][i];
+                        k++;
+                    } else {
+                        if (wi >= p->first_layer.n_fri_witness) FAIL(ORC_STAGE_FRI_FIRST, 1);
+                        v = qm31_load(p->first_layer.fri_witness + 4 * wi++);
+                    }
+                    memcpy(vals + nv, v.v, 16); nv += 4;
+                }
+            }
+        }
+        if (wi != p->first_layer.n_fri_witness) FAIL(ORC_STAGE_FRI_FIRST, 1);
+        pair_tree pt;
+        int bad = pair_tree_rebuild(max_first, has_data, pos_at[max_first], nq, vals, nv, &p->first_layer.decommitment,
+                                    p->first_layer.commitment, &pt, &o->n_perms_hints);
+        for (uint32_t i = 0; i < nq && !bad; i++) {
+            bad = pair_path_root(&pt, pos_at[max_first][i], self_v[i], sib_v[i], o->path_roots[4][i], &o->n_perms_paths,
+                                 g_hints ? g_hints->pair_sib_hash[0][i][0] : NULL);
+            if (g_hints && !bad) {
+                g_hints->pair_depth[0] = max_first;
+                memcpy(g_hints->pair_has_data[0], has_data, 33);
+                for (uint32_t h = 0; h <= max_first; h++) if (has_data[h]) {
+                    memcpy(g_hints->pair_self[0][i][h], self_v[i][h].v, 16); memcpy(g_hints->pair_sib[0][i][h], sib_v[i][h].v, 16);
+                }
+            }
+            if (!bad && memcmp(o->path_roots[4][i], p->first_layer.commitment, 32)) bad = 1;
+        }
+        pair_tree_free(&pt);
+        if (bad) FAIL(ORC_STAGE_FRI_FIRST, 1);
+        for (uint32_t g = 0; g < o->n_logs; g++) {
+            uint32_t L = o->log_sizes[g];
+            for (uint32_t i = 0; i < nq; i++) {
+                uint32_t q = pos_at[L][i];
+                /* self column must equal the computed answer (recursive/folding/src/lib.rs:36-54) */
+                if (!qm31_eq(self_v[i][L], o->fri_answers[g][i])) FAIL(ORC_STAGE_FRI_FIRST, 1);
+                cpoint pt2 = cp_dbl(absolute_point(L, q));
+                m31 y_inv = m31_inv(pt2.y);
+                qm31 l = (q & 1) ? sib_v[i][L] : self_v[i][L], r = (q & 1) ? self_v[i][L] : sib_v[i][L];
+                qm31 nl = qm31_add(l, r), nr = qm31_mul_m31(qm31_sub(l, r), y_inv);
+                o->circle_folds[g][i] = qm31_add(nl, qm31_mul(nr, o->fri_alphas[max_first - L]));
+            }
+        }
+    }
+
+    /* 8. inner layers (hints/folding.rs:459-601; recursive/folding/src/lib.rs:122-192) */
+    {
+        qm31 folded[ORC_MAX_QUERIES];
+        for (uint32_t i = 0; i < nq; i++) folded[i] = qm31_from_m31(0);
+        uint32_t log_size = max_first;
+        for (uint32_t li = 0; li < p->n_inner; li++) {
+            for (uint32_t g = 0; g < o->n_logs; g++)
+                if (o->log_sizes[g] == log_size) {
+                    qm31 a2 = qm31_mul(o->fri_alphas[li], o->fri_alphas[li]);
+                    for (uint32_t i = 0; i < nq; i++) folded[i] = qm31_add(qm31_mul(a2, folded[i]), o->circle_folds[g][i]);
+                }
+            log_size -= 1;
+            const orc_fri_layer *layer = &p->inner[li];
+            /* decommitted values: for each sorted unique position, (left, right) with missing siblings from fri_witness */
+            uint32_t sp[ORC_MAX_QUERIES];
+            memcpy(sp, pos_at[log_size], nq * 4);
+            uint32_t ns = sort_dedup(sp, nq);
+            static _Thread_local uint32_t vals[2 * ORC_MAX_QUERIES * 4];
+            uint64_t nv = 0, wi = 0;
+            uint32_t last_pair = 0xffffffffu;
+            for (uint32_t k = 0; k < ns; k++) {
+                uint32_t e = sp[k];
+                uint32_t i = 0;
+                while (pos_at[log_size][i] != e) i++;
+                qm31 v = folded[i], sv;
+                int sib_known = find_pos(sp, ns, e ^ 1);
+                if (sib_known >= 0) { uint32_t j = 0; while (pos_at[log_size][j] != (e ^ 1)) j++; sv = folded[j]; }
+                else {
+                    if (wi >= layer->n_fri_witness) FAIL(ORC_STAGE_FRI_INNER, 1);
+                    sv = qm31_load(layer->fri_witness + 4 * wi++);
+                }
+                if ((e >> 1) != last_pair) {
+                    qm31 l = (e & 1) ? sv : v, r = (e & 1) ? v : sv;
+                    memcpy(vals + nv, l.v, 16); memcpy(vals + nv + 4, r.v, 16); nv += 8;
+                    last_pair = e >> 1;
+                }
+            }
+            if (wi != layer->n_fri_witness) FAIL(ORC_STAGE_FRI_INNER, 1);
+            uint8_t has_data[33] = {0};
+            has_data[log_size] = 1;
+            pair_tree pt;
+            int bad = pair_tree_rebuild(log_size, has_data, pos_at[log_size], nq, vals, nv, &layer->decommitment,
+                                        layer->commitment, &pt, &o->n_perms_hints);
+            for (uint32_t i = 0; i < nq && !bad; i++) {
+                bad = pair_path_root(&pt, pos_at[log_size][i], self_v[i], sib_v[i], o->path_roots[5 + li][i], &o->n_perms_paths,
+                                     g_hints ? g_hints->pair_sib_hash[1 + li][i][0] : NULL);
+                if (g_hints && !bad) {
+                    g_hints->pair_depth[1 + li] = log_size;
+                    memcpy(g_hints->pair_has_data[1 + li], has_data, 33);
+                    memcpy(g_hints->pair_self[1 + li][i][log_size], self_v[i][log_size].v, 16);
+                    memcpy(g_hints->pair_sib[1 + li][i][log_size], sib_v[i][log_size].v, 16);
+                }
+                if (!bad && memcmp(o->path_roots[5 + li][i], layer->commitment, 32)) bad = 1;
+            }
+            pair_tree_free(&pt);
+            if (bad) FAIL(ORC_STAGE_FRI_INNER, 1);
+            for (uint32_t i = 0; i < nq; i++) {
+                uint32_t q = pos_at[log_size][i];
+                if (!qm31_eq(folded[i], self_v[i][log_size])) FAIL(ORC_STAGE_FRI_INNER, 1);
+                m31 x_inv = m31_inv(absolute_point(log_size, q).x);
+                qm31 l = (q & 1) ? sib_v[i][log_size] : self_v[i][log_size], r = (q & 1) ? self_v[i][log_size] : sib_v[i][log_size];
+                qm31 nl = qm31_add(l, r), nr = qm31_mul_m31(qm31_sub(l, r), x_inv);
+                folded[i] = qm31_add(nl, qm31_mul(nr, o->fri_alphas[li + 1]));
+                o->line_folds[li][i] = folded[i];
+            }
+        }
+        /* 9. last layer (recursive/folding/src/lib.rs:194-204; primitives/line/src/lib.rs:39-67) */
+        for (uint32_t i = 0; i < nq; i++) {
+            uint32_t q = pos_at[log_size][i];
+            cpoint ab = absolute_point(log_size, q);
+            m31 x = m31_sub(m31_mul(ab.x, ab.x), m31_mul(ab.y, ab.y));
+            uint32_t lg = p->log_last;
+            qm31 eval;
+            if (p->n_last_coeffs == 1) eval = qm31_load(p->last_coeffs);
+            else {
+                m31 dbl[32];
+                dbl[0] = x;
+                for (uint32_t k = 1; k < lg; k++) { m31 sq = m31_mul(dbl[k - 1], dbl[k - 1]); dbl[k] = m31_sub(m31_add(sq, sq), 1); }
+                /* fold(values, factors): lhs + rhs * factors[0], recursively -> iterative from the innermost factor */
+                static _Thread_local qm31 buf[1 << 12];
+                if (lg > 12) FAIL(ORC_STAGE_PARSE, 1);
+                uint32_t n = 1u << lg;
+                for (uint32_t k = 0; k < n; k++) buf[k] = qm31_load(p->last_coeffs + 4 * k);
+                for (uint32_t lev = lg; lev-- > 0;) {
+                    /* adjacent pairs at the deepest level use the LAST factor */
+                    n >>= 1;
+                    for (uint32_t k = 0; k < n; k++) buf[k] = qm31_add(buf[2 * k], qm31_mul_m31(buf[2 * k + 1], dbl[lev]));
+                }
+                eval = buf[0];
+            }
+            o->last_layer_evals[i] = eval;
+            if (!qm31_eq(folded[i], eval)) FAIL(ORC_STAGE_FRI_LAST, 1);
+        }
+    }
+    return 0;
+#undef FAIL
+}
+
 int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
                      uint32_t n_inputs, orc_verify_out *o) {
     static _Thread_local orc_proof P;
@@ -715,165 +885,7 @@ int orc_verify_proof(const uint8_t *blob, size_t len, const uint32_t *input_idx,
         }
     }
 
-    /* 7. FRI first layer: rebuild pair evaluations, decommit, circle folds
-     *    (hints/folding.rs:296-452; recursive/folding/src/lib.rs:22-90) */
-    static _Thread_local qm31 self_v[ORC_MAX_QUERIES][33], sib_v[ORC_MAX_QUERIES][33];
-    {
-        uint64_t wi = 0;
-        static _Thread_local uint32_t vals[ORC_MAX_LOGS * 2 * ORC_MAX_QUERIES * 4];
-        uint64_t nv = 0;
-        uint8_t has_data[33] = {0};
-        for (uint32_t g = 0; g < o->n_logs; g++) {
-            uint32_t L = o->log_sizes[g];
-            has_data[L] = 1;
-            /* sorted unique positions and the answer of each (first occurrence) */
-            uint32_t sp[ORC_MAX_QUERIES];
-            memcpy(sp, pos_at[L], nq * 4);
-            uint32_t ns = sort_dedup(sp, nq);
-            for (uint32_t k = 0; k < ns;) {
-                uint32_t start = (sp[k] >> 1) << 1;
-                for (uint32_t e = start; e < start + 2; e++) {
-                    qm31 v;
-                    if (k < ns && sp[k] == e) {
-                        uint32_t i = 0;
-                        while (pos_at[L][i] != e) i++;
-                        v = o->fri_answers[g][i];
-                        k++;
-                    } else {
-                        if (wi >= p->first_layer.n_fri_witness) FAIL(ORC_STAGE_FRI_FIRST, 1);
-                        v = qm31_load(p->first_layer.fri_witness + 4 * wi++);
-                    }
-                    memcpy(vals + nv, v.v, 16); nv += 4;
-                }
-            }
-        }
-        if (wi != p->first_layer.n_fri_witness) FAIL(ORC_STAGE_FRI_FIRST, 1);
-        pair_tree pt;
-        int bad = pair_tree_rebuild(max_first, has_data, pos_at[max_first], nq, vals, nv, &p->first_layer.decommitment,
-                                    p->first_layer.commitment, &pt, &o->n_perms_hints);
-        for (uint32_t i = 0; i < nq && !bad; i++) {
-            bad = pair_path_root(&pt, pos_at[max_first][i], self_v[i], sib_v[i], o->path_roots[4][i], &o->n_perms_paths,
-                                 g_hints ? g_hints->pair_sib_hash[0][i][0] : NULL);
-            if (g_hints && !bad) {
-                g_hints->pair_depth[0] = max_first;
-                memcpy(g_hints->pair_has_data[0], has_data, 33);
-                for (uint32_t h = 0; h <= max_first; h++) if (has_data[h]) {
-                    memcpy(g_hints->pair_self[0][i][h], self_v[i][h].v, 16); memcpy(g_hints->pair_sib[0][i][h], sib_v[i][h].v, 16);
-                }
-            }
-            if (!bad && memcmp(o->path_roots[4][i], p->first_layer.commitment, 32)) bad = 1;
-        }
-        pair_tree_free(&pt);
-        if (bad) FAIL(ORC_STAGE_FRI_FIRST, 1);
-        for (uint32_t g = 0; g < o->n_logs; g++) {
-            uint32_t L = o->log_sizes[g];
-            for (uint32_t i = 0; i < nq; i++) {
-                uint32_t q = pos_at[L][i];
-                /* self column must equal the computed answer (recursive/folding/src/lib.rs:36-54) */
-                if (!qm31_eq(self_v[i][L], o->fri_answers[g][i])) FAIL(ORC_STAGE_FRI_FIRST, 1);
-                cpoint pt2 = cp_dbl(absolute_point(L, q));
-                m31 y_inv = m31_inv(pt2.y);
-                qm31 l = (q & 1) ? sib_v[i][L] : self_v[i][L], r = (q & 1) ? self_v[i][L] : sib_v[i][L];
-                qm31 nl = qm31_add(l, r), nr = qm31_mul_m31(qm31_sub(l, r), y_inv);
-                o->circle_folds[g][i] = qm31_add(nl, qm31_mul(nr, o->fri_alphas[max_first - L]));
-            }
-        }
-    }
-
-    /* 8. inner layers (hints/folding.rs:459-601; recursive/folding/src/lib.rs:122-192) */
-    {
-        qm31 folded[ORC_MAX_QUERIES];
-        for (uint32_t i = 0; i < nq; i++) folded[i] = qm31_from_m31(0);
-        uint32_t log_size = max_first;
-        for (uint32_t li = 0; li < p->n_inner; li++) {
-            for (uint32_t g = 0; g < o->n_logs; g++)
-                if (o->log_sizes[g] == log_size) {
-                    qm31 a2 = qm31_mul(o->fri_alphas[li], o->fri_alphas[li]);
-                    for (uint32_t i = 0; i < nq; i++) folded[i] = qm31_add(qm31_mul(a2, folded[i]), o->circle_folds[g][i]);
-                }
-            log_size -= 1;
-            const orc_fri_layer *layer = &p->inner[li];
-            /* decommitted values: for each sorted unique position, (left, right) with missing siblings from fri_witness */
-            uint32_t sp[ORC_MAX_QUERIES];
-            memcpy(sp, pos_at[log_size], nq * 4);
-            uint32_t ns = sort_dedup(sp, nq);
-            static _Thread_local uint32_t vals[2 * ORC_MAX_QUERIES * 4];
-            uint64_t nv = 0, wi = 0;
-            uint32_t last_pair = 0xffffffffu;
-            for (uint32_t k = 0; k < ns; k++) {
-                uint32_t e = sp[k];
-                uint32_t i = 0;
-                while (pos_at[log_size][i] != e) i++;
-                qm31 v = folded[i], sv;
-                int sib_known = find_pos(sp, ns, e ^ 1);
-                if (sib_known >= 0) { uint32_t j = 0; while (pos_at[log_size][j] != (e ^ 1)) j++; sv = folded[j]; }
-                else {
-                    if (wi >= layer->n_fri_witness) FAIL(ORC_STAGE_FRI_INNER, 1);
-                    sv = qm31_load(layer->fri_witness + 4 * wi++);
-                }
-                if ((e >> 1) != last_pair) {
-                    qm31 l = (e & 1) ? sv : v, r = (e & 1) ? v : sv;
-                    memcpy(vals + nv, l.v, 16); memcpy(vals + nv + 4, r.v, 16); nv += 8;
-                    last_pair = e >> 1;
-                }
-            }
-            if (wi != layer->n_fri_witness) FAIL(ORC_STAGE_FRI_INNER, 1);
-            uint8_t has_data[33] = {0};
-            has_data[log_size] = 1;
-            pair_tree pt;
-            int bad = pair_tree_rebuild(log_size, has_data, pos_at[log_size], nq, vals, nv, &layer->decommitment,
-                                        layer->commitment, &pt, &o->n_perms_hints);
-            for (uint32_t i = 0; i < nq && !bad; i++) {
-                bad = pair_path_root(&pt, pos_at[log_size][i], self_v[i], sib_v[i], o->path_roots[5 + li][i], &o->n_perms_paths,
-                                     g_hints ? g_hints->pair_sib_hash[1 + li][i][0] : NULL);
-                if (g_hints && !bad) {
-                    g_hints->pair_depth[1 + li] = log_size;
-                    memcpy(g_hints->pair_has_data[1 + li], has_data, 33);
-                    memcpy(g_hints->pair_self[1 + li][i][log_size], self_v[i][log_size].v, 16);
-                    memcpy(g_hints->pair_sib[1 + li][i][log_size], sib_v[i][log_size].v, 16);
-                }
-                if (!bad && memcmp(o->path_roots[5 + li][i], layer->commitment, 32)) bad = 1;
-            }
-            pair_tree_free(&pt);
-            if (bad) FAIL(ORC_STAGE_FRI_INNER, 1);
-            for (uint32_t i = 0; i < nq; i++) {
-                uint32_t q = pos_at[log_size][i];
-                if (!qm31_eq(folded[i], self_v[i][log_size])) FAIL(ORC_STAGE_FRI_INNER, 1);
-                m31 x_inv = m31_inv(absolute_point(log_size, q).x);
-                qm31 l = (q & 1) ? sib_v[i][log_size] : self_v[i][log_size], r = (q & 1) ? self_v[i][log_size] : sib_v[i][log_size];
-                qm31 nl = qm31_add(l, r), nr = qm31_mul_m31(qm31_sub(l, r), x_inv);
-                folded[i] = qm31_add(nl, qm31_mul(nr, o->fri_alphas[li + 1]));
-                o->line_folds[li][i] = folded[i];
-            }
-        }
-        /* 9. last layer (recursive/folding/src/lib.rs:194-204; primitives/line/src/lib.rs:39-67) */
-        for (uint32_t i = 0; i < nq; i++) {
-            uint32_t q = pos_at[log_size][i];
-            cpoint ab = absolute_point(log_size, q);
-            m31 x = m31_sub(m31_mul(ab.x, ab.x), m31_mul(ab.y, ab.y));
-            uint32_t lg = p->log_last;
-            qm31 eval;
-            if (p->n_last_coeffs == 1) eval = qm31_load(p->last_coeffs);
-            else {
-                m31 dbl[32];
-                dbl[0] = x;
-                for (uint32_t k = 1; k < lg; k++) { m31 sq = m31_mul(dbl[k - 1], dbl[k - 1]); dbl[k] = m31_sub(m31_add(sq, sq), 1); }
-                /* fold(values, factors): lhs + rhs * factors[0], recursively -> iterative from the innermost factor */
-                static _Thread_local qm31 buf[1 << 12];
-                if (lg > 12) FAIL(ORC_STAGE_PARSE, 1);
-                uint32_t n = 1u << lg;
-                for (uint32_t k = 0; k < n; k++) buf[k] = qm31_load(p->last_coeffs + 4 * k);
-                for (uint32_t lev = lg; lev-- > 0;) {
-                    /* adjacent pairs at the deepest level use the LAST factor */
-                    n >>= 1;
-                    for (uint32_t k = 0; k < n; k++) buf[k] = qm31_add(buf[2 * k], qm31_mul_m31(buf[2 * k + 1], dbl[lev]));
-                }
-                eval = buf[0];
-            }
-            o->last_layer_evals[i] = eval;
-            if (!qm31_eq(folded[i], eval)) FAIL(ORC_STAGE_FRI_LAST, 1);
-        }
-    }
+    if (fri_stage(p, o, pos_at, max_first, nq)) return 0;
     o->verdict = 0; o->stage = ORC_OK;
     return 0;
 #undef FAIL
@@ -895,6 +907,91 @@ int orc_verify_proof_cfg(const uint8_t *blob, size_t len, const uint32_t *cfg, c
         return 0;
     }
     return orc_verify_proof(blob, len, input_idx, input_vals, n_inputs, o);
+}
+
+/* FRI-only verifier for the synthetic FRI + Merkle instances of BASELINE configs[4] part i: a fresh channel over
+ * the FRI commitments (the tail of `transcript` above: components/recursive/fiat_shamir/src/lib.rs:84-130), the opened first-layer values
+ * taken from the instance in place of the DEEP quotient answers, then fri_stage.  Blob layout: the 256-word header of
+ * recursive-stwo_b200/csrc/synth.cuh (shape at words 1..7, witness counts at 8 / 9 / 10+i / 42+i, nonce at 74, section offsets at 80..191).
+ * TEST INFRASTRUCTURE like the rest of oracle/. */
+int orc_fri_verify_synth(const uint32_t *w, size_t n_words, orc_verify_out *o) {
+    static _Thread_local orc_proof P;
+    orc_proof *p = &P;
+    memset(p, 0, sizeof *p);
+    memset(o, 0, sizeof *o);
+    o->verdict = 1;
+#define FAIL(stage_, verdict_) do { o->stage = (stage_); o->verdict = (verdict_); return 0; } while (0)
+    if (n_words < 256 || w[0] != 0x53594E54u || w[76] > n_words) FAIL(ORC_STAGE_PARSE, 1);
+    p->log_size_plonk = w[1]; p->log_size_poseidon = w[2]; p->pow_bits = w[3]; p->log_blowup = w[4]; p->log_last = w[5]; p->n_queries = w[6];
+    p->n_inner = w[7];
+    const uint32_t nq = p->n_queries, blow = p->log_blowup;
+    if (nq == 0 || nq > ORC_MAX_QUERIES || p->n_inner + 1 > ORC_MAX_INNER || p->log_last > 12 || p->pow_bits >= 32 || blow == 0 || blow > 16 ||
+        p->log_size_plonk == 0 || p->log_size_plonk > 28 || p->log_size_poseidon == 0 || p->log_size_poseidon > 28)
+        FAIL(ORC_STAGE_PARSE, 1);
+    const uint32_t max_first = p->log_last + blow + 1 + p->n_inner;
+    const uint32_t log_plonk = p->log_size_plonk + blow, log_pos = p->log_size_poseidon + blow;
+    if (max_first > 29 || log_plonk > max_first || log_pos > max_first) FAIL(ORC_STAGE_PARSE, 1);
+    for (size_t k = 256; k < w[76]; k++) if (w[k] >= 0x7fffffffu) FAIL(ORC_STAGE_PARSE, 1);      /* unused capacity is zero */
+    p->first_layer.commitment = w + w[80];
+    p->first_layer.fri_witness = w + w[83]; p->first_layer.n_fri_witness = w[8];
+    p->first_layer.decommitment.hash_witness = w + w[84]; p->first_layer.decommitment.n_hash_witness = w[9];
+    for (uint32_t i = 0; i < p->n_inner; i++) {
+        p->inner[i].commitment = w + w[96 + i];
+        p->inner[i].fri_witness = w + w[128 + i]; p->inner[i].n_fri_witness = w[10 + i];
+        p->inner[i].decommitment.hash_witness = w + w[160 + i]; p->inner[i].decommitment.n_hash_witness = w[42 + i];
+    }
+    p->last_coeffs = w + w[81]; p->n_last_coeffs = w[85]; p->last_log_size = p->log_last;
+    if (p->n_last_coeffs != (1ull << p->log_last)) FAIL(ORC_STAGE_PARSE, 1);
+    p->pow_nonce = (uint64_t)w[74] | ((uint64_t)w[75] << 32);
+    o->max_first_log = max_first; o->n_inner = p->n_inner; o->n_queries = nq;
+    /* channel over the FRI commitments */
+    {
+        orc_channel ch;
+        orc_channel_init(&ch);
+        uint32_t d[8];
+        orc_channel_mix_root(&ch, p->first_layer.commitment);
+        o->fri_alphas[0] = channel_draw_first(&ch);
+        for (uint32_t i = 0; i < p->n_inner; i++) {
+            orc_channel_mix_root(&ch, p->inner[i].commitment);
+            o->fri_alphas[i + 1] = channel_draw_first(&ch);
+        }
+        for (uint64_t i = 0; i < p->n_last_coeffs; i += 2)
+            orc_channel_mix_felts2(&ch, p->last_coeffs + 4 * i, i + 1 < p->n_last_coeffs ? p->last_coeffs + 4 * (i + 1) : NULL);
+        uint32_t nf[4] = { (uint32_t)(p->pow_nonce & ((1u << 22) - 1)), (uint32_t)((p->pow_nonce >> 22) & ((1u << 21) - 1)),
+                           (uint32_t)((p->pow_nonce >> 43) & ((1u << 21) - 1)), 0 };
+        orc_channel_mix_felts2(&ch, nf, NULL);
+        memcpy(o->digest_after_nonce, ch.digest, 32);
+        const int pow_ok = (ch.digest[0] & ((1u << p->pow_bits) - 1)) == 0;
+        uint32_t got = 0;
+        for (uint32_t k = 0; k < (nq + 3) / 4; k++) {
+            orc_channel_draw(&ch, d);
+            for (int j = 0; j < 8 && got < nq; j++) o->raw_queries[got++] = d[j];
+        }
+        o->n_transcript_perms = (uint32_t)ch.n_perms;
+        o->n_perms_paths += o->n_transcript_perms;
+        if (!pow_ok) FAIL(ORC_STAGE_POW, 1);
+    }
+    {
+        uint32_t ls[3] = { max_first, log_plonk, log_pos };
+        qsort(ls, 3, 4, cmp_u32);
+        o->n_logs = 0;
+        for (int i = 2; i >= 0; i--) if (o->n_logs == 0 || o->log_sizes[o->n_logs - 1] != ls[i]) o->log_sizes[o->n_logs++] = ls[i];
+    }
+    static _Thread_local uint32_t pos_at[31][ORC_MAX_QUERIES];
+    for (uint32_t L = 1; L <= max_first; L++)
+        for (uint32_t i = 0; i < nq; i++) pos_at[L][i] = (o->raw_queries[i] & ((1u << max_first) - 1)) >> (max_first - L);
+    for (uint32_t g = 0; g < o->n_logs; g++) memcpy(o->query_pos[g], pos_at[o->log_sizes[g]], nq * 4);
+    {
+        uint32_t tmp[ORC_MAX_QUERIES];
+        memcpy(tmp, pos_at[max_first], nq * 4);
+        if (sort_dedup(tmp, nq) != nq) FAIL(ORC_STAGE_UNSUPPORTED, 2);
+    }
+    for (uint32_t g = 0; g < o->n_logs; g++)
+        for (uint32_t i = 0; i < nq; i++) o->fri_answers[g][i] = qm31_load(w + w[82] + (g * nq + i) * 4);
+    if (fri_stage(p, o, pos_at, max_first, nq)) return 0;
+    o->verdict = 0; o->stage = ORC_OK;
+    return 0;
+#undef FAIL
 }
 
 int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,

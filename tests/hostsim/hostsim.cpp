@@ -236,3 +236,120 @@ extern "C" void hs_circuit_level_perms(void *h, u32 *perms_per_level) {
         perms_per_level[l] = n;
     }
 }
+
+// ---- synthetic FRI + Merkle instances (synth.cuh): the generator and the verifier stages on the host ---------------------------------------
+#include "../../recursive-stwo_b200/csrc/synth.cuh"
+extern "C" {
+u32 hs_synth_blob_words(const u32 *shape7) { verify::Shape s; memcpy(&s, shape7, 28); return synth::layout(s).total; }
+// builds instance `seed` of `shape` into blob (hs_synth_blob_words words).  Returns 0, or a negative code when the generator's own checks fail
+// (-1: the final layer is not a polynomial of the claimed degree; -2: no nonce found)
+int hs_synth_generate(const u32 *shape7, u64 seed, u32 *blob) {
+    verify::Shape s; memcpy(&s, shape7, 28);
+    const synth::Layout l = synth::layout(s);
+    synth::write_header(blob, s, l);
+    for (u32 k = synth::HDR; k < l.total; k++) blob[k] = 0;
+    static proof::Desc d; memset(&d, 0, sizeof d);
+    synth::set_offsets(s, d);
+    static fs::Out o;
+    u32 logs[fri::MAX_LOGS];
+    const u32 n_logs = fri::log_sizes(d, logs), nq = s.n_queries, mf = s.max_first();
+    std::vector<std::vector<qm31_t>> cols(n_logs);
+    for (u32 g = 0; g < n_logs; g++) { cols[g].resize((size_t)1 << logs[g]); for (u32 i = 0; i < (1u << logs[g]); i++) cols[g][i] = synth::column_value(seed, g, logs[g], s.log_blowup, i); }
+    auto build_tree = [&](u32 depth, auto data_at) {            // data_at(h) -> const std::vector<qm31_t>* or nullptr
+        std::vector<std::vector<u32>> lv(depth + 1);
+        for (u32 h = depth + 1; h-- > 0;) {
+            lv[h].resize((size_t)8 << h);
+            const std::vector<qm31_t> *dat = data_at(h);
+            for (u32 i = 0; i < (1u << h); i++)
+                synth::node_hash(h == depth ? nullptr : &lv[h + 1][16 * (size_t)i], h == depth ? nullptr : &lv[h + 1][16 * (size_t)i + 8], dat ? (*dat)[i].v : nullptr, &lv[h][8 * (size_t)i]);
+        }
+        return lv;
+    };
+    auto first = build_tree(mf, [&](u32 h) -> const std::vector<qm31_t> * { for (u32 g = 0; g < n_logs; g++) if (logs[g] == h) return &cols[g]; return nullptr; });
+    memcpy(blob + l.off_flc, first[0].data(), 32);
+    synth::transcript(blob, d, o, 1);
+    std::vector<qm31_t> cur((size_t)1 << (mf - 1), qm31::zero());
+    std::vector<std::vector<qm31_t>> layers(s.n_inner);
+    std::vector<std::vector<std::vector<u32>>> trees(s.n_inner);
+    for (u32 li = 0; li < s.n_inner; li++) {
+        for (u32 g = 0; g < n_logs; g++)
+            if (logs[g] == mf - li) {
+                const qm31_t a2 = qm31::mul(o.fri_alphas[li], o.fri_alphas[li]);
+                for (u32 j = 0; j < cur.size(); j++)
+                    cur[j] = qm31::add(qm31::mul(a2, cur[j]), synth::circle_fold_at(logs[g], j, cols[g][2 * j], cols[g][2 * j + 1], o.fri_alphas[li]));
+            }
+        const u32 L = mf - 1 - li;
+        layers[li] = cur;
+        trees[li] = build_tree(L, [&](u32 h) -> const std::vector<qm31_t> * { return h == L ? &layers[li] : nullptr; });
+        memcpy(blob + l.off_inc[li], trees[li][0].data(), 32);
+        synth::transcript(blob, d, o, 2 + li);
+        std::vector<qm31_t> nxt(cur.size() / 2);
+        for (u32 j = 0; j < nxt.size(); j++) nxt[j] = synth::line_fold_at(L, j, cur[2 * j], cur[2 * j + 1], o.fri_alphas[li + 1]);
+        cur.swap(nxt);
+    }
+    const u32 Llast = mf - 1 - s.n_inner, nc = 1u << s.log_last;
+    {
+        std::vector<qm31_t> v(cur.begin(), cur.begin() + nc), out(nc), tmp(nc);
+        synth::interpolate_line(Llast, s.log_last, v.data(), out.data(), tmp.data());
+        for (u32 k = 0; k < nc; k++) memcpy(blob + l.off_last + 4 * k, out[k].v, 16);
+        std::vector<qm31_t> buf(nc);
+        for (u32 r = 0; r < cur.size(); r++)      // the verifier's evaluation point of position r of the last layer
+            if (!qm31::eq(fri::eval_last_poly(blob + l.off_last, s.log_last, circle::dbl(fri::absolute_point(Llast + 1, 2 * r)).x, buf.data()), cur[r])) return -1;
+    }
+    bool found = false;
+    for (u64 nonce = 0; nonce < (1ull << 20) && !found; nonce++) {
+        blob[synth::H_NONCE] = (u32)nonce; blob[synth::H_NONCE + 1] = 0;
+        synth::transcript(blob, d, o, 1 + s.n_inner);
+        found = o.pow_ok && synth::queries_distinct(d, o);
+    }
+    if (!found) return -2;
+    std::vector<u32> pos(nq), sp(nq), scratch(6 * nq + 8);
+    u32 wi = 0;
+    for (u32 g = 0; g < n_logs; g++) {
+        for (u32 i = 0; i < nq; i++) { sp[i] = pos[i] = fri::position(d, o.raw_queries[i], logs[g]); memcpy(blob + l.off_ans + (g * nq + i) * 4, cols[g][pos[i]].v, 16); }
+        const u32 ns = decommit::sort_unique(sp.data(), nq);
+        for (u32 k = 0; k < ns;) {
+            const u32 start = sp[k] & ~1u;
+            for (u32 e = start; e < start + 2; e++) {
+                if (k < ns && sp[k] == e) k++;
+                else { memcpy(blob + l.off_flfw + 4 * wi, cols[g][e].v, 16); wi++; }
+            }
+        }
+    }
+    blob[synth::H_FL_NFW] = wi;
+    for (u32 i = 0; i < nq; i++) pos[i] = fri::position(d, o.raw_queries[i], mf);
+    blob[synth::H_FL_NHW] = synth::emit_hash_witness(mf, s.fri_data_mask(0), pos.data(), nq, [&](u32 h, u32 p) { return &first[h][8 * (size_t)p]; }, blob + l.off_flhw, scratch.data());
+    for (u32 li = 0; li < s.n_inner; li++) {
+        const u32 L = mf - 1 - li;
+        for (u32 i = 0; i < nq; i++) sp[i] = pos[i] = fri::position(d, o.raw_queries[i], L);
+        const u32 ns = decommit::sort_unique(sp.data(), nq);
+        u32 w2 = 0;
+        for (u32 k = 0; k < ns; k++)
+            if (decommit::find(sp.data(), ns, sp[k] ^ 1u) < 0) { memcpy(blob + l.off_infw[li] + 4 * w2, layers[li][sp[k] ^ 1u].v, 16); w2++; }
+        blob[synth::H_IN_NFW + li] = w2;
+        blob[synth::H_IN_NHW + li] = synth::emit_hash_witness(L, 1u << L, pos.data(), nq, [&](u32 h, u32 p) { return &trees[li][h][8 * (size_t)p]; }, blob + l.off_inhw[li], scratch.data());
+    }
+    return 0;
+}
+// the product's verifier stages on synthetic instances (what stwo_b200_synth_verify_batch_dev launches): returns the workspace base (hs_free)
+void *hs_synth_verify(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *shape7, int coop, verify::Detail *detail_out, verify::Workspace *ws_out) {
+    verify::Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape7, 28);
+    ws.n_proofs = n; ws.blobs = blobs; ws.blob_off = blob_off;
+    uint8_t *base = (uint8_t *)calloc(verify::carve(ws, nullptr), 1);
+    verify::carve(ws, base);
+    ws.mode = verify::MODE_FULL | (coop ? 0u : verify::MODE_PATH_KERNELS);
+    const u32 nf = ws.shape.n_fri_trees(), nq = ws.shape.n_queries;
+    std::vector<u32> tab(decommit::pair_tab_words(nq) + verify::folds_tab_words(nq) + 2 * nq + 64);
+    decommit::CoopOne one;
+    for (u32 p = 0; p < n; p++) synth::stage_open(ws, p);
+    for (u32 p = 0; p < n; p++) { if (coop) verify::stage_folds_coop(one, ws, p, tab.data()); else verify::stage_folds(ws, p); }
+    for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) { if (coop) verify::stage_pair_tree_coop(one, ws, p, f, tab.data()); else verify::stage_pair_tree(ws, p, f); }
+    if (!coop) for (u32 p = 0; p < n; p++) for (u32 f = 0; f < nf; f++) for (u32 i = 0; i < nq; i++) verify::stage_pair_path(ws, p, f, i);
+    for (u32 p = 0; p < n; p++) verify::stage_verdict(ws, p);
+    memcpy(detail_out, ws.detail, n * sizeof(verify::Detail));
+    if (ws_out) *ws_out = ws;
+    return base;
+}
+}
