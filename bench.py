@@ -353,6 +353,34 @@ def shape_leg(pkg, dev, fixture, n, reps=5):
             "ms_per_batch": ms, "proofs_per_sec": n / (ms * 1e-3)}
 
 
+def synthetic_leg(pkg, dev, shape, n=4096, reps=5):
+    """BASELINE configs[4] part i: n DISTINCT synthetic FRI + Merkle instances of the headline shape, generated on
+    the device (seed = instance index; generation untimed), through the channel replay, the circle / line folds and the FRI tree rebuilds
+    (K3, K5, K2; full mode: per-query roots + permutation record) -- next to n replicas of one instance, which is what a replica batch of
+    real proofs looks like to these kernels (same positions, same node sharing, same witness consumption order in every lane)."""
+    import torch
+    out = {"config": "BASELINE configs[4] part i: %d synthetic FRI + Merkle instances, shape of small_proof.bin without proof of work; verify = channel replay + "
+                     "folds + FRI tree rebuilds (8 trees, 2112 path permutations covered per instance)" % n}
+    for name, distinct in (("distinct", True), ("replicas", False)):
+        sb = pkg.SynthBatch(shape, n, seed0=0, distinct=distinct)
+        for _ in range(2):
+            v, _ = sb.run(full=True)
+        assert int(v.sum().item()) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            sb.run(full=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        dt = sb.fetch(n // 2, "detail")
+        out[name] = {"ms_per_batch": ms, "instances_per_sec": n / (ms * 1e-3), "perms_executed_per_instance": int(dt.n_perms_hints + dt.fs.n_transcript_perms)}
+        del sb
+        torch.cuda.empty_cache()
+    out["distinct_over_replicas"] = out["distinct"]["instances_per_sec"] / out["replicas"]["instances_per_sec"]
+    return out
+
+
 def divergence_leg(pkg, dev, n=1024, reps=5):
     """What replicas hide: lanes of a warp hold different proofs in production.  The same shape (16, 15; 10 queries) verified and
     traced as n replicas of level10-1.bin and as n proofs alternating level10-1.bin / level11-1.bin (different query positions
@@ -607,6 +635,8 @@ def main():
                                       for C, Q, T in ((4, 16, 2), (8, 128, 2), (50, 64, 2), (60, 16, 2), (60, 128, 2), (8, 32, 1), (4, 32, 64))]}
         secondary["merkle_sweep_perms_per_sec"] = secondary["merkle_sweep"][1]["perms_per_sec"]
         secondary["lane_divergence"] = divergence_leg(pkg, dev)
+        secondary["synthetic_4096"] = synthetic_leg(pkg, dev, pkg.shape_from_config(pkg.PcsConfig(0, sh.log_blowup, sh.log_last, sh.n_queries),
+                                                                                    sh.log_size_plonk, sh.log_size_poseidon))
         secondary["shape_R"] = shape_leg(pkg, dev, "recursive_proof_16_15.bin", 1024)
 
     if not args.no_secondary:

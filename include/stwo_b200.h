@@ -295,6 +295,25 @@ int32_t stwo_b200_gather_verdicts(void *comm, uint32_t rank, uint32_t world, uin
 int32_t stwo_b200_gather_trace_columns(void *comm, uint32_t rank, uint32_t world, uint32_t dst, uint64_t n_total, size_t words_per_proof,
                                        const uint32_t *values_local, uint32_t *values_all, void *stream);
 
+/* ---- synthetic FRI + Merkle instances (BASELINE configs[4] part i) ----------------------------------
+ * There is no STARK prover on this side of the boundary, so OODS-consistent synthetic proofs cannot exist; what CAN be generated, on
+ * the device and all different, is the part of a proof the query phase checks: per instance (seed = seed0 + index) low-degree
+ * columns of the shape's three log sizes, committed in one mixed-degree first-layer tree, alpha from a Poseidon channel over the
+ * roots, every inner layer folded and committed, the last-layer polynomial, the queries, and the batched decommitments in stwo's
+ * layout.  The verifier entry runs the channel replay, the circle / line folds and the FRI tree rebuilds (K3, K5, K2) on them.
+ * Instance blob = 256 header words + fixed-capacity sections (recursive-stwo_b200/csrc/synth.cuh); all instances of a batch are
+ * stwo_b200_synth_blob_words(shape) words apart.  Shapes: as for proofs, with log_last <= 6 and pow_bits <= 10 (the generator
+ * grinds the nonce one thread per instance).  status (optional, DEVICE, n int32): 0 ok, < 0 the generator's own check failed. */
+uint32_t stwo_b200_synth_blob_words(const stwo_b200_proof_shape *shape);
+size_t stwo_b200_synth_scratch_bytes(const stwo_b200_proof_shape *shape, uint32_t n);
+int32_t stwo_b200_synth_generate_dev(const stwo_b200_proof_shape *shape, uint32_t n, uint64_t seed0, uint32_t *blobs, uint64_t *blob_off,
+                                     void *scratch, size_t scratch_bytes, int32_t *status, void *stream);
+/* workspace: stwo_b200_verify_workspace_bytes(shape, n); flags: STWO_B200_VERIFY_FULL [| _PATH_KERNELS]; results are read with
+ * stwo_b200_verify_fetch like those of a proof batch (DETAIL: alphas, queries; CIRCLE_FOLDS, LINE_FOLDS, LAST_EVALS, PATH_ROOTS 4..) */
+int32_t stwo_b200_synth_verify_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                         const stwo_b200_proof_shape *shape, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                         uint8_t *verdict, uint8_t *stage, void *stream);
+
 /* ---- K6 / K7: the constraint system on the device ----------------------------------------------------------------------
  * The flat image of PlonkWithPoseidonConstraintSystem (constraint_system/src/plonk_with_poseidon.rs:18-41) after pad().
  * Wiring is shared by every batch item of a shape; values (variables, Poseidon flow hashes, swap bits) are per item.

@@ -16,9 +16,10 @@ from .verifier import (verify_proofs, VerifyBatch, VerifyStream, proof_shape, pr
                        CONFIG_FAST_PROVER2, CONFIG_FAST_VERIFIER, CONFIG_FAST_VERIFIER2, CONFIG_FAST_VERIFIER3)
 from ._lib import ProofShape, PcsConfig, VerifyDetail, STAGES
 from .circuit import VerifierCircuit, MixedBatch, VerifyTracePipeline, cached_circuit
+from .synthetic import SynthBatch
 from .stages import channel_replay, fri_answers, fri_folds, hash_column_capacity
 
-__all__ = ["channel_replay", "fri_answers", "fri_folds", "hash_column_capacity", "VerifierCircuit", "MixedBatch", "VerifyTracePipeline", "cached_circuit", "verify_proofs", "VerifyBatch", "VerifyStream", "proof_shape", "proof_perms", "shape_for", "shape_from_config", "PcsConfig", "REFERENCE_CONFIGS", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
+__all__ = ["SynthBatch", "channel_replay", "fri_answers", "fri_folds", "hash_column_capacity", "VerifierCircuit", "MixedBatch", "VerifyTracePipeline", "cached_circuit", "verify_proofs", "VerifyBatch", "VerifyStream", "proof_shape", "proof_perms", "shape_for", "shape_from_config", "PcsConfig", "REFERENCE_CONFIGS", "INPUTS_SINGLE", "INPUTS_RECURSIVE", "ProofShape",
            "VerifyDetail", "STAGES","init", "poseidon2_permute", "poseidon2_permute_host", "hash_node_batch", "merkle_commit",
            "merkle_commit_host", "merkle_decommit", "merkle_path_verify", "merkle_path_verify_host", "launch_count",
            "path_perms", "PathShape", "StwoB200Error"]

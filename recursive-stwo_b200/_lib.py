@@ -182,6 +182,10 @@ SIGNATURES = {
     "stwo_b200_cs_flow_padded_len": (_u32, [_u32]),
     "stwo_b200_cs_export_flow_dev": (_i32, [_VAL_P, _u32, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_circuit_export_flow_dev": (_i32, [_vp, _u32, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "stwo_b200_synth_blob_words": (_u32, [_PSHAPE_P]),
+    "stwo_b200_synth_scratch_bytes": (_sz, [_PSHAPE_P, _u32]),
+    "stwo_b200_synth_generate_dev": (_i32, [_PSHAPE_P, _u32, _u64, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "stwo_b200_synth_verify_batch_dev": (_i32, [_vp, _vp, _u32, _PSHAPE_P, _u32, _vp, _sz, _vp, _vp, _vp]),
     "stwo_b200_cs_eval_tape_dev": (_i32, [_TAPE_P, _u32, _vp, _VAL_P, _vp]),
     "stwo_b200_cs_eval_level_clock": (_i32, [_vp]),
     "stwo_b200_cs_check_arithmetics_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp]),

@@ -3,6 +3,7 @@
 // different proofs, so same-shape batches execute almost divergence-free.
 #include "common.cuh"
 #include "verify.cuh"
+#include "synth.cuh"
 #include <vector>
 #include <map>
 #include <algorithm>
@@ -301,6 +302,10 @@ __global__ void __launch_bounds__(kT) k_verdict(const Workspace ws, u32 p0, u32 
     if (stage) stage[p] = (uint8_t)ws.detail[p].stage;
 }
 
+__global__ void __launch_bounds__(kT) k_synth_open(const Workspace ws, u32 p0, u32 pn) {
+    u32 idx = blockIdx.x * kT + threadIdx.x;
+    if (idx < pn) synth::stage_open(ws, p0 + idx);
+}
 // stream pool for sliced batches: per slice a main chain and a side stream for the commitment-tree path recomputation
 constexpr int kSlices = 4;
 cudaStream_t g_pool[2 * kSlices] = {nullptr};
@@ -576,6 +581,36 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
         STWO_CUDA(cudaStreamWaitEvent(st, g_join[sl], 0));
         note_launch((path_kernels ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
     }
+    return cuda_status(cudaGetLastError());
+}
+
+// Verification of synthetic FRI + Merkle instances (synth.cuh; BASELINE configs[4] part i): Fiat-Shamir over the FRI commitments and the
+// opened first-layer values (k_synth_open), then the same fold and FRI tree-rebuild kernels a real proof goes through (K3 channel, K5
+// folds, K2 Merkle).  FULL: the per-query roots and the permutation record of the FRI trees are produced like for a real proof.
+extern "C" int32_t stwo_b200_synth_verify_batch_dev(const uint32_t *blobs, const uint64_t *blob_off, uint32_t n_proofs,
+                                                    const stwo_b200_proof_shape *shape, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                                    uint8_t *verdict, uint8_t *stage, void *stream) {
+    STWO_CHECK_DEVICE();
+    if (n_proofs == 0) return STWO_B200_OK;
+    if (!shape_ok(shape)) return STWO_B200_E_SHAPE;
+    if (!blobs || !blob_off || !workspace) return STWO_B200_E_BAD_ARG;
+    Workspace ws;
+    memset(&ws, 0, sizeof ws);
+    memcpy(&ws.shape, shape, sizeof ws.shape);
+    ws.n_proofs = n_proofs; ws.blobs = blobs; ws.blob_off = blob_off;
+    if (verify::carve(ws, (uint8_t *)workspace) > workspace_bytes) return STWO_B200_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool full = flags & STWO_B200_VERIFY_FULL;
+    const bool path_kernels = full && ((flags & STWO_B200_VERIFY_PATH_KERNELS) || tree_group_width(n_proofs) == 0);
+    ws.mode = (full ? verify::MODE_FULL : 0u) | (path_kernels ? verify::MODE_PATH_KERNELS : 0u);
+    const u32 n = n_proofs;
+    const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees();
+    k_synth_open<<<nblk(n), kT, 0, st>>>(ws, 0, n);
+    launch_folds(ws, 0, n, st);
+    launch_pair_tree(ws, 0, n, st);
+    if (path_kernels) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, st>>>(ws, 0, n);
+    k_verdict<<<nblk(n), kT, 0, st>>>(ws, 0, n, verdict, stage);
+    note_launch(path_kernels ? 5 : 4);
     return cuda_status(cudaGetLastError());
 }
 
