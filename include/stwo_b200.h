@@ -37,7 +37,9 @@ extern "C" {
 #define STWO_B200_MAX_DEPTH 32
 
 /* library / device lifecycle.  init selects the device for the calling thread and creates the
- * staging buffers lazily; version = 0x00MMmmpp. */
+ * staging buffers lazily; version = 0x00MMmmpp.  ONE DEVICE PER PROCESS (one process per GPU is the multi-GPU model): init on a
+ * second device returns STWO_B200_E_BAD_ARG; init on the same device again is a no-op.  The host-pointer entry points share one
+ * staging area and are not re-entrant: call them from one host thread at a time. */
 int32_t stwo_b200_init(int32_t device);
 int32_t stwo_b200_shutdown(void);
 uint32_t stwo_b200_version(void);

@@ -67,7 +67,8 @@ class VerifierCircuit:
     def trace(self, batch, check=True, export=True, preprocessed=True, timed=False, native_hints=None):
         """Trace generation for a batch that `batch.run()` has verified (VerifyBatch keeps the hints in its workspace).
         Returns dict(values=[n, 13, n_rows] | None, preprocessed=[10, n_rows] | None, bad_row=[n] | None, bad_flow=[n] | None)
-        as torch tensors on the batch's device."""
+        as torch tensors on the batch's device.  `values` is ONE buffer per circuit object (13.3 GB for 4096 proofs of shape S), reused
+        by every call: the next trace() overwrites it -- consume or copy it first."""
         import torch
         from .hashing import _dptr, _stream
         dev = batch.d_words.device

@@ -41,8 +41,10 @@ extern "C" int32_t stwo_b200_init(int32_t device) {
     STWO_CUDA(cudaGetDeviceProperties(&p, device));
     if (p.major < 10) return STWO_B200_E_NO_DEVICE;   // sm_100a code only; nothing else is built
     std::lock_guard<std::mutex> lk(g_mu);
+    // One device per process: the staging area, the stream pools and events of the batch drivers and every uploaded circuit live on the
+    // device of the first init.  A second init on ANOTHER device is refused instead of leaving those bound to the old one.
+    if (g_device >= 0 && g_device != device) return STWO_B200_E_BAD_ARG;
     if (g_device != device) {
-        if (g_stream) cudaStreamDestroy(g_stream);
         STWO_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
         g_device = device;
     }

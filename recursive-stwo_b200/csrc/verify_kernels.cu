@@ -111,35 +111,49 @@ __global__ void __launch_bounds__(kCoopThreads) k_parse_coop(const Workspace ws,
 // matrix a 4-step butterfly sum.  Same transcript order as fs::transcript (components/recursive/fiat_shamir/src/lib.rs:39-131).
 struct Lanes16 {
     unsigned mask; u32 l;                                   // l = 0..15: which state word this lane holds
+    // this lane's constants, loaded once per kernel: the chain is latency bound, a constant fetched inside a round is on the critical path
+    u32 rcf[4], rcl[4], dg, c0, c1, c2, c3;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int r = 0; r < 4; r++) { rcf[r] = poseidon2::K.rc_first[16 * r + l]; rcl[r] = poseidon2::K.rc_last[16 * r + l]; }
+        dg = poseidon2::K.diag[l];
+        const u32 row = l & 3u;
+        c0 = row == 0 ? 5u : row == 1 ? 4u : 1u; c1 = row == 0 ? 7u : row == 1 ? 6u : row == 2 ? 3u : 1u;
+        c2 = row < 2 ? 1u : row == 2 ? 5u : 4u; c3 = row == 0 ? 3u : row == 1 ? 1u : row == 2 ? 7u : 6u;
+    }
+    // any value below 2^61 whose high word is small -> canonical, in one step: hi * 2^32 + lo = 2 hi + (lo mod 2^31) + (lo >> 31) (mod p).
+    // The general m31::red64 folds twice; on this chain every dependent instruction is ~5 cycles of latency nobody else fills.
+    __device__ __forceinline__ static u32 red_small(u64 x) {
+        const u32 lo = (u32)x, hi = (u32)(x >> 32);          // hi < 2^29: the sum below is < 2p
+        return m31::canon((lo & M31_P) + (lo >> 31) + (hi << 1));
+    }
     __device__ __forceinline__ u32 get(u32 x, u32 src) const { return __shfl_sync(mask, x, src, 16); }
     __device__ __forceinline__ u32 get_xor(u32 x, u32 m) const { return __shfl_xor_sync(mask, x, m, 16); }
     // circ(2 M4, M4, M4, M4) x, M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] (primitives/poseidon31/src/implementation.rs:7-58)
     __device__ __forceinline__ u32 ext_mds(u32 x) const {
-        const u32 base = l & ~3u, row = l & 3u;
+        const u32 base = l & ~3u;
         const u32 x0 = get(x, base), x1 = get(x, base + 1), x2 = get(x, base + 2), x3 = get(x, base + 3);
-        const u32 c0 = row == 0 ? 5u : row == 1 ? 4u : 1u, c1 = row == 0 ? 7u : row == 1 ? 6u : row == 2 ? 3u : 1u;
-        const u32 c2 = row < 2 ? 1u : row == 2 ? 5u : 4u, c3 = row == 0 ? 3u : row == 1 ? 1u : row == 2 ? 7u : 6u;
-        const u32 t = m31::red64((u64)c0 * x0 + (u64)c1 * x1 + (u64)c2 * x2 + (u64)c3 * x3);
-        u32 col = m31::addc(t, get_xor(t, 4));
-        col = m31::addc(col, get_xor(col, 8));
-        return m31::addc(t, col);
+        const u32 t = red_small((u64)c0 * x0 + (u64)c1 * x1 + (u64)c2 * x2 + (u64)c3 * x3);
+        // column sum over the four blocks as one lazy 34-bit sum: two shuffles side by side instead of two dependent add-reduce steps
+        const u32 t4 = get_xor(t, 4), t8 = get_xor(t, 8), t12 = get_xor(t, 12);
+        return red_small((u64)t + t + t4 + t8 + t12);
     }
     __device__ __forceinline__ static u32 pow5(u32 x) { const u32 x2 = m31::mulc(x, x), x4 = m31::mulc(x2, x2); return m31::mulc(x4, x); }
     __device__ u32 permute(u32 x) const {                   // canonical in, canonical out; implementation.rs:108-149
         x = ext_mds(x);
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, poseidon2::K.rc_first[16 * r + l])));
-#pragma unroll 1
+#pragma unroll
+        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, rcf[r])));
+#pragma unroll
         for (int r = 0; r < 14; r++) {
             if (l == 0) x = pow5(m31::addc(x, poseidon2::K.rc_part[r]));
-            u32 sum = m31::addc(x, get_xor(x, 1));
-            sum = m31::addc(sum, get_xor(sum, 2));
-            sum = m31::addc(sum, get_xor(sum, 4));
-            sum = m31::addc(sum, get_xor(sum, 8));
-            x = m31::addc(sum, m31::mulc(x, poseidon2::K.diag[l]));
+            // sum of the 16 words: two butterfly steps on lazy sums (values < 2^31, four of them < 2^33), then one reduction
+            const u64 s1 = (u64)x + get_xor(x, 1) + get_xor(x, 2) + get_xor(x, 3);
+            const u32 q = red_small(s1);
+            const u64 s2 = (u64)q + get_xor(q, 4) + get_xor(q, 8) + get_xor(q, 12);
+            x = red_small(s2 + (u64)x * dg);
         }
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, poseidon2::K.rc_last[16 * r + l])));
+#pragma unroll
+        for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, rcl[r])));
         return x;
     }
 };
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(kT) k_transcript16(const Workspace ws, u32 p0,
     Lanes16 g;
     g.l = threadIdx.x % 16;
     g.mask = 0xffffu << (16 * ((threadIdx.x % 32) / 16));
+    g.init();
     verify::Detail &dt = ws.detail[p];
     transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0));
     __syncwarp(g.mask);
