@@ -375,6 +375,12 @@ typedef struct {
      * variables poseidon_permute_emulated creates (primitives/poseidon31/src/emulated.rs:104-221), in creation order */
     uint32_t n_eperms;
     const uint32_t *eperms;
+    /* Optional bundles (0 / NULL: every instruction is its own bundle and level_start is what separates independent instructions).
+     * A bundle = instructions [bundle_start[k], bundle_start[k + 1]) executed back to back by one warp: each may read what an earlier one
+     * of the same bundle wrote.  With bundles, level l is the bundles [level_bundle[l], level_bundle[l + 1]) and only bundles of one
+     * level are independent; level_start still gives the level's instruction range. */
+    uint32_t n_bundles;
+    const uint32_t *bundle_start /* n_bundles + 1 */, *level_bundle /* n_levels + 1 */;
 } stwo_b200_cs_tape;
 #define STWO_B200_T_ADD 1
 #define STWO_B200_T_MUL 2

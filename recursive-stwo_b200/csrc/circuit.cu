@@ -88,7 +88,7 @@ int32_t upload(stwo_b200_circuit *c) {
     size_t at = 0;
     auto take = [&](size_t bytes) { at = align_up(at, 256); size_t o = at; at += bytes; return o; };
     const size_t o_w = take(9 * nr * 4), o_jobs = take(r.jobs.size() * sizeof(circuit::ExtraJob) + 16), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
-                 o_lvl = take(r.level_start.size() * 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4),
+                 o_lvl = take(r.level_start.size() * 4), o_bs = take(r.bundle_start.size() * 4 + 4), o_lb = take(r.level_bundle.size() * 4 + 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4),
                  o_xt = take(stwo_b200_cs_export_tiles_words((u32)nr) * 4 + 16), o_mult = take((size_t)4 * nr * 4), o_scr = take(((size_t)4 * cs.n_vars + 4) * 4),
                  o_stat = take(256);
     uint8_t *d = nullptr;
@@ -105,6 +105,8 @@ int32_t upload(stwo_b200_circuit *c) {
     }
     STWO_CUDA(cudaMemcpy(d + o_ins, r.ins.data(), r.ins.size() * 16, cudaMemcpyHostToDevice));
     STWO_CUDA(cudaMemcpy(d + o_lvl, r.level_start.data(), r.level_start.size() * 4, cudaMemcpyHostToDevice));
+    STWO_CUDA(cudaMemcpy(d + o_bs, r.bundle_start.data(), r.bundle_start.size() * 4, cudaMemcpyHostToDevice));
+    STWO_CUDA(cudaMemcpy(d + o_lb, r.level_bundle.data(), r.level_bundle.size() * 4, cudaMemcpyHostToDevice));
     if (!cs.eperms.empty()) STWO_CUDA(cudaMemcpy(d + o_ep, cs.eperms.data(), cs.eperms.size() * 4, cudaMemcpyHostToDevice));
     if (!r.gather.empty()) STWO_CUDA(cudaMemcpy(d + o_g, r.gather.data(), r.gather.size() * 4, cudaMemcpyHostToDevice));
     const u32 *w = (const u32 *)(d + o_w);
@@ -125,7 +127,8 @@ int32_t upload(stwo_b200_circuit *c) {
                  xt.empty() ? nullptr : (const u32 *)(d + o_xt), xcap};
     c->jobs = (const circuit::ExtraJob *)(d + o_jobs); c->n_jobs = (u32)r.jobs.size(); c->n_extra_words = r.n_extra_words;
     c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
-                (const u32 *)(d + o_perm), (u32)(cs.eperms.size() / tape::EPOSEIDON_REC), (const u32 *)(d + o_ep)};
+                (const u32 *)(d + o_perm), (u32)(cs.eperms.size() / tape::EPOSEIDON_REC), (const u32 *)(d + o_ep),
+                (u32)r.bundle_start.size() - 1, (const u32 *)(d + o_bs), (const u32 *)(d + o_lb)};
     c->gather = (const u32 *)(d + o_g);
     c->mult = (int32_t *)(d + o_mult); c->scratch = (u32 *)(d + o_scr); c->status = (u32 *)(d + o_stat);
     {

@@ -39,9 +39,20 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
 // warp executes one instruction for 32 items (uniform control flow, coalesced variable traffic) and the CTA's warps share
 // the instructions of a level; a barrier separates levels.  Instruction words are warp-uniform broadcast loads.
 constexpr int kEvalThreads = 1024;
+// A level is a range of BUNDLES (level_start, in bundle units); bundle k is the instructions [bundle_start[k], bundle_start[k + 1]), which one
+// warp executes back to back (each may read what the one before it wrote).  bundle_start == nullptr: every instruction is its own bundle.
+__device__ __forceinline__ void eval_bundle(const tape::View &v, const tape::Ins *__restrict__ ins, const u32 *__restrict__ bundle_start, u32 k,
+                                            const tape::Perm *__restrict__ perms, const u32 *__restrict__ eperms) {
+    const u32 i0 = bundle_start ? __ldg(bundle_start + k) : k, i1 = bundle_start ? __ldg(bundle_start + k + 1) : k + 1;
+    for (u32 i = i0; i < i1; i++) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + i);
+        tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+        tape::eval<false>(v, in, perms, eperms);
+    }
+}
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                             const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
-                                                            const u32 *__restrict__ eperms) {
+                                                            const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start) {
     const u32 lane = threadIdx.x % b.lanes, slot = threadIdx.x / b.lanes, n_slots = kEvalThreads / b.lanes;
     const u32 item = blockIdx.x * b.lanes + lane;
     const bool live = item < b.n_batch;
@@ -51,11 +62,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval(const tape::Ins *__r
     for (u32 l = 0; l < n_levels; l++) {
         const u32 lo = __ldg(level_start + l), hi = __ldg(level_start + l + 1);
         if (live)
-            for (u32 k = lo + slot; k < hi; k += n_slots) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
-                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                tape::eval(v, in, perms, eperms);
-            }
+            for (u32 k = lo + slot; k < hi; k += n_slots) eval_bundle(v, ins, bundle_start, k, perms, eperms);
         __syncthreads();
     }
 }
@@ -93,7 +100,7 @@ constexpr u32 kNarrowItems = 128;     // (instructions x lane groups per CTA) up
 template <bool UNROLLED>
 __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                  const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
-                                                                 unsigned *barrier, const u32 *__restrict__ eperms) {
+                                                                 unsigned *barrier, const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start) {
     const u32 lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     const u32 n_groups = (b.n_batch + 31) / 32, n_warps = gridDim.x * (kEvalThreads / 32);
     const u32 gw = warp * gridDim.x + blockIdx.x;            // consecutive work items land on different SMs
@@ -116,11 +123,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
             const u32 n_items = (hi - lo) * groups_here;
             for (u32 t = warp; t < n_items; t += kEvalThreads / 32) {
                 const u32 k = lo + t / groups_here, item = (blockIdx.x + (t % groups_here) * gridDim.x) * 32 + lane;
-                if (item < b.n_batch) {
-                    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
-                    tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                    tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
-                }
+                if (item < b.n_batch) eval_bundle(b.view(item, input, n_input_words), ins, bundle_start, k, perms, eperms);
             }
         } else {
             const u32 n_items = (hi - lo) * n_groups;
@@ -128,11 +131,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
                 // group fastest: a warp's successive items (stride n_warps) walk through different instructions of the level, so
                 // permutations and cheap gates mix evenly; the groups of a one-instruction level land on different SMs
                 const u32 k = lo + t / n_groups, item = (t % n_groups) * 32 + lane;
-                if (item < b.n_batch) {
-                    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ins) + k);
-                    tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                    tape::eval<UNROLLED>(b.view(item, input, n_input_words), in, perms, eperms);
-                }
+                if (item < b.n_batch) eval_bundle(b.view(item, input, n_input_words), ins, bundle_start, k, perms, eperms);
             }
         }
         if (narrow && l + 1 < n_levels && is_narrow(l + 1)) __syncthreads();
@@ -153,8 +152,8 @@ constexpr int kClusterThreads = 512;
 // one CTA per SM, 5.2 ms against 3.1 ms at 4096 proofs and 1.4 against 1.1 ms at 512 -- the pass is not short of loads in flight.
 __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                        const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
-                                                                       const u32 *__restrict__ eperms) {
-    extern __shared__ u32 s_level[];                     // level_start, n_levels + 1 words: nothing of the level loop waits on it
+                                                                       const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start) {
+    extern __shared__ u32 s_level[];                     // level_start (bundle units), n_levels + 1 words: nothing of the level loop waits on it
     u32 rank, csize, grp;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
@@ -172,22 +171,27 @@ __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tap
     if (live && wi == 0) tape::prologue(v);
     __syncthreads();
     const uint4 *iw = reinterpret_cast<const uint4 *>(ins);
-    // a level's first instruction word is fetched BEFORE the barrier that ends the level before it: one L2 round trip less per level.
-    // Measured and dropped: prefetch.global.L2 of the next instruction's operands two instructions ahead (3.12 vs 3.04 ms at 4096
-    // proofs: with every lane group resident the pass already keeps ~7 MB of loads in flight, its bandwidth-latency product).
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (s_level[0] + wi < s_level[1]) w = __ldg(iw + s_level[0] + wi);
+    // The extent of this warp's first bundle of a level is fetched BEFORE the barrier that ends the level before it: one L2 round trip
+    // less per level.  Measured and dropped: prefetch.global.L2 of the next instruction's operands two instructions ahead (3.12 vs
+    // 3.04 ms at 4096 proofs: with every lane group resident the pass already keeps ~7 MB of loads in flight).
+    auto extent = [&](u32 k, u32 &i0, u32 &i1) {
+        if (bundle_start) { i0 = __ldg(bundle_start + k); i1 = __ldg(bundle_start + k + 1); } else { i0 = k; i1 = k + 1; }
+    };
+    u32 i0 = 0, i1 = 0;
+    if (s_level[0] + wi < s_level[1]) extent(s_level[0] + wi, i0, i1);
     cluster_sync();
     for (u32 l = 0; l < n_levels; l++) {
         const u32 lo = s_level[l], hi = s_level[l + 1];
         for (u32 k = lo + wi; k < hi; k += n_w) {
-            if (k != lo + wi) w = __ldg(iw + k);
-            if (live) {
-                tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
-                tape::eval<false>(v, in, perms, eperms);
-            }
+            if (k != lo + wi) extent(k, i0, i1);
+            if (live)
+                for (u32 i = i0; i < i1; i++) {
+                    const uint4 w = __ldg(iw + i);
+                    tape::Ins in; in.op = w.x; in.dst = w.y; in.a = w.z; in.b = w.w;
+                    tape::eval<false>(v, in, perms, eperms);
+                }
         }
-        if (l + 1 < n_levels && hi + wi < s_level[l + 2]) w = __ldg(iw + hi + wi);
+        if (l + 1 < n_levels && hi + wi < s_level[l + 2]) extent(hi + wi, i0, i1);
         cluster_sync();
     }
 }
@@ -575,7 +579,10 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     cudaStream_t st = (cudaStream_t)stream;
     const tape::Ins *ins = reinterpret_cast<const tape::Ins *>(t->ins);
     const tape::Perm *perms = reinterpret_cast<const tape::Perm *>(t->perms);
-    const u32 *level_start = t->level_start;
+    // with bundles the levels are ranges of bundles; without, of instructions (every instruction its own bundle)
+    const u32 *bundle_start = t->n_bundles ? t->bundle_start : nullptr;
+    const u32 *level_start = t->n_bundles ? t->level_bundle : t->level_start;
+    if (t->n_bundles && (!t->bundle_start || !t->level_bundle)) return STWO_B200_E_BAD_ARG;
     u32 n_levels = t->n_levels, n_input_words = t->n_input_words;
     const u32 *eperms = t->eperms;
     if (t->n_eperms && !eperms) return STWO_B200_E_BAD_ARG;
@@ -607,7 +614,7 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        STWO_CUDA(cudaLaunchKernelEx(&cfg, k_tape_eval_cluster, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms));
+        STWO_CUDA(cudaLaunchKernelEx(&cfg, k_tape_eval_cluster, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start));
         note_launch(1);
         return cuda_status(cudaGetLastError());
     }
@@ -618,11 +625,12 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
         if (!barriers) STWO_CUDA(cudaMalloc(&barriers, 64 * sizeof(unsigned)));
         unsigned *bar = barriers + (next++ % 64);
         STWO_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-        void *args[] = {(void *)&ins, (void *)&level_start, (void *)&n_levels, (void *)&perms, (void *)&b, (void *)&witness, (void *)&n_input_words, (void *)&bar, (void *)&eperms};
+        void *args[] = {(void *)&ins, (void *)&level_start, (void *)&n_levels, (void *)&perms, (void *)&b, (void *)&witness, (void *)&n_input_words, (void *)&bar, (void *)&eperms,
+                        (void *)&bundle_start};
         const void *fn = unrolled ? (const void *)k_tape_eval_grid<true> : (const void *)k_tape_eval_grid<false>;
         STWO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)n_sm), dim3(kEvalThreads), args, 0, st));
     } else {
-        k_tape_eval<<<n_groups, kEvalThreads, 0, st>>>(ins, level_start, n_levels, perms, b, witness, n_input_words, eperms);
+        k_tape_eval<<<n_groups, kEvalThreads, 0, st>>>(ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start);
     }
     note_launch(1);
     return cuda_status(cudaGetLastError());

@@ -2,6 +2,8 @@
 // and (for the verifier circuit) the witness-stream gather table.  Host only; built once per shape.
 #pragma once
 #include "last_layer.hpp"
+#include <stdlib.h>
+#include <algorithm>
 
 namespace stwo_b200 {
 namespace dsl {
@@ -41,48 +43,88 @@ struct RecordedCircuit {
         else f(in.dst);
     }
 
-    // Levels: an instruction's earliest level is 1 + the latest earliest level of its sources (the depth of the circuit is the longest
-    // such chain).  Within that depth every instruction is placed as LATE as its consumers allow (an instruction nobody consumes stays
-    // at its earliest level): a value is then produced just before it is first read.  The evaluator walks the levels over every batch
-    // item, so the distance between producer and consumer decides whether the operand is still in L2 -- with earliest-level placement
-    // 60 % of the verifier circuit's instructions sit in the first seven levels and are read up to 250 levels later.
+    // Bundles and levels.  A BUNDLE is a short chain of instructions one warp executes back to back for its 32 items (each reads what the
+    // one before it wrote: same thread, program order, no barrier); the instructions of different bundles of one LEVEL are independent,
+    // and a barrier separates levels.  A bundle's earliest level is 1 + the latest level among the sources it takes from other bundles,
+    // so a dependent chain of k gates costs ceil(k / kBundle) levels instead of k: the verifier circuit of shape S is 265 gates deep
+    // (the per-query fold and point chains, not the hashes) and most of those levels hold a handful of instructions -- pure barrier
+    // and load latency.  Within the resulting depth every bundle is then placed as LATE as its consumers allow (a bundle nobody consumes
+    // stays at its earliest level), so a value is produced just before it is first read and is still in L2.
+    std::vector<u32> bundle_start;         // n_bundles + 1: first instruction of each bundle (ins is bundle-major inside a level)
+    std::vector<u32> level_bundle;         // n_levels + 1: first bundle of each level
+    static u32 bundle_cap() {
+        const char *e = getenv("STWO_B200_BUNDLE");           // 1 = one instruction per bundle (profiling)
+        const int v = e ? atoi(e) : 8;
+        return v < 1 ? 1u : v > 64 ? 64u : (u32)v;
+    }
     void levelise() {
         const ConstraintSystem &c = *cs.p;
         const size_t n = c.tape_.size();
-        std::vector<u32> var_level(c.n_vars, 0), early(n, 0);
-        u32 max_level = 0;
-        for (size_t k = 0; k < n; k++) {
-            u32 l = 0;
-            for_sources(c, c.tape_[k], [&](u32 v) { l = std::max(l, var_level[v]); });
-            l += 1;
-            early[k] = l;
-            max_level = std::max(max_level, l);
-            for_outputs(c, c.tape_[k], [&](u32 v) { var_level[v] = l; });
-        }
-        // backward: consumers come after their producers in recording order
+        const u32 cap = bundle_cap();
         constexpr u32 NONE = 0xffffffffu;
-        std::vector<u32> need(c.n_vars, NONE), ins_level(n, 0);
-        for (size_t k = n; k-- > 0;) {
-            u32 first_use = NONE;
-            for_outputs(c, c.tape_[k], [&](u32 v) { first_use = std::min(first_use, need[v]); });
-            const u32 l = first_use == NONE ? early[k] : first_use - 1;
-            ins_level[k] = l;
-            for_sources(c, c.tape_[k], [&](u32 v) { need[v] = std::min(need[v], l); });
-        }
-        // levels are 1 .. max_level; level l occupies ins[level_start[l-1] .. level_start[l])
-        std::vector<u32> cnt(max_level + 1, 0);
-        for (u32 l : ins_level) cnt[l]++;
-        level_start.assign(max_level + 1, 0);
-        for (u32 l = 1; l <= max_level; l++) level_start[l] = level_start[l - 1] + cnt[l];
-        std::vector<u32> at(level_start.begin(), level_start.end());
-        ins.resize(n);
-        // inside a level the permutations go first: the evaluator deals a level's instructions round-robin to its warps, and
-        // the heavy items (a permutation is ~50x a field gate) then spread evenly instead of following the recording pattern
-        for (int pass = 0; pass < 2; pass++)
-            for (size_t k = 0; k < n; k++) {
-                const bool heavy = c.tape_[k].op == tape::T_POSEIDON || c.tape_[k].op == tape::T_EPOSEIDON;
-                if (heavy == (pass == 0)) ins[at[ins_level[k] - 1]++] = c.tape_[k];
+        std::vector<u32> var_level(c.n_vars, 0), producer(c.n_vars, NONE), bundle_of(n, 0);
+        std::vector<u32> b_level, b_len, b_tail;           // per bundle: earliest level, length, last instruction
+        std::vector<std::vector<u32>> members;
+        for (size_t k = 0; k < n; k++) {
+            const tape::Ins &in = c.tape_[k];
+            // a bundle this instruction may join: the bundle of one of its sources, if it has room and every other source is either inside
+            // that bundle too or complete before the bundle's level starts (the bundle runs in recording order on one thread per item,
+            // so anything recorded earlier inside it is visible)
+            u32 join = NONE;
+            for_sources(c, in, [&](u32 v) {
+                const u32 p = producer[v];
+                if (join != NONE || p == NONE) return;
+                const u32 b = bundle_of[p];
+                if (b_len[b] >= cap) return;
+                bool ok = true;
+                for_sources(c, in, [&](u32 w) { const u32 q = producer[w]; if (!((q != NONE && bundle_of[q] == b) || var_level[w] < b_level[b])) ok = false; });
+                if (ok) join = b;
+            });
+            u32 b;
+            if (join != NONE) { b = join; b_len[b]++; b_tail[b] = (u32)k; members[b].push_back((u32)k); }
+            else {
+                u32 l = 0;
+                for_sources(c, in, [&](u32 v) { l = std::max(l, var_level[v]); });
+                b = (u32)b_level.size();
+                b_level.push_back(l + 1); b_len.push_back(1); b_tail.push_back((u32)k); members.push_back({(u32)k});
             }
+            bundle_of[k] = b;
+            for_outputs(c, in, [&](u32 v) { var_level[v] = b_level[b]; producer[v] = (u32)k; });
+        }
+        const u32 nb = (u32)b_level.size();
+        u32 max_level = 0;
+        for (u32 l : b_level) max_level = std::max(max_level, l);
+        // as late as possible, bundle by bundle, consumers (strictly higher earliest level) first
+        std::vector<u32> order(nb), late(nb, 0), need(c.n_vars, NONE);
+        for (u32 b = 0; b < nb; b++) order[b] = b;
+        std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return b_level[x] > b_level[y]; });
+        for (u32 b : order) {
+            u32 first_use = NONE;
+            for (u32 k : members[b]) for_outputs(c, c.tape_[k], [&](u32 v) { first_use = std::min(first_use, need[v]); });
+            late[b] = first_use == NONE ? b_level[b] : first_use - 1;
+            for (u32 k : members[b])
+                for_sources(c, c.tape_[k], [&](u32 v) { const u32 q = producer[v]; if (q == NONE || bundle_of[q] != b) need[v] = std::min(need[v], late[b]); });
+        }
+        // emit: levels 1 .. max_level; inside a level the bundles holding a permutation go first (the evaluator deals a level's bundles
+        // round-robin to its warps, and the heavy ones then spread evenly)
+        std::vector<std::vector<u32>> per_level(max_level + 1);
+        for (int pass = 0; pass < 2; pass++)
+            for (u32 b = 0; b < nb; b++) {
+                bool heavy = false;
+                for (u32 k : members[b]) heavy |= c.tape_[k].op == tape::T_POSEIDON || c.tape_[k].op == tape::T_EPOSEIDON;
+                if (heavy == (pass == 0)) per_level[late[b]].push_back(b);
+            }
+        ins.clear(); ins.reserve(n);
+        bundle_start.clear(); level_bundle.assign(1, 0); level_start.assign(1, 0);
+        for (u32 l = 1; l <= max_level; l++) {
+            for (u32 b : per_level[l]) {
+                bundle_start.push_back((u32)ins.size());
+                for (u32 k : members[b]) ins.push_back(c.tape_[k]);
+            }
+            level_bundle.push_back((u32)bundle_start.size());
+            level_start.push_back((u32)ins.size());
+        }
+        bundle_start.push_back((u32)ins.size());
     }
 };
 
