@@ -427,6 +427,7 @@ def main():
     ap.add_argument("--proofs", type=int, default=4096, help="proofs per GPU per step (weak scaling) / in total (strong scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --proofs per GPU; strong: --proofs in total, ceil(proofs / N) per GPU (BASELINE configs[4]: 4096 across 8 GPUs)")
+    ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes: independent verify / trace stream pairs (VerifyTracePipeline)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the K1 / Merkle-sweep side measurements")
@@ -461,7 +462,7 @@ def main():
     # A stream of batches through the public API: VerifyTracePipeline = three device slots, the upload / verification / trace pass of
     # neighbouring batches on their own streams.  Every step verifies AND traces one whole batch; the device-resident leg skips the
     # upload, the end-to-end leg does everything.
-    pipe = pkg.VerifyTracePipeline([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE, n_slots=3)
+    pipe = pkg.VerifyTracePipeline([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE, n_slots=2 * args.lanes + 1, lanes=args.lanes)
     vb, circ = pipe.slots[0], pipe.circuit                              # the circuit is recorded once per shape (host)
     ci = circ.info
     ws_mb = (vb.ws_bytes + circ.workspace_bytes(hi - lo)) >> 20

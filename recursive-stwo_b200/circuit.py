@@ -246,16 +246,22 @@ class VerifyTracePipeline:
     pass starts: a consumer on another stream waits for pipe.traced[h] and records its own event into pipe.consumed before the next
     step() (None: nothing to wait for)."""
 
-    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, config=None, n_slots=3, check=True, export=True):
+    def __init__(self, blobs, inputs=INPUTS_RECURSIVE, config=None, n_slots=3, check=True, export=True, lanes=1):
+        """lanes: independent (verify stream, trace stream, circuit workspace + trace buffer) sets; batch k runs on lane k % lanes, so with
+        two lanes the latency-bound kernels of two batches' verifications (and of two trace passes) overlap as well -- what small batches
+        need; n_slots >= 2 * lanes + 1 keeps every lane busy."""
         import torch
         from .verifier import REFERENCE_CONFIGS, VerifyBatch
         config = REFERENCE_CONFIGS if config is None else config
         self.slots = [VerifyBatch(blobs, inputs=inputs, config=config) for _ in range(n_slots)]
         self.shape, self.n = self.slots[0].shape, self.slots[0].n
-        self.circuit = VerifierCircuit(self.shape, inputs=inputs)
+        self.circuits = [VerifierCircuit(self.shape, inputs=inputs) for _ in range(lanes)]
+        self.circuit = self.circuits[0]
         self.check, self.export = check, export
         dev = self.slots[0].d_words.device
-        self.s_copy, self.s_verify, self.s_trace = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.s_copy = torch.cuda.Stream(dev)
+        self.lane_streams = [(torch.cuda.Stream(dev), torch.cuda.Stream(dev)) for _ in range(lanes)]
+        self.s_verify, self.s_trace = self.lane_streams[0]
         self.uploaded = [torch.cuda.Event() for _ in range(n_slots)]
         self.verified = [torch.cuda.Event() for _ in range(n_slots)]
         self.traced = [torch.cuda.Event() for _ in range(n_slots)]
@@ -266,10 +272,11 @@ class VerifyTracePipeline:
         self.values = None
         self._k = 0
         cur = torch.cuda.current_stream(dev)
-        for st in (self.s_copy, self.s_verify, self.s_trace):
+        for st in [self.s_copy] + [x for pair in self.lane_streams for x in pair]:
             st.wait_stream(cur)
         for e in self.traced:
             e.record(self.s_trace)
+        self.values_of_lane = [None] * lanes
 
     def step(self, blobs=None, gather=None, upload=True):
         """enqueue one batch: upload (blobs=None re-sends the slot's pinned host copy; upload=False: the slot's device copy is used as it
@@ -278,6 +285,9 @@ class VerifyTracePipeline:
         import torch
         i = self._k % len(self.slots)
         slot = self.slots[i]
+        lane = self._k % len(self.lane_streams)
+        s_verify, s_trace = self.lane_streams[lane]
+        circuit = self.circuits[lane]
         if blobs is not None:
             from .verifier import _as_aligned
             if self._k >= len(self.slots):
@@ -294,16 +304,16 @@ class VerifyTracePipeline:
             if upload:
                 slot.upload()
             self.uploaded[i].record(self.s_copy)
-        with torch.cuda.stream(self.s_verify):
-            self.s_verify.wait_event(self.uploaded[i])
+        with torch.cuda.stream(s_verify):
+            s_verify.wait_event(self.uploaded[i])
             v, s = slot.run(full=True)
-            self.verified[i].record(self.s_verify)
-        with torch.cuda.stream(self.s_trace):
-            self.s_trace.wait_event(self.verified[i])
+            self.verified[i].record(s_verify)
+        with torch.cuda.stream(s_trace):
+            s_trace.wait_event(self.verified[i])
             if self.consumed is not None:
-                self.s_trace.wait_event(self.consumed)
-            r = self.circuit.trace(slot, check=self.check, export=self.export, preprocessed=False)
-            self.values = r["values"]
+                s_trace.wait_event(self.consumed)
+            r = circuit.trace(slot, check=self.check, export=self.export, preprocessed=False)
+            self.values = self.values_of_lane[lane] = r["values"]
             h = self.host[i]
             if self.check:
                 bad = (r["bad_row"] != -1) | (r["bad_flow"] != -1)
@@ -316,7 +326,7 @@ class VerifyTracePipeline:
                     h["verdict"], h["stage"] = torch.empty(v.numel(), dtype=torch.uint8).pin_memory(), torch.empty(v.numel(), dtype=torch.uint8).pin_memory()
             h["verdict"].copy_(v, non_blocking=True)
             h["stage"].copy_(s, non_blocking=True)
-            self.traced[i].record(self.s_trace)
+            self.traced[i].record(s_trace)
         self._k += 1
         return i
 
@@ -324,12 +334,13 @@ class VerifyTracePipeline:
         """make `stream` (default: the current one) wait for everything enqueued so far"""
         import torch
         stream = stream if stream is not None else torch.cuda.current_stream(self.slots[0].d_words.device)
-        for st in (self.s_copy, self.s_verify, self.s_trace):
+        for st in [self.s_copy] + [x for pair in self.lane_streams for x in pair]:
             stream.wait_stream(st)
 
     def join(self):
         """wait (host) until everything enqueued so far has finished"""
-        self.s_copy.synchronize(); self.s_verify.synchronize(); self.s_trace.synchronize()
+        for st in [self.s_copy] + [x for pair in self.lane_streams for x in pair]:
+            st.synchronize()
 
     def result(self, handle):
         h = self.host[handle]

@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -2
+for L in 1 2 3; do for P in 512 4096; do
+  timeout 300 python bench.py --steps 12 --warmup 4 --proofs $P --lanes $L --no-secondary --no-cpu-baseline > gpurun_out/bench_l${L}_$P.json 2> gpurun_out/bench_l${L}_$P.err || tail -3 gpurun_out/bench_l${L}_$P.err
+  python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_l${L}_$P.json'))
+print('lanes $L proofs $P','value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round(d['ms_per_step'],2))
+PY
+done; done
