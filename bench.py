@@ -598,7 +598,7 @@ def main():
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
         "perms_per_launch": h_perms, "perms_per_sec": h_rate, "launch_ms": acc[hdom], "share_of_step": acc[hdom] / total_ms,
         "traffic": ncu_traffic(kernel_of.get(hdom, ""), n_local),
-        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r01y_k_cs_check_poseidon_ncu.txt); the "
+        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r02e_k_cs_check_poseidon_ncu.txt); the "
                 "multiplier pipe bounds a permutation at ~6.1 G perms/s per GPU"}
     # `roofline` = the dominant HBM-bound kernel of the step (the trace export); `roofline_hashing` = the dominant integer-bound kernel
     # (for this path the largest kernels are co-dominant: check_poseidon_invocations, export, tape evaluation within ~10 % of each other)
