@@ -360,12 +360,28 @@ def synthetic_leg(pkg, dev, shape, n=4096, reps=5):
     real proofs looks like to these kernels (same positions, same node sharing, same witness consumption order in every lane)."""
     import torch
     out = {"config": "BASELINE configs[4] part i: %d synthetic FRI + Merkle instances, shape of small_proof.bin without proof of work; verify = channel replay + "
-                     "folds + FRI tree rebuilds (8 trees, 2112 path permutations covered per instance)" % n}
+                     "folds + FRI tree rebuilds (8 trees, 2112 path permutations covered per instance); with_folding_tape = verify + the trace pass of the "
+                     "folding-stage circuit (fri_answers as witnesses), checks on, value columns exported" % n}
+    circ = pkg.VerifierCircuit(shape, folding=True)
+    out["folding_circuit"] = {k: getattr(circ.info, k) for k in ("n_rows", "n_vars", "n_flow", "n_ins", "n_levels")}
     for name, distinct in (("distinct", True), ("replicas", False)):
         sb = pkg.SynthBatch(shape, n, seed0=0, distinct=distinct)
         for _ in range(2):
             v, _ = sb.run(full=True)
         assert int(v.sum().item()) == 0
+        if distinct:
+            for _ in range(2):
+                r = circ.trace(sb, check=True, export=True, preprocessed=False)
+            assert int((r["bad_row"] != -1).sum().item()) == 0 and int((r["bad_flow"] != -1).sum().item()) == 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                sb.run(full=True)
+                circ.trace(sb, check=True, export=True, preprocessed=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out["with_folding_tape"] = {"ms_per_batch": ms, "instances_per_sec": n / (ms * 1e-3)}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -377,6 +393,8 @@ def synthetic_leg(pkg, dev, shape, n=4096, reps=5):
         out[name] = {"ms_per_batch": ms, "instances_per_sec": n / (ms * 1e-3), "perms_executed_per_instance": int(dt.n_perms_hints + dt.fs.n_transcript_perms)}
         del sb
         torch.cuda.empty_cache()
+    del circ
+    torch.cuda.empty_cache()
     out["distinct_over_replicas"] = out["distinct"]["instances_per_sec"] / out["replicas"]["instances_per_sec"]
     return out
 

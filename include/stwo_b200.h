@@ -464,6 +464,11 @@ int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, co
  * the hashes are recomputed by the emulated Poseidon2 gadget (primitives/poseidon31/src/emulated.rs).  The trace pass of such
  * a circuit writes an 8-column preprocessed block and the same 13 per-proof value columns (the last one is op1). */
 int32_t stwo_b200_circuit_record_last_layer(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out);
+/* The folding stage on its own (FoldingResults::compute, components/recursive/folding/src/lib.rs:12-205) with everything before it
+ * supplied as witnesses: FRI commitments, last-layer polynomial, folding alphas, query positions, first-layer answers -- the circuit of
+ * BASELINE configs[4] part i ("fri_answers supplied as witnesses").  Its trace pass runs on the workspace of stwo_b200_synth_verify_batch_dev
+ * (synthetic FRI + Merkle instances) or of stwo_b200_verify_proofs_batch_dev (real proofs: the folding part of their verifier circuit). */
+int32_t stwo_b200_circuit_record_folding(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out);
 void stwo_b200_circuit_free(stwo_b200_circuit *c);
 int32_t stwo_b200_circuit_get_info(const stwo_b200_circuit *c, stwo_b200_circuit_info *out);
 #define STWO_B200_COL_A_WIRE 0

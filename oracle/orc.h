@@ -151,6 +151,8 @@ typedef struct {
 int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *input_idx, const uint32_t *input_vals,
                            uint32_t n_inputs, orc_verify_out *out, orc_hints *hints);
 
+int orc_fri_verify_synth_hints(const uint32_t *words, size_t n_words, orc_verify_out *out, orc_hints *hints);
+
 /* independent proofs on n_threads pthreads (CPU baseline); off = n+1 byte offsets; returns permutations executed */
 uint64_t orc_verify_batch_mt(const uint8_t *blobs, const uint64_t *off, uint32_t n, const uint32_t *idx, const uint32_t *vals,
                              uint32_t n_inputs, uint8_t *verdict, uint8_t *stage, unsigned n_threads);

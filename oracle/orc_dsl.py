@@ -1821,6 +1821,53 @@ def verifier_circuit(blob, inputs, multipliers=1, verify_out_cls=None, finalize=
     return cs, out
 
 
+class FriOnlyShape:
+    """the part of Shape the folding stage reads, from the seven shape words of a synthetic instance"""
+    def __init__(self, words):
+        self.log_plonk, self.log_poseidon, self.pow_bits, self.blowup, self.log_last, self.n_queries, n_inner = [int(x) for x in words[1:8]]
+        self.n_inner = n_inner
+        self.max_first = self.log_last + self.blowup + 1 + n_inner
+        self.all_log_sizes = sorted({self.log_plonk + self.blowup, self.log_poseidon + self.blowup, self.max_first})
+
+
+def folding_circuit(words, verify_out_cls, finalize=True):
+    """The folding stage alone (components/recursive/folding/src/lib.rs:12-205) over a synthetic FRI + Merkle instance (BASELINE
+    configs[4] part i: "fri_answers supplied as witnesses"): commitments, last-layer polynomial, alphas, query positions and first-layer
+    answers are witnesses, in that order; then `folding` as in the verifier circuit.  words: the instance blob (uint32)."""
+    lib = _orc()
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    out, hints = verify_out_cls(), Hints()
+    lib.orc_fri_verify_synth_hints(w.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w.size), ctypes.byref(out), ctypes.byref(hints))
+    assert out.verdict == 0, "the reference panics on a rejected instance (stage %d)" % out.stage
+    shape = FriOnlyShape(w)
+    nq, n_inner = shape.n_queries, shape.n_inner
+    cs = CS()
+
+    class _P:
+        pass
+    pv = _P()
+    pv.first_layer_commitment = Half.new_witness(cs, [int(x) for x in w[w[80]: w[80] + 8]])
+    pv.inner_layer_commitments = [Half.new_witness(cs, [int(x) for x in w[w[96 + i]: w[96 + i] + 8]]) for i in range(n_inner)]
+    pv.last_poly = [qm31_witness(cs, tuple(int(x) for x in w[w[81] + 4 * k: w[81] + 4 * k + 4])) for k in range(1 << shape.log_last)]
+    fs = {"fri_alphas": [qm31_witness(cs, tuple(out.fri_alphas[l])) for l in range(n_inner + 1)]}
+    mask = (1 << shape.max_first) - 1
+    fs["raw_queries"] = [m31_witness(cs, int(out.raw_queries[i]) & mask) for i in range(nq)]
+    qpos = query_positions_per_log_size(shape.log_last + shape.blowup + 1, shape.max_first, fs["raw_queries"])
+    fri_answers = {}
+    for g, L in enumerate(sorted(shape.all_log_sizes, reverse=True)):
+        assert int(out.log_sizes[g]) == L
+        fri_answers[L] = [qm31_witness(cs, tuple(out.fri_answers[g][i])) for i in range(nq)]
+    folding(cs, pv, shape, fs, {"qpos": qpos, "fri_answers": fri_answers}, hints)
+    if finalize:
+        cs.pad()
+        bad = cs.check_arithmetics()
+        assert bad < 0, "check_arithmetics fails at row %d" % bad
+        cs.populate_logup_arguments()
+        bad = cs.check_poseidon_invocations()
+        assert bad < 0, "check_poseidon_invocations fails at entry %d" % bad
+    return cs, out
+
+
 # ---- the last-layer circuit (components/last/*, examples/last-layer/src/main.rs:26-94) --------------------------------
 def native_hash_rate(words):
     """Poseidon31MerkleHasher::hash_column_get_capacity then permute_get_rate([0; 8] || capacity)

@@ -1003,6 +1003,15 @@ int orc_verify_proof_hints(const uint8_t *blob, size_t len, const uint32_t *inpu
     return r;
 }
 
+/* the per-query FRI hints of a synthetic instance (the pair_* part of orc_hints; the single_* part stays zero) */
+int orc_fri_verify_synth_hints(const uint32_t *w, size_t n_words, orc_verify_out *o, orc_hints *h) {
+    memset(h, 0, sizeof *h);
+    g_hints = h;
+    int r = orc_fri_verify_synth(w, n_words, o);
+    g_hints = NULL;
+    return r;
+}
+
 /* ---- pthread batch driver for the CPU baseline: proofs are independent ----------------------------------- */
 #include <pthread.h>
 typedef struct {

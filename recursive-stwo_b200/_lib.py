@@ -198,6 +198,7 @@ SIGNATURES = {
     "stwo_b200_cs_export_tiles_build": (_i32, [_WIR_P, _vp, _vp]),
     "stwo_b200_circuit_record_verifier": (_i32, [_PSHAPE_P, _vp, _vp, _u32, _u32, ctypes.POINTER(_vp)]),
     "stwo_b200_circuit_record_last_layer": (_i32, [_PSHAPE_P, ctypes.POINTER(_vp)]),
+    "stwo_b200_circuit_record_folding": (_i32, [_PSHAPE_P, ctypes.POINTER(_vp)]),
     "stwo_b200_circuit_free": (None, [_vp]),
     "stwo_b200_circuit_get_info": (_i32, [_vp, _INFO_P]),
     "stwo_b200_circuit_get_column": (_i32, [_vp, _u32, _vp, _sz]),

@@ -27,11 +27,14 @@ COLUMN_NAMES_WITHOUT = ("mult_c", "a_wire", "b_wire", "c_wire", "op1", "op2", "o
 
 class VerifierCircuit:
     """A recorded verifier circuit for one proof shape.  last_layer=True records the circuit of examples/last-layer
-    (components/last/*, Plonk-without-Poseidon system, emulated Poseidon2) instead of the recursive verifier."""
+    (components/last/*, Plonk-without-Poseidon system, emulated Poseidon2) instead of the recursive verifier; folding=True the folding
+    stage alone over witnesses (FoldingResults::compute; BASELINE configs[4] part i), which traces a verified SynthBatch or VerifyBatch."""
 
-    def __init__(self, shape, inputs=INPUTS_RECURSIVE, multipliers=1, last_layer=False):
+    def __init__(self, shape, inputs=INPUTS_RECURSIVE, multipliers=1, last_layer=False, folding=False):
         h = ctypes.c_void_p()
-        if last_layer:
+        if folding:
+            _lib.call("stwo_b200_circuit_record_folding", ctypes.byref(shape), ctypes.byref(h))
+        elif last_layer:
             _lib.call("stwo_b200_circuit_record_last_layer", ctypes.byref(shape), ctypes.byref(h))
         else:
             idx = np.ascontiguousarray(inputs[0], dtype=np.uint32)

@@ -187,6 +187,20 @@ extern "C" int32_t stwo_b200_circuit_record_last_layer(const stwo_b200_proof_sha
         return STWO_B200_OK;
     } catch (const std::exception &) { return STWO_B200_E_SHAPE; }
 }
+extern "C" int32_t stwo_b200_circuit_record_folding(const stwo_b200_proof_shape *shape, stwo_b200_circuit **out) {
+    if (!shape || !out) return STWO_B200_E_BAD_ARG;
+    if (!proof::shape_consistent(shape->log_size_plonk, shape->log_size_poseidon, shape->pow_bits, shape->log_blowup, shape->log_last,
+                                 shape->n_queries, shape->n_inner))
+        return STWO_B200_E_SHAPE;
+    try {
+        dsl::ProofShape s;
+        memcpy(&s, shape, sizeof s);
+        stwo_b200_circuit *c = new stwo_b200_circuit();
+        c->rec = dsl::record_folding(s);
+        *out = c;
+        return STWO_B200_OK;
+    } catch (const std::exception &) { return STWO_B200_E_SHAPE; }
+}
 extern "C" void stwo_b200_circuit_free(stwo_b200_circuit *c) {
     if (!c) return;
     if (c->dev) cudaFree(c->dev);

@@ -38,6 +38,7 @@ HD u32 gather_word(const verify::Workspace &ws, u32 p, u32 src, const u32 *extra
         return q->v[k & 3u];
     }
     case tape::S_EXTRA: return extra ? extra[k] : 0;
+    case tape::S_ANSWER: return ws.q4(ws.answers, p, a, fri::MAX_LOGS, i)[k];
     default: return 0;
     }
 }

@@ -137,6 +137,15 @@ inline std::unique_ptr<RecordedCircuit> record_verifier(const ProofShape &shape,
     return r;
 }
 
+inline std::unique_ptr<RecordedCircuit> record_folding(const ProofShape &shape) {
+    VerifierCircuit vc = record_folding_circuit(shape);
+    std::unique_ptr<RecordedCircuit> r(new RecordedCircuit());
+    r->cs = vc.cs; r->gather = std::move(vc.gather); r->words_per_instance = vc.words_per_instance;
+    r->multipliers = 1; r->shape = shape;
+    r->levelise();
+    return r;
+}
+
 inline std::unique_ptr<RecordedCircuit> record_last_layer(const ProofShape &shape) {
     LastLayerCircuit lc = record_last_layer_circuit(shape);
     std::unique_ptr<RecordedCircuit> r(new RecordedCircuit());

@@ -830,5 +830,39 @@ inline VerifierCircuit record_verifier_circuit(const ProofShape &shape, const st
     return out;
 }
 
+// The folding stage on its own (components/recursive/folding/src/lib.rs:12-205) with everything before it supplied as witnesses: the
+// FRI commitments and the last-layer polynomial (from the instance), the folding alphas and the query positions (from the native
+// transcript) and the first-layer answers (from the native answer stage, or from the instance itself when it is one of the synthetic
+// FRI + Merkle instances of BASELINE configs[4] part i, synth.cuh).  Same rows as the folding part of the verifier circuit; the
+// queries are allocated as M31 witnesses holding the position at the largest log size.
+inline VerifierCircuit record_folding_circuit(const ProofShape &shape) {
+    const ShapeFacts f(shape);
+    WitnessStream w{ConstraintSystemRef::new_plonk_with_poseidon_ref(), {}};
+    const ConstraintSystemRef &cs = w.cs;
+    cs->native_hints = true;
+    PlonkWithPoseidonProofVar proof;
+    proof.first_layer_commitment = HashVar::new_witness(cs, w.take(tape::S_FRI_COMMITMENT, 0, 0, 0, 8));
+    for (u32 l = 0; l < f.s.n_inner; l++) proof.inner_layer_commitments.push_back(HashVar::new_witness(cs, w.take(tape::S_FRI_COMMITMENT, 1 + l, 0, 0, 8)));
+    proof.last_poly.cs = cs;
+    for (u32 k = 0; k < (1u << f.s.log_last); k++) proof.last_poly.coeffs.push_back(QM31Var::new_witness(cs, Def::input_qm31(w.take(tape::S_LAST_COEFFS, 0, 0, 4 * k, 4))));
+    FiatShamirResults fs;
+    for (u32 l = 0; l <= f.s.n_inner; l++) fs.fri_alphas.push_back(QM31Var::new_witness(cs, Def::input_qm31(w.take(tape::S_FS, 0, 0, 20 + 4 * l, 4))));
+    for (u32 i = 0; i < f.s.n_queries; i++) fs.raw_queries.push_back(M31Var::new_witness(cs, Def::input_m31(w.take(tape::S_FS, 0, 0, tape::FS_QUERY_BASE + i, 1))));
+    AnswerResults ans;
+    ans.query_positions_per_log_size.reset(new QueryPositionsPerLogSizeVar(f.s.log_last + f.s.log_blowup + 1, f.max_first, fs.raw_queries));
+    u32 g = 0;                                                        // the native stages index log sizes in descending order
+    for (auto it = f.all_log_sizes.rbegin(); it != f.all_log_sizes.rend(); ++it, ++g)
+        for (u32 i = 0; i < f.s.n_queries; i++)
+            ans.fri_answers[*it].push_back(QM31Var::new_witness(cs, Def::input_qm31(w.take(tape::S_ANSWER, g, i, 0, 4))));
+    FoldingResults::compute(w, proof, f, fs, ans);
+    if (!cs->hint_queue.empty()) throw std::logic_error("native-hint slots left over: the circuit recorded fewer permutations than it announced");
+    VerifierCircuit out;
+    out.words_per_instance = cs->n_input_words;
+    cs->pad();
+    out.cs = cs;
+    out.gather = w.gather;
+    return out;
+}
+
 }  // namespace dsl
 }  // namespace stwo_b200

@@ -261,7 +261,9 @@ HD void stage_open(const verify::Workspace &ws, u32 p) {
     proof::Desc &d = ws.desc[p];
     verify::Detail &dt = ws.detail[p];
     verify::reset_detail(dt);
-    if (ws.hint_trees) ws.hint_trees[p] = 0;
+    // the four commitment trees have no part in an instance, so nothing of theirs can be missing from the permutation record: the
+    // count starts at 4 and reaches n_trees() when every FRI tree's part is complete (what the folding-stage circuit waits for)
+    if (ws.hint_trees) ws.hint_trees[p] = 4;
     const u32 *w = ws.blob(p);
     if (!fill_desc(w, ws.blob_words(p), ws.shape, d)) { d.ok = 0; verify::fail(dt, proof::ST_PARSE); return; }
     transcript(w, d, dt.fs, 1 + d.n_inner);

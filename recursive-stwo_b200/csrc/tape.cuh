@@ -63,7 +63,10 @@ enum : u32 {
                  // after_sampled_values_random_coeff, fri_alphas[..]}; FS_QUERY_BASE + i: position of query i at the largest
                  // log size; FS_ZERO: the constant 0 (padding of packed public inputs)
     S_EXTRA,     // word k of the per-proof public-input hashes the last-layer circuit takes (circuit.cuh, k_last_extra)
+    S_ANSWER,    // word k of the first-layer FRI answer of query i at the a-th log size (descending): the folding-stage circuit takes
+                 // the answers as witnesses (dsl::record_folding_circuit)
 };
+static_assert(S_ANSWER < 16, "a source section is four bits");
 constexpr u32 FS_QUERY_BASE = 1024, FS_ZERO = 4095;
 HD u32 src_pack(u32 section, u32 a, u32 i, u32 k) { return section | (a << 4) | (i << 10) | (k << 17); }
 HD u32 src_section(u32 s) { return s & 15u; }

@@ -50,6 +50,7 @@ class SynthBatch:
 
     def run(self, full=True, path_kernels=False):
         flags = (VERIFY_FULL if full else 0) | (VERIFY_PATH_KERNELS if path_kernels else 0)
+        self.last_full = bool(full)                 # VerifierCircuit(folding=True).trace(self) takes the permutation record then
         _lib.call("stwo_b200_synth_verify_batch_dev", _dptr(self.d_words), _dptr(self.d_off), self.n, ctypes.byref(self.shape), flags,
                   _dptr(self.d_ws), self.ws_bytes, _dptr(self.d_verdict), _dptr(self.d_stage), _stream())
         return self.d_verdict, self.d_stage

@@ -156,6 +156,12 @@ void *hs_circuit_record_last(const u32 *shape) {
         return stwo_b200::dsl::record_last_layer(s).release();
     } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record_last: %s\n", e.what()); return nullptr; }
 }
+void *hs_circuit_record_folding(const u32 *shape) {
+    try {
+        stwo_b200::dsl::ProofShape s{shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6]};
+        return stwo_b200::dsl::record_folding(s).release();
+    } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record_folding: %s\n", e.what()); return nullptr; }
+}
 void hs_circuit_free(void *h) { delete (RecordedCircuit *)h; }
 // info: n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance
 void hs_circuit_info(void *h, u32 *info) {

@@ -76,3 +76,58 @@ def test_tampered_instances(pkg, gpu, orc):
         o = oracle_verify(orc, sb.blob(p))
         assert (verdict[p], stage[p]) == (o.verdict, o.stage), p
     assert verdict.sum() == len(spots)
+
+
+def test_folding_circuit_trace_of_instances(pkg, gpu, orc):
+    """the tape of configs[4] part i: the folding-stage circuit traced for a batch of distinct instances -- variables, Poseidon flow and
+    the 13 value columns against the oracle DSL's `folding` on sampled instances; every instance satisfies it; a tampered one does not"""
+    from circuit_common import D
+    shape = _shape_S(pkg)
+    n = 70
+    sb = pkg.SynthBatch(shape, n, seed0=300)
+    sb.d_words[41 * sb.words + int(sb.blob(0)[82]) + 2] ^= 1                # an answer word of instance 41
+    verdict, _ = sb.run(full=True)
+    verdict = verdict.cpu().numpy()
+    assert verdict[41] == 1 and verdict.sum() == 1
+    circ = pkg.VerifierCircuit(shape, folding=True)
+    assert circ.info.n_flow == 2112 and circ.info.num_input == 3        # no public inputs beyond the three constants
+    r = circ.trace(sb, check=True, export=True)
+    bad_row, bad_flow = r["bad_row"].cpu().numpy(), r["bad_flow"].cpu().numpy()
+    assert bad_row[41] >= 0 and (np.delete(bad_row, 41) == -1).all() and (bad_flow == -1).all()
+    for p in (0, 33, n - 1):
+        cs, _ = D.folding_circuit(sb.blob(p), O.VerifyOut)
+        assert np.array_equal(circ.fetch(p, "variables"), np.array(cs.variables, dtype=np.uint32))
+        wire, addr, wh, wsw = cs.flow_arrays()
+        assert np.array_equal(circ.fetch(p, "flow_hash"), wh) and np.array_equal(circ.fetch(p, "flow_swap"), wsw)
+        got = pkg.VerifierCircuit.assemble_trace(r["preprocessed"], r["values"][p])
+        assert np.array_equal(got, cs.trace_columns())
+    # the same trace with every permutation recomputed by the tape instead of taken from the tree rebuilds' record
+    keep = r["values"].clone()
+    r2 = circ.trace(sb, check=True, export=True, native_hints=False)
+    assert (r2["values"] == keep).all()
+
+
+def test_folding_circuit_on_a_real_proof(pkg, gpu, orc):
+    """the same circuit over the workspace of a real proof's verification = the folding part of its verifier circuit"""
+    import os
+    blob = open(os.path.join(O.PROOFS_DIR, "small_proof.bin"), "rb").read()
+    vb = pkg.VerifyBatch([blob] * 33, inputs=pkg.INPUTS_SINGLE)
+    verdict, _ = vb.run(full=True)
+    assert not verdict.cpu().numpy().any()
+    circ = pkg.VerifierCircuit(vb.shape, folding=True)
+    r = circ.trace(vb, check=True, export=True)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    assert (r["values"][0] == r["values"][32]).all()
+
+
+def test_folding_circuit_full_batch(pkg, gpu, orc):
+    """BASELINE configs[4] part i at full size: 4096 distinct instances, every one accepted and its folding circuit satisfied"""
+    shape = _shape_S(pkg)
+    sb = pkg.SynthBatch(shape, 4096, seed0=5000)
+    verdict, _ = sb.run(full=True)
+    assert not verdict.cpu().numpy().any()
+    circ = pkg.VerifierCircuit(shape, folding=True)
+    r = circ.trace(sb, check=True, export=True, preprocessed=False)
+    assert (r["bad_row"].cpu().numpy() == -1).all() and (r["bad_flow"].cpu().numpy() == -1).all()
+    v = r["values"]
+    assert not (v[0] == v[1]).all() and not (v[100] == v[4095]).all()      # distinct instances, distinct traces

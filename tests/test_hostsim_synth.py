@@ -89,3 +89,89 @@ def test_tampered_instances_are_rejected_alike(hostsim, orc, name):
             assert (dt.verdict, dt.stage) == (o.verdict, o.stage), (dt.verdict, dt.stage, o.verdict, o.stage)
             stages.add(O.STAGES[o.stage])
     assert {"ok", "fri_first", "fri_inner"} <= stages and ("fri_last" in stages or "pow" in stages)
+
+
+# ---- the folding-stage circuit over an instance (the tape of configs[4] part i) ----------------------------------------------------------
+INFO = ("n_rows", "n_rows_unpadded", "n_vars", "n_flow", "n_flow_padded", "n_input_words", "n_ins", "n_levels", "num_input", "words_per_instance")
+
+
+@pytest.mark.parametrize("name", ["three-sizes", "two-sizes", "deep"])
+def test_folding_circuit_matches_oracle(hostsim, orc, name):
+    """FoldingResults::compute alone, everything before it as witnesses: the product's recorder + tape evaluator against the oracle DSL's
+    `folding` fed by the oracle's FRI-only verifier -- same wiring, same variables, same Poseidon flow; and the same again with every
+    permutation taken from the record the product's tree rebuilds leave behind."""
+    from circuit_common import D, compare_wiring
+    shape = SHAPES[name]
+    blobs = [generate(hostsim, shape, seed) for seed in (3, 4)]
+    cs, out = D.folding_circuit(blobs[0], O.VerifyOut)
+    hostsim.hs_circuit_record_folding.restype = ctypes.c_void_p
+    sh = np.array(shape, dtype=np.uint32)
+    h = ctypes.c_void_p(hostsim.hs_circuit_record_folding(O.vp(sh)))
+    assert h, "recorder failed"
+    info = np.zeros(len(INFO), dtype=np.uint32)
+    hostsim.hs_circuit_info(h, O.vp(info))
+    info = dict(zip(INFO, (int(x) for x in info)))
+
+    def get(what, n):
+        o = np.zeros(n, dtype=np.uint32)
+        hostsim.hs_circuit_get(h, what, O.vp(o))
+        return o
+    compare_wiring(cs, info, get)
+    assert hostsim.hs_circuit_hint_count(h) == info["n_flow"] == len(cs.flow)
+    hostsim.hs_synth_verify.restype = ctypes.c_void_p
+    words = np.concatenate(blobs)
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([b.size for b in blobs])
+    results = []
+    for coop, use_hints in ((1, 0), (1, 1), (0, 1)):
+        dt = (Detail * len(blobs))()
+        ws = np.zeros(4096, dtype=np.uint8)
+        base = hostsim.hs_synth_verify(O.vp(words), O.vp(off), len(blobs), O.vp(sh), coop, dt, O.vp(ws))
+        assert [(d.verdict, d.stage) for d in dt] == [(0, 0)] * len(blobs)
+        variables = np.zeros((len(blobs), info["n_vars"], 4), dtype=np.uint32)
+        fh = np.zeros((len(blobs), info["n_flow"], 32), dtype=np.uint32)
+        fsw = np.zeros((len(blobs), info["n_flow"]), dtype=np.uint8)
+        bad = np.zeros(len(blobs), dtype=np.int64)
+        hostsim.hs_circuit_eval(h, O.vp(ws), len(blobs), O.vp(variables), O.vp(fh), O.vp(fsw), None, O.vp(bad), use_hints)
+        hostsim.hs_free(ctypes.c_void_p(base))
+        assert list(bad) == [-1, -1]
+        results.append((variables, fh, fsw))
+    want = np.array(cs.variables, dtype=np.uint32)
+    diff = np.nonzero((results[0][0][0] != want).any(axis=1))[0]
+    assert diff.size == 0, "variable %d differs: %s != %s" % (diff[0], results[0][0][0][diff[0]], want[diff[0]])
+    wire, addr, wh, wsw = cs.flow_arrays()
+    assert np.array_equal(results[0][1][0], wh) and np.array_equal(results[0][2][0], wsw)
+    for r in results[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(r, results[0]))
+    # the second instance satisfies the same circuit with its own values
+    cs2, _ = D.folding_circuit(blobs[1], O.VerifyOut)
+    assert np.array_equal(results[0][0][1], np.array(cs2.variables, dtype=np.uint32))
+    hostsim.hs_circuit_free(h)
+
+
+def test_folding_circuit_of_a_tampered_instance_is_unsatisfied(hostsim, orc):
+    shape = SHAPES["three-sizes"]
+    good = generate(hostsim, shape, 5)
+    bad_blob = good.copy()
+    bad_blob[int(good[82])] ^= 1                                           # first answer word
+    sh = np.array(shape, dtype=np.uint32)
+    hostsim.hs_circuit_record_folding.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(hostsim.hs_circuit_record_folding(O.vp(sh)))
+    info = np.zeros(len(INFO), dtype=np.uint32)
+    hostsim.hs_circuit_info(h, O.vp(info))
+    info = dict(zip(INFO, (int(x) for x in info)))
+    hostsim.hs_synth_verify.restype = ctypes.c_void_p
+    words = np.concatenate([good, bad_blob])
+    off = np.array([0, good.size, 2 * good.size], dtype=np.uint64)
+    dt = (Detail * 2)()
+    ws = np.zeros(4096, dtype=np.uint8)
+    base = hostsim.hs_synth_verify(O.vp(words), O.vp(off), 2, O.vp(sh), 1, dt, O.vp(ws))
+    variables = np.zeros((2, info["n_vars"], 4), dtype=np.uint32)
+    fh = np.zeros((2, info["n_flow"], 32), dtype=np.uint32)
+    fsw = np.zeros((2, info["n_flow"]), dtype=np.uint8)
+    bad = np.zeros(2, dtype=np.int64)
+    hostsim.hs_circuit_eval(h, O.vp(ws), 2, O.vp(variables), O.vp(fh), O.vp(fsw), None, O.vp(bad), 1)
+    hostsim.hs_free(ctypes.c_void_p(base))
+    assert (dt[0].verdict, bad[0]) == (0, -1)
+    assert dt[1].verdict == 1 and bad[1] >= 0                              # the reference would panic inside equalverify
+    hostsim.hs_circuit_free(h)
