@@ -22,6 +22,8 @@ in HBM for the prover that consumes them; shipping them to the host instead woul
 4096-proof batch at 200 GB/s).
 Prints ONE JSON line on rank 0.
 """
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before the CUDA context exists (see recursive-stwo_b200/__init__.py)
 import argparse
 import ctypes
 import importlib
@@ -272,8 +274,22 @@ def multi_proofs_leg(pkg, sharding, rank, world, dev, n_total=256, reps=3):
     parts = [pkg.MixedBatch([blobs[f] for f in mine if f.startswith("small") == sm], inputs=pkg.INPUTS_SINGLE if sm else pkg.INPUTS_RECURSIVE)
              for sm in (True, False) if any(f.startswith("small") == sm for f in mine)]
 
+    # the two resident batches run beside each other too: each on its own stream, joined on the current one
+    side = [torch.cuda.Stream(dev) for _ in parts]
+
+    def run_parts():
+        cur = torch.cuda.current_stream(dev)
+        out = []
+        for mb, st in zip(parts, side):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out.append(mb.run(trace=True, export=True)[0])
+        for st in side:
+            cur.wait_stream(st)
+        return out
+
     def step():
-        return sum(int(mb.run(trace=True, export=True)[0].sum().item()) for mb in parts)
+        return sum(int(v.sum().item()) for v in run_parts())
 
     assert step() == 0, "every fixture must be accepted and every circuit consistent"
     step()
@@ -283,20 +299,22 @@ def multi_proofs_leg(pkg, sharding, rank, world, dev, n_total=256, reps=3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for mb in parts:
-            mb.run(trace=True, export=True)
+        run_parts()
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / reps, float(sum(cost[lo:hi])), float(hi - lo)], dtype=torch.float64, device=dev)
     tmax = t.clone()
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, t)
     ms = float(tmax[0].item())
     rows = sum(g.circuit.info.n_rows * len(g.ids) for mb in parts for g in mb.groups)
     return {"config": "BASELINE configs[3]: 256 proofs = 15 fixtures cycled; verify + circuit trace (check + export) per proof; one recorded circuit per shape; "
                       "ranks take contiguous blocks of the shape-sorted order cut by work",
             "proofs": n_total, "shapes": len({tuple(shape_of[f].key()) for f in names}), "ms_per_batch": ms, "proofs_per_sec": n_total / (ms * 1e-3),
-            "max_rank_work_share": float(tmax[1].item()) / sum(cost), "max_rank_proofs": int(tmax[2].item()), "rank0_trace_rows": rows}
+            "max_rank_work_share": float(tmax[1].item()) / sum(cost), "max_rank_proofs": int(tmax[2].item()), "rank0_trace_rows": rows,
+            "per_rank": [{"ms": round(float(x[0].item()), 3), "work_share": round(float(x[1].item()) / sum(cost), 3), "proofs": int(x[2].item())} for x in per_rank]}
 
 
 def trace_gather_leg(sharding, values, rank, world, dev, n_each=256, reps=3):
@@ -445,7 +463,7 @@ def main():
     ap.add_argument("--proofs", type=int, default=4096, help="proofs per GPU per step (weak scaling) / in total (strong scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --proofs per GPU; strong: --proofs in total, ceil(proofs / N) per GPU (BASELINE configs[4]: 4096 across 8 GPUs)")
-    ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes: independent verify / trace stream pairs (VerifyTracePipeline)")
+    ap.add_argument("--lanes", type=int, default=None, help="pipeline lanes: independent verify / trace stream pairs (VerifyTracePipeline; default: its own choice)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the K1 / Merkle-sweep side measurements")
@@ -480,7 +498,7 @@ def main():
     # A stream of batches through the public API: VerifyTracePipeline = three device slots, the upload / verification / trace pass of
     # neighbouring batches on their own streams.  Every step verifies AND traces one whole batch; the device-resident leg skips the
     # upload, the end-to-end leg does everything.
-    pipe = pkg.VerifyTracePipeline([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE, n_slots=2 * args.lanes + 1, lanes=args.lanes)
+    pipe = pkg.VerifyTracePipeline([blob] * (hi - lo), inputs=pkg.INPUTS_SINGLE, lanes=args.lanes)
     vb, circ = pipe.slots[0], pipe.circuit                              # the circuit is recorded once per shape (host)
     ci = circ.info
     ws_mb = (vb.ws_bytes + circ.workspace_bytes(hi - lo)) >> 20
@@ -707,7 +725,8 @@ def main():
                        "perms_per_proof": perms_per_proof,
                        "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace + %d MB of trace columns per step" % (blob_mb, ws_mb, trace_mb),
                        "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only",
-                       "pipeline": "3 device slots; upload | verification | trace pass of neighbouring steps on their own streams"},
+                       "pipeline": "%d device slots, %d lane(s); upload | verification | trace pass of neighbouring steps on their own streams; "
+                                   "CUDA_DEVICE_MAX_CONNECTIONS=%s" % (len(pipe.slots), len(pipe.lane_streams), os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"))},
             "poseidon31_perms_per_sec": value * perms_per_proof,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

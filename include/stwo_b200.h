@@ -13,10 +13,11 @@
  *  - `*_dev` entry points take DEVICE pointers and a cudaStream_t (as void*) and only enqueue work;
  *    the un-suffixed entry points take HOST pointers, stage through pinned buffers owned by the
  *    library and return after the result is in the caller's buffer.
- *  - One host thread per device.  `*_dev` calls only enqueue on the given stream and are re-entrant across streams, with two
- *    exceptions that keep per-device scratch (a stream pool and its events; the grid-barrier word of the cooperative tape
- *    evaluation): stwo_b200_verify_proofs_batch[_pinned]_dev and stwo_b200_cs_eval_tape_dev / stwo_b200_circuit_trace_batch_dev
- *    -- keep one of each in flight per device (queue them on one stream, or order the streams with events).
+ *  - One host thread per device.  `*_dev` calls only enqueue on the given stream, and calls on different streams run beside each other
+ *    (the shape groups of a mixed batch, the stages of a pipeline): stwo_b200_verify_proofs_batch[_pinned]_dev keeps one pool of worker
+ *    streams per CALLER stream (six pools; further caller streams share the last one, which only serialises them), and the tape evaluation
+ *    is a plain thread-block-cluster launch.  Only the cooperative-grid evaluation (STWO_B200_EVAL_MODE=grid, profiling) keeps a
+ *    grid-barrier word per launch slot: one of those in flight at a time.
  *  - There is no CPU fallback: without a CUDA device every call returns STWO_B200_E_NO_DEVICE.
  */
 #ifndef STWO_B200_H

@@ -5,8 +5,15 @@ the C ABI in libstwo_b200.so (include/stwo_b200.h); torch is used only to own de
 streams.  The directory name has a hyphen: import it with
 `importlib.import_module("recursive-stwo_b200")` (see __graft_entry__.py).
 """
-from . import _lib
-from ._lib import PathShape, StwoB200Error
+import os as _os
+
+# Hardware work queues: the batch drivers use a dozen streams; with the driver's default of 8 queues independent chains alias onto one
+# queue and wait for each other.  Read at context creation, so it is set on import, before the first CUDA call (runtime.cu does the same
+# in stwo_b200_init for hosts without this package).
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from . import _lib  # noqa: E402
+from ._lib import PathShape, StwoB200Error  # noqa: E402
 from .hashing import (init, poseidon2_permute, poseidon2_permute_host, hash_node_batch, merkle_commit,
                       merkle_commit_host, merkle_decommit, merkle_path_verify, merkle_path_verify_host,
                       launch_count, path_perms)

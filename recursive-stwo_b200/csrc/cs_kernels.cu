@@ -84,6 +84,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned n_ctas,
     __syncthreads();
 }
 __device__ unsigned long long *g_level_clock = nullptr;      // diagnostics (stwo_b200_cs_eval_level_clock)
+bool g_level_clock_host = false;
 __device__ __forceinline__ void stamp_level(u32 l) {
     if (g_level_clock && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -148,8 +149,14 @@ __global__ void __launch_bounds__(kEvalThreads) k_tape_eval_grid(const tape::Ins
 // before it wrote (the grid-wide form sweeps every group's variables at every level).
 // Consecutive instructions of a level go to different CTAs of the cluster (different SMs).
 constexpr int kClusterThreads = 512;
+// Measured and dropped (round 2): a bundle loop that keeps a one-variable instruction's result in registers for its successor and requests
+// the successor's other operand before computing (the chain link then waits for no load): 1.27 against 1.01 ms at 512 proofs under the
+// 64-register cap and 1.82 ms with 120 registers and one CTA per SM -- the extra copy of the arithmetic cases and the lost co-residency
+// cost more than the round trips saved; hoisting the hint loads of a permutation above its flow stores: spills at 64 registers, slower.
 // Measured and dropped: four instructions of a level per warp at once (all operand loads issued before any is consumed): 110 registers,
 // one CTA per SM, 5.2 ms against 3.1 ms at 4096 proofs and 1.4 against 1.1 ms at 512 -- the pass is not short of loads in flight.
+// CLOCK: cluster 0 stamps the global timer after every level (tools/level_clock.py)
+template <bool CLOCK>
 __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                        const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
                                                                        const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start) {
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tap
     u32 i0 = 0, i1 = 0;
     if (s_level[0] + wi < s_level[1]) extent(s_level[0] + wi, i0, i1);
     cluster_sync();
+    if (CLOCK) stamp_level(0);
     for (u32 l = 0; l < n_levels; l++) {
         const u32 lo = s_level[l], hi = s_level[l + 1];
         for (u32 k = lo + wi; k < hi; k += n_w) {
@@ -193,6 +201,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tap
         }
         if (l + 1 < n_levels && hi + wi < s_level[l + 2]) extent(hi + wi, i0, i1);
         cluster_sync();
+        if (CLOCK) stamp_level(l + 1);
     }
 }
 
@@ -605,16 +614,17 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
     // spread over many SMs), two when the batch alone fills the GPU (4096 proofs: all 128 clusters resident at once).
     if (v->lanes == 32 && (grid_mode == 2 || grid_mode < 0)) {
         int c = cluster > 0 ? cluster : (n_groups <= 2 ? 16 : n_groups <= 24 ? 8 : n_groups <= 64 ? 4 : 2);
-        if (c > 8) STWO_CUDA(cudaFuncSetAttribute(k_tape_eval_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        auto kernel = g_level_clock_host ? k_tape_eval_cluster<true> : k_tape_eval_cluster<false>;
+        if (c > 8) STWO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         const size_t smem = ((size_t)n_levels + 1) * 4;
-        if (smem > 48 * 1024) STWO_CUDA(cudaFuncSetAttribute(k_tape_eval_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) STWO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(n_groups * (unsigned)c); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        STWO_CUDA(cudaLaunchKernelEx(&cfg, k_tape_eval_cluster, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start));
+        STWO_CUDA(cudaLaunchKernelEx(&cfg, kernel, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start));
         note_launch(1);
         return cuda_status(cudaGetLastError());
     }
@@ -638,6 +648,7 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
 extern "C" int32_t stwo_b200_cs_eval_level_clock(uint64_t *level_clock) {
     STWO_CHECK_DEVICE();
     unsigned long long *p = (unsigned long long *)level_clock;
+    g_level_clock_host = p != nullptr;
     return cuda_status(cudaMemcpyToSymbol(g_level_clock, &p, sizeof p));
 }
 extern "C" int32_t stwo_b200_cs_check_arithmetics_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, int64_t *first_bad,

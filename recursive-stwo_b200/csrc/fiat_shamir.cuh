@@ -237,47 +237,55 @@ HD void eval_plonk(EvalRow &e) {
     e.finalize_logup(2);
 }
 
+// The 52 preprocessed and 48 trace masks of the Poseidon component are read where they are used (they sit in the proof blob, a few
+// cache lines): held in registers they are 96 QM31 = 384 words, which spilled; live now are the 16-element state and the accumulators.
 HD void eval_poseidon(EvalRow &e) {
     const qm31_t one = qm31::one();
-    qm31_t is_first = e.mask(0), is_last = e.mask(0), is_full = e.mask(0);
-    qm31_t not_first = qsub(one, is_first), not_last = qsub(one, is_last), is_partial = qsub(not_first, is_full);
-    qm31_t round_id = e.mask(0);
-    qm31_t rc0[16], rc1[16], in[16], mid[16], out[16], s[16];
-    for (int i = 0; i < 16; i++) rc0[i] = e.mask(0);
-    for (int i = 0; i < 16; i++) rc1[i] = e.mask(0);
-    qm31_t ext1 = e.mask(0), ext2 = e.mask(0), ext1_nz = e.mask(0), ext2_nz = e.mask(0);
-    for (int i = 0; i < 16; i++) in[i] = e.mask(1);
-    for (int i = 0; i < 16; i++) mid[i] = e.mask(1);
-    for (int i = 0; i < 16; i++) out[i] = e.mask(1);
-    qm31_t swap = mid[0], nswap = qsub(one, swap);
+    const u32 *w = e.w;
+    const proof::Desc &d = *e.d;
+    const u32 b0 = e.base[0] + e.col[0], b1 = e.base[1] + e.col[1];
+    auto pre = [&](u32 c) { return qload(w + proof::sample_off(d, 0, b0 + c, 0)); };      // is_first, is_last, is_full, round_id, rc0[16], rc1[16], ext..
+    auto trc = [&](u32 c) { return qload(w + proof::sample_off(d, 1, b1 + c, 0)); };      // in[16], mid[16], out[16]
+    auto rc0 = [&](u32 i) { return pre(4 + i); };
+    auto rc1 = [&](u32 i) { return pre(20 + i); };
+    auto in = [&](u32 i) { return trc(i); };
+    auto mid = [&](u32 i) { return trc(16 + i); };
+    auto out = [&](u32 i) { return trc(32 + i); };
+    e.col[0] += 40; e.col[1] += 48;
+    const qm31_t is_first = pre(0), is_last = pre(1), is_full = pre(2);
+    const qm31_t not_first = qsub(one, is_first), not_last = qsub(one, is_last), is_partial = qsub(not_first, is_full);
+    qm31_t s[16];
+    const qm31_t swap = mid(0), nswap = qsub(one, swap);
     for (int i = 0; i < 16; i++)
-        s[i] = i < 8 ? qadd(qmul(in[i], nswap), qmul(in[i + 8], swap)) : qadd(qmul(in[i - 8], swap), qmul(in[i], nswap));
+        s[i] = i < 8 ? qadd(qmul(in(i), nswap), qmul(in(i + 8), swap)) : qadd(qmul(in(i - 8), swap), qmul(in(i), nswap));
     ext_matrix(s);
-    for (int i = 0; i < 16; i++) e.constraint(qmul(is_first, qsub(s[i], out[i])));
-    for (int i = 0; i < 16; i++) s[i] = pow5(qadd(in[i], rc0[i]));
-    for (int i = 0; i < 16; i++) { e.constraint(qmul(is_full, qsub(mid[i], s[i]))); s[i] = mid[i]; }
+    for (int i = 0; i < 16; i++) e.constraint(qmul(is_first, qsub(s[i], out(i))));
+    for (int i = 0; i < 16; i++) s[i] = pow5(qadd(in(i), rc0(i)));
+    for (int i = 0; i < 16; i++) { const qm31_t m = mid(i); e.constraint(qmul(is_full, qsub(m, s[i]))); s[i] = m; }
     ext_matrix(s);
-    for (int i = 0; i < 16; i++) s[i] = pow5(qadd(s[i], rc1[i]));
+    for (int i = 0; i < 16; i++) s[i] = pow5(qadd(s[i], rc1(i)));
     ext_matrix(s);
-    for (int i = 0; i < 16; i++) e.constraint(qmul(is_full, qsub(out[i], s[i])));
-    for (int i = 0; i < 16; i++) s[i] = in[i];
+    for (int i = 0; i < 16; i++) e.constraint(qmul(is_full, qsub(out(i), s[i])));
+    for (int i = 0; i < 16; i++) s[i] = in(i);
     for (int r = 0; r < 14; r++) {
-        s[0] = pow5(qadd(s[0], rc0[r]));
-        e.constraint(qmul(is_partial, qsub(mid[r], s[0])));
-        s[0] = mid[r];
+        s[0] = pow5(qadd(s[0], rc0(r)));
+        const qm31_t m = mid(r);
+        e.constraint(qmul(is_partial, qsub(m, s[0])));
+        s[0] = m;
         int_matrix(s);
     }
-    for (int i = 0; i < 16; i++) e.constraint(qmul(is_partial, qsub(out[i], s[i])));
-    qm31_t in_left = qadd(round_id, round_id), in_right = qadd(in_left, one), out_left = qadd(in_right, one), out_right = qadd(out_left, one);
+    for (int i = 0; i < 16; i++) e.constraint(qmul(is_partial, qsub(out(i), s[i])));
+    const qm31_t round_id = pre(3), ext1 = pre(36), ext2 = pre(37), ext1_nz = pre(38), ext2_nz = pre(39);
+    const qm31_t in_left = qadd(round_id, round_id), in_right = qadd(in_left, one), out_left = qadd(in_right, one), out_right = qadd(out_left, one);
     e.relation3(qsub(qmul(ext1_nz, is_first), not_first), qadd(qmul(is_first, ext1), qmul(not_first, in_left)),
-                combine_ef(in[0], in[1], in[2], in[3]), combine_ef(in[4], in[5], in[6], in[7]));
+                combine_ef(in(0), in(1), in(2), in(3)), combine_ef(in(4), in(5), in(6), in(7)));
     e.relation3(qsub(qmul(ext2_nz, is_first), not_first), qadd(qmul(is_first, ext2), qmul(not_first, in_right)),
-                combine_ef(in[8], in[9], in[10], in[11]), combine_ef(in[12], in[13], in[14], in[15]));
+                combine_ef(in(8), in(9), in(10), in(11)), combine_ef(in(12), in(13), in(14), in(15)));
     e.relation3(qadd(qmul(ext1_nz, is_last), not_last), qadd(qmul(is_last, ext1), qmul(not_last, out_left)),
-                combine_ef(out[0], out[1], out[2], out[3]), combine_ef(out[4], out[5], out[6], out[7]));
+                combine_ef(out(0), out(1), out(2), out(3)), combine_ef(out(4), out(5), out(6), out(7)));
     e.relation3(qadd(qmul(ext2_nz, is_last), not_last), qadd(qmul(is_last, ext2), qmul(not_last, out_right)),
-                combine_ef(out[8], out[9], out[10], out[11]), combine_ef(out[12], out[13], out[14], out[15]));
-    e.relation2(qmul(is_first, not_last), swap, rc0[0]);
+                combine_ef(out(8), out(9), out(10), out(11)), combine_ef(out(12), out(13), out(14), out(15)));
+    e.relation2(qmul(is_first, not_last), swap, rc0(0));
     e.finalize_logup(3);
 }
 

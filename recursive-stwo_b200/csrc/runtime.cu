@@ -1,4 +1,5 @@
 // Library lifecycle, staging memory and launch accounting for the C ABI.
+#include <cstdlib>
 #include "common.cuh"
 #include <atomic>
 #include <mutex>
@@ -32,6 +33,11 @@ int32_t stage_reserve(size_t dev_bytes) {
 using namespace stwo_b200;
 
 extern "C" int32_t stwo_b200_init(int32_t device) {
+    // The batch drivers spread a pass over a dozen streams (worker pools, pipeline stages, shape groups).  With the driver's default of 8
+    // hardware work queues, streams alias onto queues and independent chains wait for each other (measured on B200: 512-proof pipeline
+    // 2.79 -> 2.33 ms, mixed 256-proof batch 14.6 -> 12.1 ms with 32).  Read when the context is created: this helps only if the library
+    // is initialised before anything else touches CUDA in the process; a host that creates the context itself exports the variable itself.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return STWO_B200_E_NO_DEVICE;

@@ -109,8 +109,13 @@ __global__ void __launch_bounds__(kCoopThreads) k_parse_coop(const Workspace ws,
 // LATENCY of one permutation: ~6.3 us with the state in one thread's registers (tools/perm_latency_microbench.cu), ~2 us
 // with one state word per lane: the S-boxes of a full round run in parallel, the external matrix is 6 shuffles, the internal
 // matrix a 4-step butterfly sum.  Same transcript order as fs::transcript (components/recursive/fiat_shamir/src/lib.rs:39-131).
+// The warp holds two proofs (one per half) and stays CONVERGENT from the first instruction to the last: the shuffles name all 32 lanes
+// (width 16 keeps them inside a half), so they compile to bare SHFL -- with a half-warp mask every one of the ~150 shuffles of a
+// permutation came wrapped in WARPSYNC.COLLECTIVE / BSSY / BSYNC (2 500 of them in the kernel), on the critical path of a latency chain.
+// A half without a proof of its own (ragged tail, a proof that did not parse) repeats its neighbour's and stores nothing.
 struct Lanes16 {
-    unsigned mask; u32 l;                                   // l = 0..15: which state word this lane holds
+    u32 l;                                                  // l = 0..15: which state word this lane holds
+    bool active;                                            // this half owns a proof: its stores count
     // this lane's constants, loaded once per kernel: the chain is latency bound, a constant fetched inside a round is on the critical path
     u32 rcf[4], rcl[4], dg, c0, c1, c2, c3;
     __device__ __forceinline__ void init() {
@@ -127,8 +132,8 @@ struct Lanes16 {
         const u32 lo = (u32)x, hi = (u32)(x >> 32);          // hi < 2^29: the sum below is < 2p
         return m31::canon((lo & M31_P) + (lo >> 31) + (hi << 1));
     }
-    __device__ __forceinline__ u32 get(u32 x, u32 src) const { return __shfl_sync(mask, x, src, 16); }
-    __device__ __forceinline__ u32 get_xor(u32 x, u32 m) const { return __shfl_xor_sync(mask, x, m, 16); }
+    __device__ __forceinline__ u32 get(u32 x, u32 src) const { return __shfl_sync(0xffffffffu, x, src, 16); }
+    __device__ __forceinline__ u32 get_xor(u32 x, u32 m) const { return __shfl_xor_sync(0xffffffffu, x, m, 16); }
     // circ(2 M4, M4, M4, M4) x, M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] (primitives/poseidon31/src/implementation.rs:7-58)
     __device__ __forceinline__ u32 ext_mds(u32 x) const {
         const u32 base = l & ~3u;
@@ -145,7 +150,8 @@ struct Lanes16 {
         for (int r = 0; r < 4; r++) x = ext_mds(pow5(m31::addc(x, rcf[r])));
 #pragma unroll
         for (int r = 0; r < 14; r++) {
-            if (l == 0) x = pow5(m31::addc(x, poseidon2::K.rc_part[r]));
+            const u32 sb = pow5(m31::addc(x, poseidon2::K.rc_part[r]));     // every lane computes it, lane 0 keeps it: no branch
+            x = l == 0 ? sb : x;
             // sum of the 16 words: two butterfly steps on lazy sums (values < 2^31, four of them < 2^33), then one reduction
             const u64 s1 = (u64)x + get_xor(x, 1) + get_xor(x, 2) + get_xor(x, 3);
             const u32 q = red_small(s1);
@@ -160,22 +166,26 @@ struct Lanes16 {
 struct Channel16 {                                          // primitives/channel/src/lib.rs:23-58 on a lane-spread state
     Lanes16 g; u32 s, n_sent, n_perms;
     u32 *sink;                                              // optional: output state of permutation k at sink[16 k ..], a word per lane
-    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); if (sink) sink[16 * (size_t)n_perms + g.l] = s; n_sent = 0; n_perms++; }
+    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); if (sink && g.active) sink[16 * (size_t)n_perms + g.l] = s; n_sent = 0; n_perms++; }
     __device__ void mix8(const u32 *w8) { absorb(g.l < 8 ? w8[g.l] : 0u); }
     __device__ void mix4(const u32 *w4) { absorb(g.l < 4 ? w4[g.l] : 0u); }
     __device__ void mix4v(u32 v) { absorb(g.l < 4 ? v : 0u); }              // lanes 0..3 already hold the four words
     __device__ void mix44(const u32 *a, const u32 *b) { absorb(g.l < 4 ? a[g.l] : g.l < 8 ? b[g.l - 4] : 0u); }
     __device__ u32 draw() {                                 // lanes 0..7 return the eight drawn words
         const u32 t = g.permute(g.l == 0 ? n_sent : g.l < 8 ? 0u : s);
-        if (sink) sink[16 * (size_t)n_perms + g.l] = t;
+        if (sink && g.active) sink[16 * (size_t)n_perms + g.l] = t;
         n_sent++; n_perms++;
         return t;
     }
 };
-__device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o, u32 *sink) {
+// Trip counts come from the batch's shape (a kernel parameter: provably warp-uniform, so the loops stay convergent for the compiler too),
+// not from the proof's descriptor (equal for every proof that parsed, but loaded from memory).
+__device__ __forceinline__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o, u32 *sink, const u32 n_inner,
+                                             const u32 n_last_coeffs, const u32 n_queries, const u32 pow_bits) {
     Channel16 ch{g, 0u, 0u, 0u, sink};
     const u32 l = g.l;
-    auto store_q = [&](qm31_t *dst, u32 t, u32 first_lane) { if (l >= first_lane && l < first_lane + 4) dst->v[l - first_lane] = t; };
+    const bool act = g.active;
+    auto store_q = [&](qm31_t *dst, u32 t, u32 first_lane) { if (act && l >= first_lane && l < first_lane + 4) dst->v[l - first_lane] = t; };
     ch.mix8(w + d.commitments[0]);
     ch.mix4v(l == 0 ? d.log_size_plonk : 0u);
     ch.mix4v(l == 0 ? d.log_size_poseidon : 0u);
@@ -190,7 +200,7 @@ __device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &
     {
         // the OODS point from t (every lane computes it from the broadcast words; lane 0 stores)
         const qm31_t ot = qm31::mk(g.get(t, 0), g.get(t, 1), g.get(t, 2), g.get(t, 3));
-        if (l == 0) {
+        if (act && l == 0) {
             const qm31_t t2 = fs::qmul(ot, ot);
             const qm31_t inv = fs::qinv(qm31::add_m31(t2, 1));
             o.oods_x = fs::qmul(fs::qsub(qm31::one(), t2), inv);
@@ -228,16 +238,16 @@ __device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &
     t = ch.draw(); store_q(&o.after_coeff, t, 0);
     {
         u32 cur = l < 8 ? w[d.fl_commitment + l] : 0u;
-        for (u32 i = 0; i <= d.n_inner; i++) {
-            const u32 nxt = (i < d.n_inner && l < 8) ? w[d.in_commitment[i] + l] : 0u;
+        for (u32 i = 0; i <= n_inner; i++) {
+            const u32 nxt = (i < n_inner && l < 8) ? w[d.in_commitment[i] + l] : 0u;
             ch.absorb(cur);
             t = ch.draw(); store_q(&o.fri_alphas[i], t, 0);
             cur = nxt;
         }
     }
     {
-        const u32 n_mix = (d.n_last_coeffs + 1) / 2;
-        auto coeff_word = [&](u32 i) -> u32 { return (l < 8 && 8 * i + l < 4 * d.n_last_coeffs) ? w[d.last_coeffs + 8 * i + l] : 0u; };
+        const u32 n_mix = (n_last_coeffs + 1) / 2;
+        auto coeff_word = [&](u32 i) -> u32 { return (l < 8 && 8 * i + l < 4 * n_last_coeffs) ? w[d.last_coeffs + 8 * i + l] : 0u; };
         u32 cur = coeff_word(0);
         for (u32 i = 0; i < n_mix; i++) {
             const u32 nxt = i + 1 < n_mix ? coeff_word(i + 1) : 0u;
@@ -248,30 +258,31 @@ __device__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &
     const u64 nonce = (u64)w[d.pow_nonce] | ((u64)w[d.pow_nonce + 1] << 32);
     const u32 limb = l == 0 ? (u32)(nonce & ((1u << 22) - 1)) : l == 1 ? (u32)((nonce >> 22) & ((1u << 21) - 1)) : l == 2 ? (u32)((nonce >> 43) & ((1u << 21) - 1)) : 0u;
     ch.mix4v(limb);
-    if (l >= 8) o.digest_after_nonce[l - 8] = ch.s;
-    if (l == 8) o.pow_ok = (ch.s & ((1u << d.pow_bits) - 1)) == 0;
+    if (act && l >= 8) o.digest_after_nonce[l - 8] = ch.s;
+    if (act && l == 8) o.pow_ok = (ch.s & ((1u << pow_bits) - 1)) == 0;
     u32 got = 0;
-    for (u32 k = 0; k < (d.n_queries + 3) / 4; k++) {
+    for (u32 k = 0; k < (n_queries + 3) / 4; k++) {
         t = ch.draw();
-        if (l < 8 && got + l < d.n_queries) o.raw_queries[got + l] = t;
+        if (act && l < 8 && got + l < n_queries) o.raw_queries[got + l] = t;
         got += 8;
     }
-    if (l == 0) o.n_transcript_perms = ch.n_perms;
+    if (act && l == 0) o.n_transcript_perms = ch.n_perms;
 }
 __global__ void __launch_bounds__(kT) k_transcript16(const Workspace ws, u32 p0, u32 pn) {
     const u32 grp = (blockIdx.x * kT + threadIdx.x) / 16;
-    if (grp >= pn) return;
-    const u32 p = p0 + grp;
+    const bool own = grp < pn && ws.desc[p0 + grp].ok;
+    const bool other = __shfl_xor_sync(0xffffffffu, own ? 1u : 0u, 16) != 0;
+    if (!own && !other) return;                              // whole warps leave together
+    const u32 p = p0 + (own ? grp : (grp ^ 1u));             // a half without a proof shadows its neighbour (same shape, same trip counts)
     const proof::Desc &d = ws.desc[p];
-    if (!d.ok) return;                                       // whole groups leave together
     Lanes16 g;
     g.l = threadIdx.x % 16;
-    g.mask = 0xffffu << (16 * ((threadIdx.x % 32) / 16));
+    g.active = own;
     g.init();
     verify::Detail &dt = ws.detail[p];
-    transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0));
-    __syncwarp(g.mask);
-    if (g.l == 0) verify::stage_after_transcript(ws, p);
+    transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0), ws.shape.n_inner, 1u << ws.shape.log_last, ws.shape.n_queries, ws.shape.pow_bits);
+    __syncwarp();
+    if (own && g.l == 0) verify::stage_after_transcript(ws, p);
 }
 __global__ void __launch_bounds__(kT) k_transcript(const Workspace ws, u32 p0, u32 pn) {
     u32 idx = blockIdx.x * kT + threadIdx.x;
@@ -321,21 +332,33 @@ __global__ void __launch_bounds__(kT) k_synth_open(const Workspace ws, u32 p0, u
     u32 idx = blockIdx.x * kT + threadIdx.x;
     if (idx < pn) synth::stage_open(ws, p0 + idx);
 }
-// stream pool for sliced batches: per slice a main chain and a side stream for the commitment-tree path recomputation
-constexpr int kSlices = 4;
-cudaStream_t g_pool[2 * kSlices] = {nullptr};
-cudaEvent_t g_fork = nullptr, g_fs_done[kSlices] = {nullptr}, g_tree_done[kSlices] = {nullptr}, g_side_done[kSlices] = {nullptr}, g_join[kSlices] = {nullptr};
-bool pool_init() {
-    if (g_fork) return true;
-    for (int i = 0; i < 2 * kSlices; i++) if (cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess) return false;
-    for (int i = 0; i < kSlices; i++) {
-        if (cudaEventCreateWithFlags(&g_tree_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
-        if (cudaEventCreateWithFlags(&g_fs_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
-        if (cudaEventCreateWithFlags(&g_side_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
-        if (cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+// stream pools for sliced batches: per slice a main chain and a side stream for what does not gate the FRI chain.  One pool per CALLER
+// stream (up to kPools; later callers share the last one): passes a caller issues on different streams -- the shape groups of a mixed
+// batch, the lanes of a pipeline -- then really run beside each other instead of queueing on one set of pooled streams.
+constexpr int kSlices = 4, kPools = 6;
+struct Pool {
+    cudaStream_t owner = nullptr, s[2 * kSlices] = {nullptr};
+    cudaEvent_t fork = nullptr, fs_done[kSlices] = {nullptr}, tree_done[kSlices] = {nullptr}, side_done[kSlices] = {nullptr}, join[kSlices] = {nullptr};
+    bool ready = false;
+    bool init(cudaStream_t st) {
+        for (auto &x : s) if (cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        for (int i = 0; i < kSlices; i++)
+            for (cudaEvent_t *e : {&fs_done[i], &tree_done[i], &side_done[i], &join[i]})
+                if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
+        owner = st; ready = true;
+        return true;
     }
-    return true;
+};
+Pool g_pools[kPools];
+Pool *pool_for(cudaStream_t st) {
+    static int n_pools = 0;                                // STWO_B200_VERIFY_POOLS=k (1..6): profiling
+    if (!n_pools) { const char *e = getenv("STWO_B200_VERIFY_POOLS"); n_pools = e ? atoi(e) : kPools; if (n_pools < 1 || n_pools > kPools) n_pools = kPools; }
+    for (int i = 0; i < n_pools; i++) {
+        if (g_pools[i].ready && g_pools[i].owner == st) return &g_pools[i];
+        if (!g_pools[i].ready) return g_pools[i].init(st) ? &g_pools[i] : nullptr;
+    }
+    return &g_pools[n_pools - 1];
 }
 
 // group width of the tree-rebuild kernels: 0 = one thread per tree (decommit.cuh); STWO_B200_TREE_G overrides the choice
@@ -564,36 +587,37 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
     }
     // sliced: the per-proof and per-tree stages have far fewer threads than the GPU holds, so independent slices of the
     // batch run concurrently on pooled streams, and the commitment-tree path recomputation runs beside the FRI chain
-    if (!pool_init()) return cuda_status(cudaGetLastError());
-    STWO_CUDA(cudaEventRecord(g_fork, st));
+    Pool *pool = pool_for(st);
+    if (!pool) return cuda_status(cudaGetLastError());
+    STWO_CUDA(cudaEventRecord(pool->fork, st));
     for (int sl = 0; sl < kSlices; sl++) {
         const u32 p0 = (u32)((uint64_t)n_proofs * sl / kSlices), p1 = (u32)((uint64_t)n_proofs * (sl + 1) / kSlices), n = p1 - p0;
-        cudaStream_t a = g_pool[2 * sl], b = g_pool[2 * sl + 1];
-        STWO_CUDA(cudaStreamWaitEvent(a, g_fork, 0));
+        cudaStream_t a = pool->s[2 * sl], b = pool->s[2 * sl + 1];
+        STWO_CUDA(cudaStreamWaitEvent(a, pool->fork, 0));
         if (host_blobs && n)     // this slice's blobs, on the stream that consumes them: overlaps the other slices' kernels
             STWO_CUDA(cudaMemcpyAsync(const_cast<uint32_t *>(blobs) + host_blob_off[p0], host_blobs + host_blob_off[p0],
                                       (host_blob_off[p1] - host_blob_off[p0]) * 4, cudaMemcpyHostToDevice, a));
         launch_parse_transcript(ws, p0, n, a);
         // the side stream takes what does not gate the FRI chain: the OODS / logup check, then the commitment-tree paths
-        STWO_CUDA(cudaEventRecord(g_fs_done[sl], a));
-        STWO_CUDA(cudaStreamWaitEvent(b, g_fs_done[sl], 0));
+        STWO_CUDA(cudaEventRecord(pool->fs_done[sl], a));
+        STWO_CUDA(cudaStreamWaitEvent(b, pool->fs_done[sl], 0));
         launch_oods(ws, p0, n, b);
         launch_single_tree(ws, p0, n, a);
         if (path_kernels) {
-            STWO_CUDA(cudaEventRecord(g_tree_done[sl], a));
-            STWO_CUDA(cudaStreamWaitEvent(b, g_tree_done[sl], 0));
+            STWO_CUDA(cudaEventRecord(pool->tree_done[sl], a));
+            STWO_CUDA(cudaStreamWaitEvent(b, pool->tree_done[sl], 0));
             k_single_path<<<nblk((size_t)n * 4 * nq), kT, 0, b>>>(ws, p0, n);
         }
-        STWO_CUDA(cudaEventRecord(g_side_done[sl], b));
+        STWO_CUDA(cudaEventRecord(pool->side_done[sl], b));
         launch_group(ws, p0, n, a);
         k_answer<<<nblk((size_t)n * fri::MAX_LOGS * nq), kT, 0, a>>>(ws, p0, n);
         launch_folds(ws, p0, n, a);
         launch_pair_tree(ws, p0, n, a);
         if (path_kernels) k_pair_path<<<nblk((size_t)n * nf * nq), kT, 0, a>>>(ws, p0, n);
-        STWO_CUDA(cudaStreamWaitEvent(a, g_side_done[sl], 0));
+        STWO_CUDA(cudaStreamWaitEvent(a, pool->side_done[sl], 0));
         k_verdict<<<nblk(n), kT, 0, a>>>(ws, p0, n, verdict, stage);
-        STWO_CUDA(cudaEventRecord(g_join[sl], a));
-        STWO_CUDA(cudaStreamWaitEvent(st, g_join[sl], 0));
+        STWO_CUDA(cudaEventRecord(pool->join[sl], a));
+        STWO_CUDA(cudaStreamWaitEvent(st, pool->join[sl], 0));
         note_launch((path_kernels ? 9 : 7) + (tree_group_width(ws.n_proofs) ? 2 : 0));      // parse + transcript + oods instead of one kernel
     }
     return cuda_status(cudaGetLastError());

@@ -37,7 +37,8 @@ def hostsim():
     """Device arithmetic headers compiled for the host (tests/hostsim)."""
     out = os.path.join(ROOT, "build", "libhostsim.so")
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "recursive-stwo_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "recursive-stwo_b200", "csrc")) if f.endswith(".cuh")]
+    csrc = os.path.join(ROOT, "recursive-stwo_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")] + [os.path.join(csrc, "dsl", f) for f in os.listdir(os.path.join(csrc, "dsl"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         _run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", out, src])

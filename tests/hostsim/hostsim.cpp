@@ -359,3 +359,48 @@ void *hs_synth_verify(const u32 *blobs, const u64 *blob_off, u32 n, const u32 *s
     return base;
 }
 }
+// bundle statistics of the levelised tape (analysis): out[0] bundles, [1] instructions, [2] instructions that are not first in their bundle,
+// [3] of those: an operand is the output of the instruction just before, [4] an operand is an output of any earlier instruction of the
+// bundle, [5] permutations inside bundles of length > 1, [6] non-first instructions with BOTH variable operands from inside the bundle
+extern "C" void hs_circuit_bundle_stats(void *h, u32 *out) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    const auto &c = *r->cs.p;
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[0] = (u32)r->bundle_start.size() - 1; out[1] = (u32)r->ins.size();
+    for (size_t b = 0; b + 1 < r->bundle_start.size(); b++) {
+        const u32 i0 = r->bundle_start[b], i1 = r->bundle_start[b + 1];
+        std::vector<u32> outs;
+        u32 prev_first = 0, prev_n = 0;
+        for (u32 i = i0; i < i1; i++) {
+            const tape::Ins &in = r->ins[i];
+            if (i > i0) {
+                out[2]++;
+                bool from_prev = false, from_any = false, all_in = true; u32 ns = 0;
+                RecordedCircuit::for_sources(c, in, [&](u32 v) {
+                    ns++;
+                    bool in_b = false;
+                    for (size_t q = 0; q < outs.size(); q++) if (outs[q] == v) { in_b = true; if (q >= prev_first && q < prev_first + prev_n) from_prev = true; }
+                    from_any |= in_b; all_in &= in_b;
+                });
+                out[3] += from_prev; out[4] += from_any; out[6] += (ns >= 2 && all_in);
+                if (in.op == tape::T_POSEIDON && i1 - i0 > 1) out[5]++;
+            } else if (in.op == tape::T_POSEIDON && i1 - i0 > 1) out[5]++;
+            prev_first = (u32)outs.size(); prev_n = 0;
+            RecordedCircuit::for_outputs(c, in, [&](u32 v) { outs.push_back(v); prev_n++; });
+        }
+    }
+}
+// per level (5 words each): bundles, instructions, permutations, most permutations in one bundle, most instructions in one bundle
+extern "C" void hs_circuit_level_profile(void *h, u32 *out) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    for (u32 l = 0; l < r->n_levels(); l++) {
+        u32 nb = r->level_bundle[l + 1] - r->level_bundle[l], ni = r->level_start[l + 1] - r->level_start[l], np = 0, mp = 0, mi = 0;
+        for (u32 b = r->level_bundle[l]; b < r->level_bundle[l + 1]; b++) {
+            u32 p = 0;
+            for (u32 i = r->bundle_start[b]; i < r->bundle_start[b + 1]; i++) p += r->ins[i].op == tape::T_POSEIDON;
+            np += p; mp = std::max(mp, p); mi = std::max(mi, r->bundle_start[b + 1] - r->bundle_start[b]);
+        }
+        const u32 v[5] = {nb, ni, np, mp, mi};
+        memcpy(out + 5 * l, v, sizeof v);
+    }
+}
