@@ -70,11 +70,11 @@ struct CoopGroup {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 constexpr int kCoopThreads = 64;          // upper bound; the launch shrinks the block when the group tables would not fit
-#ifndef STWO_TREE_MIN_BLOCKS
-#define STWO_TREE_MIN_BLOCKS 1
-#endif
-template <int G>
-__global__ void __launch_bounds__(kCoopThreads, STWO_TREE_MIN_BLOCKS) k_single_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+constexpr int kTreeBlocksDefault = 8;     // measured on B200 at 4096 proofs: 1.46 + 2.38 ms (1) -> 1.40 + 2.27 ms (8) -> 1.37 + 2.31 ms (10)
+// MB: resident blocks per SM the register allocation aims at (1: unconstrained = 152 registers, 6 blocks; 8: 128 registers, no spills;
+// 10: 96 registers, a few spilled words): STWO_B200_TREE_BLOCKS selects, see tree_min_blocks()
+template <int G, int MB>
+__global__ void __launch_bounds__(kCoopThreads, MB) k_single_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
     extern __shared__ u32 smem[];
     const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (grp >= pn * 4) return;                                       // whole groups leave together
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kCoopThreads, STWO_TREE_MIN_BLOCKS) k_single_t
     co.mask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * ((threadIdx.x % 32) / G));
     verify::stage_single_tree_coop(co, ws, p0 + grp % pn, grp / pn, smem + (threadIdx.x / G) * tab_words);
 }
-template <int G>
-__global__ void __launch_bounds__(kCoopThreads, STWO_TREE_MIN_BLOCKS) k_pair_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
+template <int G, int MB>
+__global__ void __launch_bounds__(kCoopThreads, MB) k_pair_tree_coop(const Workspace ws, u32 p0, u32 pn, u32 tab_words) {
     extern __shared__ u32 smem[];
     const u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (grp >= pn * ws.shape.n_fri_trees()) return;
@@ -383,14 +383,35 @@ bool coop_launch(K kernel, int G, size_t groups, u32 tab_words, const Workspace 
     kernel<<<(unsigned)((groups * G + threads - 1) / threads), threads, smem, st>>>(ws, p0, n, tab_words);
     return true;
 }
+int tree_min_blocks() {
+    static int mb = -1;
+    if (mb < 0) { const char *e = getenv("STWO_B200_TREE_BLOCKS"); const int v = e ? atoi(e) : kTreeBlocksDefault; mb = v >= 10 ? 10 : v >= 8 ? 8 : 1; }
+    return mb;
+}
+template <int G>
+bool launch_single_tree_g(size_t groups, u32 tab, const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    switch (tree_min_blocks()) {
+    case 10: return coop_launch(k_single_tree_coop<G, 10>, G, groups, tab, ws, p0, n, st);
+    case 8: return coop_launch(k_single_tree_coop<G, 8>, G, groups, tab, ws, p0, n, st);
+    default: return coop_launch(k_single_tree_coop<G, 1>, G, groups, tab, ws, p0, n, st);
+    }
+}
+template <int G>
+bool launch_pair_tree_g(size_t groups, u32 tab, const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
+    switch (tree_min_blocks()) {
+    case 10: return coop_launch(k_pair_tree_coop<G, 10>, G, groups, tab, ws, p0, n, st);
+    case 8: return coop_launch(k_pair_tree_coop<G, 8>, G, groups, tab, ws, p0, n, st);
+    default: return coop_launch(k_pair_tree_coop<G, 1>, G, groups, tab, ws, p0, n, st);
+    }
+}
 void launch_single_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     const int G = tree_group_width(ws.n_proofs);
     const u32 nq = ws.shape.n_queries, tab = decommit::single_tab_words(nq) + nq;
     const size_t groups = (size_t)n * 4;
     bool done = false;
-    if (G == 16) done = coop_launch(k_single_tree_coop<16>, 16, groups, tab, ws, p0, n, st);
-    else if (G == 8) done = coop_launch(k_single_tree_coop<8>, 8, groups, tab, ws, p0, n, st);
-    else if (G == 4) done = coop_launch(k_single_tree_coop<4>, 4, groups, tab, ws, p0, n, st);
+    if (G == 16) done = launch_single_tree_g<16>(groups, tab, ws, p0, n, st);
+    else if (G == 8) done = launch_single_tree_g<8>(groups, tab, ws, p0, n, st);
+    else if (G == 4) done = launch_single_tree_g<4>(groups, tab, ws, p0, n, st);
     if (!done) k_single_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
@@ -398,9 +419,9 @@ void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     const u32 nq = ws.shape.n_queries, tab = decommit::pair_tab_words(nq) + nq;
     const size_t groups = (size_t)n * ws.shape.n_fri_trees();
     bool done = false;
-    if (G == 16) done = coop_launch(k_pair_tree_coop<16>, 16, groups, tab, ws, p0, n, st);
-    else if (G == 8) done = coop_launch(k_pair_tree_coop<8>, 8, groups, tab, ws, p0, n, st);
-    else if (G == 4) done = coop_launch(k_pair_tree_coop<4>, 4, groups, tab, ws, p0, n, st);
+    if (G == 16) done = launch_pair_tree_g<16>(groups, tab, ws, p0, n, st);
+    else if (G == 8) done = launch_pair_tree_g<8>(groups, tab, ws, p0, n, st);
+    else if (G == 4) done = launch_pair_tree_g<4>(groups, tab, ws, p0, n, st);
     if (!done) k_pair_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 
