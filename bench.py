@@ -524,10 +524,11 @@ def main():
     tr = pkg.VerifierCircuit.assemble_trace(r0["preprocessed"], r0["values"][(hi - lo) // 2])
     assert hashlib.sha256(np.ascontiguousarray(tr, dtype="<u4").tobytes()).hexdigest() == gold["trace_sha256"], "trace differs from the golden"
     dt0 = vb.fetch(0, "detail")
-    # permutations EXECUTED per proof: transcript + tree rebuilds (every node of the partial trees once) + check_poseidon_invocations.
-    # The per-query paths are not hashed again: each node's states are handed to the queries whose path runs through it, and the
-    # tape evaluation takes the circuit's permutations from that record (STWO_B200_TRACE_NATIVE_HINTS).
-    perms_per_proof = dt0.n_perms_hints + dt0.fs.n_transcript_perms + ci.n_flow
+    # permutations EXECUTED per proof: transcript + tree rebuilds -- every distinct permutation of a proof once.  The per-query paths are
+    # not hashed again (each node's states are handed to the queries whose path runs through it), the tape evaluation takes the circuit's
+    # permutations from that record (STWO_B200_TRACE_NATIVE_HINTS), and check_poseidon_invocations compares each of the circuit's
+    # ci.n_flow flow entries with the recorded (input, output) pair of the execution instead of executing it a third time.
+    perms_per_proof = dt0.n_perms_hints + dt0.fs.n_transcript_perms
     assert dt0.n_perms_paths == 3481, "permutation count the record covers differs from the reference's circuit (SURVEY App. C)"
 
     def check_last(h):
@@ -597,6 +598,10 @@ def main():
         circ.trace(vb, check=True, export=True, preprocessed=False, timed=True)
         for k, t in circ.stage_ms().items():
             acc["trace_" + k] = acc.get("trace_" + k, 0.0) + t / reps
+    # the same check by re-execution of every flow entry (STWO_B200_TRACE_RECHECK_POSEIDON), for the record
+    r_re = circ.trace(vb, check=True, export=True, preprocessed=False, timed=True, recheck=True)
+    recheck_ms = circ.stage_ms()["check_poseidon"]
+    assert int((r_re["bad_flow"] != -1).sum().item()) == 0
     total_ms = sum(acc.values())
     dom = max(acc, key=acc.get)
     n_local = hi - lo
@@ -624,7 +629,7 @@ def main():
     pair_paths = pkg.proof_perms(sh) - single_paths
     share = single_paths / float(single_paths + pair_paths)
     perms_of = {"fiat_shamir": dt0.fs.n_transcript_perms, "single_path": single_paths, "pair_path": pair_paths,
-                "trace_check_poseidon": ci.n_flow, "single_tree": dt0.n_perms_hints * share, "pair_tree": dt0.n_perms_hints * (1 - share)}
+                "single_tree": dt0.n_perms_hints * share, "pair_tree": dt0.n_perms_hints * (1 - share)}
     hdom = max(perms_of, key=lambda k: acc.get(k, 0.0))
     h_perms = perms_of[hdom] * n_local
     h_rate = h_perms / (acc[hdom] * 1e-3)
@@ -634,8 +639,11 @@ def main():
         "frac": achieved / pk["int_tlops"], "peak_src": pk["int_src"], "lane_ops_per_perm": LANE_OPS_PER_PERM,
         "perms_per_launch": h_perms, "perms_per_sec": h_rate, "launch_ms": acc[hdom], "share_of_step": acc[hdom] / total_ms,
         "traffic": ncu_traffic(kernel_of.get(hdom, ""), n_local),
-        "note": "ncu on this kernel: sm__pipe_fmaheavy_cycles_active 69 %, ALU pipe 62 % (profiles/r02e_k_cs_check_poseidon_ncu.txt); the "
-                "multiplier pipe bounds a permutation at ~6.1 G perms/s per GPU"}
+        "check_poseidon_by_reexecution": {"launch_ms": recheck_ms, "perms_per_sec": ci.n_flow * n_local / (recheck_ms * 1e-3),
+                                          "frac": ci.n_flow * n_local / (recheck_ms * 1e-3) * LANE_OPS_PER_PERM / 1e12 / pk["int_tlops"]},
+        "note": "the tree rebuild is a layer-parallel walk with G lanes per tree (idle lanes at narrow layers, 128 registers, 16 warps per SM) that "
+                "also writes the permutation record; the bare permutation kernel K1 reaches 0.70 of the peak (secondary.k1_frac_of_int_peak) and "
+                "check_poseidon_invocations by re-execution 0.64 (check_poseidon_by_reexecution; ncu: profiles/r02e_k_cs_check_poseidon_ncu.txt)"}
     # `roofline` = the dominant HBM-bound kernel of the step (the trace export); `roofline_hashing` = the dominant integer-bound kernel
     # (for this path the largest kernels are co-dominant: check_poseidon_invocations, export, tape evaluation within ~10 % of each other)
     roofline = dict(roofline_export)
@@ -723,6 +731,7 @@ def main():
                                    "tape_levels": ci.n_levels, "witness_words": ci.n_input_words},
                        "shape": dict(zip(("log_size_plonk", "log_size_poseidon", "pow_bits", "log_blowup", "log_last", "n_queries", "n_inner"), sh.key())),
                        "perms_per_proof": perms_per_proof,
+                       "perms_compared_with_record_per_proof": ci.n_flow,
                        "l2": "inputs larger than L2: %d MB of proof blobs + %d MB of workspace + %d MB of trace columns per step" % (blob_mb, ws_mb, trace_mb),
                        "parallelism": "proofs sharded by rank in contiguous blocks; NCCL all-gather of verdict bytes only",
                        "pipeline": "%d device slots, %d lane(s); upload | verification | trace pass of neighbouring steps on their own streams; "

@@ -246,6 +246,7 @@ typedef struct {
 #define STWO_B200_FETCH_PERM_RECORD 10    /* [stwo_b200_proof_record_slots][16] the permutation record (STWO_B200_VERIFY_FULL); slots the
                                              shape does not use (transcript slots beyond n_transcript_perms) are not written */
 #define STWO_B200_FETCH_RECORD_TREES 11   /* u32: trees of this proof whose part of the record is complete (4 + 1 + n_inner = all) */
+#define STWO_B200_FETCH_PERM_RECORD_INPUTS 12   /* the INPUT state of every recorded permutation, same slots as STWO_B200_FETCH_PERM_RECORD */
 int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200_proof_shape *shape, uint32_t n_proofs, uint32_t p,
                                uint32_t what, void *out, size_t out_bytes, void *stream);
 
@@ -357,7 +358,7 @@ typedef struct {
     /* Optional (NULL / 0 = none), read by stwo_b200_cs_eval_tape_dev only: output states of permutations that were executed
      * before -- item b's record k is the 16 words at perm_hints[b * perm_hint_stride + 16 k] (item-major, NOT lane-interleaved).
      * A tape permutation whose record names a slot (word 11 of its 12 words = k + 1) takes its output from there instead
-     * of permuting; stwo_b200_cs_check_poseidon_dev re-executes every flow entry regardless. */
+     * of permuting. */
     const uint32_t *perm_hints;
     uint32_t perm_hint_stride;
     /* Optional gate on the hints, per item: item b's hints are used only when perm_hint_ready[b] == perm_hint_need (NULL: always).
@@ -365,6 +366,12 @@ typedef struct {
      * proof that was rejected half-way, or a workspace last used without STWO_B200_VERIFY_FULL, is evaluated by permuting. */
     const uint32_t *perm_hint_ready;
     uint32_t perm_hint_need;
+    /* Optional (NULL = none), read by stwo_b200_cs_check_poseidon_dev only: the INPUT states of the same executed permutations, same
+     * layout and stride as perm_hints.  With it (and a tape), a flow entry whose permutation names a record slot is checked against the
+     * executed permutation -- entry input == recorded input and entry output == recorded output -- instead of being executed once more:
+     * out = permute(in) holds for the record by construction (the native verifier computed it), so the two comparisons are the
+     * reference's assertion.  Items whose record is not complete (perm_hint_ready), and entries without a slot, are re-executed. */
+    const uint32_t *perm_hint_inputs;
 } stwo_b200_cs_values;
 /* The value definitions of a recorded circuit, sorted by dependency level (instructions of a level are independent).
  * ins: n_ins x {op, dst, a, b} (STWO_B200_T_*); perms: n_perms x 12 words {l_kind, l_a, l_b, r_kind, r_a, r_b, swap_var,
@@ -422,6 +429,10 @@ int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w, int32_t *m
  * or -1.  Needs mult_poseidon and the scratch of populate_logup. */
 int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
                                         const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream);
+/* The same with the tape at hand (its permutation records name the slots of v->perm_hints / perm_hint_inputs): entries covered by a
+ * complete record are compared with it, the rest re-executed.  tape == NULL or v->perm_hint_inputs == NULL: every entry is re-executed. */
+int32_t stwo_b200_cs_check_poseidon_recorded_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const stwo_b200_cs_tape *tape,
+                                                 const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream);
 /* generate_plonk_with_poseidon_circuit (:521-628).  preprocessed (optional): 10 columns x n_rows in the struct-literal
  * order mult_a, mult_b, mult_c, poseidon_wire, mult_poseidon, enforce_c_m31, a_wire, b_wire, c_wire, op (wiring only;
  * op holds the shape constant).  values: per item 13 columns x n_rows, plain [item][column][row]: a_val_0..3, b_val_0..3,
@@ -493,8 +504,13 @@ int32_t stwo_b200_circuit_get_column(const stwo_b200_circuit *c, uint32_t what, 
 #define STWO_B200_TRACE_TIMED 4u
 /* the batch was verified with STWO_B200_VERIFY_FULL on this workspace: the circuit's Poseidon permutations (transcript and
  * per-query authentication paths) are the ones the native verifier just executed and recorded there; K6 takes their output
- * states as hints instead of permuting again (check_poseidon_invocations still re-executes all of them) */
+ * states as hints instead of permuting again, and check_poseidon_invocations compares every such flow entry with the recorded
+ * (input, output) pair of the permutation that WAS executed instead of executing it a third time.  A proof whose record is not
+ * complete (rejected half-way) is evaluated and checked by permuting, like without the flag. */
 #define STWO_B200_TRACE_NATIVE_HINTS 8u
+/* with NATIVE_HINTS: check_poseidon_invocations re-executes every flow entry all the same (the round-1 behaviour; the checker of the
+ * record-based check in the tests, and a belt-and-braces mode for a caller who wants it) */
+#define STWO_B200_TRACE_RECHECK_POSEIDON 16u
 /* stage kernels of the trace pass in launch order: gather (+ public-input hashes), eval, check_arithmetics, check_poseidon, export */
 #define STWO_B200_N_TRACE_STAGES 5
 size_t stwo_b200_circuit_workspace_bytes(const stwo_b200_circuit *c, uint32_t n_proofs);

@@ -96,7 +96,7 @@ VERIFY_TIMED = 2
 VERIFY_PATH_KERNELS = 8
 STAGE_KERNELS = ("fiat_shamir", "single_tree", "group", "answer", "folds", "pair_tree", "single_path", "pair_path", "verdict")
 FETCH = {"detail": 0, "domain_points": 1, "answers": 2, "circle_folds": 3, "line_folds": 4, "last_evals": 5, "path_roots": 6,
-         "path_cols": 7, "path_siblings": 8, "pair_hints": 9, "perm_record": 10, "record_trees": 11}
+         "path_cols": 7, "path_siblings": 8, "pair_hints": 9, "perm_record": 10, "record_trees": 11, "perm_record_inputs": 12}
 STAGES = {0: "ok", 1: "parse", 2: "pow", 3: "logup", 4: "oods", 5: "merkle", 6: "fri_first", 7: "fri_inner", 8: "fri_last",
           9: "unsupported"}
 
@@ -112,7 +112,7 @@ class CsValues(ctypes.Structure):
     """stwo_b200_cs_values"""
     _fields_ = [("n_batch", ctypes.c_uint32), ("lanes", ctypes.c_uint32), ("variables", ctypes.c_void_p), ("flow_hash", ctypes.c_void_p),
                 ("flow_swap", ctypes.c_void_p), ("perm_hints", ctypes.c_void_p), ("perm_hint_stride", ctypes.c_uint32),
-                ("perm_hint_ready", ctypes.c_void_p), ("perm_hint_need", ctypes.c_uint32)]
+                ("perm_hint_ready", ctypes.c_void_p), ("perm_hint_need", ctypes.c_uint32), ("perm_hint_inputs", ctypes.c_void_p)]
 
 
 class CsTape(ctypes.Structure):
@@ -128,7 +128,7 @@ class CircuitInfo(ctypes.Structure):
                                                "n_levels", "num_input", "words_per_instance", "kind", "n_preprocessed_columns")]
 
 
-TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED, TRACE_NATIVE_HINTS = 1, 2, 4, 8
+TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED, TRACE_NATIVE_HINTS, TRACE_RECHECK_POSEIDON = 1, 2, 4, 8, 16
 TRACE_STAGES = ("gather", "eval", "check_arithmetics", "check_poseidon", "export")
 COLUMNS = {"a_wire": 0, "b_wire": 1, "c_wire": 2, "poseidon_wire": 3, "enforce_c_m31": 4, "op": 5, "op_follows_c": 6, "flow_wire": 7,
            "flow_swap_addr": 8, "level_start": 10, "op2": 11, "op3": 12, "op4": 13}
@@ -192,6 +192,7 @@ SIGNATURES = {
     "stwo_b200_cs_check_arithmetics_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp]),
     "stwo_b200_cs_populate_logup_dev": (_i32, [_WIR_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_check_poseidon_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp]),
+    "stwo_b200_cs_check_poseidon_recorded_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_export_trace_dev": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stwo_b200_cs_finalize": (_i32, [_WIR_P, _VAL_P, _vp, _vp, _vp]),
     "stwo_b200_cs_export_tiles_words": (_sz, [_u32]),

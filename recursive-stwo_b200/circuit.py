@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import (CircuitInfo, COLUMNS, CFETCH, TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED, TRACE_NATIVE_HINTS, TRACE_STAGES)
+from ._lib import (CircuitInfo, COLUMNS, CFETCH, TRACE_CHECK_ARITHMETICS, TRACE_CHECK_POSEIDON, TRACE_TIMED, TRACE_NATIVE_HINTS, TRACE_RECHECK_POSEIDON,
+                   TRACE_STAGES)
 from .verifier import INPUTS_RECURSIVE
 
 COLUMN_NAMES = ("mult_a", "mult_b", "mult_c", "poseidon_wire", "mult_poseidon", "enforce_c_m31", "a_wire", "b_wire", "c_wire", "op",
@@ -68,7 +69,7 @@ class VerifierCircuit:
     def workspace_bytes(self, n_proofs):
         return int(_lib.load().stwo_b200_circuit_workspace_bytes(self._h, n_proofs))
 
-    def trace(self, batch, check=True, export=True, preprocessed=True, timed=False, native_hints=None):
+    def trace(self, batch, check=True, export=True, preprocessed=True, timed=False, native_hints=None, recheck=False):
         """Trace generation for a batch that `batch.run()` has verified (VerifyBatch keeps the hints in its workspace).
         Returns dict(values=[n, 13, n_rows] | None, preprocessed=[10, n_rows] | None, bad_row=[n] | None, bad_flow=[n] | None)
         as torch tensors on the batch's device.  `values` is ONE buffer per circuit object (13.3 GB for 4096 proofs of shape S), reused
@@ -94,6 +95,8 @@ class VerifierCircuit:
         flags = ((TRACE_CHECK_ARITHMETICS | TRACE_CHECK_POSEIDON) if check else 0) | (TRACE_TIMED if timed else 0)
         if native_hints if native_hints is not None else getattr(batch, "last_full", False):
             flags |= TRACE_NATIVE_HINTS
+        if recheck:                                  # check_poseidon_invocations re-executes every entry instead of comparing with the record
+            flags |= TRACE_RECHECK_POSEIDON
         p = lambda t: _dptr(t) if t is not None else None
         _lib.call("stwo_b200_circuit_trace_batch_dev", self._h, _dptr(batch.d_words), _dptr(batch.d_off), n, _dptr(batch.d_ws), _dptr(self._ws),
                   self._ws.numel(), flags, p(out["preprocessed"]), p(out["values"]), p(out["bad_row"]), p(out["bad_flow"]), _stream())

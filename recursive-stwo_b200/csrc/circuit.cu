@@ -278,11 +278,13 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
     }
     k_gather_witness<<<dim3((nw + 31) / 32, (unsigned)groups), kT, 0, st>>>(ws, c->gather, nw, k.witness, c->n_jobs ? k.extra : nullptr, c->n_extra_words);
     note_launch(1);
-    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0};
+    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0, nullptr};
     // per proof: only a record that the verification of THIS workspace just completed is used (verify::Workspace::hint_trees)
     if ((flags & STWO_B200_TRACE_NATIVE_HINTS) && c->wiring.kind == 0 && ws.perm_out) {
         v.perm_hints = ws.perm_out; v.perm_hint_stride = ws.hint_total * 16;
         v.perm_hint_ready = ws.hint_trees; v.perm_hint_need = ws.shape.n_trees();
+        // the record-based check_poseidon_invocations (entry == executed permutation) unless the caller asks for the re-execution
+        if (!(flags & STWO_B200_TRACE_RECHECK_POSEIDON) && stwo_b200::record_inputs()) v.perm_hint_inputs = ws.perm_in;
     }
     MARK();
     if ((rc = stwo_b200_cs_eval_tape_dev(&c->tape_, c->wiring.n_vars, k.witness, &v, st))) return rc;
@@ -311,10 +313,10 @@ extern "C" int32_t stwo_b200_circuit_trace_batch_dev(stwo_b200_circuit *c, const
         }
         STWO_CUDA(cudaEventRecord(g_side_fork, st));
         STWO_CUDA(cudaStreamWaitEvent(g_side, g_side_fork, 0));
-        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, g_side, g_beside_ctas))) return rc;
+        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, g_side, g_beside_ctas, &c->tape_))) return rc;
         STWO_CUDA(cudaEventRecord(g_side_join, g_side));
     } else if (do_check_poseidon)
-        if ((rc = stwo_b200_cs_check_poseidon_dev(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, st))) return rc;
+        if ((rc = cs_check_poseidon_launch(&c->wiring, &v, mult + 3 * nr, c->scratch, bad_flow, st, 0, &c->tape_))) return rc;
     MARK();
     if (preprocessed || values)
         if ((rc = stwo_b200_cs_export_trace_dev(&c->wiring, &v, mult, mult + nr, mult + 2 * nr, mult + 3 * nr, preprocessed, values,
@@ -369,6 +371,6 @@ extern "C" int32_t stwo_b200_circuit_export_flow_dev(stwo_b200_circuit *c, uint3
     if (r.cs.p->without()) return STWO_B200_E_BAD_ARG;              // the Plonk-without-Poseidon system has no flow
     const Carve k = carve(r, n_proofs, (uint8_t *)circuit_workspace);
     if (k.bytes > circuit_workspace_bytes) return STWO_B200_E_BAD_ARG;
-    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0};
+    stwo_b200_cs_values v = {n_proofs, 32, k.vars, k.flow_hash, k.flow_swap, nullptr, 0, nullptr, 0, nullptr};
     return stwo_b200_cs_export_flow_dev(&v, r.cs.p->num_poseidon_invocations(), pad_constants, k.status + 8, flow_hash_out, flow_swap_out, stream);
 }

@@ -21,6 +21,7 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
     u32 n_batch, lanes, n_vars, n_flow;
     const u32 *hints; u32 hint_stride;
     const u32 *hint_ready; u32 hint_need;
+    const u32 *hint_inputs;
     __device__ __forceinline__ tape::View view(u32 item, const u32 *input, u32 n_input_words) const {
         const size_t g = item / lanes, l = item % lanes;
         tape::View v;
@@ -271,8 +272,13 @@ __global__ void __launch_bounds__(kT) k_cs_mult(stwo_b200_cs_wiring w, const u32
 // ---- K7: check_poseidon_invocations ----------------------------------------------------------------------------------------
 // thread = (flow entry, item), item fastest. Persistent: the grid is a fixed number of CTAs per SM looping over the flow, so that it
 // can run as a thin, fully resident layer (2-3 CTAs per SM) under the HBM-bound export on another stream, or fill the SMs alone.
+// RECORDED: a flow entry whose permutation the native verifier executed (perms[e].hint names its record slot) is compared with that
+// execution -- entry input == recorded input, entry output == recorded output -- instead of being executed once more; the record holds
+// out = permute(in) by construction.  The slot is a property of the entry (warp-uniform); an item whose record is incomplete, and an
+// entry without a slot (none in the verifier circuits), is re-executed.
+template <bool RECORDED>
 __global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w, Batch b, const int32_t *mult_poseidon,
-                                                           const u32 *first_prow, unsigned long long *first_bad) {
+                                                           const u32 *first_prow, unsigned long long *first_bad, const tape::Perm *__restrict__ perms) {
     const u32 padded = (b.n_batch + b.lanes - 1) / b.lanes * b.lanes;
     const size_t total = (size_t)w.n_flow * padded;
     for (size_t g = blockIdx.x * (size_t)128 + threadIdx.x; g < total; g += (size_t)gridDim.x * 128) {
@@ -294,13 +300,31 @@ __global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w
             const qm31_t l = tape::ldv(v, w.a_wire[row]), r = tape::ldv(v, w.b_wire[row]);
             for (int j = 0; j < 4; j++) ok &= (l.v[j] == hh[8 * k + j]) & (r.v[j] == hh[8 * k + 4 + j]);
         }
-        u32 st[16];
         const bool swap = v.flow_swap[(size_t)e * v.stride] != 0;
+        const u32 slot = RECORDED ? __ldg(&perms[e].hint) : 0u;
+        if (RECORDED && slot && v.hint) {
+            // v.hint is set only for an item whose record is complete (Batch::view); the input record runs parallel to the output record
+            const uint4 *ro = reinterpret_cast<const uint4 *>(v.hint + (size_t)(slot - 1) * 16);
+            const uint4 *ri = reinterpret_cast<const uint4 *>(v.hint + (b.hint_inputs - b.hints) + (size_t)(slot - 1) * 16);
+            u32 d = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { st[j] = swap ? hh[8 + j] : hh[j]; st[8 + j] = swap ? hh[j] : hh[8 + j]; }    // selects: hh stays in registers
-        poseidon2::permute<false>(st);
+            for (int q = 0; q < 4; q++) {
+                const uint4 o4 = ro[q], i4 = ri[q];
+                // the permutation's input is the two halves in executed order: swapped when the swap bit is set
+                const int lo = 4 * q, sw = (4 * q + 8) & 15;
+                d |= (o4.x ^ hh[16 + lo]) | (o4.y ^ hh[17 + lo]) | (o4.z ^ hh[18 + lo]) | (o4.w ^ hh[19 + lo]);
+                d |= (i4.x ^ (swap ? hh[sw] : hh[lo])) | (i4.y ^ (swap ? hh[sw + 1] : hh[lo + 1])) | (i4.z ^ (swap ? hh[sw + 2] : hh[lo + 2])) |
+                     (i4.w ^ (swap ? hh[sw + 3] : hh[lo + 3]));
+            }
+            ok &= d == 0;
+        } else {
+            u32 st[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
+            for (int j = 0; j < 8; j++) { st[j] = swap ? hh[8 + j] : hh[j]; st[8 + j] = swap ? hh[j] : hh[8 + j]; }    // selects: hh stays in registers
+            poseidon2::permute<false>(st);
+#pragma unroll
+            for (int j = 0; j < 16; j++) ok &= st[j] == hh[16 + j];
+        }
         if (!ok) atomicMin(first_bad + item, (unsigned long long)e);
     }
 }
@@ -571,6 +595,7 @@ Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
     b.n_batch = v->n_batch; b.lanes = v->lanes; b.n_vars = n_vars; b.n_flow = n_flow;
     b.hints = v->perm_hints; b.hint_stride = v->perm_hint_stride;
     b.hint_ready = v->perm_hint_ready; b.hint_need = v->perm_hint_need;
+    b.hint_inputs = v->perm_hint_inputs;
     return b;
 }
 }  // namespace
@@ -685,9 +710,12 @@ extern "C" int32_t stwo_b200_cs_populate_logup_dev(const stwo_b200_cs_wiring *w,
 }
 // ctas_per_sm: 0 = fill the SMs (the kernel alone), k = a resident layer of k CTAs per SM (beside another kernel)
 int32_t stwo_b200::cs_check_poseidon_launch(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_poseidon,
-                                            const uint32_t *scratch, int64_t *first_bad, cudaStream_t st, int ctas_per_sm) {
+                                            const uint32_t *scratch, int64_t *first_bad, cudaStream_t st, int ctas_per_sm,
+                                            const stwo_b200_cs_tape *tape) {
     STWO_CHECK_DEVICE();
     if (!wiring_ok(w) || !values_ok(v) || !first_bad || !mult_poseidon || !scratch) return STWO_B200_E_BAD_ARG;
+    // the record-based check needs the tape's permutation records (entry -> slot), both records and one record per flow entry
+    const bool recorded = tape && tape->perms && tape->n_perms == w->n_flow && v->perm_hints && v->perm_hint_inputs && v->perm_hint_stride;
     k_fill64<<<nblk(v->n_batch), kT, 0, st>>>((unsigned long long *)first_bad, v->n_batch, ~0ull);
     note_launch(1);
     if (w->n_flow) {
@@ -697,8 +725,13 @@ int32_t stwo_b200::cs_check_poseidon_launch(const stwo_b200_cs_wiring *w, const 
         static int n_sm = 0;
         if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
         const size_t want = nblk((size_t)w->n_flow * padded, 128), cap = (size_t)n_sm * (ctas_per_sm > 0 ? ctas_per_sm : 16);
-        k_cs_check_poseidon<<<(unsigned)(want < cap ? want : cap), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
-                                                                               (unsigned long long *)first_bad);
+        if (recorded)
+            k_cs_check_poseidon<true><<<(unsigned)(want < cap ? want : cap), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
+                                                                                         (unsigned long long *)first_bad,
+                                                                                         reinterpret_cast<const tape::Perm *>(tape->perms));
+        else
+            k_cs_check_poseidon<false><<<(unsigned)(want < cap ? want : cap), 128, 0, st>>>(*w, b, mult_poseidon, scratch + 2 * (size_t)w->n_vars,
+                                                                                          (unsigned long long *)first_bad, nullptr);
         note_launch(1);
     }
     return cuda_status(cudaGetLastError());
@@ -706,6 +739,10 @@ int32_t stwo_b200::cs_check_poseidon_launch(const stwo_b200_cs_wiring *w, const 
 extern "C" int32_t stwo_b200_cs_check_poseidon_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v,
                                                    const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream) {
     return stwo_b200::cs_check_poseidon_launch(w, v, mult_poseidon, scratch, first_bad, (cudaStream_t)stream, 0);
+}
+extern "C" int32_t stwo_b200_cs_check_poseidon_recorded_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const stwo_b200_cs_tape *tape,
+                                                            const int32_t *mult_poseidon, const uint32_t *scratch, int64_t *first_bad, void *stream) {
+    return stwo_b200::cs_check_poseidon_launch(w, v, mult_poseidon, scratch, first_bad, (cudaStream_t)stream, 0, tape);
 }
 extern "C" int32_t stwo_b200_cs_export_trace_dev(const stwo_b200_cs_wiring *w, const stwo_b200_cs_values *v, const int32_t *mult_a,
                                                  const int32_t *mult_b, const int32_t *mult_c, const int32_t *mult_poseidon,
@@ -864,7 +901,7 @@ extern "C" int32_t stwo_b200_cs_finalize(const stwo_b200_cs_wiring *hw, const st
     w.a_wire = dw; w.b_wire = dw + nr; w.c_wire = dw + 2 * nr; w.poseidon_wire = dw + 3 * nr; w.enforce_c_m31 = dw + 4 * nr; w.op = dw + 5 * nr;
     w.op_follows_c = hw->op_follows_c ? d + o_follow : nullptr;
     w.flow_wire = (u32 *)(d + o_fw); w.flow_swap_addr = (u32 *)(d + o_fa);
-    stwo_b200_cs_values v = {1, 1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs, nullptr, 0, nullptr, 0};
+    stwo_b200_cs_values v = {1, 1, (u32 *)(d + o_vars), (u32 *)(d + o_fh), d + o_fs, nullptr, 0, nullptr, 0, nullptr};
     int32_t *m = (int32_t *)(d + o_mult);
     int64_t *bad = (int64_t *)(d + o_bad);
     u32 *scr = (u32 *)(d + o_scr), *stat = (u32 *)(d + o_stat), *pre = (u32 *)(d + o_pre), *vals = (u32 *)(d + o_vals);

@@ -27,15 +27,20 @@ HD void st8(const Strided &s, u32 k, const u32 in[8]) { for (u32 i = 0; i < 8; i
 
 // hash_node on register-resident children (L == nullptr: leaf); cols is contiguous memory (the proof blob).
 // primitives/merkle/src/lib.rs:9-181
-// sink (optional, advanced): receives the 16-word output state of every permutation, in execution order
+// sink (optional, advanced): receives the 16-word output state of every permutation, in execution order; with in_delta != 0 the
+// 16-word INPUT state of the same permutation goes in_delta words further (the input record runs parallel to the output record)
 HD void tap(u32 **sink, const u32 *st) {
     if (sink && *sink) { for (int i = 0; i < 16; i++) (*sink)[i] = st[i]; *sink += 16; }
 }
-HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr, u32 **sink = nullptr) {
+HD void tap_in(u32 **sink, const u32 *st, size_t in_delta) {
+    if (sink && *sink && in_delta) for (int i = 0; i < 16; i++) (*sink)[in_delta + i] = st[i];
+}
+HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out = nullptr, u32 **sink = nullptr, size_t in_delta = 0) {
     u32 st[16];
     u32 tree[8];
     if (L) {
         for (int i = 0; i < 8; i++) { st[i] = L[i]; st[8 + i] = R[i]; }
+        tap_in(sink, st, in_delta);
         permute_mem(st);
         tap(sink, st);
         if (tree_out) for (int i = 0; i < 8; i++) tree_out[i] = st[i];
@@ -46,16 +51,18 @@ HD void hash_node2(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out
     u32 n_chunks = nc ? (nc + 7) / 8 : 1;
     for (u32 c = 0; c < n_chunks; c++) {
         for (u32 i = 0; i < 8; i++) st[i] = 8 * c + i < nc ? cols[8 * c + i] : 0u;
+        tap_in(sink, st, in_delta);
         permute_mem(st);
         tap(sink, st);
     }
     for (int i = 0; i < 8; i++) st[i] = L ? tree[i] : 0u;
+    tap_in(sink, st, in_delta);
     permute_mem(st);
     tap(sink, st);
     for (int i = 0; i < 8; i++) out[i] = st[i];
 }
-// The same node with a callback after every permutation: tap(j, st) sees the 16-word output state of the node's j-th permutation
-// (execution order: [hash of the children,] sponge chunks, finalisation).  The cooperative tree rebuilds use it to hand each
+// The same node with a callback around every permutation: tap(j, st, false) sees the 16-word input state of the node's j-th permutation,
+// tap(j, st, true) its output state (execution order: [hash of the children,] sponge chunks, finalisation).  The cooperative tree rebuilds use it to hand each
 // state to the queries whose authentication path runs through this node (decommit_coop.cuh).
 template <class Tap>
 HD void hash_node2_tap(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 *out, u32 *tree_out, Tap tap) {
@@ -64,8 +71,9 @@ HD void hash_node2_tap(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 
     u32 j = 0;
     if (L) {
         for (int i = 0; i < 8; i++) { st[i] = L[i]; st[8 + i] = R[i]; }
+        tap(j, st, false);
         permute_mem(st);
-        tap(j++, st);
+        tap(j++, st, true);
         if (tree_out) for (int i = 0; i < 8; i++) tree_out[i] = st[i];
         if (nc == 0) { for (int i = 0; i < 8; i++) out[i] = st[i]; return; }
         for (int i = 0; i < 8; i++) tree[i] = st[i];
@@ -74,12 +82,14 @@ HD void hash_node2_tap(const u32 *L, const u32 *R, const u32 *cols, u32 nc, u32 
     u32 n_chunks = nc ? (nc + 7) / 8 : 1;
     for (u32 c = 0; c < n_chunks; c++) {
         for (u32 i = 0; i < 8; i++) st[i] = 8 * c + i < nc ? cols[8 * c + i] : 0u;
+        tap(j, st, false);
         permute_mem(st);
-        tap(j++, st);
+        tap(j++, st, true);
     }
     for (int i = 0; i < 8; i++) st[i] = L ? tree[i] : 0u;
+    tap(j, st, false);
     permute_mem(st);
-    tap(j++, st);
+    tap(j++, st, true);
     for (int i = 0; i < 8; i++) out[i] = st[i];
 }
 HD u32 node_perms(bool leaf, u32 nc) { return leaf ? (nc ? (nc + 7) / 8 : 1) + 1 : 1 + (nc ? (nc + 7) / 8 + 1 : 0); }
@@ -288,12 +298,12 @@ HD bool pair_tree(u32 depth, u32 data_mask, const u32 *q, u32 nq, const u32 *val
 // SinglePairMerkleProof::verify for one query (components/hints/src/folding.rs:33-91): recompute the root from the
 // per-query hints.  Returns the root in out[8].
 HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals, const u32 *sib_vals, const u32 *sib_hashes,
-                       u32 *out, u32 *perms, u32 *sink = nullptr) {
+                       u32 *out, u32 *perms, u32 *sink = nullptr, size_t in_delta = 0) {
     u32 self_h[8], sib_h[8];
     u32 d_idx = 0, np = 4;
     u32 **sk = sink ? &sink : nullptr;
-    hash_node2(nullptr, nullptr, self_vals, 4, self_h, nullptr, sk);
-    hash_node2(nullptr, nullptr, sib_vals, 4, sib_h, nullptr, sk);
+    hash_node2(nullptr, nullptr, self_vals, 4, self_h, nullptr, sk, in_delta);
+    hash_node2(nullptr, nullptr, sib_vals, 4, sib_h, nullptr, sk, in_delta);
     d_idx = 1;
     for (u32 i = 0; i < depth; i++) {
         const u32 h = depth - i - 1;
@@ -301,20 +311,22 @@ HD void pair_path_root(u32 depth, u32 data_mask, u32 qpos, const u32 *self_vals,
         const u32 *L = ((qpos >> i) & 1u) ? sib_h : self_h, *R = ((qpos >> i) & 1u) ? self_h : sib_h;
         u32 nxt[8];
         if (!data) {
-            hash_node2(L, R, nullptr, 0, nxt, nullptr, sk);
+            hash_node2(L, R, nullptr, 0, nxt, nullptr, sk, in_delta);
             np += 1;
             if (i != depth - 1) cp8(sib_h, sib_hashes + 8 * i);
         } else {
-            hash_node2(L, R, self_vals + 4 * d_idx, 4, nxt, nullptr, sk);
+            hash_node2(L, R, self_vals + 4 * d_idx, 4, nxt, nullptr, sk, in_delta);
             np += 3;
             if (h >= 1) {
                 // sibling = rate(perm(sibling tree hash || capacity(sibling evaluation)))
                 u32 st[16];
                 for (int k = 0; k < 4; k++) st[k] = sib_vals[4 * d_idx + k];
                 for (int k = 4; k < 16; k++) st[k] = 0;
+                tap_in(sk, st, in_delta);
                 permute_mem(st);
                 tap(sk, st);
                 for (int k = 0; k < 8; k++) st[k] = sib_hashes[8 * i + k];
+                tap_in(sk, st, in_delta);
                 permute_mem(st);
                 tap(sk, st);
                 cp8(sib_h, st);

@@ -42,7 +42,10 @@ struct PermRec {
     u32 *base;            // slot 0 of query 0 of this tree; nullptr: no record
     u32 per_query;        // slots per query
     u32 *roots;           // nq x 8: the recomputed root per query (= the rebuilt root); may be null
+    size_t in_delta = 0;  // != 0: the input state of a permutation is recorded in_delta words beyond its output state
     HDM u32 *slot(u32 query, u32 k) const { return base + ((size_t)query * per_query + k) * 16; }
+    // where the state seen by a tap goes: the output record, or (before the permutation) the parallel input record; nullptr = nowhere
+    HDM u32 *slot(u32 query, u32 k, bool after) const { return after ? slot(query, k) : in_delta ? slot(query, k) + in_delta : nullptr; }
 };
 HD void st16(u32 *dst, const u32 *st) {
 #if defined(__CUDA_ARCH__)
@@ -92,8 +95,8 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
     if (!ctl[3]) {
         for (u32 k = L; k < m; k += G) {
             u32 h8[8];
-            hash_node2_tap(nullptr, nullptr, values + (size_t)k * nc, nc, h8, nullptr, [&](u32 j, const u32 *st) {
-                if (rec.base) for (u32 i = 0; i < nq; i++) if (qnode[i] == k) st16(rec.slot(i, j), st);
+            hash_node2_tap(nullptr, nullptr, values + (size_t)k * nc, nc, h8, nullptr, [&](u32 j, const u32 *st, bool after) {
+                if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) if (qnode[i] == k) st16(rec.slot(i, j, after), st);
             });
             for (int i = 0; i < 8; i++) chash[8 * k + i] = h8[i];
         }
@@ -143,8 +146,8 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
                 u32 l8[8], r8[8], h8[8];
                 if (ps & 1u) { load_hash(chash, hw, s, l8); load_hash(chash, hw, k, r8); }
                 else { load_hash(chash, hw, k, l8); load_hash(chash, hw, s, r8); }
-                hash_node2_tap(l8, r8, values + vi0 + (size_t)j * nc, nc, h8, nullptr, [&](u32 jj, const u32 *st) {
-                    if (rec.base) for (u32 i = 0; i < nq; i++) if (par[qnode[i]] == j) st16(rec.slot(i, slot_off + jj), st);
+                hash_node2_tap(l8, r8, values + vi0 + (size_t)j * nc, nc, h8, nullptr, [&](u32 jj, const u32 *st, bool after) {
+                    if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) if (par[qnode[i]] == j) st16(rec.slot(i, slot_off + jj, after), st);
                 });
                 for (int i = 0; i < 8; i++) phash[8 * j + i] = h8[i];
                 ppos[j] = ps >> 1;
@@ -259,10 +262,10 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
                 if (h == depth) {
                     // a leaf is the self opening of the queries at its position (slots 0, 1) and the sibling opening of the
                     // queries at the other member of its pair (slots 2, 3)
-                    hash_node2_tap(nullptr, nullptr, val, 4, h8, nullptr, [&](u32 j, const u32 *st) {
-                        if (rec.base) for (u32 i = 0; i < nq; i++) {
-                            if (q[i] == pos) st16(rec.slot(i, j), st);
-                            else if ((q[i] ^ 1u) == pos) st16(rec.slot(i, 2 + j), st);
+                    hash_node2_tap(nullptr, nullptr, val, 4, h8, nullptr, [&](u32 j, const u32 *st, bool after) {
+                        if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) {
+                            if (q[i] == pos) st16(rec.slot(i, j, after), st);
+                            else if ((q[i] ^ 1u) == pos) st16(rec.slot(i, 2 + j, after), st);
                         }
                     });
                     for (int i = 0; i < 8; i++) nhash[8 * a + i] = h8[i];
@@ -271,11 +274,11 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
                     load_hash(chash, hw, rsrc[a], r8);
                     // self node of a query: all its permutations; sibling node at a data layer: the two that fold the sibling's
                     // own evaluation into its tree hash (the tree hash itself is a hint of the path)
-                    hash_node2_tap(l8, r8, val, data ? 4 : 0, h8, t8, [&](u32 j, const u32 *st) {
-                        if (rec.base) for (u32 i = 0; i < nq; i++) {
+                    hash_node2_tap(l8, r8, val, data ? 4 : 0, h8, t8, [&](u32 j, const u32 *st, bool after) {
+                        if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) {
                             const u32 qh = q[i] >> sh_q;
-                            if (qh == pos) st16(rec.slot(i, slot_off + j), st);
-                            else if (data && h >= 1 && j >= 1 && (qh ^ 1u) == pos) st16(rec.slot(i, slot_off + 2 + j), st);
+                            if (qh == pos) st16(rec.slot(i, slot_off + j, after), st);
+                            else if (data && h >= 1 && j >= 1 && (qh ^ 1u) == pos) st16(rec.slot(i, slot_off + 2 + j, after), st);
                         }
                     });
                     for (int i = 0; i < 8; i++) { nhash[8 * a + i] = h8[i]; ntree[8 * a + i] = t8[i]; nL[8 * a + i] = l8[i]; nR[8 * a + i] = r8[i]; }

@@ -51,10 +51,13 @@ struct Channel {
     u32 n_sent;
     u32 n_perms;
     u32 *sink;         // optional: the 16-word output state of permutation k goes to sink[16 k ..]
-    HDM void init(u32 *sink_ = nullptr) { for (int i = 0; i < 16; i++) st[i] = 0; n_sent = 0; n_perms = 0; sink = sink_; }
+    size_t in_delta;   // != 0: its input state goes in_delta words further (the parallel input record)
+    HDM void init(u32 *sink_ = nullptr, size_t in_delta_ = 0) { for (int i = 0; i < 16; i++) st[i] = 0; n_sent = 0; n_perms = 0; sink = sink_; in_delta = in_delta_; }
     HDM void emit(const u32 *t) { if (sink) for (int i = 0; i < 16; i++) sink[16 * (size_t)n_perms + i] = t[i]; }
+    HDM void emit_in(const u32 *t) { if (sink && in_delta) for (int i = 0; i < 16; i++) sink[in_delta + 16 * (size_t)n_perms + i] = t[i]; }
     HDM void mix8(const u32 *w8) {            // mix_root / mix_two_felts: digest <- capacity(perm(w8 || digest))
         for (int i = 0; i < 8; i++) st[i] = w8[i];
+        emit_in(st);
         permute_mem(st);
         emit(st);
         n_sent = 0; n_perms++;
@@ -72,6 +75,7 @@ struct Channel {
         t[0] = n_sent++;
         for (int i = 1; i < 8; i++) t[i] = 0;
         for (int i = 8; i < 16; i++) t[i] = st[i];
+        emit_in(t);
         permute_mem(t);
         emit(t);
         for (int i = 0; i < 8; i++) out[i] = t[i];
@@ -88,9 +92,9 @@ struct Out {                                   // Fiat-Shamir results of one pro
     u32 pow_ok;
 };
 
-HD void transcript(const u32 *w, const proof::Desc &d, Out &o, u32 *sink = nullptr) {
+HD void transcript(const u32 *w, const proof::Desc &d, Out &o, u32 *sink = nullptr, size_t in_delta = 0) {
     Channel ch;
-    ch.init(sink);
+    ch.init(sink, in_delta);
     ch.mix8(w + d.commitments[0]);
     u32 f[4] = {d.log_size_plonk, 0, 0, 0};
     ch.mix4(f);

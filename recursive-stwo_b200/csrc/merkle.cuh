@@ -62,7 +62,8 @@ HD void hash_node(const u32 *children, LoadCol load_col, u32 n_cols, u32 out[8])
 //   cols: this path's column values (leaf layer first, then injected layers, descending log size)
 //   sib : depth x 8 sibling words, leaf level first
 // sink (optional): receives the 16-word output state of every permutation, in execution order
-HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols, const u32 *sib, u32 out[8], u32 *sink = nullptr) {
+// in_delta != 0: the input state of each permutation goes in_delta words beyond its output state (the parallel input record)
+HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols, const u32 *sib, u32 out[8], u32 *sink = nullptr, size_t in_delta = 0) {
     enum { PH_SPONGE = 0, PH_FINAL_LEAF = 1, PH_NODE = 2, PH_COMBINE = 3 };
     u32 st[16];
     u32 saved[8];
@@ -98,6 +99,10 @@ HD void path_root(const stwo_b200_path_shape &shape, u32 index, const u32 *cols,
         } else {   // PH_COMBINE: tree hash || capacity of this layer's columns (already in st[8..16])
 #pragma unroll
             for (int i = 0; i < 8; i++) st[i] = saved[i];
+        }
+        if (sink && in_delta) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) sink[in_delta + i] = st[i];
         }
         poseidon2::permute<false>(st);
         if (sink) {

@@ -113,6 +113,8 @@ struct Workspace {
     u32 *pair_scratch;                   // [p][f][88 * nq]
     u32 *fold_buf;                       // [p][max(1, 2^(log_last-1))][4]  last-layer polynomial fold buffer
     u32 *perm_out;                       // [p][HintLayout::total][16]  output state of every transcript / per-query path permutation
+    u32 *perm_in;                        // [p][HintLayout::total][16]  its input state (same slots): what check_poseidon_invocations compares
+                                         //      a flow entry with, instead of executing the permutation a second time
     u32 *hint_trees;                     // [p]  trees (of n_trees()) whose part of perm_out is complete for THIS run; the circuit's tape
                                          //      evaluation takes a proof's permutations from perm_out only when all of them are
     u32 mode;                            // MODE_* (set by the host per run)
@@ -139,6 +141,7 @@ struct Workspace {
     HDM u32 *q4(u32 *base, u32 p, u32 a, u32 na, u32 i) const { return base + (((size_t)p * na + a) * nq() + i) * 4; }
     u32 hint_total, pair_hint_base;      // HintLayout::total / pair_base[0] of `shape` (set by carve)
     HDM u32 *perm_out_of(u32 p, u32 slot) const { return perm_out ? perm_out + ((size_t)p * hint_total + slot) * 16 : nullptr; }
+    HDM size_t in_delta() const { return perm_out && perm_in ? (size_t)(perm_in - perm_out) : 0; }   // input slot = output slot + in_delta words
 };
 
 // MODE_FULL: record the circuit's permutations (perm_out) and the per-query roots.  MODE_PATH_KERNELS: the record is produced by
@@ -168,7 +171,7 @@ HD void stage_after_transcript(const Workspace &ws, u32 p);
 HD void stage_transcript(const Workspace &ws, u32 p) {
     Desc &d = ws.desc[p];
     if (!d.ok) return;
-    fs::transcript(ws.blob(p), d, ws.detail[p].fs, ws.perm_out_of(p, 0));
+    fs::transcript(ws.blob(p), d, ws.detail[p].fs, ws.perm_out_of(p, 0), ws.in_delta());
     stage_after_transcript(ws, p);
 }
 HD void stage_after_transcript(const Workspace &ws, u32 p) {
@@ -282,7 +285,7 @@ HD void stage_single_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 t, 
         stwo_b200_path_shape shp;
         u32 at = HINT_TRANSCRIPT_SLOTS;
         for (u32 tt = 0; tt <= t; tt++) { single_path_shape(ws.shape, tt, shp); if (tt < t) at += merkle::path_perms(shp) * nq; }
-        rec.base = ws.perm_out_of(p, at); rec.per_query = merkle::path_perms(shp); rec.roots = ws.root_of(p, t, 0);
+        rec.base = ws.perm_out_of(p, at); rec.per_query = merkle::path_perms(shp); rec.roots = ws.root_of(p, t, 0); rec.in_delta = ws.in_delta();
     }
     const bool ok = decommit::single_tree_coop(co, sh, q, nq, w + d.queried[t], d.n_queried[t], w + d.hash_witness[t], d.n_hash_witness[t],
                                                w + d.commitments[t], ws.cols_of(p, t, 0), PATH_COLS_STRIDE, ws.sib_of(p, t, 0), MAX_DEPTH * 8,
@@ -319,6 +322,7 @@ HD void stage_pair_tree_coop(const Co &co, const Workspace &ws, u32 p, u32 f, u3
         u32 at = ws.pair_hint_base;
         for (u32 ff = 0; ff < f; ff++) at += decommit::pair_path_perms(ws.shape.fri_depth(ff), ws.shape.fri_data_mask(ff)) * nq;
         rec.base = ws.perm_out_of(p, at); rec.per_query = decommit::pair_path_perms(depth, ws.shape.fri_data_mask(f)); rec.roots = ws.root_of(p, 4 + f, 0);
+        rec.in_delta = ws.in_delta();
     }
     const bool ok = decommit::pair_tree_coop(co, depth, ws.shape.fri_data_mask(f), q, nq, ws.vals_of(p, f), *ws.nvals_of(p, f), hw, n_hw, root,
                                              self_vals, sib_vals, sib_hashes, nodes, tab, &perms, rec);
@@ -348,7 +352,7 @@ HD void stage_single_path(const Workspace &ws, u32 p, u32 t, u32 i) {
         for (u32 tt = 0; tt < t; tt++) { stwo_b200_path_shape o; single_path_shape(ws.shape, tt, o); at += merkle::path_perms(o) * ws.nq(); }
         sink = ws.perm_out_of(p, at + i * merkle::path_perms(shp));
     }
-    merkle::path_root(shp, fri::position(d, dt.fs.raw_queries[i], depth), ws.cols_of(p, t, i), ws.sib_of(p, t, i), root, sink);
+    merkle::path_root(shp, fri::position(d, dt.fs.raw_queries[i], depth), ws.cols_of(p, t, i), ws.sib_of(p, t, i), root, sink, ws.in_delta());
     decommit::cp8(ws.root_of(p, t, i), root);
     VERIFY_ATOMIC_ADD(&dt.n_perms_paths, merkle::path_perms(shp));
     if (!decommit::eq8(root, ws.blob(p) + d.commitments[t])) fail_shared(&dt, proof::ST_MERKLE);
@@ -769,7 +773,8 @@ HD void stage_pair_path(const Workspace &ws, u32 p, u32 f, u32 i) {
         for (u32 ff = 0; ff < f; ff++) at += decommit::pair_path_perms(ws.shape.fri_depth(ff), ws.shape.fri_data_mask(ff)) * ws.nq();
         sink = ws.perm_out_of(p, at + i * decommit::pair_path_perms(depth, ws.shape.fri_data_mask(f)));
     }
-    decommit::pair_path_root(depth, ws.shape.fri_data_mask(f), q, hint_self(ws, p, f, i), hint_sib(ws, p, f, i), hint_hashes(ws, p, f, i), root, &perms, sink);
+    decommit::pair_path_root(depth, ws.shape.fri_data_mask(f), q, hint_self(ws, p, f, i), hint_sib(ws, p, f, i), hint_hashes(ws, p, f, i), root, &perms, sink,
+                             ws.in_delta());
     decommit::cp8(ws.root_of(p, 4 + f, i), root);
     VERIFY_ATOMIC_ADD(&dt.n_perms_paths, perms);
     const u32 *want = ws.blob(p) + (f ? d.in_commitment[f - 1] : d.fl_commitment);
@@ -827,6 +832,7 @@ inline size_t carve(Workspace &ws, uint8_t *base) {
     const HintLayout hl = hint_layout(ws.shape);
     ws.hint_total = hl.total; ws.pair_hint_base = hl.pair_base[0];
     ws.perm_out = c.take<u32>(n * (size_t)hl.total * 16);
+    ws.perm_in = c.take<u32>(n * (size_t)hl.total * 16);
     ws.hint_trees = c.take<u32>(n);
     return (c.at + 255) & ~(size_t)255;
 }

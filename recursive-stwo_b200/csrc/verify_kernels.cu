@@ -166,13 +166,22 @@ struct Lanes16 {
 struct Channel16 {                                          // primitives/channel/src/lib.rs:23-58 on a lane-spread state
     Lanes16 g; u32 s, n_sent, n_perms;
     u32 *sink;                                              // optional: output state of permutation k at sink[16 k ..], a word per lane
-    __device__ void absorb(u32 rate_word) { s = g.l < 8 ? rate_word : s; s = g.permute(s); if (sink && g.active) sink[16 * (size_t)n_perms + g.l] = s; n_sent = 0; n_perms++; }
+    size_t in_delta;                                        // != 0: its input state in_delta words further
+    __device__ void absorb(u32 rate_word) {
+        s = g.l < 8 ? rate_word : s;
+        if (sink && in_delta && g.active) sink[in_delta + 16 * (size_t)n_perms + g.l] = s;
+        s = g.permute(s);
+        if (sink && g.active) sink[16 * (size_t)n_perms + g.l] = s;
+        n_sent = 0; n_perms++;
+    }
     __device__ void mix8(const u32 *w8) { absorb(g.l < 8 ? w8[g.l] : 0u); }
     __device__ void mix4(const u32 *w4) { absorb(g.l < 4 ? w4[g.l] : 0u); }
     __device__ void mix4v(u32 v) { absorb(g.l < 4 ? v : 0u); }              // lanes 0..3 already hold the four words
     __device__ void mix44(const u32 *a, const u32 *b) { absorb(g.l < 4 ? a[g.l] : g.l < 8 ? b[g.l - 4] : 0u); }
     __device__ u32 draw() {                                 // lanes 0..7 return the eight drawn words
-        const u32 t = g.permute(g.l == 0 ? n_sent : g.l < 8 ? 0u : s);
+        const u32 t0 = g.l == 0 ? n_sent : g.l < 8 ? 0u : s;
+        if (sink && in_delta && g.active) sink[in_delta + 16 * (size_t)n_perms + g.l] = t0;
+        const u32 t = g.permute(t0);
         if (sink && g.active) sink[16 * (size_t)n_perms + g.l] = t;
         n_sent++; n_perms++;
         return t;
@@ -180,9 +189,9 @@ struct Channel16 {                                          // primitives/channe
 };
 // Trip counts come from the batch's shape (a kernel parameter: provably warp-uniform, so the loops stay convergent for the compiler too),
 // not from the proof's descriptor (equal for every proof that parsed, but loaded from memory).
-__device__ __forceinline__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o, u32 *sink, const u32 n_inner,
-                                             const u32 n_last_coeffs, const u32 n_queries, const u32 pow_bits) {
-    Channel16 ch{g, 0u, 0u, 0u, sink};
+__device__ __forceinline__ void transcript16(const Lanes16 &g, const u32 *w, const proof::Desc &d, fs::Out &o, u32 *sink, const size_t in_delta,
+                                             const u32 n_inner, const u32 n_last_coeffs, const u32 n_queries, const u32 pow_bits) {
+    Channel16 ch{g, 0u, 0u, 0u, sink, in_delta};
     const u32 l = g.l;
     const bool act = g.active;
     auto store_q = [&](qm31_t *dst, u32 t, u32 first_lane) { if (act && l >= first_lane && l < first_lane + 4) dst->v[l - first_lane] = t; };
@@ -280,7 +289,8 @@ __global__ void __launch_bounds__(kT) k_transcript16(const Workspace ws, u32 p0,
     g.active = own;
     g.init();
     verify::Detail &dt = ws.detail[p];
-    transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0), ws.shape.n_inner, 1u << ws.shape.log_last, ws.shape.n_queries, ws.shape.pow_bits);
+    transcript16(g, ws.blob(p), d, dt.fs, ws.perm_out_of(p, 0), ws.in_delta(), ws.shape.n_inner, 1u << ws.shape.log_last, ws.shape.n_queries,
+                 ws.shape.pow_bits);
     __syncwarp();
     if (own && g.l == 0) verify::stage_after_transcript(ws, p);
 }
@@ -559,6 +569,7 @@ static int32_t verify_batch_impl(const uint32_t *host_blobs, const uint64_t *hos
     ws.n_proofs = n_proofs; ws.blobs = blobs; ws.blob_off = blob_off;
     ws.input_idx = input_idx; ws.input_vals = input_vals; ws.n_inputs = n_inputs;
     if (verify::carve(ws, (uint8_t *)workspace) > workspace_bytes) return STWO_B200_E_BAD_ARG;
+    if (!stwo_b200::record_inputs()) ws.perm_in = nullptr;         // STWO_B200_RECORD_INPUTS=0 (profiling): outputs only, the check re-executes
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nq = shape->n_queries, nf = ws.shape.n_fri_trees();
     const bool timed = flags & STWO_B200_VERIFY_TIMED, full = flags & STWO_B200_VERIFY_FULL;
@@ -706,6 +717,7 @@ extern "C" int32_t stwo_b200_verify_fetch(const void *workspace, const stwo_b200
         case STWO_B200_FETCH_PATH_SIBLINGS: src = ws.path_sib + (size_t)p * 4 * nq * verify::MAX_DEPTH * 8; bytes = 4 * nq * verify::MAX_DEPTH * 32; break;
         case STWO_B200_FETCH_PAIR_HINTS: src = ws.pair_hints + (size_t)p * nf * nq * verify::PAIR_HINT_WORDS; bytes = nf * nq * verify::PAIR_HINT_WORDS * 4; break;
         case STWO_B200_FETCH_PERM_RECORD: src = ws.perm_out_of(p, 0); bytes = (size_t)ws.hint_total * 64; break;
+        case STWO_B200_FETCH_PERM_RECORD_INPUTS: src = ws.perm_out_of(p, 0) + ws.in_delta(); bytes = (size_t)ws.hint_total * 64; break;
         case STWO_B200_FETCH_RECORD_TREES: src = ws.hint_trees + p; bytes = 4; break;
         default: return STWO_B200_E_BAD_ARG;
     }

@@ -67,7 +67,8 @@ class SynthBatch:
                       ctypes.sizeof(out), _stream())
             return out
         shapes = {"circle_folds": (3, nq, 4), "line_folds": (32, nq, 4), "last_evals": (nq, 4), "path_roots": (4 + nf, nq, 8), "answers": (3, nq, 4),
-                  "record_trees": (1,), "perm_record": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16)}
+                  "record_trees": (1,), "perm_record": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16),
+                  "perm_record_inputs": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16)}
         out = np.zeros(shapes[what], dtype=np.uint32)
         _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what],
                   out.ctypes.data_as(ctypes.c_void_p), out.nbytes, _stream())

@@ -174,7 +174,8 @@ class VerifyBatch:
         shapes = {"domain_points": (3, nq, 2), "answers": (3, nq, 4), "circle_folds": (3, nq, 4), "line_folds": (32, nq, 4),
                   "last_evals": (nq, 4), "path_roots": (4 + nf, nq, 8), "path_cols": (4, nq, 64), "path_siblings": (4, nq, 30, 8),
                   "pair_hints": (nf, nq * 256), "record_trees": (1,),
-                  "perm_record": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16)}
+                  "perm_record": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16),
+                  "perm_record_inputs": (int(_lib.load().stwo_b200_proof_record_slots(ctypes.byref(self.shape))), 16)}
         out = np.zeros(shapes[what], dtype=np.uint32)
         _lib.call("stwo_b200_verify_fetch", _dptr(self.d_ws), ctypes.byref(self.shape), self.n, p, FETCH[what],
                   out.ctypes.data_as(ctypes.c_void_p), out.nbytes, _stream())

@@ -104,8 +104,12 @@ int hs_build_group_lanes(const verify::Workspace *ws, u32 G) {
     return 0;
 }
 // the permutation record of proof p (ws from hs_verify_batch's ws_out): hint_total x 16 words; returns hint_total
+// optional second destination of hs_perm_record: the INPUT states of the same slots (set, call, clear)
+static u32 *g_record_inputs_out = nullptr;
+void hs_perm_record_inputs_to(u32 *dst) { g_record_inputs_out = dst; }
 u32 hs_perm_record(const verify::Workspace *ws, u32 p, u32 *out, u32 *trees_complete) {
     if (out) memcpy(out, ws->perm_out_of(p, 0), (size_t)ws->hint_total * 64);
+    if (g_record_inputs_out) memcpy(g_record_inputs_out, ws->perm_out_of(p, 0) + ws->in_delta(), (size_t)ws->hint_total * 64);
     if (trees_complete) *trees_complete = ws->hint_trees[p];
     return ws->hint_total;
 }

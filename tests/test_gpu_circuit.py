@@ -198,3 +198,62 @@ def test_last_layer_trace_matches_oracle(pkg, gpu, orc, name):
     assert v2.cpu().numpy().tolist() == [0, 1]
     br = r2["bad_row"].cpu().numpy()
     assert br[0] == -1 and br[1] >= 0
+
+
+def test_recorded_check_equals_reexecution(pkg, gpu, orc):
+    """check_poseidon_invocations against the record of executed permutations (entry input == recorded input, entry output == recorded
+    output: the default after run(full=True)) and by executing every flow entry again (recheck=True): same verdict per proof, for
+    accepted proofs and for rejected ones (whose record is incomplete, so both ways re-execute)"""
+    name = "small_proof.bin"
+    buf, n = O.load_proof(name)
+    offs = O.proof_offsets(buf, n)
+    blobs = []
+    for k, region in enumerate([None, "queried0", None, "fri_first_witness", "sampled0", None] * 7):
+        b = buf.copy()
+        if region:
+            b[offs[region] + 1] ^= 1 << (k % 5)
+        blobs.append(bytes(b[:n]))
+    vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_SINGLE)
+    vb.run(full=True)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)
+    got = {}
+    for recheck in (False, True):
+        r = circ.trace(vb, check=True, export=True, recheck=recheck)
+        got[recheck] = (r["bad_row"].cpu().numpy().copy(), r["bad_flow"].cpu().numpy().copy(), r["values"].cpu().numpy().copy())
+    for a, b in zip(got[False], got[True]):
+        assert np.array_equal(a, b)
+    assert (got[False][1] == -1).all() and (got[False][0] == -1).sum() == 21
+
+
+def test_recorded_check_is_live(pkg, gpu, orc):
+    """the record-based check really compares: one flipped word in the INPUT record of a path permutation of one proof is reported as
+    that proof's first bad flow entry (the evaluation never reads the input record, so every row still holds); the re-execution does
+    not look at the record and stays clean"""
+    import torch
+    blob = open(os.path.join(O.PROOFS_DIR, "small_proof.bin"), "rb").read()
+    n = 34
+    vb = pkg.VerifyBatch([blob] * n, inputs=pkg.INPUTS_SINGLE)
+    vb.run(full=True)
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)
+    r = circ.trace(vb, check=True, export=False, preprocessed=False)
+    assert (r["bad_flow"].cpu().numpy() == -1).all()
+    # locate proof 33's input record inside the workspace through a sentinel: fetch, find the words, flip one on the device
+    rec_in = vb.fetch(33, "perm_record_inputs")
+    slot = 512 + 700                                                       # a path slot of the second commitment tree
+    ws32 = vb.d_ws[: vb.d_ws.numel() // 4 * 4].view(torch.int32)
+    needle = torch.from_numpy(rec_in[slot].view(np.int32).copy()).to(ws32.device)
+    cand = (ws32[:-16] == needle[0]).nonzero().flatten()
+    hits = [int(h) for h in cand.tolist() if bool((ws32[h: h + 16] == needle).all())]
+    mine = None
+    for h in hits:                                                         # replicas: every proof holds the same 16 words; take proof 33's
+        ws32[h + 3] ^= 1
+        if vb.fetch(33, "perm_record_inputs")[slot][3] != rec_in[slot][3]:
+            mine = h
+            break
+        ws32[h + 3] ^= 1
+    assert mine is not None
+    r = circ.trace(vb, check=True, export=False, preprocessed=False)
+    bad_flow, bad_row = r["bad_flow"].cpu().numpy(), r["bad_row"].cpu().numpy()
+    assert bad_flow[33] >= 0 and (np.delete(bad_flow, 33) == -1).all() and (bad_row == -1).all()
+    r = circ.trace(vb, check=True, export=False, preprocessed=False, recheck=True)
+    assert (r["bad_flow"].cpu().numpy() == -1).all()

@@ -1,4 +1,5 @@
 """GPU tier: the batched verifier through the C ABI, every intermediate value bit-exact against the oracle."""
+import ctypes
 import os
 
 import numpy as np
@@ -227,12 +228,17 @@ def test_tree_rebuild_record_equals_path_kernels(pkg, gpu, orc, name, n):
         v, _ = vb.run(full=True, path_kernels=pk)
         assert not v.cpu().numpy().any()
         got[pk] = [(vb.fetch(p, "perm_record").copy(), vb.fetch(p, "path_roots").copy(), vb.fetch(p, "detail").n_perms_paths,
-                    int(vb.fetch(p, "record_trees")[0])) for p in (0, n // 2, n - 1)]
+                    int(vb.fetch(p, "record_trees")[0]), vb.fetch(p, "perm_record_inputs").copy()) for p in (0, n // 2, n - 1)]
     used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, got[True][0][0].shape[0])]
     for a, b in zip(got[False], got[True]):
         assert np.array_equal(a[0][used], b[0][used]) and np.array_equal(a[1], b[1])
         assert a[2] == b[2] == o.n_perms_paths and a[3] == b[3] == 5 + o.n_inner
         assert a[0][512:].any(axis=1).all()
+        assert np.array_equal(a[4][used], b[4][used])                      # the parallel INPUT record, from both producers
+    # ... and it is the input of the recorded output: permute(input) == output, slot by slot (the oracle's permutation as the checker)
+    st = np.ascontiguousarray(got[False][0][4][used])
+    orc.orc_poseidon2_permute_batch(O.vp(st), ctypes.c_size_t(st.shape[0]))
+    assert np.array_equal(st, got[False][0][0][used])
     # a verdict-only run leaves no usable record: the marker is reset, the tape evaluation then permutes itself
     vb.run(full=False)
     assert int(vb.fetch(0, "record_trees")[0]) == 0

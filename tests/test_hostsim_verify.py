@@ -185,15 +185,23 @@ def test_tree_rebuild_record_equals_path_kernels(hostsim, orc, name):
         base = hostsim.hs_verify_batch(O.vp(words), O.vp(off), 1, O.vp(shape), O.vp(idx), O.vp(vals), idx.size, mode, dt, O.vp(ws))
         total = hostsim.hs_perm_record(O.vp(ws), 0, None, None)
         rec = np.zeros((total, 16), dtype=np.uint32)
+        rec_in = np.zeros((total, 16), dtype=np.uint32)
         trees = ctypes.c_uint32(0)
+        hostsim.hs_perm_record_inputs_to(O.vp(rec_in))
         hostsim.hs_perm_record(O.vp(ws), 0, O.vp(rec), ctypes.byref(trees))
+        hostsim.hs_perm_record_inputs_to(None)
         hostsim.hs_free(ctypes.c_void_p(base))
         assert dt[0].verdict == 0 and dt[0].n_perms_paths == o.n_perms_paths and dt[0].n_perms_hints == o.n_perms_hints
         assert trees.value == 5 + o.n_inner
-        recs[mode] = rec
-    used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, recs[3].shape[0])]        # transcript slots beyond the chain are unused
-    assert np.array_equal(recs[3][used], recs[7][used]) and np.array_equal(recs[7][used], recs[1][used])
-    assert recs[3][512:].any(axis=1).all()                                                   # every path slot was written
+        recs[mode] = (rec, rec_in)
+    used = np.r_[np.arange(o.n_transcript_perms), np.arange(512, recs[3][0].shape[0])]     # transcript slots beyond the chain are unused
+    for k in (0, 1):                                                                         # outputs, then the parallel input record
+        assert np.array_equal(recs[3][k][used], recs[7][k][used]) and np.array_equal(recs[7][k][used], recs[1][k][used])
+    assert recs[3][0][512:].any(axis=1).all()                                                # every path slot was written
+    # the input record is what check_poseidon_invocations compares a flow entry with: output == permute(input), slot by slot
+    st = np.ascontiguousarray(recs[3][1][used])
+    hostsim.hs_poseidon2_permute(O.vp(st), ctypes.c_size_t(st.shape[0]))
+    assert np.array_equal(st, recs[3][0][used])
 
 
 @pytest.mark.parametrize("name", ["small_proof.bin", "level1-5.bin", "level7-1.bin"])
