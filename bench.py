@@ -642,7 +642,7 @@ def main():
         "check_poseidon_by_reexecution": {"launch_ms": recheck_ms, "perms_per_sec": ci.n_flow * n_local / (recheck_ms * 1e-3),
                                           "frac": ci.n_flow * n_local / (recheck_ms * 1e-3) * LANE_OPS_PER_PERM / 1e12 / pk["int_tlops"]},
         "note": "the tree rebuild is a layer-parallel walk with G lanes per tree (idle lanes at narrow layers, 128 registers, 16 warps per SM) that "
-                "also writes the permutation record; the bare permutation kernel K1 reaches 0.70 of the peak (secondary.k1_frac_of_int_peak) and "
+                "also writes the permutation record; the bare permutation kernel K1 reaches 0.63 of the peak (secondary.k1_frac_of_int_peak) and "
                 "check_poseidon_invocations by re-execution 0.64 (check_poseidon_by_reexecution; ncu: profiles/r02e_k_cs_check_poseidon_ncu.txt)"}
     # `roofline` = the dominant HBM-bound kernel of the step (the trace export); `roofline_hashing` = the dominant integer-bound kernel
     # (for this path the largest kernels are co-dominant: check_poseidon_invocations, export, tape evaluation within ~10 % of each other)
@@ -737,6 +737,9 @@ def main():
                        "pipeline": "%d device slots, %d lane(s); upload | verification | trace pass of neighbouring steps on their own streams; "
                                    "CUDA_DEVICE_MAX_CONNECTIONS=%s" % (len(pipe.slots), len(pipe.lane_streams), os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"))},
             "poseidon31_perms_per_sec": value * perms_per_proof,
+            # what the reference's own path executes for the same proofs: hints (every tree node once) + transcript, the DSL's per-query
+            # paths + transcript again, check_poseidon_invocations a third time -- the work this rate of proofs stands for
+            "poseidon31_perms_reference_equivalent_per_sec": value * (perms_per_proof + 2 * ci.n_flow),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t_e.item()) / e2e_steps * 1e3},
