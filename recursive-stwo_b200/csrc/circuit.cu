@@ -153,6 +153,14 @@ int g_beside_ctas = [] { const char *e = getenv("STWO_B200_BESIDE_CTAS"); return
 bool g_timed_valid = false;
 }  // namespace
 
+void stwo_b200::circuit_streams_destroy() {
+    if (g_side) cudaStreamDestroy(g_side);
+    if (g_side_fork) cudaEventDestroy(g_side_fork);
+    if (g_side_join) cudaEventDestroy(g_side_join);
+    g_side = nullptr; g_side_fork = g_side_join = nullptr;
+    for (auto &e : g_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    g_timed_valid = false;
+}
 static_assert(sizeof(dsl::ProofShape) == sizeof(stwo_b200_proof_shape), "shape mirrors");
 
 extern "C" int32_t stwo_b200_circuit_record_verifier(const stwo_b200_proof_shape *shape, const uint32_t *input_idx, const uint32_t *input_vals,

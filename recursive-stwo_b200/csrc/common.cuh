@@ -24,6 +24,9 @@ inline bool record_inputs() {
     if (v < 0) { const char *e = getenv("STWO_B200_RECORD_INPUTS"); v = !(e && e[0] == '0'); }
     return v != 0;
 }
+// per-device resources of the batch drivers, released by stwo_b200_shutdown (verify_kernels.cu / circuit.cu)
+void verify_pools_destroy();
+void circuit_streams_destroy();
 inline int32_t cuda_status(cudaError_t e) { return e == cudaSuccess ? STWO_B200_OK : -(int32_t)e; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace stwo_b200

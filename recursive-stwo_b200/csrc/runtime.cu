@@ -63,6 +63,8 @@ extern "C" int32_t stwo_b200_shutdown(void) {
     g_dev = nullptr; g_dev_cap = 0;
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
+    stwo_b200::verify_pools_destroy();          // worker-stream pools and their events
+    stwo_b200::circuit_streams_destroy();       // the side stream / events of the trace pass
     g_device = -1;
     return STWO_B200_OK;
 }

@@ -361,6 +361,16 @@ struct Pool {
     }
 };
 Pool g_pools[kPools];
+void pools_destroy() {
+    for (Pool &p : g_pools) {
+        if (!p.ready) continue;
+        for (auto &x : p.s) if (x) cudaStreamDestroy(x);
+        if (p.fork) cudaEventDestroy(p.fork);
+        for (int i = 0; i < kSlices; i++)
+            for (cudaEvent_t e : {p.fs_done[i], p.tree_done[i], p.side_done[i], p.join[i]}) if (e) cudaEventDestroy(e);
+        p = Pool();
+    }
+}
 Pool *pool_for(cudaStream_t st) {
     static int n_pools = 0;                                // STWO_B200_VERIFY_POOLS=k (1..6): profiling
     if (!n_pools) { const char *e = getenv("STWO_B200_VERIFY_POOLS"); n_pools = e ? atoi(e) : kPools; if (n_pools < 1 || n_pools > kPools) n_pools = kPools; }
@@ -380,6 +390,13 @@ int tree_group_width(u32 n_proofs) {
     }
     if (forced >= 0) return forced;
     return n_proofs <= 1024 ? 16 : 8;
+}
+// ... and for the stages whose unit of work is one QUERY (a node of a tree layer per query, a fold chain per query): a whole warp per
+// unit when the shape has more queries than 32 lanes would leave idle and the batch is small -- the 80-query shapes of a mixed batch are
+// a latency chain (34 proofs: 2.2 + 2.8 + 1.0 ms in the two tree stages and the folds with 16 lanes)
+int query_group_width(u32 n_proofs, u32 n_queries) {
+    const int g = tree_group_width(n_proofs);
+    return (g == 16 && n_queries > 32 && n_proofs <= 256) ? 32 : g;
 }
 // shared memory of a block = (threads / G) group tables; large query counts need the opt-in limit
 constexpr size_t kCoopSmemMax = 160 * 1024;
@@ -415,21 +432,23 @@ bool launch_pair_tree_g(size_t groups, u32 tab, const Workspace &ws, u32 p0, u32
     }
 }
 void launch_single_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
-    const int G = tree_group_width(ws.n_proofs);
+    const int G = query_group_width(ws.n_proofs, ws.shape.n_queries);
     const u32 nq = ws.shape.n_queries, tab = decommit::single_tab_words(nq) + nq;
     const size_t groups = (size_t)n * 4;
     bool done = false;
-    if (G == 16) done = launch_single_tree_g<16>(groups, tab, ws, p0, n, st);
+    if (G == 32) done = launch_single_tree_g<32>(groups, tab, ws, p0, n, st);
+    else if (G == 16) done = launch_single_tree_g<16>(groups, tab, ws, p0, n, st);
     else if (G == 8) done = launch_single_tree_g<8>(groups, tab, ws, p0, n, st);
     else if (G == 4) done = launch_single_tree_g<4>(groups, tab, ws, p0, n, st);
     if (!done) k_single_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
 void launch_pair_tree(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
-    const int G = tree_group_width(ws.n_proofs);
+    const int G = query_group_width(ws.n_proofs, ws.shape.n_queries);
     const u32 nq = ws.shape.n_queries, tab = decommit::pair_tab_words(nq) + nq;
     const size_t groups = (size_t)n * ws.shape.n_fri_trees();
     bool done = false;
-    if (G == 16) done = launch_pair_tree_g<16>(groups, tab, ws, p0, n, st);
+    if (G == 32) done = launch_pair_tree_g<32>(groups, tab, ws, p0, n, st);
+    else if (G == 16) done = launch_pair_tree_g<16>(groups, tab, ws, p0, n, st);
     else if (G == 8) done = launch_pair_tree_g<8>(groups, tab, ws, p0, n, st);
     else if (G == 4) done = launch_pair_tree_g<4>(groups, tab, ws, p0, n, st);
     if (!done) k_pair_tree<<<(unsigned)((groups + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
@@ -450,10 +469,11 @@ void launch_oods(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
 }
 void launch_folds(const Workspace &ws, u32 p0, u32 n, cudaStream_t st) {
     // one query per lane: 16 lanes per proof (8 when the batch alone fills the GPU)
-    const int G = tree_group_width(ws.n_proofs);
+    const int G = query_group_width(ws.n_proofs, ws.shape.n_queries);
     const u32 tab = verify::folds_tab_words(ws.shape.n_queries);
     bool done = false;
-    if (G == 16) done = coop_launch(k_folds_coop<16>, 16, n, tab, ws, p0, n, st);
+    if (G == 32) done = coop_launch(k_folds_coop<32>, 32, n, tab, ws, p0, n, st);
+    else if (G == 16) done = coop_launch(k_folds_coop<16>, 16, n, tab, ws, p0, n, st);
     else if (G == 8 || G == 4) done = coop_launch(k_folds_coop<8>, 8, n, tab, ws, p0, n, st);
     if (!done) k_folds<<<(unsigned)((n + kT - 1) / kT), kT, 0, st>>>(ws, p0, n);
 }
@@ -471,6 +491,7 @@ bool shape_ok(const stwo_b200_proof_shape *s) {
 }
 }  // namespace
 
+void stwo_b200::verify_pools_destroy() { pools_destroy(); }
 static_assert(sizeof(stwo_b200_proof_shape) == sizeof(verify::Shape), "shape mirrors");
 static_assert(sizeof(stwo_b200_verify_detail) == sizeof(verify::Detail), "detail mirrors");
 
