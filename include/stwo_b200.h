@@ -376,6 +376,14 @@ typedef struct {
 /* The value definitions of a recorded circuit, sorted by dependency level (instructions of a level are independent).
  * ins: n_ins x {op, dst, a, b} (STWO_B200_T_*); perms: n_perms x 12 words {l_kind, l_a, l_b, r_kind, r_a, r_b, swap_var,
  * out[4], hint}: half kind 0 = the two QM31 variables (a, b), kind 1 = eight witness-stream words at slot a. */
+/* Optional second order of a tape for items whose permutation record is complete (cs_values.perm_hints + perm_hint_ready): every
+ * permutation that names a record slot is split into STWO_B200_T_PERM_OUT + STWO_B200_T_PERM_FLOW, so the transcript and the
+ * authentication paths stop being dependency chains and the tape is only as deep as its arithmetic.  Same perms / eperms as the tape
+ * it belongs to; bundles are mandatory here.  The evaluation picks it per group of `lanes` items, when all of them have a complete record. */
+typedef struct {
+    uint32_t n_ins, n_levels, n_bundles;
+    const uint32_t *ins, *bundle_start /* n_bundles + 1 */, *level_bundle /* n_levels + 1 */;
+} stwo_b200_cs_tape_order;
 typedef struct {
     uint32_t n_ins, n_perms, n_levels, n_input_words;
     const uint32_t *ins, *level_start /* n_levels + 1 */, *perms;
@@ -389,6 +397,7 @@ typedef struct {
      * level are independent; level_start still gives the level's instruction range. */
     uint32_t n_bundles;
     const uint32_t *bundle_start /* n_bundles + 1 */, *level_bundle /* n_levels + 1 */;
+    const stwo_b200_cs_tape_order *recorded_order;   /* HOST pointer to the struct (its arrays are device arrays); NULL: none */
 } stwo_b200_cs_tape;
 #define STWO_B200_T_ADD 1
 #define STWO_B200_T_MUL 2
@@ -408,6 +417,8 @@ typedef struct {
 #define STWO_B200_T_GRANDSUM 16
 #define STWO_B200_T_POW4 17
 #define STWO_B200_T_EPOSEIDON 18
+#define STWO_B200_T_PERM_OUT 19    /* recorded_order only: output variables of permutation record dst <- the item's permutation record */
+#define STWO_B200_T_PERM_FLOW 20   /* recorded_order only: the flow entry of permutation record dst (reads the halves, defines nothing) */
 
 /* K6: variables[] (and the Poseidon flow) of every batch item from its witness stream (n_input_words words per item,
  * lane-interleaved like the values).  Replaces the `value` arithmetic of every DSL call: primitives/fields/src/{m31,cm31,qm31}.rs,

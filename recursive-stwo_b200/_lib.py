@@ -119,7 +119,8 @@ class CsTape(ctypes.Structure):
     """stwo_b200_cs_tape"""
     _fields_ = [(n, ctypes.c_uint32) for n in ("n_ins", "n_perms", "n_levels", "n_input_words")] + [
         (n, ctypes.c_void_p) for n in ("ins", "level_start", "perms")] + [("n_eperms", ctypes.c_uint32), ("eperms", ctypes.c_void_p),
-                                                                           ("n_bundles", ctypes.c_uint32), ("bundle_start", ctypes.c_void_p), ("level_bundle", ctypes.c_void_p)]
+                                                                           ("n_bundles", ctypes.c_uint32), ("bundle_start", ctypes.c_void_p), ("level_bundle", ctypes.c_void_p),
+                                                                           ("recorded_order", ctypes.c_void_p)]
 
 
 class CircuitInfo(ctypes.Structure):

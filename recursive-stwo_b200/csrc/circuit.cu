@@ -16,6 +16,7 @@ struct stwo_b200_circuit {
     uint8_t *dev = nullptr;
     stwo_b200_cs_wiring wiring{};
     stwo_b200_cs_tape tape_{};
+    stwo_b200_cs_tape_order order2_{};     // the order for items with a complete permutation record (tape_.recorded_order points here)
     const u32 *gather = nullptr;
     const circuit::ExtraJob *jobs = nullptr;      // last-layer circuit only
     u32 n_jobs = 0, n_extra_words = 0;
@@ -90,7 +91,8 @@ int32_t upload(stwo_b200_circuit *c) {
     const size_t o_w = take(9 * nr * 4), o_jobs = take(r.jobs.size() * sizeof(circuit::ExtraJob) + 16), o_fol = take(nr), o_fw = take(nf * 16 + 16), o_fa = take(nf * 4 + 4), o_ins = take(r.ins.size() * 16 + 16),
                  o_lvl = take(r.level_start.size() * 4), o_bs = take(r.bundle_start.size() * 4 + 4), o_lb = take(r.level_bundle.size() * 4 + 4), o_perm = take(cs.perms.size() * sizeof(tape::Perm) + 16), o_g = take(r.gather.size() * 4 + 4), o_ep = take(cs.eperms.size() * 4 + 4),
                  o_xt = take(stwo_b200_cs_export_tiles_words((u32)nr) * 4 + 16), o_mult = take((size_t)4 * nr * 4), o_scr = take(((size_t)4 * cs.n_vars + 4) * 4),
-                 o_stat = take(256);
+                 o_stat = take(256),
+                 o_ins2 = take(r.recorded.ins.size() * 16 + 16), o_bs2 = take(r.recorded.bundle_start.size() * 4 + 4), o_lb2 = take(r.recorded.level_bundle.size() * 4 + 4);
     uint8_t *d = nullptr;
     STWO_CUDA(cudaMalloc(&d, at));
     const std::vector<u32> *cols[9] = {&cs.a_wire, &cs.b_wire, &cs.c_wire, &cs.poseidon_wire, &cs.enforce_c_m31, &cs.op, &cs.op2, &cs.op3, &cs.op4};
@@ -108,6 +110,11 @@ int32_t upload(stwo_b200_circuit *c) {
     STWO_CUDA(cudaMemcpy(d + o_bs, r.bundle_start.data(), r.bundle_start.size() * 4, cudaMemcpyHostToDevice));
     STWO_CUDA(cudaMemcpy(d + o_lb, r.level_bundle.data(), r.level_bundle.size() * 4, cudaMemcpyHostToDevice));
     if (!cs.eperms.empty()) STWO_CUDA(cudaMemcpy(d + o_ep, cs.eperms.data(), cs.eperms.size() * 4, cudaMemcpyHostToDevice));
+    if (r.recorded.n_levels()) {
+        STWO_CUDA(cudaMemcpy(d + o_ins2, r.recorded.ins.data(), r.recorded.ins.size() * 16, cudaMemcpyHostToDevice));
+        STWO_CUDA(cudaMemcpy(d + o_bs2, r.recorded.bundle_start.data(), r.recorded.bundle_start.size() * 4, cudaMemcpyHostToDevice));
+        STWO_CUDA(cudaMemcpy(d + o_lb2, r.recorded.level_bundle.data(), r.recorded.level_bundle.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (!r.gather.empty()) STWO_CUDA(cudaMemcpy(d + o_g, r.gather.data(), r.gather.size() * 4, cudaMemcpyHostToDevice));
     const u32 *w = (const u32 *)(d + o_w);
     // per 32-row tile of the export pass: the distinct variables its wires name
@@ -128,7 +135,12 @@ int32_t upload(stwo_b200_circuit *c) {
     c->jobs = (const circuit::ExtraJob *)(d + o_jobs); c->n_jobs = (u32)r.jobs.size(); c->n_extra_words = r.n_extra_words;
     c->tape_ = {(u32)r.ins.size(), (u32)cs.perms.size(), r.n_levels(), cs.n_input_words, (const u32 *)(d + o_ins), (const u32 *)(d + o_lvl),
                 (const u32 *)(d + o_perm), (u32)(cs.eperms.size() / tape::EPOSEIDON_REC), (const u32 *)(d + o_ep),
-                (u32)r.bundle_start.size() - 1, (const u32 *)(d + o_bs), (const u32 *)(d + o_lb)};
+                (u32)r.bundle_start.size() - 1, (const u32 *)(d + o_bs), (const u32 *)(d + o_lb), nullptr};
+    if (r.recorded.n_levels()) {
+        c->order2_ = {(u32)r.recorded.ins.size(), r.recorded.n_levels(), (u32)r.recorded.bundle_start.size() - 1, (const u32 *)(d + o_ins2),
+                      (const u32 *)(d + o_bs2), (const u32 *)(d + o_lb2)};
+        c->tape_.recorded_order = &c->order2_;
+    }
     c->gather = (const u32 *)(d + o_g);
     c->mult = (int32_t *)(d + o_mult); c->scratch = (u32 *)(d + o_scr); c->status = (u32 *)(d + o_stat);
     {

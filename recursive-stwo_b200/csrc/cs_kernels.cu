@@ -157,10 +157,15 @@ constexpr int kClusterThreads = 512;
 // Measured and dropped: four instructions of a level per warp at once (all operand loads issued before any is consumed): 110 registers,
 // one CTA per SM, 5.2 ms against 3.1 ms at 4096 proofs and 1.4 against 1.1 ms at 512 -- the pass is not short of loads in flight.
 // CLOCK: cluster 0 stamps the global timer after every level (tools/level_clock.py)
+// Second order (ins2 != nullptr): the tape with every recorded permutation split into "outputs from the record" and "flow entry"
+// (dsl::RecordedCircuit::recorded): far fewer levels, valid for a lane group whose 32 items all have a complete permutation record.
+// Every warp of the cluster holds the same 32 items, so every warp reaches the same verdict without talking to the others.
 template <bool CLOCK>
 __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tape::Ins *__restrict__ ins, const u32 *__restrict__ level_start, u32 n_levels,
                                                                        const tape::Perm *__restrict__ perms, Batch b, const u32 *input, u32 n_input_words,
-                                                                       const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start) {
+                                                                       const u32 *__restrict__ eperms, const u32 *__restrict__ bundle_start,
+                                                                       const tape::Ins *__restrict__ ins2, const u32 *__restrict__ level_start2, u32 n_levels2,
+                                                                       const u32 *__restrict__ bundle_start2) {
     extern __shared__ u32 s_level[];                     // level_start (bundle units), n_levels + 1 words: nothing of the level loop waits on it
     u32 rank, csize, grp;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -171,6 +176,9 @@ __global__ void __launch_bounds__(kClusterThreads) k_tape_eval_cluster(const tap
     const u32 item = grp * 32 + lane;
     const bool live = item < b.n_batch;
     const tape::View v = b.view(live ? item : 0, input, n_input_words);
+    if (ins2 && __all_sync(0xffffffffu, !live || v.hint != nullptr)) {
+        ins = ins2; level_start = level_start2; n_levels = n_levels2; bundle_start = bundle_start2;
+    }
     auto cluster_sync = [] {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -601,6 +609,7 @@ Batch batch_of(const stwo_b200_cs_values *v, u32 n_vars, u32 n_flow) {
 }  // namespace
 
 static_assert(sizeof(tape::Perm) == 48 && sizeof(tape::Ins) == 16, "tape records mirror the C ABI");
+static_assert(tape::T_PERM_OUT == STWO_B200_T_PERM_OUT && tape::T_PERM_FLOW == STWO_B200_T_PERM_FLOW, "opcodes mirror the C ABI");
 static_assert(tape::T_EPOSEIDON == STWO_B200_T_EPOSEIDON && tape::T_M4 == STWO_B200_T_M4 && tape::T_POSEIDON == STWO_B200_T_POSEIDON && tape::T_ADD == STWO_B200_T_ADD && tape::T_BIT == STWO_B200_T_BIT, "opcodes mirror the C ABI");
 
 extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32_t n_vars, const uint32_t *witness, const stwo_b200_cs_values *v,
@@ -641,7 +650,11 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
         int c = cluster > 0 ? cluster : (n_groups <= 2 ? 16 : n_groups <= 24 ? 8 : n_groups <= 64 ? 4 : 2);
         auto kernel = g_level_clock_host ? k_tape_eval_cluster<true> : k_tape_eval_cluster<false>;
         if (c > 8) STWO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        const size_t smem = ((size_t)n_levels + 1) * 4;
+        // the second order: usable when the caller has a permutation record at all (the kernel decides per lane group)
+        const stwo_b200_cs_tape_order *o2 = (t->recorded_order && v->perm_hints && t->recorded_order->ins && t->recorded_order->n_bundles) ? t->recorded_order : nullptr;
+        // (the recorder builds that order only under STWO_B200_RECORDED_ORDER=1: see dsl/recorded.hpp for the measurements)
+        const u32 max_levels = o2 && o2->n_levels > n_levels ? o2->n_levels : n_levels;
+        const size_t smem = ((size_t)max_levels + 1) * 4;
         if (smem > 48 * 1024) STWO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(n_groups * (unsigned)c); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -649,7 +662,9 @@ extern "C" int32_t stwo_b200_cs_eval_tape_dev(const stwo_b200_cs_tape *t, uint32
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        STWO_CUDA(cudaLaunchKernelEx(&cfg, kernel, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start));
+        STWO_CUDA(cudaLaunchKernelEx(&cfg, kernel, ins, level_start, n_levels, perms, b, witness, n_input_words, eperms, bundle_start,
+                                     o2 ? reinterpret_cast<const tape::Ins *>(o2->ins) : (const tape::Ins *)nullptr, o2 ? o2->level_bundle : (const u32 *)nullptr,
+                                     o2 ? o2->n_levels : 0u, o2 ? o2->bundle_start : (const u32 *)nullptr));
         note_launch(1);
         return cuda_status(cudaGetLastError());
     }

@@ -26,19 +26,21 @@ struct RecordedCircuit {
         case tape::T_ADD: case tape::T_MUL: case tape::T_POW5M4: case tape::T_HADAMARD: case tape::T_GRANDSUM: f(in.a); f(in.b); break;
         case tape::T_MULC: case tape::T_INV_M31: case tape::T_INV_QM31: case tape::T_INV_CM31_RE: case tape::T_INV_CM31_IM:
         case tape::T_COORD: case tape::T_BIT: case tape::T_M4: case tape::T_POW4: f(in.a); break;
-        case tape::T_POSEIDON: {
+        case tape::T_POSEIDON: case tape::T_PERM_FLOW: {
             const tape::Perm &p = c.perms[in.dst];
             if (p.l_kind == 0) { f(p.l_a); f(p.l_b); }
             if (p.r_kind == 0) { f(p.r_a); f(p.r_b); }
             if (p.swap_var != tape::NO_VAR) f(p.swap_var);
             break;
         }
+        case tape::T_PERM_OUT: break;                  // the outputs come from the record of executed permutations
         case tape::T_EPOSEIDON: for (u32 q = 0; q < 4; q++) f(c.eperms[(size_t)in.dst * tape::EPOSEIDON_REC + q]); break;
         default: break;
         }
     }
     template <class F> static void for_outputs(const ConstraintSystem &c, const tape::Ins &in, F f) {
-        if (in.op == tape::T_POSEIDON) { for (u32 o : c.perms[in.dst].out) if (o != tape::NO_VAR) f(o); }
+        if (in.op == tape::T_POSEIDON || in.op == tape::T_PERM_OUT) { for (u32 o : c.perms[in.dst].out) if (o != tape::NO_VAR) f(o); }
+        else if (in.op == tape::T_PERM_FLOW) {}
         else if (in.op == tape::T_EPOSEIDON) { for (u32 q = 0; q < tape::EPOSEIDON_VARS; q++) f(c.eperms[(size_t)in.dst * tape::EPOSEIDON_REC + 4 + q]); }
         else f(in.dst);
     }
@@ -52,6 +54,13 @@ struct RecordedCircuit {
     // stays at its earliest level), so a value is produced just before it is first read and is still in L2.
     std::vector<u32> bundle_start;         // n_bundles + 1: first instruction of each bundle (ins is bundle-major inside a level)
     std::vector<u32> level_bundle;         // n_levels + 1: first bundle of each level
+    // A SECOND ORDER of the same tape, for items whose permutation record is complete (the native verifier executed every permutation of
+    // the circuit and kept its output): each recorded permutation is split into T_PERM_OUT (output variables <- record; no sources) and
+    // T_PERM_FLOW (the flow entry: reads the input halves, defines nothing).  The transcript (100-255 permutations, each absorbing what
+    // the one before produced) and the authentication paths (a permutation per tree level) then stop being dependency chains: what is
+    // left of the depth is the arithmetic.  Empty when the circuit has no recorded permutations.
+    struct Order { std::vector<tape::Ins> ins; std::vector<u32> level_start, bundle_start, level_bundle; u32 n_levels() const { return level_start.empty() ? 0u : (u32)level_start.size() - 1; } };
+    Order recorded;
     static u32 bundle_cap() {
         const char *e = getenv("STWO_B200_BUNDLE");           // 1 = one instruction per bundle (profiling)
         const int v = e ? atoi(e) : 8;
@@ -59,14 +68,36 @@ struct RecordedCircuit {
     }
     void levelise() {
         const ConstraintSystem &c = *cs.p;
-        const size_t n = c.tape_.size();
+        Order o;
+        build_order(c.tape_, o);
+        ins = std::move(o.ins); level_start = std::move(o.level_start); bundle_start = std::move(o.bundle_start); level_bundle = std::move(o.level_bundle);
+        std::vector<tape::Ins> split;
+        bool any = false;
+        for (const tape::Ins &in : c.tape_) {
+            if (in.op == tape::T_POSEIDON && c.perms[in.dst].hint) {
+                split.push_back(tape::Ins{tape::T_PERM_OUT, in.dst, 0, 0});
+                split.push_back(tape::Ins{tape::T_PERM_FLOW, in.dst, 0, 0});
+                any = true;
+            } else split.push_back(in);
+        }
+        recorded = Order();
+        // Built on request only (STWO_B200_RECORDED_ORDER=1).  Measured on B200: 74 -> 55 levels for shape S (100 / 107 -> 55 for the
+        // larger shapes), tape evaluation 1.00 -> 0.92 ms at 512 proofs and 2.02 -> 1.92 ms for 34 proofs of an 80-query shape, but
+        // 2.80 -> 3.18 ms at 4096 proofs (7 % more instructions, the record read twice per permutation: the large batch is bound by
+        // throughput, not by depth) and no change of the pipelined step at any size -- not adopted as the default.
+        const char *e = getenv("STWO_B200_RECORDED_ORDER");
+        if (any && e && e[0] == '1') build_order(split, recorded);
+    }
+    void build_order(const std::vector<tape::Ins> &tape_in, Order &out) const {
+        const ConstraintSystem &c = *cs.p;
+        const size_t n = tape_in.size();
         const u32 cap = bundle_cap();
         constexpr u32 NONE = 0xffffffffu;
         std::vector<u32> var_level(c.n_vars, 0), producer(c.n_vars, NONE), bundle_of(n, 0);
         std::vector<u32> b_level, b_len, b_tail;           // per bundle: earliest level, length, last instruction
         std::vector<std::vector<u32>> members;
         for (size_t k = 0; k < n; k++) {
-            const tape::Ins &in = c.tape_[k];
+            const tape::Ins &in = tape_in[k];
             // a bundle this instruction may join: the bundle of one of its sources, if it has room and every other source is either inside
             // that bundle too or complete before the bundle's level starts (the bundle runs in recording order on one thread per item,
             // so anything recorded earlier inside it is visible)
@@ -100,10 +131,10 @@ struct RecordedCircuit {
         std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return b_level[x] > b_level[y]; });
         for (u32 b : order) {
             u32 first_use = NONE;
-            for (u32 k : members[b]) for_outputs(c, c.tape_[k], [&](u32 v) { first_use = std::min(first_use, need[v]); });
+            for (u32 k : members[b]) for_outputs(c, tape_in[k], [&](u32 v) { first_use = std::min(first_use, need[v]); });
             late[b] = first_use == NONE ? b_level[b] : first_use - 1;
             for (u32 k : members[b])
-                for_sources(c, c.tape_[k], [&](u32 v) { const u32 q = producer[v]; if (q == NONE || bundle_of[q] != b) need[v] = std::min(need[v], late[b]); });
+                for_sources(c, tape_in[k], [&](u32 v) { const u32 q = producer[v]; if (q == NONE || bundle_of[q] != b) need[v] = std::min(need[v], late[b]); });
         }
         // emit: levels 1 .. max_level; inside a level the bundles holding a permutation go first (the evaluator deals a level's bundles
         // round-robin to its warps, and the heavy ones then spread evenly)
@@ -111,20 +142,20 @@ struct RecordedCircuit {
         for (int pass = 0; pass < 2; pass++)
             for (u32 b = 0; b < nb; b++) {
                 bool heavy = false;
-                for (u32 k : members[b]) heavy |= c.tape_[k].op == tape::T_POSEIDON || c.tape_[k].op == tape::T_EPOSEIDON;
+                for (u32 k : members[b]) heavy |= tape_in[k].op == tape::T_POSEIDON || tape_in[k].op == tape::T_EPOSEIDON || tape_in[k].op == tape::T_PERM_FLOW;
                 if (heavy == (pass == 0)) per_level[late[b]].push_back(b);
             }
-        ins.clear(); ins.reserve(n);
-        bundle_start.clear(); level_bundle.assign(1, 0); level_start.assign(1, 0);
+        out.ins.clear(); out.ins.reserve(n);
+        out.bundle_start.clear(); out.level_bundle.assign(1, 0); out.level_start.assign(1, 0);
         for (u32 l = 1; l <= max_level; l++) {
             for (u32 b : per_level[l]) {
-                bundle_start.push_back((u32)ins.size());
-                for (u32 k : members[b]) ins.push_back(c.tape_[k]);
+                out.bundle_start.push_back((u32)out.ins.size());
+                for (u32 k : members[b]) out.ins.push_back(tape_in[k]);
             }
-            level_bundle.push_back((u32)bundle_start.size());
-            level_start.push_back((u32)ins.size());
+            out.level_bundle.push_back((u32)out.bundle_start.size());
+            out.level_start.push_back((u32)out.ins.size());
         }
-        bundle_start.push_back((u32)ins.size());
+        out.bundle_start.push_back((u32)out.ins.size());
     }
 };
 

@@ -31,6 +31,10 @@ enum : u32 {
     T_GRANDSUM,                                 // dst = (s, s, s, s), s = sum of the 8 coordinates of a and b
     T_POW4,                                     // dst = a^4 coordinate-wise  (the witness of pow5m4 / pow5, emulated.rs:37-78)
     T_EPOSEIDON,                                // one whole emulated permutation: record dst defines its 401 variables
+    // the two halves of a RECORDED permutation (record dst names a slot of the item's permutation record), used by the second tape
+    // order only (dsl::RecordedCircuit::recorded), which runs for items whose record is complete:
+    T_PERM_OUT,                                 // output variables <- the recorded output state; reads no variable
+    T_PERM_FLOW,                                // the flow entry (halves as given, recorded output, swap bit); defines no variable
 };
 // A whole poseidon_permute_emulated call (primitives/poseidon31/src/emulated.rs:104-221, after the swap) as ONE instruction:
 // the 401 variables it creates form a dependency chain ~170 levels deep, which one warp walks in registers instead of the
@@ -147,6 +151,27 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(st[4 * k], st[4 * k + 1], st[4 * k + 2], st[4 * k + 3]));
 }
 
+// T_PERM_OUT / T_PERM_FLOW: eval_poseidon of a recorded permutation in two independent steps (v.hint is set: the order that holds these
+// instructions is chosen only for items whose record is complete)
+HD void eval_perm_out(const View &v, const Perm &p) {
+    const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
+    for (int k = 0; k < 4; k++)
+        if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+}
+HD void eval_perm_flow(const View &v, const Perm &p, u32 entry) {
+    u32 in[16];
+    load_half(v, p.l_kind, p.l_a, p.l_b, in);
+    load_half(v, p.r_kind, p.r_a, p.r_b, in + 8);
+    const bool swap = p.swap_var != NO_VAR && ldv(v, p.swap_var).v[0] != 0;
+    if (v.flow_hash) {
+        u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
+        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];
+        const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
+        for (int k = 0; k < 16; k++) fh[(size_t)(16 + k) * v.stride] = h[k];
+    }
+    if (v.flow_swap) v.flow_swap[(size_t)entry * v.stride] = swap ? 1 : 0;
+}
+
 HD void eval_eposeidon(const View &v, const u32 *rec) {
     const u32 *out = rec + 4;
     u32 k = 0;
@@ -214,6 +239,8 @@ HD void eval(const View &v, const Ins &in, const Perm *perms, const u32 *eperms 
     case T_GRANDSUM: stv(v, in.dst, q_grandsum(ldv(v, in.a), ldv(v, in.b))); break;
     case T_POW4: stv(v, in.dst, q_pow4(ldv(v, in.a))); break;
     case T_EPOSEIDON: eval_eposeidon(v, eperms + (size_t)in.dst * EPOSEIDON_REC); break;
+    case T_PERM_OUT: eval_perm_out(v, perms[in.dst]); break;
+    case T_PERM_FLOW: eval_perm_flow(v, perms[in.dst], in.dst); break;
     default: break;
     }
 }

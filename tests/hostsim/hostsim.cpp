@@ -167,6 +167,11 @@ void *hs_circuit_record_folding(const u32 *shape) {
     } catch (const std::exception &e) { fprintf(stderr, "hs_circuit_record_folding: %s\n", e.what()); return nullptr; }
 }
 void hs_circuit_free(void *h) { delete (RecordedCircuit *)h; }
+// levels / bundles / instructions of the second order (0 when the circuit has none)
+void hs_circuit_recorded_order(void *h, u32 *out3) {
+    RecordedCircuit *r = (RecordedCircuit *)h;
+    out3[0] = r->recorded.n_levels(); out3[1] = r->recorded.bundle_start.empty() ? 0u : (u32)r->recorded.bundle_start.size() - 1; out3[2] = (u32)r->recorded.ins.size();
+}
 // info: n_rows, n_rows_unpadded, n_vars, n_flow, n_flow_padded, n_input_words, n_ins, n_levels, num_input, words_per_instance
 void hs_circuit_info(void *h, u32 *info) {
     RecordedCircuit *r = (RecordedCircuit *)h;
@@ -203,7 +208,10 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
                      flow_swap + (size_t)p * c.num_poseidon_invocations(), 1,
                      use_hints && !c.without() && ws.hint_trees[p] == ws.shape.n_trees() ? ws.perm_out_of(p, 0) : nullptr};
         tape::prologue(v);
-        for (const tape::Ins &in : r->ins) tape::eval(v, in, c.perms.data(), c.eperms.data());
+        // use_hints == 2: the second order of the tape (recorded permutations split into outputs-from-the-record + flow entry), which the
+        // device picks for a lane group whose records are all complete
+        const bool second = use_hints == 2 && v.hint && r->recorded.n_levels();
+        for (const tape::Ins &in : (second ? r->recorded.ins : r->ins)) tape::eval(v, in, c.perms.data(), c.eperms.data());
         bad_row[p] = -1;
         for (u32 i = 0; i < c.num_plonk_rows(); i++) {
             bool ok;

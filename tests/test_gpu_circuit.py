@@ -257,3 +257,28 @@ def test_recorded_check_is_live(pkg, gpu, orc):
     assert bad_flow[33] >= 0 and (np.delete(bad_flow, 33) == -1).all() and (bad_row == -1).all()
     r = circ.trace(vb, check=True, export=False, preprocessed=False, recheck=True)
     assert (r["bad_flow"].cpu().numpy() == -1).all()
+
+
+def test_second_tape_order_is_bit_identical(pkg, gpu, orc, monkeypatch):
+    """the opt-in second order of the tape (STWO_B200_RECORDED_ORDER=1: every recorded permutation split into outputs-from-the-record +
+    flow entry, 74 -> 55 levels) gives the very same variables, flow and trace; a lane group holding a rejected proof falls back to the
+    first order on its own"""
+    name = "small_proof.bin"
+    buf, n = O.load_proof(name)
+    offs = O.proof_offsets(buf, n)
+    bad = buf.copy()
+    bad[offs["queried0"] + 1] ^= 2
+    blobs = [bytes(buf[:n])] * 40 + [bytes(bad[:n])] + [bytes(buf[:n])] * 9          # group 0 clean, group 1 holds the rejected proof
+    vb = pkg.VerifyBatch(blobs, inputs=pkg.INPUTS_SINGLE)
+    vb.run(full=True)
+    base = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)
+    r0 = base.trace(vb, check=True, export=True)
+    keep = (r0["values"].cpu().numpy().copy(), r0["bad_row"].cpu().numpy().copy(), r0["bad_flow"].cpu().numpy().copy(),
+            base.fetch(3, "variables").copy(), base.fetch(3, "flow_hash").copy())
+    monkeypatch.setenv("STWO_B200_RECORDED_ORDER", "1")
+    circ = pkg.VerifierCircuit(vb.shape, inputs=pkg.INPUTS_SINGLE)                     # recorded under the switch: both orders
+    r1 = circ.trace(vb, check=True, export=True)
+    got = (r1["values"].cpu().numpy(), r1["bad_row"].cpu().numpy(), r1["bad_flow"].cpu().numpy(), circ.fetch(3, "variables"), circ.fetch(3, "flow_hash"))
+    for a, b in zip(keep, got):
+        assert np.array_equal(a, b)
+    assert keep[1][40] >= 0 and (np.delete(keep[1], 40) == -1).all()

@@ -66,7 +66,8 @@ def evaluate(hs, h, info, blobs, shape, inputs, use_hints=0, full=1):
 
 @pytest.mark.parametrize("name,mult", [("small_proof.bin", 1), ("level13-1.bin", 1), ("level7-1.bin", 1), ("level9-1.bin", 1),
                                        ("small_proof.bin", 2)])
-def test_recorded_circuit_matches_oracle(hostsim, orc, name, mult):
+def test_recorded_circuit_matches_oracle(hostsim, orc, name, mult, monkeypatch):
+    monkeypatch.setenv("STWO_B200_RECORDED_ORDER", "1")      # also build the second order of the tape (opt-in), checked below
     cs, out = oracle_circuit(name, mult)
     buf, n = O.load_proof(name)
     shape = shape_of(buf)
@@ -89,6 +90,13 @@ def test_recorded_circuit_matches_oracle(hostsim, orc, name, mult):
     dt3, variables3, fh3, fs3, bad3 = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name), use_hints=1, full=3)
     assert dt3[0].n_perms_paths == out.n_perms_paths
     assert bad3[0] == -1 and np.array_equal(variables3, variables) and np.array_equal(fh3, fh) and np.array_equal(fs3, fs)
+    # ... and in the SECOND ORDER of the tape (every recorded permutation split into outputs-from-the-record + flow entry: the
+    # transcript and path chains are no dependency chains any more): fewer levels, the very same variables and flow
+    o2 = np.zeros(3, dtype=np.uint32)
+    hostsim.hs_circuit_recorded_order(h, O.vp(o2))
+    assert 0 < o2[0] < info["n_levels"] and o2[2] == info["n_ins"] + info["n_flow"]
+    dt4, variables4, fh4, fs4, bad4 = evaluate(hostsim, h, info, [(buf, n)], shape, O.inputs_for(name), use_hints=2, full=3)
+    assert bad4[0] == -1 and np.array_equal(variables4, variables) and np.array_equal(fh4, fh) and np.array_equal(fs4, fs)
     wire, addr, wh, wsw = cs.flow_arrays()
     assert np.array_equal(fh[0], wh) and np.array_equal(fs[0], wsw)
     hostsim.hs_circuit_free(h)
