@@ -180,6 +180,21 @@ extern "C" int32_t stwo_b200_poseidon2_permute_dev_variant(uint32_t *states, siz
     if (n == 0) return STWO_B200_OK;
     if (!states || ((uintptr_t)states & 15)) return STWO_B200_E_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    // 10 + v / 20 + v: variant v (0 or 2) with the residency cut to 2 / 3 blocks per SM by a dynamic shared-memory request -- how the
+    // permutation rate depends on resident warps, with one and with two states per thread (the tree rebuilds run at 16 warps per SM)
+    if (variant >= 10) {
+        const int base = variant % 10;
+        const size_t smem = variant < 20 ? 100 * 1024 : 64 * 1024;
+        if (base == 2) {
+            STWO_CUDA(cudaFuncSetAttribute(k_poseidon2_permute_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_poseidon2_permute_x2<<<blocks_for((n + 1) / 2), kThreads, smem, st>>>(states, n);
+        } else {
+            STWO_CUDA(cudaFuncSetAttribute(k_poseidon2_permute<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_poseidon2_permute<false><<<blocks_for(n), kThreads, smem, st>>>(states, n);
+        }
+        note_launch();
+        return cuda_status(cudaGetLastError());
+    }
     if (variant == 2) k_poseidon2_permute_x2<<<blocks_for((n + 1) / 2), kThreads, 0, st>>>(states, n);
     else if (variant == 3) k_poseidon2_permute_occ<8><<<blocks_for(n), kThreads, 0, st>>>(states, n);
     else if (variant == 4) k_poseidon2_permute_occ<10><<<blocks_for(n), kThreads, 0, st>>>(states, n);

@@ -9,7 +9,8 @@ pkg.init(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 st = torch.randint(0, 2**31 - 1, (n, 16), dtype=torch.int32, device="cuda")
 res = {}
-for variant, name in ((0, "rolled"), (1, "unrolled"), (2, "rolled_x2"), (3, "rolled_occ8"), (4, "rolled_occ10"), (5, "rolled_occ5")):
+for variant, name in ((0, "rolled"), (1, "unrolled"), (2, "rolled_x2"), (3, "rolled_occ8"), (4, "rolled_occ10"), (5, "rolled_occ5"),
+                      (10, "rolled_2_blocks_per_sm"), (12, "rolled_x2_2_blocks_per_sm"), (20, "rolled_3_blocks_per_sm"), (22, "rolled_x2_3_blocks_per_sm")):
     for _ in range(3):
         pkg.poseidon2_permute(st, variant=variant)
     torch.cuda.synchronize()
