@@ -118,6 +118,30 @@ HD void prologue(const View &v) {
     stv(v, 0, qm31::mk(0, 0, 0, 0)); stv(v, 1, qm31::mk(1, 0, 0, 0)); stv(v, 2, qm31::mk(0, 1, 0, 0)); stv(v, 3, qm31::mk(0, 0, 1, 0));
 }
 
+// a permutation record of the tape: 12 words, 16-byte aligned, the same for every lane -> three 16-byte loads on the device
+HD Perm ld_perm(const Perm *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    Perm r;
+    r.l_kind = a.x; r.l_a = a.y; r.l_b = a.z; r.r_kind = a.w; r.r_a = b.x; r.r_b = b.y; r.swap_var = b.z; r.out[0] = b.w;
+    r.out[1] = c.x; r.out[2] = c.y; r.out[3] = c.z; r.hint = c.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+// one slot of the permutation record: 16 words, 64-byte aligned, contiguous per item -> four 16-byte loads on the device
+HD void ld_slot(const u32 *h, u32 *st) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
+    const uint4 a = h4[0], b = h4[1], c = h4[2], d = h4[3];
+    st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w; st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+    st[8] = c.x; st[9] = c.y; st[10] = c.z; st[11] = c.w; st[12] = d.x; st[13] = d.y; st[14] = d.z; st[15] = d.w;
+#else
+    for (int k = 0; k < 16; k++) st[k] = h[k];
+#endif
+}
 HD void load_half(const View &v, u32 kind, u32 a, u32 b, u32 *h) {
     if (kind == 0) {
         const qm31_t l = ldv(v, a), r = ldv(v, b);
@@ -139,8 +163,7 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];          // PoseidonEntry 1, 2: the halves as given
     }
     if (v.hint && p.hint) {                     // executed once already by the native verifier: take its output state
-        const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
-        for (int k = 0; k < 16; k++) st[k] = h[k];
+        ld_slot(v.hint + (size_t)(p.hint - 1) * 16, st);
     } else poseidon2::permute<UNROLLED>(st);
     if (v.flow_hash) {
         u32 *fh = v.flow_hash + ((size_t)entry * 32 + 16) * v.stride;
@@ -232,7 +255,7 @@ HD void eval(const View &v, const Ins &in, const Perm *perms, const u32 *eperms 
     case T_INV_CM31_IM: stv(v, in.dst, qm31::from_m31(cm31::inv(qm31::lo(ldv(v, in.a))).b)); break;
     case T_COORD: stv(v, in.dst, qm31::from_m31(ldv(v, in.a).v[in.b & 3u])); break;
     case T_BIT: stv(v, in.dst, qm31::from_m31((ldv(v, in.a).v[0] >> (in.b & 31u)) & 1u)); break;
-    case T_POSEIDON: eval_poseidon<UNROLLED>(v, perms[in.dst], in.dst); break;
+    case T_POSEIDON: eval_poseidon<UNROLLED>(v, ld_perm(perms + in.dst), in.dst); break;
     case T_M4: stv(v, in.dst, q_m4(ldv(v, in.a))); break;
     case T_POW5M4: stv(v, in.dst, q_m4(q_had(ldv(v, in.a), ldv(v, in.b)))); break;
     case T_HADAMARD: stv(v, in.dst, q_had(ldv(v, in.a), ldv(v, in.b))); break;
