@@ -177,7 +177,8 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
 // T_PERM_OUT / T_PERM_FLOW: eval_poseidon of a recorded permutation in two independent steps (v.hint is set: the order that holds these
 // instructions is chosen only for items whose record is complete)
 HD void eval_perm_out(const View &v, const Perm &p) {
-    const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
+    u32 h[16];
+    ld_slot(v.hint + (size_t)(p.hint - 1) * 16, h);
     for (int k = 0; k < 4; k++)
         if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
 }
@@ -189,7 +190,8 @@ HD void eval_perm_flow(const View &v, const Perm &p, u32 entry) {
     if (v.flow_hash) {
         u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
         for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];
-        const u32 *h = v.hint + (size_t)(p.hint - 1) * 16;
+        u32 h[16];
+        ld_slot(v.hint + (size_t)(p.hint - 1) * 16, h);
         for (int k = 0; k < 16; k++) fh[(size_t)(16 + k) * v.stride] = h[k];
     }
     if (v.flow_swap) v.flow_swap[(size_t)entry * v.stride] = swap ? 1 : 0;
@@ -262,8 +264,8 @@ HD void eval(const View &v, const Ins &in, const Perm *perms, const u32 *eperms 
     case T_GRANDSUM: stv(v, in.dst, q_grandsum(ldv(v, in.a), ldv(v, in.b))); break;
     case T_POW4: stv(v, in.dst, q_pow4(ldv(v, in.a))); break;
     case T_EPOSEIDON: eval_eposeidon(v, eperms + (size_t)in.dst * EPOSEIDON_REC); break;
-    case T_PERM_OUT: eval_perm_out(v, perms[in.dst]); break;
-    case T_PERM_FLOW: eval_perm_flow(v, perms[in.dst], in.dst); break;
+    case T_PERM_OUT: eval_perm_out(v, ld_perm(perms + in.dst)); break;
+    case T_PERM_FLOW: eval_perm_flow(v, ld_perm(perms + in.dst), in.dst); break;
     default: break;
     }
 }
