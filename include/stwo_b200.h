@@ -353,7 +353,8 @@ int32_t stwo_b200_cs_export_tiles_build(const stwo_b200_cs_wiring *host_wiring, 
 typedef struct {
     uint32_t n_batch, lanes;                         /* lanes: 1 or 32 */
     uint32_t *variables;                             /* n_vars QM31 per item */
-    uint32_t *flow_hash;                             /* n_flow x 32 words per item (PoseidonEntry.hash of entries 1..4) */
+    uint32_t *flow_hash;                             /* n_flow x 32 words per item (PoseidonEntry.hash of entries 1..4); the interleaved
+                                                      * ELEMENT is 4 words (16 bytes), like a variable: n_flow x 8 elements per item */
     uint8_t *flow_swap;                              /* n_flow bytes per item (SwapOption.swap) */
     /* Optional (NULL / 0 = none), read by stwo_b200_cs_eval_tape_dev only: output states of permutations that were executed
      * before -- item b's record k is the 16 words at perm_hints[b * perm_hint_stride + 16 k] (item-major, NOT lane-interleaved).

@@ -366,7 +366,7 @@ extern "C" int32_t stwo_b200_circuit_fetch(const stwo_b200_circuit *c, const voi
     const uint8_t *src; size_t elem, n;
     switch (what) {
         case STWO_B200_CFETCH_VARIABLES: elem = 16; n = cs.n_vars; src = (const uint8_t *)k.vars; break;
-        case STWO_B200_CFETCH_FLOW_HASH: elem = 4; n = (size_t)cs.num_poseidon_invocations() * 32; src = (const uint8_t *)k.flow_hash; break;
+        case STWO_B200_CFETCH_FLOW_HASH: elem = 16; n = (size_t)cs.num_poseidon_invocations() * 8; src = (const uint8_t *)k.flow_hash; break;   // 16-byte elements
         case STWO_B200_CFETCH_FLOW_SWAP: elem = 1; n = cs.num_poseidon_invocations(); src = k.flow_swap; break;
         case STWO_B200_CFETCH_WITNESS: elem = 4; n = cs.n_input_words; src = (const uint8_t *)k.witness; break;
         default: return STWO_B200_E_BAD_ARG;

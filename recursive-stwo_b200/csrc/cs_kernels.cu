@@ -27,7 +27,7 @@ struct Batch {                       // stwo_b200_cs_values + sizes, passed by v
         tape::View v;
         v.vars = vars + g * n_vars * lanes + l;
         v.input = input ? input + g * n_input_words * lanes + l : nullptr;
-        v.flow_hash = flow_hash ? flow_hash + g * n_flow * 32 * lanes + l : nullptr;
+        v.flow_hash = flow_hash ? reinterpret_cast<tape::Q4 *>(flow_hash) + g * n_flow * 8 * lanes + l : nullptr;
         v.flow_swap = flow_swap ? flow_swap + g * n_flow * lanes + l : nullptr;
         v.stride = lanes;
         v.hint = hints && (!hint_ready || hint_ready[item] == hint_need) ? hints + (size_t)item * hint_stride : nullptr;
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(128) k_cs_check_poseidon(stwo_b200_cs_wiring w
         const u32 e = (u32)(t % w.n_flow), grp = (u32)(t / w.n_flow), item = grp * b.lanes + lane;
         if (item >= b.n_batch) continue;
         const tape::View v = b.view(item, nullptr, 0);
-        const u32 *h = v.flow_hash + (size_t)e * 32 * v.stride;
+        const tape::Q4 *h = v.flow_hash + (size_t)e * 8 * v.stride;
         u32 hh[32];
 #pragma unroll
-        for (int k = 0; k < 32; k++) hh[k] = h[(size_t)k * v.stride];
+        for (int q = 0; q < 8; q++) { const tape::Q4 t = h[(size_t)q * v.stride]; hh[4 * q] = t.x; hh[4 * q + 1] = t.y; hh[4 * q + 2] = t.z; hh[4 * q + 3] = t.w; }
         bool ok = true;
         for (int k = 0; k < 4; k++) {
             const u32 wire = w.flow_wire[4 * e + k];
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kXThreads, 2) k_cs_export_vals_stream(stwo_b20
     }
 }
 // ---- K7: PoseidonFlow export ---------------------------------------------------------------------------------------------------
-// The flow the tape evaluation recorded (lane-interleaved: [group][entry][32 words][32 lanes]) as plain per-item arrays
+// The flow the tape evaluation recorded (lane-interleaved 16-byte elements: [group][entry][8 quads][32 lanes][4 words]) as plain per-item arrays
 // hash[item][entry][32], swap[item][entry], padded to n_pad entries the way pad() does (plonk_with_poseidon.rs:296-321): entries
 // (wire 0, C1), (0, C1), (0, C2), (0, C3), swap = false.  A warp transposes one (group, entry) tile through shared memory: reads
 // are 128-byte rows across the lanes, writes the 128 contiguous bytes of one item's entry.
@@ -571,9 +571,12 @@ __global__ void __launch_bounds__(256) k_cs_export_flow(Batch b, u32 n_pad, cons
         const u32 grp = (u32)(t / n_pad), e = (u32)(t % n_pad);
         const u32 item = grp * 32 + lane;
         if (e < b.n_flow) {
-            const u32 *src = b.flow_hash + ((size_t)grp * b.n_flow + e) * 32 * 32;
-#pragma unroll 8
-            for (u32 w = 0; w < 32; w++) tile[warp][w][lane] = src[w * 32 + lane];
+            const tape::Q4 *src = reinterpret_cast<const tape::Q4 *>(b.flow_hash) + ((size_t)grp * b.n_flow + e) * 8 * 32;
+#pragma unroll
+            for (u32 q = 0; q < 8; q++) {
+                const tape::Q4 t = src[q * 32 + lane];
+                tile[warp][4 * q][lane] = t.x; tile[warp][4 * q + 1][lane] = t.y; tile[warp][4 * q + 2][lane] = t.z; tile[warp][4 * q + 3][lane] = t.w;
+            }
             __syncwarp();
             for (u32 it = 0; it < 32; it++)
                 if (grp * 32 + it < b.n_batch) hash_out[((size_t)(grp * 32 + it) * n_pad + e) * 32 + lane] = tile[warp][lane][it];

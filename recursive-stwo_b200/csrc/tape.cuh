@@ -82,7 +82,7 @@ HD u32 src_k(u32 s) { return s >> 17; }
 struct View {
     Q4 *vars;                                   // + element * stride
     const u32 *input;                           // + word * stride
-    u32 *flow_hash;                             // + (entry * 32 + word) * stride     may be null
+    Q4 *flow_hash;                              // + (entry * 8 + quad) * stride: 16-byte elements, like vars     may be null
     uint8_t *flow_swap;                         // + entry * stride                   may be null
     u32 stride;
     const u32 *hint;                            // the item's permutation hints, 16 consecutive words per slot; may be null
@@ -142,6 +142,11 @@ HD void ld_slot(const u32 *h, u32 *st) {
     for (int k = 0; k < 16; k++) st[k] = h[k];
 #endif
 }
+// 16 words of a flow entry (quads q0 .. q0 + 3 of its eight 16-byte elements)
+HD void st_flow(const View &v, u32 entry, u32 q0, const u32 *w) {
+    Q4 *f = v.flow_hash + (size_t)(entry * 8 + q0) * v.stride;
+    for (int q = 0; q < 4; q++) { Q4 t; t.x = w[4 * q]; t.y = w[4 * q + 1]; t.z = w[4 * q + 2]; t.w = w[4 * q + 3]; f[(size_t)q * v.stride] = t; }
+}
 HD void load_half(const View &v, u32 kind, u32 a, u32 b, u32 *h) {
     if (kind == 0) {
         const qm31_t l = ldv(v, a), r = ldv(v, b);
@@ -158,17 +163,11 @@ HD void eval_poseidon(const View &v, const Perm &p, u32 entry) {
     load_half(v, p.r_kind, p.r_a, p.r_b, in + 8);
     const bool swap = p.swap_var != NO_VAR && ldv(v, p.swap_var).v[0] != 0;
     for (int k = 0; k < 8; k++) { st[k] = swap ? in[8 + k] : in[k]; st[8 + k] = swap ? in[k] : in[8 + k]; }
-    if (v.flow_hash) {
-        u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
-        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];          // PoseidonEntry 1, 2: the halves as given
-    }
+    if (v.flow_hash) st_flow(v, entry, 0, in);                                  // PoseidonEntry 1, 2: the halves as given
     if (v.hint && p.hint) {                     // executed once already by the native verifier: take its output state
         ld_slot(v.hint + (size_t)(p.hint - 1) * 16, st);
     } else poseidon2::permute<UNROLLED>(st);
-    if (v.flow_hash) {
-        u32 *fh = v.flow_hash + ((size_t)entry * 32 + 16) * v.stride;
-        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = st[k];          // PoseidonEntry 3, 4: the full output
-    }
+    if (v.flow_hash) st_flow(v, entry, 4, st);                                  // PoseidonEntry 3, 4: the full output
     if (v.flow_swap) v.flow_swap[(size_t)entry * v.stride] = swap ? 1 : 0;
     for (int k = 0; k < 4; k++)
         if (p.out[k] != NO_VAR) stv(v, p.out[k], qm31::mk(st[4 * k], st[4 * k + 1], st[4 * k + 2], st[4 * k + 3]));
@@ -188,11 +187,10 @@ HD void eval_perm_flow(const View &v, const Perm &p, u32 entry) {
     load_half(v, p.r_kind, p.r_a, p.r_b, in + 8);
     const bool swap = p.swap_var != NO_VAR && ldv(v, p.swap_var).v[0] != 0;
     if (v.flow_hash) {
-        u32 *fh = v.flow_hash + (size_t)entry * 32 * v.stride;
-        for (int k = 0; k < 16; k++) fh[(size_t)k * v.stride] = in[k];
+        st_flow(v, entry, 0, in);
         u32 h[16];
         ld_slot(v.hint + (size_t)(p.hint - 1) * 16, h);
-        for (int k = 0; k < 16; k++) fh[(size_t)(16 + k) * v.stride] = h[k];
+        st_flow(v, entry, 4, h);
     }
     if (v.flow_swap) v.flow_swap[(size_t)entry * v.stride] = swap ? 1 : 0;
 }

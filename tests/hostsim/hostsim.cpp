@@ -204,7 +204,7 @@ void hs_circuit_eval(void *h, void *ws_base, u32 n, u32 *vars, u32 *flow_hash, u
         }
         for (u32 k = 0; k < c.n_input_words; k++) stream[k] = circuit::gather_word(ws, p, r->gather[k], extra.data());
         if (stream_out) memcpy(stream_out + (size_t)p * c.n_input_words, stream.data(), stream.size() * 4);
-        tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), flow_hash + (size_t)p * c.num_poseidon_invocations() * 32,
+        tape::View v{(tape::Q4 *)(vars + (size_t)p * c.n_vars * 4), stream.data(), (tape::Q4 *)(flow_hash + (size_t)p * c.num_poseidon_invocations() * 32),
                      flow_swap + (size_t)p * c.num_poseidon_invocations(), 1,
                      use_hints && !c.without() && ws.hint_trees[p] == ws.shape.n_trees() ? ws.perm_out_of(p, 0) : nullptr};
         tape::prologue(v);
