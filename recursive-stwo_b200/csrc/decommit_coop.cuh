@@ -47,6 +47,29 @@ struct PermRec {
     // where the state seen by a tap goes: the output record, or (before the permutation) the parallel input record; nullptr = nowhere
     HDM u32 *slot(u32 query, u32 k, bool after) const { return after ? slot(query, k) : in_delta ? slot(query, k) + in_delta : nullptr; }
 };
+// The queries whose path runs through one node, as a bit set (n_queries <= 128): built once per node, walked once per permutation
+// state -- scanning all queries for every state costs 2 x n_queries steps per permutation, a fifth of the permutation itself at 80 queries.
+struct QSet {
+    u32 w[4];
+    HDM void clear() { w[0] = w[1] = w[2] = w[3] = 0; }
+    template <class F> HDM void build(u32 nq, F member) {
+        for (u32 k = 0; k < 4; k++) {
+            u32 m = 0;
+            for (u32 b = 0; b < 32 && 32 * k + b < nq; b++) if (member(32 * k + b)) m |= 1u << b;
+            w[k] = m;
+        }
+    }
+    template <class F> HDM void each(F f) const {
+        for (u32 k = 0; k < 4; k++)
+            for (u32 m = w[k]; m; m &= m - 1) {
+#if defined(__CUDA_ARCH__)
+                f(32 * k + (u32)__ffs((int)m) - 1);
+#else
+                f(32 * k + (u32)__builtin_ctz(m));
+#endif
+            }
+    }
+};
 HD void st16(u32 *dst, const u32 *st) {
 #if defined(__CUDA_ARCH__)
     uint4 *d = reinterpret_cast<uint4 *>(dst);          // slots are 64-byte aligned
@@ -95,8 +118,10 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
     if (!ctl[3]) {
         for (u32 k = L; k < m; k += G) {
             u32 h8[8];
+            QSet mine; mine.clear();
+            if (rec.base) mine.build(nq, [&](u32 i) { return qnode[i] == k; });
             hash_node2_tap(nullptr, nullptr, values + (size_t)k * nc, nc, h8, nullptr, [&](u32 j, const u32 *st, bool after) {
-                if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) if (qnode[i] == k) st16(rec.slot(i, j, after), st);
+                if (rec.base && (after || rec.in_delta)) mine.each([&](u32 i) { st16(rec.slot(i, j, after), st); });
             });
             for (int i = 0; i < 8; i++) chash[8 * k + i] = h8[i];
         }
@@ -146,8 +171,10 @@ HD bool single_tree_coop(const Co &co, const SingleShape &sh, const u32 *q, u32 
                 u32 l8[8], r8[8], h8[8];
                 if (ps & 1u) { load_hash(chash, hw, s, l8); load_hash(chash, hw, k, r8); }
                 else { load_hash(chash, hw, k, l8); load_hash(chash, hw, s, r8); }
+                QSet mine; mine.clear();
+                if (rec.base) mine.build(nq, [&](u32 i) { return par[qnode[i]] == j; });
                 hash_node2_tap(l8, r8, values + vi0 + (size_t)j * nc, nc, h8, nullptr, [&](u32 jj, const u32 *st, bool after) {
-                    if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) if (par[qnode[i]] == j) st16(rec.slot(i, slot_off + jj, after), st);
+                    if (rec.base && (after || rec.in_delta)) mine.each([&](u32 i) { st16(rec.slot(i, slot_off + jj, after), st); });
                 });
                 for (int i = 0; i < 8; i++) phash[8 * j + i] = h8[i];
                 ppos[j] = ps >> 1;
@@ -262,10 +289,12 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
                 if (h == depth) {
                     // a leaf is the self opening of the queries at its position (slots 0, 1) and the sibling opening of the
                     // queries at the other member of its pair (slots 2, 3)
+                    QSet self, sibl; self.clear(); sibl.clear();
+                    if (rec.base) { self.build(nq, [&](u32 i) { return q[i] == pos; }); sibl.build(nq, [&](u32 i) { return (q[i] ^ 1u) == pos; }); }
                     hash_node2_tap(nullptr, nullptr, val, 4, h8, nullptr, [&](u32 j, const u32 *st, bool after) {
-                        if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) {
-                            if (q[i] == pos) st16(rec.slot(i, j, after), st);
-                            else if ((q[i] ^ 1u) == pos) st16(rec.slot(i, 2 + j, after), st);
+                        if (rec.base && (after || rec.in_delta)) {
+                            self.each([&](u32 i) { st16(rec.slot(i, j, after), st); });
+                            sibl.each([&](u32 i) { st16(rec.slot(i, 2 + j, after), st); });
                         }
                     });
                     for (int i = 0; i < 8; i++) nhash[8 * a + i] = h8[i];
@@ -274,11 +303,15 @@ HD bool pair_tree_coop(const Co &co, u32 depth, u32 data_mask, const u32 *q, u32
                     load_hash(chash, hw, rsrc[a], r8);
                     // self node of a query: all its permutations; sibling node at a data layer: the two that fold the sibling's
                     // own evaluation into its tree hash (the tree hash itself is a hint of the path)
+                    QSet self, sibl; self.clear(); sibl.clear();
+                    if (rec.base) {
+                        self.build(nq, [&](u32 i) { return (q[i] >> sh_q) == pos; });
+                        if (data && h >= 1) sibl.build(nq, [&](u32 i) { return ((q[i] >> sh_q) ^ 1u) == pos; });
+                    }
                     hash_node2_tap(l8, r8, val, data ? 4 : 0, h8, t8, [&](u32 j, const u32 *st, bool after) {
-                        if (rec.base && (after || rec.in_delta)) for (u32 i = 0; i < nq; i++) {
-                            const u32 qh = q[i] >> sh_q;
-                            if (qh == pos) st16(rec.slot(i, slot_off + j, after), st);
-                            else if (data && h >= 1 && j >= 1 && (qh ^ 1u) == pos) st16(rec.slot(i, slot_off + 2 + j, after), st);
+                        if (rec.base && (after || rec.in_delta)) {
+                            self.each([&](u32 i) { st16(rec.slot(i, slot_off + j, after), st); });
+                            if (j >= 1) sibl.each([&](u32 i) { st16(rec.slot(i, slot_off + 2 + j, after), st); });
                         }
                     });
                     for (int i = 0; i < 8; i++) { nhash[8 * a + i] = h8[i]; ntree[8 * a + i] = t8[i]; nL[8 * a + i] = l8[i]; nR[8 * a + i] = r8[i]; }
